@@ -1,0 +1,312 @@
+// Host orchestration of the forward path: encoder (Cross-Gating block), init state, one word step,
+// greedy decode loop, teacher-forced training forward.
+#pragma once
+#include "xg_context.cuh"
+#include "xg_fwd_kernels.cuh"
+
+namespace xg {
+
+#define P_(ctx, id) ((ctx)->P[id])
+
+static inline int ew_grid(long n, int block = 256) {
+  long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > 148L * 16) g = 148L * 16;
+  return (int)g;
+}
+
+static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) { return gemm_simt(ctx->es, p, st); }
+
+// ------------------------------------------------------------------------------------
+// EncoderLstm_two_fc.forward (sub_modules.py:118-159)
+// ------------------------------------------------------------------------------------
+static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, const float* fmask, int B, int K,
+                       int train, uint64_t seed, EncBufs& eb, float* V_out, float* Uv_out,
+                       float* const* state_out, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn;
+  const int BK = B * K;
+  const float* X[2] = {rgb, opfl};
+  const int din[2] = {d.feat_rgb, d.feat_opfl};
+  const int pw[2] = {XG_P_EMB_RGB_W, XG_P_EMB_OPFL_W};
+  const int plstm[2] = {XG_P_LSTM_RGB_WIH, XG_P_LSTM_OPFL_WIH};
+  const uint32_t site_emb[2] = {XG_DROP_ENC_EMB_RGB, XG_DROP_ENC_EMB_OPFL};
+  const int RS = bn_row_splits(BK);
+
+  for (int s = 0; s < 2; ++s) {
+    // visual_emb_*.0 : Linear over the flattened (B*K) rows, padded rows included (:121,126)
+    GemmP g = gemm_nt(X[s], din[s], P_(ctx, pw[s]), din[s], eb.Y[s], H, BK, H, din[s]);
+    g.ep.bias0 = P_(ctx, pw[s] + 1);
+    XG_TRY(gemm_run(ctx, g, st));
+    // visual_emb_*.1 : BatchNorm1d
+    if (train) {
+      colstats_partial_kernel<<<dim3(ceil_div(H, 32), RS), dim3(32, 8), 0, st>>>(eb.Y[s], BK, H, eb.part);
+      XG_LAUNCH_CHECK(ctx->es);
+    }
+    bn_finalize_kernel<<<ceil_div(H, 128), 128, 0, st>>>(eb.part, RS, BK, H, train, P_(ctx, pw[s] + 2),
+                                                        P_(ctx, pw[s] + 3), ctx->bn[2 * s], ctx->bn[2 * s + 1],
+                                                        d.bn_eps, d.bn_momentum, train ? 1 : 0, eb.scale[s],
+                                                        eb.shift[s], eb.mean[s], eb.invstd[s]);
+    XG_LAUNCH_CHECK(ctx->es);
+    // ReLU, dropout, frame mask; output frame-major (:123,128)
+    bn_apply_kernel<<<ew_grid((long)BK * H), 256, 0, st>>>(eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
+                                                          make_drop(train, d.drop_prob, seed, site_emb[s]), eb.E[s]);
+    XG_LAUNCH_CHECK(ctx->es);
+    // nn.LSTMCell input projection hoisted over all frames: XG = E . W_ih^T + b_ih + b_hh
+    GemmP gi = gemm_nt(eb.E[s], H, P_(ctx, plstm[s]), H, eb.G[s], 4 * H, BK, 4 * H, H);
+    gi.ep.bias0 = P_(ctx, plstm[s] + 2);
+    gi.ep.bias1 = P_(ctx, plstm[s] + 3);
+    XG_TRY(gemm_run(ctx, gi, st));
+  }
+  // recurrence over frames (:132-147); the two streams are independent
+  for (int t = 0; t < K; ++t) {
+    for (int s = 0; s < 2; ++s) {
+      float* Zt = eb.G[s] + (long)t * B * 4 * H;
+      if (t > 0) {
+        GemmP gh = gemm_nt(eb.Hs[s] + (long)(t - 1) * B * H, H, P_(ctx, plstm[s] + 1), H, Zt, 4 * H, B, 4 * H, H);
+        gh.ep.beta = 1.f;
+        XG_TRY(gemm_run(ctx, gh, st));
+      }
+      enc_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(Zt, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
+                                                           fmask, K, t, B, H, eb.Cs[s] + (long)t * B * H,
+                                                           eb.Hs[s] + (long)t * B * H);
+      XG_LAUNCH_CHECK(ctx->es);
+    }
+  }
+  // cross gates batched over all frames (:151-152): g_tgt = h_tgt * (1 + dropout(relu(Linear(h_src))))
+  {
+    const int gw[2] = {XG_P_GATE_RGB_W, XG_P_GATE_OPFL_W};
+    const uint32_t site_gate[2] = {XG_DROP_ENC_GATE_RGB, XG_DROP_ENC_GATE_OPFL};
+    for (int s = 0; s < 2; ++s) {
+      const int src = 1 - s;
+      GemmP g = gemm_nt(eb.Hs[src], H, P_(ctx, gw[s]), H, eb.GG + (long)s * H, 2 * H, BK, H, H);
+      g.ep.bias0 = P_(ctx, gw[s] + 1);
+      g.ep.act = XG_ACT_RELU;
+      g.ep.drop = make_drop(train, d.drop_prob, seed, site_gate[s]);
+      g.ep.aux = eb.R[s];
+      g.ep.ldaux = H;
+      g.ep.tgt = eb.Hs[s];
+      g.ep.ldt = H;
+      XG_TRY(gemm_run(ctx, g, st));
+    }
+  }
+  // late fusion (:158), rows back to batch-major
+  {
+    GemmP g = gemm_nt(eb.GG, 2 * H, P_(ctx, XG_P_FUSION_W), 2 * H, V_out, H, BK, H, 2 * H);
+    g.ep.bias0 = P_(ctx, XG_P_FUSION_B);
+    g.ep.act = d.fusion_act;
+    g.ep.drop = make_drop(train, d.drop_prob, seed, XG_DROP_ENC_FUSION);
+    g.perm_rb = B;
+    g.perm_rs = K;
+    XG_TRY(gemm_run(ctx, g, st));
+  }
+  if (Uv_out) {  // v2a(V): loop invariant of the word loop (sub_modules.py:677)
+    GemmP g = gemm_nt(V_out, H, P_(ctx, XG_P_V2A_W), H, Uv_out, d.att, BK, d.att, H);
+    g.ep.bias0 = P_(ctx, XG_P_V2A_B);
+    XG_TRY(gemm_run(ctx, g, st));
+  }
+  if (state_out) {  // SAModel.init_hidden (SAModel.py:58-65)
+    masked_mean_kernel<<<B, 128, 0, st>>>(V_out, fmask, B, K, H, eb.meanV);
+    XG_LAUNCH_CHECK(ctx->es);
+    const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
+    for (int q = 0; q < 4; ++q) {
+      GemmP g = gemm_nt(eb.meanV, H, P_(ctx, iw[q]), H, state_out[q], H, B, H, H);
+      g.ep.bias0 = P_(ctx, iw[q] + 1);
+      XG_TRY(gemm_run(ctx, g, st));
+    }
+  }
+  return XG_OK;
+}
+
+static int init_hidden_core(xg_context* ctx, const float* V, const float* fmask, int B, int K, float* meanV,
+                            float* const* state_out, long ld_out, cudaStream_t st) {
+  const int H = ctx->d.rnn;
+  masked_mean_kernel<<<B, 128, 0, st>>>(V, fmask, B, K, H, meanV);
+  XG_LAUNCH_CHECK(ctx->es);
+  const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
+  for (int q = 0; q < 4; ++q) {
+    GemmP g = gemm_nt(meanV, H, P_(ctx, iw[q]), H, state_out[q], q % 2 == 0 ? ld_out : H, B, H, H);
+    g.ep.bias0 = P_(ctx, iw[q] + 1);
+    XG_TRY(gemm_run(ctx, g, st));
+  }
+  return XG_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// LSTMCore_two_layer_gate.forward (sub_modules.py:671-687), inference form (nothing hoisted)
+// ------------------------------------------------------------------------------------
+struct StepState {
+  const float* h1p; long ld_h1p; const float* c1p; const float* h2p; long ld_h2p; const float* c2p;
+  float* h1n; long ld_h1n; float* c1n; float* h2n; long ld_h2n; float* c2n;
+};
+
+static int decode_step_core(xg_context* ctx, const float* xt, const float* mask, long mask_stride, const float* V,
+                            const float* Uv, const float* pos, const StepState& s, StepBufs& sb, float* alpha_out,
+                            int B, int K, int feat_div, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, E = d.embed, A = d.att;
+  // attention on the PREVIOUS states
+  {
+    GemmP g = gemm_nt(s.h1p, s.ld_h1p, P_(ctx, XG_P_H2A_W), 2 * H, sb.AH, A, B, A, H);
+    g.ep.bias0 = P_(ctx, XG_P_H2A_B);
+    XG_TRY(gemm_run(ctx, g, st));
+    GemmP g2 = gemm_nt(s.h2p, s.ld_h2p, P_(ctx, XG_P_H2A_W) + H, 2 * H, sb.AH, A, B, A, H);
+    g2.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, g2, st));
+    att_fwd_kernel<<<B, 256, (A + K) * sizeof(float), st>>>(sb.AH, Uv, V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K, A,
+                                                           H, feat_div, alpha_out, sb.AF);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  // POS gate: gp = pos * (1 + relu(Linear(xt)))
+  {
+    GemmP g = gemm_nt(xt, E, P_(ctx, XG_P_DGATE_W), E, sb.GP, H, B, H, E);
+    g.ep.bias0 = P_(ctx, XG_P_DGATE_B);
+    g.ep.act = XG_ACT_RELU;
+    g.ep.tgt = pos;
+    g.ep.ldt = H;
+    g.ep.tgt_div = feat_div > 1 ? feat_div : 0;
+    XG_TRY(gemm_run(ctx, g, st));
+  }
+  // lstm_1
+  {
+    GemmP g = gemm_nt(xt, E, P_(ctx, XG_P_L1_I2H_W), E, sb.Z1, 4 * H, B, 4 * H, E);
+    g.ep.bias0 = P_(ctx, XG_P_L1_I2H_B); g.ep.bias1 = P_(ctx, XG_P_L1_A2H_B); g.ep.bias2 = P_(ctx, XG_P_L1_H2H_B);
+    XG_TRY(gemm_run(ctx, g, st));
+    GemmP ga = gemm_nt(sb.GP, H, P_(ctx, XG_P_L1_A2H_W), H, sb.Z1, 4 * H, B, 4 * H, H);
+    ga.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, ga, st));
+    GemmP gh = gemm_nt(s.h1p, s.ld_h1p, P_(ctx, XG_P_L1_H2H_W), H, sb.Z1, 4 * H, B, 4 * H, H);
+    gh.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, gh, st));
+    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(sb.Z1, s.c1p, s.h1p, s.ld_h1p, mask, mask_stride, B, H,
+                                                         make_drop(false, 0.f, 0, 0), s.c1n, s.h1n, s.ld_h1n, nullptr, 0);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  // lstm_2
+  {
+    GemmP g = gemm_nt(s.h1n, s.ld_h1n, P_(ctx, XG_P_L2_I2H_W), H, sb.Z2, 4 * H, B, 4 * H, H);
+    g.ep.bias0 = P_(ctx, XG_P_L2_I2H_B); g.ep.bias1 = P_(ctx, XG_P_L2_A2H_B); g.ep.bias2 = P_(ctx, XG_P_L2_H2H_B);
+    XG_TRY(gemm_run(ctx, g, st));
+    GemmP ga = gemm_nt(sb.AF, H, P_(ctx, XG_P_L2_A2H_W), H, sb.Z2, 4 * H, B, 4 * H, H);
+    ga.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, ga, st));
+    GemmP gh = gemm_nt(s.h2p, s.ld_h2p, P_(ctx, XG_P_L2_H2H_W), H, sb.Z2, 4 * H, B, 4 * H, H);
+    gh.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, gh, st));
+    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(sb.Z2, s.c2p, s.h2p, s.ld_h2p, mask, mask_stride, B, H,
+                                                         make_drop(false, 0.f, 0, 0), s.c2n, s.h2n, s.ld_h2n, nullptr, 0);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  return XG_OK;
+}
+
+// logits (rows, V) = out (rows, H; ld) . W_logit^T + b
+static int logits_core(xg_context* ctx, const float* out, long ld_out, int rows, float* logits, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  GemmP g = gemm_nt(out, ld_out, P_(ctx, XG_P_LOGIT_W), d.rnn, logits, d.vocab, rows, d.vocab, d.rnn);
+  g.ep.bias0 = P_(ctx, XG_P_LOGIT_B);
+  return gemm_run(ctx, g, st);
+}
+
+// ------------------------------------------------------------------------------------
+// SAModel.forward (SAModel.py:67-115), teacher forced; everything that depends only on the
+// ground-truth tokens is hoisted out of the word loop and batched over all L' steps.
+// ------------------------------------------------------------------------------------
+static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, const float* fmask, const float* pos,
+                          const int64_t* seq, const float* seq_mask, int B, int K, int L, int Lp, int train,
+                          uint64_t seed, float* logp, float* cat, TrainSaved& S, float* logits_scratch,
+                          float* cls_scratch, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab, C = d.categories, Q = d.cls_hidden;
+  const long LB = (long)Lp * B;
+  float* st0[4] = {S.H12, S.C1, S.H12 + H, S.C2};   // h1 | h2 interleaved in H12[0] with ld 2H
+  // encoder + Uv; the init state goes straight into H12[0] / C1[0] / C2[0]
+  XG_TRY(encode_core(ctx, rgb, opfl, fmask, B, K, train, seed, S.enc, S.V, S.Uv, nullptr, st));
+  XG_TRY(init_hidden_core(ctx, S.V, fmask, B, K, S.enc.meanV, st0, 2 * H, st));
+  // hoisted over all steps: embedding, POS gate, input parts of lstm_1
+  gather_rows_kernel<<<(int)LB, 128, 0, st>>>(P_(ctx, XG_P_EMBED_W), seq, L, 1, B, (int)LB, E, V, S.XT);
+  XG_LAUNCH_CHECK(ctx->es);
+  {
+    GemmP g = gemm_nt(S.XT, E, P_(ctx, XG_P_DGATE_W), E, S.GP, H, (int)LB, H, E);
+    g.ep.bias0 = P_(ctx, XG_P_DGATE_B);
+    g.ep.act = XG_ACT_RELU;
+    g.ep.drop = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_GATE);
+    g.ep.aux = S.RG; g.ep.ldaux = H;
+    g.ep.tgt = pos; g.ep.ldt = H; g.ep.tgt_mod = B;
+    XG_TRY(gemm_run(ctx, g, st));
+    GemmP gi = gemm_nt(S.XT, E, P_(ctx, XG_P_L1_I2H_W), E, S.G1, 4 * H, (int)LB, 4 * H, E);
+    gi.ep.bias0 = P_(ctx, XG_P_L1_I2H_B); gi.ep.bias1 = P_(ctx, XG_P_L1_A2H_B); gi.ep.bias2 = P_(ctx, XG_P_L1_H2H_B);
+    XG_TRY(gemm_run(ctx, gi, st));
+    GemmP ga = gemm_nt(S.GP, H, P_(ctx, XG_P_L1_A2H_W), H, S.G1, 4 * H, (int)LB, 4 * H, H);
+    ga.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, ga, st));
+  }
+  for (int i = 0; i < Lp; ++i) {
+    const float* h12p = S.H12 + (long)i * B * 2 * H;
+    float* h12n = S.H12 + (long)(i + 1) * B * 2 * H;
+    float* AHi = S.AH + (long)i * B * A;
+    float* AFi = S.AF + (long)i * B * H;
+    float* Z1 = S.G1 + (long)i * B * 4 * H;
+    float* Z2 = S.G2 + (long)i * B * 4 * H;
+    const float* m = seq_mask + i;   // (B,) stride L
+    // attention on previous [h1,h2]
+    GemmP g = gemm_nt(h12p, 2 * H, P_(ctx, XG_P_H2A_W), 2 * H, AHi, A, B, A, 2 * H);
+    g.ep.bias0 = P_(ctx, XG_P_H2A_B);
+    XG_TRY(gemm_run(ctx, g, st));
+    att_fwd_kernel<<<B, 256, (A + K) * sizeof(float), st>>>(AHi, S.Uv, S.V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K,
+                                                           A, H, 1, S.ALPHA + (long)i * B * K, AFi);
+    XG_LAUNCH_CHECK(ctx->es);
+    // lstm_1: recurrent part only
+    GemmP gh = gemm_nt(h12p, 2 * H, P_(ctx, XG_P_L1_H2H_W), H, Z1, 4 * H, B, 4 * H, H);
+    gh.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, gh, st));
+    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+        Z1, S.C1 + (long)i * B * H, h12p, 2 * H, m, L, B, H,
+        make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1, (uint64_t)i * B * H), S.C1 + (long)(i + 1) * B * H, h12n,
+        2 * H, nullptr, 0);
+    XG_LAUNCH_CHECK(ctx->es);
+    // lstm_2
+    GemmP g2 = gemm_nt(h12n, 2 * H, P_(ctx, XG_P_L2_I2H_W), H, Z2, 4 * H, B, 4 * H, H);
+    g2.ep.bias0 = P_(ctx, XG_P_L2_I2H_B); g2.ep.bias1 = P_(ctx, XG_P_L2_A2H_B); g2.ep.bias2 = P_(ctx, XG_P_L2_H2H_B);
+    XG_TRY(gemm_run(ctx, g2, st));
+    GemmP g2a = gemm_nt(AFi, H, P_(ctx, XG_P_L2_A2H_W), H, Z2, 4 * H, B, 4 * H, H);
+    g2a.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, g2a, st));
+    GemmP g2h = gemm_nt(h12p + H, 2 * H, P_(ctx, XG_P_L2_H2H_W), H, Z2, 4 * H, B, 4 * H, H);
+    g2h.ep.beta = 1.f;
+    XG_TRY(gemm_run(ctx, g2h, st));
+    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+        Z2, S.C2 + (long)i * B * H, h12p + H, 2 * H, m, L, B, H,
+        make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2, (uint64_t)i * B * H), S.C2 + (long)(i + 1) * B * H,
+        h12n + H, 2 * H, nullptr, 0);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  // heads, batched over all steps: OUT = H12[1..Lp][:, H:2H] is a (L'B, H) matrix with ld 2H
+  const float* OUT = S.H12 + (long)B * 2 * H + H;
+  if (logp) {
+    // logits land directly in the (B,L',V) output buffer (row (i,b) -> b*L'+i), log-softmax in place
+    GemmP g = gemm_nt(OUT, 2 * H, P_(ctx, XG_P_LOGIT_W), H, logp, V, (int)LB, V, H);
+    g.ep.bias0 = P_(ctx, XG_P_LOGIT_B);
+    g.perm_rb = B; g.perm_rs = Lp;
+    XG_TRY(gemm_run(ctx, g, st));
+    logsoftmax_rows_kernel<<<(int)LB, 256, 0, st>>>(logp, V, V, 0, 0, logp, V);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  if (cat) {
+    GemmP g = gemm_nt(OUT, 2 * H, P_(ctx, XG_P_CLS0_W), H, S.Hc, Q, (int)LB, Q, H);
+    g.ep.bias0 = P_(ctx, XG_P_CLS0_B);
+    g.ep.act = XG_ACT_RELU;
+    g.ep.drop = make_drop(train, d.drop_prob, seed, XG_DROP_CLS);
+    XG_TRY(gemm_run(ctx, g, st));
+    GemmP g3 = gemm_nt(S.Hc, Q, P_(ctx, XG_P_CLS3_W), Q, cat, C, (int)LB, C, Q);
+    g3.ep.bias0 = P_(ctx, XG_P_CLS3_B);
+    g3.perm_rb = B; g3.perm_rs = Lp;
+    XG_TRY(gemm_run(ctx, g3, st));
+    logsoftmax_rows_kernel<<<(int)LB, 128, 0, st>>>(cat, C, C, 0, 0, cat, C);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  (void)logits_scratch; (void)cls_scratch;
+  return XG_OK;
+}
+
+}  // namespace xg

@@ -1,0 +1,347 @@
+// Forward-path kernels that are not dense contractions: BatchNorm statistics/apply, the two LSTM
+// cell updates, temporal soft attention, embedding gather, masked mean, row log-softmax, greedy pick.
+// All of this is HBM/L2-bandwidth or latency bound integer/float streaming work: coalesced
+// (lane == innermost index) accesses, warp-shuffle reductions, no atomics (deterministic sums).
+#pragma once
+#include "xg_common.cuh"
+
+namespace xg {
+
+// ------------------------------------------------------------------------------------
+// BatchNorm1d over the (B*K) rows of the embedded stream (sub_modules.py:97-104,121,126)
+// ------------------------------------------------------------------------------------
+// partial column sums in double: grid (ceil(H/32), RS), block (32, 8)
+__global__ void colstats_partial_kernel(const float* __restrict__ Y, int M, int H, double* __restrict__ part) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int RS = gridDim.y;
+  const int rows_per = (M + RS - 1) / RS;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(M, r0 + rows_per);
+  double a = 0.0, b = 0.0;
+  if (j < H) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v = Y[(long)r * H + j];
+      a += (double)v;
+      b += (double)v * (double)v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < H) {
+    for (int y = 1; y < 8; ++y) { a += s1[y][threadIdx.x]; b += s2[y][threadIdx.x]; }
+    part[((long)blockIdx.y * H + j) * 2 + 0] = a;
+    part[((long)blockIdx.y * H + j) * 2 + 1] = b;
+  }
+}
+
+// train: batch statistics (+ running-stat update, unbiased variance, momentum);  eval: running stats.
+// Outputs the folded affine  y = x*scale + shift  and (train) mean / invstd for the backward pass.
+__global__ void bn_finalize_kernel(const double* __restrict__ part, int RS, int M, int H, int train,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var,
+                                   float eps, float momentum, int update_running,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  float mean, var;
+  if (train) {
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < RS; ++s) { a += part[((long)s * H + j) * 2]; b += part[((long)s * H + j) * 2 + 1]; }
+    double mu = a / M;
+    double vr = b / M - mu * mu;
+    if (vr < 0.0) vr = 0.0;
+    mean = (float)mu;
+    var = (float)vr;
+    if (update_running) {
+      double unb = M > 1 ? vr * ((double)M / (double)(M - 1)) : vr;
+      run_mean[j] = (1.f - momentum) * run_mean[j] + momentum * mean;
+      run_var[j] = (1.f - momentum) * run_var[j] + momentum * (float)unb;
+    }
+  } else {
+    mean = run_mean[j];
+    var = run_var[j];
+  }
+  const float invstd = 1.0f / sqrtf(var + eps);
+  const float sc = gamma[j] * invstd;
+  scale[j] = sc;
+  shift[j] = beta[j] - mean * sc;
+  if (mean_out) mean_out[j] = mean;
+  if (invstd_out) invstd_out[j] = invstd;
+}
+
+// E[(k*B+b), j] = relu(Y[(b*K+k), j]*scale + shift) * drop(b,k,j) * fmask[b,k]    (frame-major out)
+__global__ void bn_apply_kernel(const float* __restrict__ Y, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const float* __restrict__ fmask,
+                                int B, int K, int H, DropSpec drop, float* __restrict__ E) {
+  const long n = (long)B * K * H;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % H);
+    const long r = e / H;  // b*K + k
+    const int k = (int)(r % K);
+    const int b = (int)(r / K);
+    float v = Y[e] * scale[j] + shift[j];
+    v = v > 0.f ? v : 0.f;
+    v *= drop.factor((uint64_t)e);
+    v *= fmask[r];
+    E[((long)k * B + b) * H + j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// encoder nn.LSTMCell pointwise part (gate order i,f,g,o) + zeroing frame mask
+// (sub_modules.py:138-140,145-147).  Z (B,4H) holds x.W_ih^T + h.W_hh^T + biases and is
+// overwritten with the activated gates (kept for the backward pass).
+// ------------------------------------------------------------------------------------
+__global__ void enc_cell_kernel(float* __restrict__ Z, const float* __restrict__ c_prev,
+                                const float* __restrict__ fmask, int mask_stride, int t, int B, int H,
+                                float* __restrict__ c_out, float* __restrict__ h_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * H) return;
+  const int b = e / H, j = e % H;
+  float* z = Z + (long)b * 4 * H;
+  const float i = sigmoid_f(z[j]);
+  const float f = sigmoid_f(z[H + j]);
+  const float g = tanhf(z[2 * H + j]);
+  const float o = sigmoid_f(z[3 * H + j]);
+  const float m = fmask[(long)b * mask_stride + t];
+  const float cp = c_prev ? c_prev[e] : 0.f;
+  const float c2 = f * cp + i * g;
+  const float h = o * tanhf(c2) * m;      // h' = o*tanh(c2) ; h' *= mask   (:138-139)
+  const float c = c2 * m;                 // c2 *= mask                     (:140)
+  z[j] = i; z[H + j] = f; z[2 * H + j] = g; z[3 * H + j] = o;
+  c_out[e] = c;
+  h_out[e] = h;
+}
+
+// ------------------------------------------------------------------------------------
+// decoder two_inputs_lstmcell pointwise part (gate order i,f,o,g; the mask CARRIES the state;
+// dropout on the carried h)  (sub_modules.py:753-767)
+// ------------------------------------------------------------------------------------
+__global__ void dec_cell_kernel(float* __restrict__ Z, const float* __restrict__ c_prev,
+                                const float* __restrict__ h_prev, long ld_hprev,
+                                const float* __restrict__ mask, long mask_stride, int B, int H, DropSpec drop,
+                                float* __restrict__ c_out, float* __restrict__ h_out, long ld_hout,
+                                float* __restrict__ h_out2, long ld_hout2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * H) return;
+  const int b = e / H, j = e % H;
+  float* z = Z + (long)b * 4 * H;
+  const float i = sigmoid_f(z[j]);
+  const float f = sigmoid_f(z[H + j]);
+  const float o = sigmoid_f(z[2 * H + j]);
+  const float g = tanhf(z[3 * H + j]);
+  const float m = mask ? mask[(long)b * mask_stride] : 1.f;
+  const float cp = c_prev[e];
+  const float hp = h_prev[(long)b * ld_hprev + j];
+  float c = f * cp + i * g;
+  c = c * m + cp * (1.f - m);
+  float h = o * tanhf(c);
+  h = h * m + hp * (1.f - m);
+  h *= drop.factor((uint64_t)e);
+  z[j] = i; z[H + j] = f; z[2 * H + j] = o; z[3 * H + j] = g;
+  c_out[e] = c;
+  h_out[(long)b * ld_hout + j] = h;
+  if (h_out2) h_out2[(long)b * ld_hout2 + j] = h;
+}
+
+// ------------------------------------------------------------------------------------
+// embedding gather: out[r, :] = emb[tok(r), :],  r = i*B + b,  tok(r) = tokens[b*sb + i*si]
+// ------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ emb, const int64_t* __restrict__ tokens,
+                                   long sb, long si, int B, int rows, int E, int V, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const int b = r % B, i = r / B;
+  long t = tokens[(long)b * sb + (long)i * si];
+  if (t < 0) t = 0;
+  if (t >= V) t = V - 1;
+  const float* src = emb + t * E;
+  for (int j = threadIdx.x; j < E; j += blockDim.x) out[(long)r * E + j] = src[j];
+}
+
+// ------------------------------------------------------------------------------------
+// init_hidden mean: mean[b,:] = sum_k V[b,k,:] / sum_k fmask[b,k]   (SAModel.py:59-61)
+// ------------------------------------------------------------------------------------
+__global__ void masked_mean_kernel(const float* __restrict__ V, const float* __restrict__ fmask, int B, int K, int H,
+                                   float* __restrict__ mean) {
+  const int b = blockIdx.x;
+  float cnt = 0.f;
+  for (int k = 0; k < K; ++k) cnt += fmask[(long)b * K + k];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += V[((long)b * K + k) * H + j];
+    mean[(long)b * H + j] = s / cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// temporal soft attention for one word step (sub_modules.py:677-680), one CTA per caption:
+//   s_k = a2w . tanh(AH[b] + Uv[b,k,:]) + b ;  alpha = softmax_k(s) (NO frame mask) ;
+//   af = sum_k alpha_k V[b,k,:]
+// dynamic smem: A + K floats.
+// ------------------------------------------------------------------------------------
+__global__ void att_fwd_kernel(const float* __restrict__ AH, const float* __restrict__ Uv,
+                               const float* __restrict__ V, const float* __restrict__ wa,
+                               const float* __restrict__ ba, int K, int A, int H, int feat_div,
+                               float* __restrict__ alpha_out, float* __restrict__ af_out) {
+  extern __shared__ float sm[];
+  float* ah = sm;        // A
+  float* sc = sm + A;    // K
+  const int b = blockIdx.x;            // state row
+  const int fb = b / feat_div;         // feature row (beam rows of one video share V / Uv)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int a = threadIdx.x; a < A; a += blockDim.x) ah[a] = AH[(long)b * A + a];
+  __syncthreads();
+  for (int k = warp; k < K; k += nwarp) {
+    const float* u = Uv + ((long)fb * K + k) * A;
+    float p = 0.f;
+    for (int a = lane; a < A; a += 32) p += wa[a] * tanhf(ah[a] + u[a]);
+    p = warp_sum(p);
+    if (lane == 0) sc[k] = p + ba[0];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, sc[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < K; k += 32) { float e = expf(sc[k] - mx); sc[k] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int k = lane; k < K; k += 32) sc[k] *= inv;
+  }
+  __syncthreads();
+  if (alpha_out)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) alpha_out[(long)b * K + k] = sc[k];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += sc[k] * V[((long)fb * K + k) * H + j];
+    af_out[(long)b * H + j] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// block reductions (value / value+index) for the vocabulary-wide row kernels
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < nw; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < nw; ++w) r += red[w];   // fixed order: deterministic
+  return r;
+}
+
+// row log-softmax: out[orow(r), :] = x - max - log(sum exp(x - max));  one CTA per row.
+// orow(r) = perm_rb ? (r % perm_rb) * perm_rs + r / perm_rb : r.   In-place safe when no permutation.
+__global__ void logsoftmax_rows_kernel(const float* __restrict__ X, long ldx, int N, int perm_rb, int perm_rs,
+                                       float* __restrict__ out, long ldo) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const float* x = X + (long)r * ldx;
+  const long orow = perm_rb ? (long)(r % perm_rb) * perm_rs + r / perm_rb : (long)r;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) mx = fmaxf(mx, x[j]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s += expf(x[j] - mx);
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  float* o = out + orow * ldo;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) o[j] = x[j] - lse;
+}
+
+// ------------------------------------------------------------------------------------
+// greedy / multinomial pick for SAModel.sample (SAModel.py:185-210), one CTA per caption row.
+// Reads the step's logits (not log-probs: only max, argmax and logsumexp are needed for greedy),
+// updates the bookkeeping the reference keeps on the host:
+//   it = argmax (lowest index on ties, as torch.max) ; unfinished &= it > 0 ;
+//   seq[b,t-1] = it * unfinished ; logp[b,t-1] = max logp ; next token = RAW it ; step mask = unfinished.
+// flags[t-1] is set if any row is still unfinished (the reference's loop break at :206).
+// ------------------------------------------------------------------------------------
+__global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, int t /* >= 1 */, int T,
+                                   int sample_max, float inv_temperature, uint64_t seed,
+                                   int64_t* __restrict__ seq, float* __restrict__ seqlogp,
+                                   int64_t* __restrict__ next_tok, float* __restrict__ unfinished,
+                                   int* __restrict__ flags) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  __shared__ float s_pick;
+  const int b = blockIdx.x;
+  const float* x = logits + (long)b * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // argmax with lowest-index tie break
+  float best = -INFINITY; int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float v = x[j];
+    if (v > best) { best = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) { red[warp] = best; redi[warp] = bi; }
+  __syncthreads();
+  best = red[0]; bi = redi[0];
+  for (int w = 1; w < nw; ++w)
+    if (red[w] > best || (red[w] == best && redi[w] < bi)) { best = red[w]; bi = redi[w]; }
+  const float mx = best;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(x[j] - mx);
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  int pick = bi;
+  float pick_logp = mx - lse;
+  if (!sample_max) {
+    // multinomial over p ~ exp(logp / temperature): inverse-CDF with one Philox uniform per (row, step).
+    // sequential scan by one warp in fixed order (deterministic for a given seed).
+    float tot = 0.f;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) tot += expf((x[j] - lse) * inv_temperature);
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) {
+      const float u = philox_uniform(seed, 0x5a4d0000u + (uint32_t)t, (uint64_t)b) * tot;
+      float acc = 0.f; int sel = V - 1;
+      for (int j = 0; j < V; ++j) {
+        acc += expf((x[j] - lse) * inv_temperature);
+        if (acc > u) { sel = j; break; }
+      }
+      redi[0] = sel;
+      s_pick = x[sel] - lse;
+    }
+    __syncthreads();
+    pick = redi[0];
+    pick_logp = s_pick;
+  }
+  if (threadIdx.x == 0) {
+    float unf = (t == 1) ? 1.f : unfinished[b];
+    unf = (unf != 0.f && pick > 0) ? 1.f : 0.f;
+    unfinished[b] = unf;
+    seq[(long)b * T + (t - 1)] = unf != 0.f ? (int64_t)pick : 0;
+    seqlogp[(long)b * T + (t - 1)] = pick_logp;
+    next_tok[b] = (int64_t)pick;
+    if (unf != 0.f) flags[t - 1] = 1;   // benign race: every writer stores the same value
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long n, float v) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
+}
+
+}  // namespace xg
