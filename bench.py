@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the gated-fusion caption decoder hot path on B200 (BASELINE.json metric:
+captions/sec, train fwd+bwd and greedy decode, MSRVTT-shape synthetic batches).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path)
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPU
+
+Headline workload (config.workload): BASELINE.json configs[1] — batch 64, 28 frames, 1536+1024 features,
+hidden 512, vocab 10k, seq_len 30, greedy decode.  One "step" = one `SAModel.sample()` call on one batch
+(Cross-Gating encoder + init state + 30 word steps).  `value` = captions/s with inputs resident in HBM;
+`e2e` = the same call with pinned HOST inputs (H2D inside the timed region) and the token ids read back.
+The train (config 3 / config 4) and beam (config 5) figures ride along in `train` / `beam` sub-objects.
+One process per GPU; ranks work on independent batches (weak scaling, no collective on the decode path;
+the train sub-object adds the one NCCL gradient allreduce per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = dict(R=1536, F=1024, H=512, E=468, A=1536, V=10000, C=14)
+K_FRAMES, T_SEQ, BATCH = 28, 30, 64
+METRIC = "captions/sec (train fwd+bwd; greedy decode) MSRVTT-shape batch"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_opt(drop):
+    return argparse.Namespace(vocab_size=DIMS["V"], category_size=DIMS["C"], input_encoding_size=DIMS["E"],
+                              rnn_size=DIMS["H"], num_layers=1, drop_prob_lm=drop, seq_length=T_SEQ, seed=1024,
+                              feat_size=DIMS["R"], feat_size2=DIMS["F"], att_size=DIMS["A"], fusion_activity="ReLU")
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm, all host threads)
+# ----------------------------------------------------------------------------------------------
+def cpu_greedy_seconds(P, batch, reps):
+    import torch
+    from oracle import xgating_oracle as O
+    best = None
+    with torch.no_grad():
+        O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)     # warm-up
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
+        best = (time.perf_counter() - t0) / reps
+    return best
+
+
+def cpu_train_seconds(P, batch, reps):
+    from oracle import xgating_oracle as O
+    O.train_step_grads(P, batch, train=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.train_step_grads(P, batch, train=True)
+    return (time.perf_counter() - t0) / reps
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm (oracle port: same op sequence incl. the per-step
+    v2a(V) recomputation, torch CPU fp32) on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import xgating_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = O.synth_params(DIMS, 1024)
+    P["logit.bias"][0] = -1e4
+    batch = O.synth_inputs(DIMS, BATCH, K_FRAMES, T_SEQ, 0)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
+        dt = (time.perf_counter() - t0) / args.steps
+    val = BATCH / dt
+    tr = cpu_train_seconds(P, batch, max(1, min(args.steps, 3)))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "captions/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: greedy decode, batch 64, 28 frames, 1536+1024 feats, hidden 512, vocab 10k, seq_len 30",
+                       "sample": "each step = one full batch of 64 captions on the host CPU"},
+            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": "port",
+                             "sample": "%d greedy batches of 64 captions" % args.steps},
+            "train": {"value": BATCH / tr, "unit": "captions/s", "ms_per_step": tr * 1e3,
+                      "workload": "config3: train fwd+bwd (XE loss), batch 64"},
+            "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xgating", choices=["xgating", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the train / beam sub-objects")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the xgating path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import controllable_xgating_b200 as X
+    import controllable_xgating_b200.SAModel as XS
+    from controllable_xgating_b200 import _lib as XL
+    from controllable_xgating_b200.parallel import DataParallelSAModel
+    from oracle import xgating_oracle as O          # input / weight generators + the CPU baseline leg only
+    XS.VERBOSE = False
+    dev = torch.device("cuda", local)
+
+    P = O.synth_params(DIMS, 1024)
+    P["logit.bias"][0] = -1e4                       # EOS never chosen: every run executes all T steps
+    batch = O.synth_inputs(DIMS, BATCH, K_FRAMES, T_SEQ, seed=rank)
+    model = X.SAModel(make_opt(0.5))
+    model.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+    model.cuda().eval()
+    d = {k: v.to(dev) for k, v in batch.items() if isinstance(v, torch.Tensor)}
+    pinned = {k: batch[k].pin_memory() for k in ("rgb", "opfl", "feat_mask", "pos", "seq", "seq_mask")}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    gopt = {"sample_max": 1, "beam_size": 1}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """per-step CUDA events on the current stream; L2 flushed (256 MiB write) before every step, outside
+        the timed interval; returns (total_ms over `steps`, max over ranks)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([tot], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t)
+        return tot
+
+    # ---- (1) greedy decode, inputs resident in HBM -------------------------------------------------
+    steps_seen = []
+
+    def greedy_resident():
+        seq, _ = model.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], gopt)
+        steps_seen.append(seq.shape[1])
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms = timed(greedy_resident, args.steps, args.warmup)
+    value = world * BATCH * args.steps / (ms * 1e-3)
+
+    # ---- (2) end to end through the public API: pinned host inputs, ids read back ---------------------
+    def greedy_e2e():
+        rgb = pinned["rgb"].to(dev, non_blocking=True); opfl = pinned["opfl"].to(dev, non_blocking=True)
+        fm = pinned["feat_mask"].to(dev, non_blocking=True); pos = pinned["pos"].to(dev, non_blocking=True)
+        seq, lp = model.sample(rgb, opfl, fm, pos, gopt)
+        return seq.cpu(), lp.cpu()
+
+    ms_e2e = timed(greedy_e2e, args.steps, args.warmup)
+    clk = clocks.stop()
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("rgb", "opfl", "feat_mask", "pos"))
+    d2h = BATCH * T_SEQ * (8 + 4)
+
+    # ---- (3) per-kernel timing pass (CUDA events around every launch, same workload) ------------------
+    eng = model._engine
+    lib = XL.load()
+    XL.check(lib.xg_profile_enable(eng.handle, 1), "xg_profile_enable", eng.handle)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        flush.fill_(1)
+        greedy_resident()
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 20)
+    XL.check(lib.xg_profile_report(eng.handle, buf, len(buf)), "xg_profile_report", eng.handle)
+    XL.check(lib.xg_profile_enable(eng.handle, 0), "xg_profile_enable", eng.handle)
+    prof = json.loads(buf.value.decode())
+    launches_per_step = sum(p["launches"] for p in prof) / prof_steps
+    prof.sort(key=lambda p: -p["ms"])
+    tot_prof_ms = sum(p["ms"] for p in prof)
+    top = prof[0]
+    peak, peak_src = peaks()
+
+    def algorithmic_bytes(name):
+        # DESIGN.md "algorithmic bytes": a GEMM launch must read both operands once and write C once
+        if name.startswith("gemm_"):
+            m, n, k = (int(x) for x in name.split("_")[2].split("x"))
+            return 4.0 * (m * k + n * k + m * n)
+        if name == "att_fwd":      # AH + Uv + V read, alpha + context written, per caption row
+            return 4.0 * BATCH * (DIMS["A"] + K_FRAMES * DIMS["A"] + K_FRAMES * DIMS["H"] + K_FRAMES + DIMS["H"])
+        return None
+
+    ab = algorithmic_bytes(top["name"])
+    avg_ms = top["ms"] / top["launches"]
+    roofline = {"kernel": top["name"], "bound": "hbm", "achieved": (ab / (avg_ms * 1e-3) / 1e9) if ab else None,
+                "peak": peak, "unit": "GB/s", "frac": (ab / (avg_ms * 1e-3) / 1e9 / peak) if ab else None,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                "avg_launch_us": avg_ms * 1e3, "share_of_step": top["ms"] / tot_prof_ms,
+                "top5": [{"name": p["name"], "launches_per_step": p["launches"] / prof_steps,
+                          "us_per_launch": p["ms"] / p["launches"] * 1e3, "share": p["ms"] / tot_prof_ms} for p in prof[:5]]}
+
+    line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: greedy decode, batch 64 per GPU, 28 frames, 1536+1024 feats, hidden 512, vocab 10k, seq_len 30",
+                       "word_steps_executed": int(min(steps_seen)) if steps_seen else None,
+                       "l2": "flushed (256 MiB write) before every timed step", "weights": "random init (reference init distributions)",
+                       "parallelism": "dp%d (independent batches, no collective on the decode path)" % world},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "roofline": roofline}
+
+    # ---- (4) train fwd+bwd (config 3 at N=1; config 4 = global batch 512 at N>1) + beam-5 (config 5) ------
+    if not args.skip_extra:
+        tb = BATCH if world == 1 else 512 // world
+        tbatch = O.synth_inputs(DIMS, tb, K_FRAMES, T_SEQ, seed=100 + rank, full_length=False)
+        td = {k: v.to(dev) for k, v in tbatch.items() if isinstance(v, torch.Tensor)}
+        tp = {k: tbatch[k].pin_memory() for k in ("rgb", "opfl", "feat_mask", "pos", "seq", "seq_mask")}
+        tmodel = X.SAModel(make_opt(0.5))
+        tmodel.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
+        tmodel.cuda().train()
+        crit = X.LanguageModelCriterion()
+        dp = DataParallelSAModel(tmodel) if world > 1 else None
+        fwd = dp if dp is not None else tmodel
+
+        def train_step(src):
+            for p_ in tmodel.parameters():
+                p_.grad = None
+            logp, _ = fwd(src["rgb"], src["opfl"], src["feat_mask"], src["pos"], src["seq"], src["seq_mask"])
+            loss = crit(logp, src["seq"], src["seq_mask"])
+            loss.backward()
+            return loss
+
+        ms_t = timed(lambda: train_step(td), max(3, args.steps // 2), args.warmup)
+        nst = max(3, args.steps // 2)
+
+        def train_e2e():
+            src = {k: v.to(dev, non_blocking=True) for k, v in tp.items()}
+            return float(train_step(src))
+        ms_te = timed(train_e2e, nst, 1)
+        line["train"] = {"workload": ("config3: train fwd+bwd (XE loss, dropout 0.5), batch 64" if world == 1 else
+                                      "config4: train fwd+bwd, global batch 512 (%d per GPU), one NCCL gradient allreduce per step" % tb),
+                         "value": world * tb * nst / (ms_t * 1e-3), "unit": "captions/s", "ms_per_step": ms_t / nst,
+                         "e2e": {"value": world * tb * nst / (ms_te * 1e-3), "unit": "captions/s",
+                                 "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in tp.values()),
+                                 "d2h_bytes_per_step": 4},
+                         "allreduce_bytes_per_step": (dp.hook.bytes // max(dp.hook.calls, 1)) if dp else 0}
+        if world == 1:
+            bopt = {"beam_size": 5}
+            ms_b = timed(lambda: model.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], bopt), 3, 1)
+            line["beam"] = {"workload": "config5: sample_beam beam_size 5, batch 64", "value": BATCH * 3 / (ms_b * 1e-3),
+                            "unit": "captions/s", "ms_per_step": ms_b / 3}
+
+    # ---- (5) CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) --------------------
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        reps = 10
+        cb = {k: v for k, v in batch.items()}
+        sec = cpu_greedy_seconds(P, cb, reps)
+        line["cpu_baseline"] = {"value": BATCH / sec, "unit": "captions/s", "cores": cores, "kind": "port",
+                                "sample": "%d greedy batches of 64 captions (config 2) with the oracle port, torch CPU fp32, %d threads"
+                                          % (reps, cores)}
+        if not args.skip_extra:
+            sect = cpu_train_seconds(P, tbatch, 3)
+            line["cpu_baseline"]["train_value"] = BATCH / sect
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,8 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "xg_nll_criterion_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xg_profile_enable": (c_int, [c_void_p, c_int]),
+    "xg_profile_report": (c_int, [c_void_p, c_char_p, c_size_t]),
     "xg_debug_dropout_mask": (c_int, [c_uint64, c_int, c_size_t, c_float, c_void_p, c_void_p]),
     "xg_debug_gemm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

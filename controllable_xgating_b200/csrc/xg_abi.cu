@@ -1,4 +1,5 @@
 // libxgating.so — C ABI entry points (include/xgating.h).  Single translation unit, sm_100a.
+#include <cstring>
 #include <new>
 
 #include "xg_backward.cuh"
@@ -249,8 +250,7 @@ int xg_decode_step(xg_handle h, const int64_t* tokens, const float* xt, const fl
     Uv = sb.Uv;
   }
   if (tokens) {
-    gather_rows_kernel<<<B, 128, 0, st>>>(h->P[XG_P_EMBED_W], tokens, 1, 0, B, B, d.embed, d.vocab, sb.step.XT);
-    XG_LAUNCH_CHECK(h->es);
+    XG_TRY(launch(h, "gather_rows", gather_rows_kernel, B, 128, 0, st, h->P[XG_P_EMBED_W], tokens, 1, 0, B, B, d.embed, d.vocab, sb.step.XT));
     xt = sb.step.XT;
   }
   StepState s{state_in[0], H, state_in[1], state_in[2], H, state_in[3],
@@ -259,8 +259,7 @@ int xg_decode_step(xg_handle h, const int64_t* tokens, const float* xt, const fl
   if (out) XG_CUDA_TRY(h->es, cudaMemcpyAsync(out, state_out[2], sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
   if (logp) {
     XG_TRY(logits_core(h, state_out[2], H, B, logp, st));
-    logsoftmax_rows_kernel<<<B, 256, 0, st>>>(logp, d.vocab, d.vocab, 0, 0, logp, d.vocab);
-    XG_LAUNCH_CHECK(h->es);
+    XG_TRY(launch(h, "logsoftmax_rows", logsoftmax_rows_kernel, B, 256, 0, st, logp, d.vocab, d.vocab, 0, 0, logp, d.vocab));
   }
   return XG_OK;
 }
@@ -295,13 +294,11 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
   StepState s{g.st[0], H, g.st[1], g.st[2], H, g.st[3], g.st[0], H, g.st[1], g.st[2], H, g.st[3]};
   for (int t = 0; t <= T; ++t) {
     if (t >= 1) {
-      greedy_pick_kernel<<<B, 256, 0, st>>>(g.logits, d.vocab, t, T, sample_max, sample_max ? 1.f : 1.f / temperature, seed,
-                                           seq_out, logp_out, g.tok, g.unfinished, g.flags);
-      XG_LAUNCH_CHECK(h->es);
+      XG_TRY(launch(h, "greedy_pick", greedy_pick_kernel, B, 256, 0, st, g.logits, d.vocab, t, T, sample_max, sample_max ? 1.f : 1.f / temperature, seed,
+                                           seq_out, logp_out, g.tok, g.unfinished, g.flags));
     }
     if (t == T) break;   // the reference runs one more (unused) word step here (SAModel.py:216-217)
-    gather_rows_kernel<<<B, 128, 0, st>>>(h->P[XG_P_EMBED_W], g.tok, 1, 0, B, B, d.embed, d.vocab, g.step.XT);
-    XG_LAUNCH_CHECK(h->es);
+    XG_TRY(launch(h, "gather_rows", gather_rows_kernel, B, 128, 0, st, h->P[XG_P_EMBED_W], g.tok, 1, 0, B, B, d.embed, d.vocab, g.step.XT));
     XG_TRY(decode_step_core(h, g.step.XT, t == 0 ? nullptr : g.unfinished, 1, V, Uv, pos, s, g.step, nullptr, B, K, 1, st));
     XG_TRY(logits_core(h, g.st[2], H, B, g.logits, st));
   }
@@ -334,8 +331,7 @@ int xg_seq_steps(xg_handle h, const int64_t* seq, int B, int L, int* steps_out, 
   CHECK_PTR(h, seq); CHECK_PTR(h, steps_out); CHECK_POS(h, B); CHECK_POS(h, L);
   XG_TRY(set_device(h));
   cudaStream_t st = (cudaStream_t)stream;
-  seq_steps_kernel<<<1, 128, 0, st>>>(seq, B, L, h->d_small);
-  XG_LAUNCH_CHECK(h->es);
+  XG_TRY(launch(h, "seq_steps", seq_steps_kernel, 1, 128, 0, st, seq, B, L, h->d_small));
   XG_CUDA_TRY(h->es, cudaMemcpyAsync(h->h_pinned, h->d_small, sizeof(int), cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(h->es, cudaStreamSynchronize(st));
   *steps_out = h->h_pinned[0];
@@ -412,6 +408,44 @@ int xg_nll_criterion_bwd(int N, const int64_t* target, const float* mask, const 
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return XG_ERR_CUDA; }
+  return XG_OK;
+}
+
+// ---- profiling ------------------------------------------------------------------------
+int xg_profile_enable(xg_handle h, int on) {
+  CHECK_HANDLE(h);
+  h->prof_on = on != 0;
+  return XG_OK;
+}
+
+int xg_profile_report(xg_handle h, char* buf, size_t buf_bytes) {
+  CHECK_HANDLE(h);
+  CHECK_PTR(h, buf);
+  XG_TRY(set_device(h));
+  XG_CUDA_TRY(h->es, cudaDeviceSynchronize());
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[r.name];
+    a.first += 1;
+    a.second += ms;
+    h->prof_pool.push_back(r.e0);
+    h->prof_pool.push_back(r.e1);
+  }
+  h->prof_recs.clear();
+  std::string out = "[";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"launches\": %ld, \"ms\": %.6f}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "]";
+  if (out.size() + 1 > buf_bytes) return fail(h, XG_ERR_WORKSPACE, "xg_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
   return XG_OK;
 }
 

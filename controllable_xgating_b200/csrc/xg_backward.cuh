@@ -66,8 +66,7 @@ inline void carve_bwd(Arena& a, const xg_dims& d, int B, int K, int L, BwdBufs& 
 
 static int colsum_run(xg_context* ctx, const float* X, long ld, int R, int N, float beta, float* o0, float* o1,
                       float* o2, cudaStream_t st) {
-  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, st>>>(X, ld, R, N, beta, o0, o1, o2);
-  XG_LAUNCH_CHECK(ctx->es);
+  XG_TRY(launch(ctx, "colsum", colsum_kernel, ceil_div(N, 32), dim3(32, 8), 0, st, X, ld, R, N, beta, o0, o1, o2));
   return XG_OK;
 }
 
@@ -92,8 +91,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
 
   // ---------------- heads ----------------
   if (dlogp) {
-    logsoftmax_bwd_rows_kernel<<<LB, 256, 0, st>>>(logp, dlogp, B, Lp, V, W.DLOGITS);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 256, 0, st, logp, dlogp, B, Lp, V, W.DLOGITS));
     XG_TRY(wgrad(ctx, W.DLOGITS, V, OUT, ldo, G[XG_P_LOGIT_W], V, H, LB, beta, st));
     XG_TRY(colsum_run(ctx, W.DLOGITS, V, LB, V, beta, G[XG_P_LOGIT_B], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.DLOGITS, V, P_(ctx, XG_P_LOGIT_W), H, W.dOUT, H, LB, H, V);
@@ -106,14 +104,12 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     }
   }
   if (dcat) {
-    logsoftmax_bwd_rows_kernel<<<LB, 128, 0, st>>>(cat, dcat, B, Lp, C, W.dCL);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 128, 0, st, cat, dcat, B, Lp, C, W.dCL));
     XG_TRY(wgrad(ctx, W.dCL, C, S.Hc, Q, G[XG_P_CLS3_W], C, Q, LB, beta, st));
     XG_TRY(colsum_run(ctx, W.dCL, C, LB, C, beta, G[XG_P_CLS3_B], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.dCL, C, P_(ctx, XG_P_CLS3_W), Q, W.dHc, Q, LB, Q, C);
     XG_TRY(gemm_run(ctx, g, st));
-    relu_drop_bwd_kernel<<<ew_grid((long)LB * Q), 256, 0, st>>>(W.dHc, S.Hc, (long)LB * Q, keep);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "relu_drop_bwd", relu_drop_bwd_kernel, ew_grid((long)LB * Q), 256, 0, st, W.dHc, S.Hc, (long)LB * Q, keep));
     XG_TRY(wgrad(ctx, W.dHc, Q, OUT, ldo, G[XG_P_CLS0_W], Q, H, LB, beta, st));
     XG_TRY(colsum_run(ctx, W.dHc, Q, LB, Q, beta, G[XG_P_CLS0_B], nullptr, nullptr, st));
     GemmP g2 = gemm_nn(W.dHc, Q, P_(ctx, XG_P_CLS0_W), H, W.dOUT, H, LB, H, Q);
@@ -142,10 +138,9 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     float* dz2 = G2 + (long)i * B * 4 * H;
     float* dz1 = G1 + (long)i * B * 4 * H;
     // (a) lstm_2 cell backward: dh_out = dOUT[i] + carried dh2
-    dec_cell_bwd_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+    XG_TRY(launch(ctx, "dec_cell_bwd", dec_cell_bwd_kernel, ceil_div(B * H, 256), 256, 0, st, 
         dz2, S.C2 + (long)(i + 1) * B * H, S.C2 + (long)i * B * H, W.dOUT + (long)i * B * H, H, W.dHcar + H, 2 * H, W.dC2,
-        m, L, B, H, make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2, (uint64_t)i * B * H), W.dHcar + H, 2 * H);
-    XG_LAUNCH_CHECK(ctx->es);
+        m, L, B, H, make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2, (uint64_t)i * B * H), W.dHcar + H, 2 * H));
     // (b) dh1_new += dz2 . W_i2h ; (c) dAF = dz2 . W_a2h ; (d) dh2_prev += dz2 . W_h2h
     GemmP gb = gemm_nn(dz2, 4 * H, P_(ctx, XG_P_L2_I2H_W), H, W.dHcar, 2 * H, B, H, 4 * H);
     gb.ep.beta = 1.f;
@@ -156,15 +151,13 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     gd.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gd, st));
     // (e) attention backward
-    att_bwd_kernel<<<B, 256, att_smem, st>>>(W.dAF, S.AH + (long)i * B * A, S.Uv, S.V, P_(ctx, XG_P_A2W_W),
+    XG_TRY(launch(ctx, "att_bwd", att_bwd_kernel, B, 256, att_smem, st, W.dAF, S.AH + (long)i * B * A, S.Uv, S.V, P_(ctx, XG_P_A2W_W),
                                             S.ALPHA + (long)i * B * K, K, A, H, W.dV, W.dUv,
-                                            W.DAH + (long)i * B * A, W.dwa_part, W.dba_part);
-    XG_LAUNCH_CHECK(ctx->es);
+                                            W.DAH + (long)i * B * A, W.dwa_part, W.dba_part));
     // (f) lstm_1 cell backward on dh1_new
-    dec_cell_bwd_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+    XG_TRY(launch(ctx, "dec_cell_bwd", dec_cell_bwd_kernel, ceil_div(B * H, 256), 256, 0, st, 
         dz1, S.C1 + (long)(i + 1) * B * H, S.C1 + (long)i * B * H, W.dHcar, 2 * H, nullptr, 0, W.dC1, m, L, B, H,
-        make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1, (uint64_t)i * B * H), W.dHcar, 2 * H);
-    XG_LAUNCH_CHECK(ctx->es);
+        make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1, (uint64_t)i * B * H), W.dHcar, 2 * H));
     // (g) dh1_prev += dz1 . W_h2h ; (h) d[h1|h2]_prev += dAH . W_h2a
     GemmP gg = gemm_nn(dz1, 4 * H, P_(ctx, XG_P_L1_H2H_W), H, W.dHcar, 2 * H, B, H, 4 * H);
     gg.ep.beta = 1.f;
@@ -202,8 +195,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     // POS gate + embedding
     GemmP gp = gemm_nn(G1, 4 * H, P_(ctx, XG_P_L1_A2H_W), H, W.dGP, H, LB, H, 4 * H);
     XG_TRY(gemm_run(ctx, gp, st));
-    dgate_bwd_kernel<<<ew_grid((long)LB * H), 256, 0, st>>>(W.dGP, S.RG, pos, B, LB, H, keep, W.dGP);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "dgate_bwd", dgate_bwd_kernel, ew_grid((long)LB * H), 256, 0, st, W.dGP, S.RG, pos, B, LB, H, keep, W.dGP));
     XG_TRY(wgrad(ctx, W.dGP, H, S.XT, E, G[XG_P_DGATE_W], H, E, LB, beta, st));
     XG_TRY(colsum_run(ctx, W.dGP, H, LB, H, beta, G[XG_P_DGATE_B], nullptr, nullptr, st));
     GemmP gx = gemm_nn(G1, 4 * H, P_(ctx, XG_P_L1_I2H_W), E, W.dXT, E, LB, E, 4 * H);
@@ -212,8 +204,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     gx2.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gx2, st));
     if (beta == 0.f) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(G[XG_P_EMBED_W], 0, sizeof(float) * (size_t)V * E, st));
-    embed_scatter_add_kernel<<<LB, 128, 0, st>>>(W.dXT, seq, B, L, LB, E, V, G[XG_P_EMBED_W]);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "embed_scatter_add", embed_scatter_add_kernel, LB, 128, 0, st, W.dXT, seq, B, L, LB, E, V, G[XG_P_EMBED_W]));
     // v2a
     XG_TRY(wgrad(ctx, W.dUv, A, S.V, H, G[XG_P_V2A_W], A, H, KB, beta, st));
     XG_TRY(colsum_run(ctx, W.dUv, A, KB, A, beta, G[XG_P_V2A_B], nullptr, nullptr, st));
@@ -224,9 +215,8 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
 
   // ---------------- encoder backward (rows (k,b)) ----------------
   const EncBufs& eb = S.enc;
-  fusion_bwd_kernel<<<ew_grid((long)KB * H), 256, 0, st>>>(W.dV, S.V, B, K, H, d.fusion_act,
-                                                          make_drop(train, d.drop_prob, seed, XG_DROP_ENC_FUSION), W.dF);
-  XG_LAUNCH_CHECK(ctx->es);
+  XG_TRY(launch(ctx, "fusion_bwd", fusion_bwd_kernel, ew_grid((long)KB * H), 256, 0, st, W.dV, S.V, B, K, H, d.fusion_act,
+                                                          make_drop(train, d.drop_prob, seed, XG_DROP_ENC_FUSION), W.dF));
   XG_TRY(wgrad(ctx, W.dF, H, eb.GG, 2 * H, G[XG_P_FUSION_W], H, 2 * H, KB, beta, st));
   XG_TRY(colsum_run(ctx, W.dF, H, KB, H, beta, G[XG_P_FUSION_B], nullptr, nullptr, st));
   {
@@ -235,9 +225,8 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   }
   const int gw[2] = {XG_P_GATE_RGB_W, XG_P_GATE_OPFL_W};
   for (int s = 0; s < 2; ++s) {
-    gate_bwd_kernel<<<ew_grid((long)KB * H), 256, 0, st>>>(W.dGG + (long)s * H, 2 * H, eb.R[s], eb.Hs[s], KB, H, keep,
-                                                          W.dH[s], W.dR[s]);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "gate_bwd", gate_bwd_kernel, ew_grid((long)KB * H), 256, 0, st, W.dGG + (long)s * H, 2 * H, eb.R[s], eb.Hs[s], KB, H, keep,
+                                                          W.dH[s], W.dR[s]));
   }
   for (int s = 0; s < 2; ++s) {
     const int src = 1 - s;
@@ -258,10 +247,9 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     XG_CUDA_TRY(ctx->es, cudaMemsetAsync(W.dcc, 0, sizeof(float) * (size_t)B * H, st));
     for (int t = K - 1; t >= 0; --t) {
       float* dzt = DZ + (long)t * B * 4 * H;
-      enc_cell_bwd_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+      XG_TRY(launch(ctx, "enc_cell_bwd", enc_cell_bwd_kernel, ceil_div(B * H, 256), 256, 0, st, 
           dzt, eb.Cs[s] + (long)t * B * H, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
-          W.dH[s] + (long)t * B * H, t < K - 1 ? W.dhc : nullptr, W.dcc, fmask, K, t, B, H);
-      XG_LAUNCH_CHECK(ctx->es);
+          W.dH[s] + (long)t * B * H, t < K - 1 ? W.dhc : nullptr, W.dcc, fmask, K, t, B, H));
       if (t > 0) {
         GemmP g = gemm_nn(dzt, 4 * H, P_(ctx, plstm[s] + 1), H, W.dhc, H, B, H, 4 * H);
         XG_TRY(gemm_run(ctx, g, st));
@@ -280,18 +268,14 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
       XG_TRY(gemm_run(ctx, g, st));
     }
     // through mask, dropout, ReLU and BatchNorm
-    bn_bwd_prep_kernel<<<ew_grid((long)KB * H), 256, 0, st>>>(W.dE, eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
-                                                             make_drop(train, d.drop_prob, seed, site_emb[s]), W.dy);
-    XG_LAUNCH_CHECK(ctx->es);
-    bn_bwd_stats_kernel<<<dim3(ceil_div(H, 32), RS), dim3(32, 8), 0, st>>>(W.dy, eb.Y[s], eb.mean[s], eb.invstd[s], KB, H,
-                                                                          W.part);
-    XG_LAUNCH_CHECK(ctx->es);
-    bn_bwd_finalize_kernel<<<ceil_div(H, 128), 128, 0, st>>>(W.part, RS, H, beta, G[pw[s] + 2], G[pw[s] + 3], W.s_dy,
-                                                            W.s_dyx);
-    XG_LAUNCH_CHECK(ctx->es);
-    bn_bwd_apply_kernel<<<ew_grid((long)KB * H), 256, 0, st>>>(W.dy, eb.Y[s], eb.mean[s], eb.invstd[s],
-                                                              P_(ctx, pw[s] + 2), W.s_dy, W.s_dyx, KB, H, train);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "bn_bwd_prep", bn_bwd_prep_kernel, ew_grid((long)KB * H), 256, 0, st, W.dE, eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
+                                                             make_drop(train, d.drop_prob, seed, site_emb[s]), W.dy));
+    XG_TRY(launch(ctx, "bn_bwd_stats", bn_bwd_stats_kernel, dim3(ceil_div(H, 32), RS), dim3(32, 8), 0, st, W.dy, eb.Y[s], eb.mean[s], eb.invstd[s], KB, H,
+                                                                          W.part));
+    XG_TRY(launch(ctx, "bn_bwd_finalize", bn_bwd_finalize_kernel, ceil_div(H, 128), 128, 0, st, W.part, RS, H, beta, G[pw[s] + 2], G[pw[s] + 3], W.s_dy,
+                                                            W.s_dyx));
+    XG_TRY(launch(ctx, "bn_bwd_apply", bn_bwd_apply_kernel, ew_grid((long)KB * H), 256, 0, st, W.dy, eb.Y[s], eb.mean[s], eb.invstd[s],
+                                                              P_(ctx, pw[s] + 2), W.s_dy, W.s_dyx, KB, H, train));
     XG_TRY(wgrad(ctx, W.dy, H, X[s], din[s], G[pw[s]], H, din[s], KB, beta, st));
     XG_TRY(colsum_run(ctx, W.dy, H, KB, H, beta, G[pw[s] + 1], nullptr, nullptr, st));
   }

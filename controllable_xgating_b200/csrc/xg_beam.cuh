@@ -231,8 +231,7 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
   }
   XG_TRY(init_hidden_core(ctx, V, fmask, B, K, w.meanV, w.st0, H, st));
   for (int q = 0; q < 4; ++q) {
-    beam_expand_kernel<<<n, 128, 0, st>>>(w.st0[q], beam, H, w.st[0][q]);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "beam_expand", beam_expand_kernel, n, 128, 0, st, w.st0[q], beam, H, w.st[0][q]));
   }
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(w.tokens, 0, sizeof(int64_t) * (size_t)n, st));   // <bos> (:150)
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(w.sum, 0, sizeof(float) * (size_t)n, st));
@@ -243,32 +242,26 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
   int sb = 0;      // seq buffer holding the current beams
   for (int t = -1; t < T; ++t) {
     if (t >= 0) {
-      beam_topk_kernel<<<n, 256, 0, st>>>(w.logits, Vn, beam, w.ys, w.ix);
-      XG_LAUNCH_CHECK(ctx->es);
-      beam_merge_kernel<<<ceil_div(B, 64), 64, 0, st>>>(w.ys, w.ix, B, beam, T, t, w.seq[sb], w.lps[sb], w.seq[sb ^ 1],
+      XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));
+      XG_TRY(launch(ctx, "beam_merge", beam_merge_kernel, ceil_div(B, 64), 64, 0, st, w.ys, w.ix, B, beam, T, t, w.seq[sb], w.lps[sb], w.seq[sb ^ 1],
                                                        w.lps[sb ^ 1], w.sum, w.parent, w.tokens, w.done_seq, w.done_lps,
-                                                       w.done_p, w.done_n);
-      XG_LAUNCH_CHECK(ctx->es);
+                                                       w.done_p, w.done_n));
       sb ^= 1;
       if (t == T - 1) break;   // the reference's last get_logprobs_state result is never used
-      beam_gather_state_kernel<<<n, 128, 0, st>>>(w.parent, H, w.st[cur][0], w.st[cur][1], w.st[cur][2], w.st[cur][3],
-                                                 w.st[cur ^ 1][0], w.st[cur ^ 1][1], w.st[cur ^ 1][2], w.st[cur ^ 1][3]);
-      XG_LAUNCH_CHECK(ctx->es);
+      XG_TRY(launch(ctx, "beam_gather_state", beam_gather_state_kernel, n, 128, 0, st, w.parent, H, w.st[cur][0], w.st[cur][1], w.st[cur][2], w.st[cur][3],
+                                                 w.st[cur ^ 1][0], w.st[cur ^ 1][1], w.st[cur ^ 1][2], w.st[cur ^ 1][3]));
       cur ^= 1;
     }
     // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154)
-    gather_rows_kernel<<<n, 128, 0, st>>>(P_(ctx, XG_P_EMBED_W), w.tokens, 1, 0, n, n, E, Vn, w.step.XT);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, n, 128, 0, st, P_(ctx, XG_P_EMBED_W), w.tokens, 1, 0, n, n, E, Vn, w.step.XT));
     StepState s{w.st[cur][0], H, w.st[cur][1], w.st[cur][2], H, w.st[cur][3],
                 w.st[cur][0], H, w.st[cur][1], w.st[cur][2], H, w.st[cur][3]};
     XG_TRY(decode_step_core(ctx, w.step.XT, nullptr, 0, V, w.Uv, pos, s, w.step, nullptr, n, K, beam, st));
     XG_TRY(logits_core(ctx, w.st[cur][2], H, n, w.logits, st));
-    logsoftmax_rows_kernel<<<n, 256, 0, st>>>(w.logits, Vn, Vn, 0, 0, w.logits, Vn);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_kernel, n, 256, 0, st, w.logits, Vn, Vn, 0, 0, w.logits, Vn));
   }
-  beam_finalize_kernel<<<ceil_div(B, 64), 64, 0, st>>>(w.done_seq, w.done_lps, w.done_p, w.done_n, B, beam, T, seq_out,
-                                                      logp_out, done_seq, done_lps, done_p, done_count);
-  XG_LAUNCH_CHECK(ctx->es);
+  XG_TRY(launch(ctx, "beam_finalize", beam_finalize_kernel, ceil_div(B, 64), 64, 0, st, w.done_seq, w.done_lps, w.done_p, w.done_n, B, beam, T, seq_out,
+                                                      logp_out, done_seq, done_lps, done_p, done_count));
   return XG_OK;
 }
 

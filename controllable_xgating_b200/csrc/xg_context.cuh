@@ -1,5 +1,7 @@
 // Handle, parameter table, buffer carving shared by the entry points.
 #pragma once
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "xg_common.cuh"
@@ -16,11 +18,44 @@ struct xg_context {
   xg::ErrorSink es;
   int* h_pinned = nullptr;   // small pinned staging area for SYNC read-backs
   int* d_small = nullptr;    // matching device words
+  // optional per-kernel timing with CUDA events on the launching stream (xg_profile_enable/_report)
+  bool prof_on = false;
+  struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
   static constexpr int kPinnedInts = 1024;
   static constexpr int kSmallInts = 1 << 18;   // device scratch words (criterion terms etc.)
 };
 
 namespace xg {
+
+// RAII timing scope around one launch (no-op unless profiling is enabled on the handle)
+struct ProfScope {
+  xg_context* c; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; const char* name; std::string dyn;
+  static cudaEvent_t get(xg_context* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  ProfScope(xg_context* ctx, const char* nm, cudaStream_t s) : c(ctx), st(s), name(nm) {
+    if (c && c->prof_on) { e0 = get(c); e1 = get(c); cudaEventRecord(e0, st); }
+  }
+  ProfScope(xg_context* ctx, std::string nm, cudaStream_t s) : c(ctx), st(s), name(nullptr), dyn(std::move(nm)) {
+    if (c && c->prof_on) { e0 = get(c); e1 = get(c); cudaEventRecord(e0, st); }
+  }
+  ~ProfScope() {
+    if (e0) { cudaEventRecord(e1, st); c->prof_recs.push_back({name ? std::string(name) : dyn, e0, e1}); }
+  }
+};
+
+// every non-GEMM kernel goes through this launcher (launch check + optional timing)
+template <typename... KArgs, typename... Args>
+static int launch(xg_context* ctx, const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                  cudaStream_t st, Args&&... args) {
+  ProfScope ps(ctx, name, st);
+  kernel<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
+  XG_LAUNCH_CHECK(ctx->es);
+  return XG_OK;
+}
 
 inline void param_shape(const xg_dims& d, int idx, int* rows, int* cols) {
   const int H = d.rnn, R = d.feat_rgb, F = d.feat_opfl, E = d.embed, A = d.att, V = d.vocab, C = d.categories,

@@ -15,7 +15,16 @@ static inline int ew_grid(long n, int block = 256) {
   return (int)g;
 }
 
-static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) { return gemm_simt(ctx->es, p, st); }
+static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) {
+  if (ctx->prof_on) {
+    char tag[96];
+    const char* lay = (p.sa_r == 1) ? (p.sb_r == 1 ? "nt" : "nn") : "tn";
+    snprintf(tag, sizeof(tag), "gemm_%s_%dx%dx%d", lay, p.M, p.N, p.K);
+    ProfScope ps(ctx, std::string(tag), st);
+    return gemm_simt(ctx->es, p, st);
+  }
+  return gemm_simt(ctx->es, p, st);
+}
 
 // ------------------------------------------------------------------------------------
 // EncoderLstm_two_fc.forward (sub_modules.py:118-159)
@@ -40,18 +49,15 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
     XG_TRY(gemm_run(ctx, g, st));
     // visual_emb_*.1 : BatchNorm1d
     if (train) {
-      colstats_partial_kernel<<<dim3(ceil_div(H, 32), RS), dim3(32, 8), 0, st>>>(eb.Y[s], BK, H, eb.part);
-      XG_LAUNCH_CHECK(ctx->es);
+      XG_TRY(launch(ctx, "colstats_partial", colstats_partial_kernel, dim3(ceil_div(H, 32), RS), dim3(32, 8), 0, st, eb.Y[s], BK, H, eb.part));
     }
-    bn_finalize_kernel<<<ceil_div(H, 128), 128, 0, st>>>(eb.part, RS, BK, H, train, P_(ctx, pw[s] + 2),
+    XG_TRY(launch(ctx, "bn_finalize", bn_finalize_kernel, ceil_div(H, 128), 128, 0, st, eb.part, RS, BK, H, train, P_(ctx, pw[s] + 2),
                                                         P_(ctx, pw[s] + 3), ctx->bn[2 * s], ctx->bn[2 * s + 1],
                                                         d.bn_eps, d.bn_momentum, train ? 1 : 0, eb.scale[s],
-                                                        eb.shift[s], eb.mean[s], eb.invstd[s]);
-    XG_LAUNCH_CHECK(ctx->es);
+                                                        eb.shift[s], eb.mean[s], eb.invstd[s]));
     // ReLU, dropout, frame mask; output frame-major (:123,128)
-    bn_apply_kernel<<<ew_grid((long)BK * H), 256, 0, st>>>(eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
-                                                          make_drop(train, d.drop_prob, seed, site_emb[s]), eb.E[s]);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "bn_apply", bn_apply_kernel, ew_grid((long)BK * H), 256, 0, st, eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
+                                                          make_drop(train, d.drop_prob, seed, site_emb[s]), eb.E[s]));
     // nn.LSTMCell input projection hoisted over all frames: XG = E . W_ih^T + b_ih + b_hh
     GemmP gi = gemm_nt(eb.E[s], H, P_(ctx, plstm[s]), H, eb.G[s], 4 * H, BK, 4 * H, H);
     gi.ep.bias0 = P_(ctx, plstm[s] + 2);
@@ -67,10 +73,9 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
         gh.ep.beta = 1.f;
         XG_TRY(gemm_run(ctx, gh, st));
       }
-      enc_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(Zt, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
+      XG_TRY(launch(ctx, "enc_cell", enc_cell_kernel, ceil_div(B * H, 256), 256, 0, st, Zt, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
                                                            fmask, K, t, B, H, eb.Cs[s] + (long)t * B * H,
-                                                           eb.Hs[s] + (long)t * B * H);
-      XG_LAUNCH_CHECK(ctx->es);
+                                                           eb.Hs[s] + (long)t * B * H));
     }
   }
   // cross gates batched over all frames (:151-152): g_tgt = h_tgt * (1 + dropout(relu(Linear(h_src))))
@@ -106,8 +111,7 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
     XG_TRY(gemm_run(ctx, g, st));
   }
   if (state_out) {  // SAModel.init_hidden (SAModel.py:58-65)
-    masked_mean_kernel<<<B, 128, 0, st>>>(V_out, fmask, B, K, H, eb.meanV);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "masked_mean", masked_mean_kernel, B, 128, 0, st, V_out, fmask, B, K, H, eb.meanV));
     const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
     for (int q = 0; q < 4; ++q) {
       GemmP g = gemm_nt(eb.meanV, H, P_(ctx, iw[q]), H, state_out[q], H, B, H, H);
@@ -121,8 +125,7 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
 static int init_hidden_core(xg_context* ctx, const float* V, const float* fmask, int B, int K, float* meanV,
                             float* const* state_out, long ld_out, cudaStream_t st) {
   const int H = ctx->d.rnn;
-  masked_mean_kernel<<<B, 128, 0, st>>>(V, fmask, B, K, H, meanV);
-  XG_LAUNCH_CHECK(ctx->es);
+  XG_TRY(launch(ctx, "masked_mean", masked_mean_kernel, B, 128, 0, st, V, fmask, B, K, H, meanV));
   const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
   for (int q = 0; q < 4; ++q) {
     GemmP g = gemm_nt(meanV, H, P_(ctx, iw[q]), H, state_out[q], q % 2 == 0 ? ld_out : H, B, H, H);
@@ -153,9 +156,8 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     GemmP g2 = gemm_nt(s.h2p, s.ld_h2p, P_(ctx, XG_P_H2A_W) + H, 2 * H, sb.AH, A, B, A, H);
     g2.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, g2, st));
-    att_fwd_kernel<<<B, 256, (A + K) * sizeof(float), st>>>(sb.AH, Uv, V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K, A,
-                                                           H, feat_div, alpha_out, sb.AF);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "att_fwd", att_fwd_kernel, B, 256, (A + K) * sizeof(float), st, sb.AH, Uv, V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K, A,
+                                                           H, feat_div, alpha_out, sb.AF));
   }
   // POS gate: gp = pos * (1 + relu(Linear(xt)))
   {
@@ -178,9 +180,8 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     GemmP gh = gemm_nt(s.h1p, s.ld_h1p, P_(ctx, XG_P_L1_H2H_W), H, sb.Z1, 4 * H, B, 4 * H, H);
     gh.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gh, st));
-    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(sb.Z1, s.c1p, s.h1p, s.ld_h1p, mask, mask_stride, B, H,
-                                                         make_drop(false, 0.f, 0, 0), s.c1n, s.h1n, s.ld_h1n, nullptr, 0);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, sb.Z1, s.c1p, s.h1p, s.ld_h1p, mask, mask_stride, B, H,
+                                                         make_drop(false, 0.f, 0, 0), s.c1n, s.h1n, s.ld_h1n, nullptr, 0));
   }
   // lstm_2
   {
@@ -193,9 +194,8 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     GemmP gh = gemm_nt(s.h2p, s.ld_h2p, P_(ctx, XG_P_L2_H2H_W), H, sb.Z2, 4 * H, B, 4 * H, H);
     gh.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gh, st));
-    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(sb.Z2, s.c2p, s.h2p, s.ld_h2p, mask, mask_stride, B, H,
-                                                         make_drop(false, 0.f, 0, 0), s.c2n, s.h2n, s.ld_h2n, nullptr, 0);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, sb.Z2, s.c2p, s.h2p, s.ld_h2p, mask, mask_stride, B, H,
+                                                         make_drop(false, 0.f, 0, 0), s.c2n, s.h2n, s.ld_h2n, nullptr, 0));
   }
   return XG_OK;
 }
@@ -224,8 +224,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   XG_TRY(encode_core(ctx, rgb, opfl, fmask, B, K, train, seed, S.enc, S.V, S.Uv, nullptr, st));
   XG_TRY(init_hidden_core(ctx, S.V, fmask, B, K, S.enc.meanV, st0, 2 * H, st));
   // hoisted over all steps: embedding, POS gate, input parts of lstm_1
-  gather_rows_kernel<<<(int)LB, 128, 0, st>>>(P_(ctx, XG_P_EMBED_W), seq, L, 1, B, (int)LB, E, V, S.XT);
-  XG_LAUNCH_CHECK(ctx->es);
+  XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, (int)LB, 128, 0, st, P_(ctx, XG_P_EMBED_W), seq, L, 1, B, (int)LB, E, V, S.XT));
   {
     GemmP g = gemm_nt(S.XT, E, P_(ctx, XG_P_DGATE_W), E, S.GP, H, (int)LB, H, E);
     g.ep.bias0 = P_(ctx, XG_P_DGATE_B);
@@ -253,18 +252,16 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     GemmP g = gemm_nt(h12p, 2 * H, P_(ctx, XG_P_H2A_W), 2 * H, AHi, A, B, A, 2 * H);
     g.ep.bias0 = P_(ctx, XG_P_H2A_B);
     XG_TRY(gemm_run(ctx, g, st));
-    att_fwd_kernel<<<B, 256, (A + K) * sizeof(float), st>>>(AHi, S.Uv, S.V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K,
-                                                           A, H, 1, S.ALPHA + (long)i * B * K, AFi);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "att_fwd", att_fwd_kernel, B, 256, (A + K) * sizeof(float), st, AHi, S.Uv, S.V, P_(ctx, XG_P_A2W_W), P_(ctx, XG_P_A2W_B), K,
+                                                           A, H, 1, S.ALPHA + (long)i * B * K, AFi));
     // lstm_1: recurrent part only
     GemmP gh = gemm_nt(h12p, 2 * H, P_(ctx, XG_P_L1_H2H_W), H, Z1, 4 * H, B, 4 * H, H);
     gh.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gh, st));
-    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+    XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, 
         Z1, S.C1 + (long)i * B * H, h12p, 2 * H, m, L, B, H,
         make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1, (uint64_t)i * B * H), S.C1 + (long)(i + 1) * B * H, h12n,
-        2 * H, nullptr, 0);
-    XG_LAUNCH_CHECK(ctx->es);
+        2 * H, nullptr, 0));
     // lstm_2
     GemmP g2 = gemm_nt(h12n, 2 * H, P_(ctx, XG_P_L2_I2H_W), H, Z2, 4 * H, B, 4 * H, H);
     g2.ep.bias0 = P_(ctx, XG_P_L2_I2H_B); g2.ep.bias1 = P_(ctx, XG_P_L2_A2H_B); g2.ep.bias2 = P_(ctx, XG_P_L2_H2H_B);
@@ -275,11 +272,10 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     GemmP g2h = gemm_nt(h12p + H, 2 * H, P_(ctx, XG_P_L2_H2H_W), H, Z2, 4 * H, B, 4 * H, H);
     g2h.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, g2h, st));
-    dec_cell_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(
+    XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, 
         Z2, S.C2 + (long)i * B * H, h12p + H, 2 * H, m, L, B, H,
         make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2, (uint64_t)i * B * H), S.C2 + (long)(i + 1) * B * H,
-        h12n + H, 2 * H, nullptr, 0);
-    XG_LAUNCH_CHECK(ctx->es);
+        h12n + H, 2 * H, nullptr, 0));
   }
   // heads, batched over all steps: OUT = H12[1..Lp][:, H:2H] is a (L'B, H) matrix with ld 2H
   const float* OUT = S.H12 + (long)B * 2 * H + H;
@@ -289,8 +285,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     g.ep.bias0 = P_(ctx, XG_P_LOGIT_B);
     g.perm_rb = B; g.perm_rs = Lp;
     XG_TRY(gemm_run(ctx, g, st));
-    logsoftmax_rows_kernel<<<(int)LB, 256, 0, st>>>(logp, V, V, 0, 0, logp, V);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_kernel, (int)LB, 256, 0, st, logp, V, V, 0, 0, logp, V));
   }
   if (cat) {
     GemmP g = gemm_nt(OUT, 2 * H, P_(ctx, XG_P_CLS0_W), H, S.Hc, Q, (int)LB, Q, H);
@@ -302,8 +297,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     g3.ep.bias0 = P_(ctx, XG_P_CLS3_B);
     g3.perm_rb = B; g3.perm_rs = Lp;
     XG_TRY(gemm_run(ctx, g3, st));
-    logsoftmax_rows_kernel<<<(int)LB, 128, 0, st>>>(cat, C, C, 0, 0, cat, C);
-    XG_LAUNCH_CHECK(ctx->es);
+    XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_kernel, (int)LB, 128, 0, st, cat, C, C, 0, 0, cat, C));
   }
   (void)logits_scratch; (void)cls_scratch;
   return XG_OK;

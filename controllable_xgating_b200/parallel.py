@@ -1,0 +1,91 @@
+"""Batch-axis data parallelism for the training path (the reference is single-GPU).
+
+One process per GPU.  Captions are independent in forward / decode / beam search, so those need no
+communication: each rank runs its own contiguous batch shard.  Training needs exactly one exchange:
+a sum-allreduce of the flat fp32 gradient buffer the backward pass fills (26.3 M floats at V=10k),
+issued from inside the backward hook before autograd hands the views to `.grad`.
+
+Loss normalisation: `LanguageModelCriterion` divides by the LOCAL sum(mask) (SAModel.py:233).  With
+`exact=True` each replica's gradient is rescaled by local_mask_sum / global_mask_sum before the sum, so
+the result equals the single-device gradient of the loss over the concatenated batch (up to BatchNorm,
+whose train-mode statistics stay per replica).  With `exact=False` gradients are averaged (DDP style).
+Elementwise clamping (`myutils.clip_gradient`) happens after the reduction, as in the reference.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: dict, world: int, rank: int) -> dict:
+    n = next(v for v in batch.values() if isinstance(v, torch.Tensor)).shape[0]
+    lo, hi = shard_bounds(n, world, rank)
+    return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
+
+
+class GradAllReduce:
+    """Callable installed as `model._grad_hook`: reduces the flat gradient buffer in place."""
+
+    def __init__(self, group=None, exact: bool = True):
+        self.group = group
+        self.exact = exact
+        self.local_mask_sum: Optional[torch.Tensor] = None
+        self.calls = 0
+        self.bytes = 0
+
+    def set_mask(self, seq_mask: torch.Tensor):
+        self.local_mask_sum = seq_mask.sum().reshape(1).to(torch.float32)
+
+    def __call__(self, flat: torch.Tensor):
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return
+        if self.exact:
+            if self.local_mask_sum is None:
+                raise RuntimeError("GradAllReduce(exact=True): call set_mask(seq_mask) before backward")
+            tot = self.local_mask_sum.to(flat.device).clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(self.local_mask_sum.to(flat.device) / tot)
+        else:
+            flat.div_(world)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        self.bytes += flat.numel() * 4
+
+
+class DataParallelSAModel(torch.nn.Module):
+    """Thin wrapper: same forward()/sample() surface; forward() works on this rank's shard and the
+    backward hook all-reduces gradients.  Parameters are broadcast from rank 0 at construction, and
+    BatchNorm running statistics can be re-synchronised with sync_buffers()."""
+
+    def __init__(self, model, group=None, exact: bool = True, broadcast: bool = True):
+        super().__init__()
+        self.module = model
+        self.group = group
+        self.hook = GradAllReduce(group, exact)
+        object.__setattr__(model, "_grad_hook", self.hook)
+        if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for p in model.parameters():
+                dist.broadcast(p.data, src=0, group=group)
+            self.sync_buffers()
+
+    def sync_buffers(self):
+        for b in self.module.buffers():
+            if b.dtype.is_floating_point:
+                dist.broadcast(b, src=0, group=self.group)
+
+    def forward(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):
+        self.hook.set_mask(seq_mask)
+        return self.module(feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask)
+
+    def sample(self, *a, **k):
+        return self.module.sample(*a, **k)

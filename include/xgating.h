@@ -225,6 +225,14 @@ int xg_nll_criterion_bwd(int N, const int64_t* target, const float* mask, const 
                          int ld, int rotate, int B, int Lp, const float* denom,
                          const float* grad_out, float* dlogp, void* stream);
 
+/* ---- profiling ------------------------------------------------------------------------- */
+/* Per-kernel timing with CUDA events recorded on the launching stream around every launch the
+ * handle makes (GEMMs are tagged by layout and shape).  Costs two event records per launch, so
+ * throughput numbers are never taken with it enabled.  xg_profile_report is SYNC: it writes a JSON
+ * array [{"name","launches","ms"}...] into buf and clears the records. */
+int xg_profile_enable(xg_handle h, int on);
+int xg_profile_report(xg_handle h, char* buf, size_t buf_bytes);
+
 /* ---- test / diagnostics hooks -------------------------------------------------------- */
 /* the dropout mask (0 or 1/(1-p)) the kernels apply at `site` for logical element indices
  * [0,n) under `seed`, so a train-mode run can be replayed in the CPU oracle. */
