@@ -136,6 +136,10 @@ int xg_create(const xg_dims* dims, int device, xg_handle* out) {
 int xg_destroy(xg_handle h) {
   if (!h) return XG_OK;
   cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  tc_release(h);
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->d_small) cudaFree(h->d_small);
   delete h;
@@ -170,7 +174,16 @@ int xg_bind_bn_buffers(xg_handle h, float* rm_rgb, float* rv_rgb, float* rm_opfl
 
 int xg_params_changed(xg_handle h) {
   CHECK_HANDLE(h);
-  return XG_OK;   // no derived parameter copies are cached by the SIMT engine
+  XG_TRY(set_device(h));
+  XG_CUDA_TRY(h->es, cudaDeviceSynchronize());
+  tc_invalidate_weights(h);   // tf32 hi/lo splits of the bound parameters
+  return XG_OK;
+}
+
+int xg_set_engine(xg_handle h, int tensor_cores) {
+  CHECK_HANDLE(h);
+  h->tc_mode = tensor_cores ? 1 : 0;
+  return XG_OK;
 }
 
 size_t xg_workspace_bytes(xg_handle h, int kind, int B, int K, int L_or_T, int beam) {
@@ -468,12 +481,24 @@ int xg_debug_dropout_mask(uint64_t seed, int site, size_t n, float p, float* out
 int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float* C, int M, int N, int K, void* stream) {
   if (!A || !B || !C) return fail(nullptr, XG_ERR_NULL_POINTER, "xg_debug_gemm: null pointer");
   if (M <= 0 || N <= 0 || K <= 0) return fail(nullptr, XG_ERR_BAD_SHAPE, "xg_debug_gemm: non-positive size");
-  if (engine == 2) return fail(nullptr, XG_ERR_UNSUPPORTED, "xg_debug_gemm: tcgen05 engine not built in this version");
   GemmP p;
   if (layout == 0) p = gemm_nt(A, K, B, K, C, N, M, N, K);
   else if (layout == 1) p = gemm_nn(A, K, B, N, C, N, M, N, K);
   else if (layout == 2) p = gemm_tn(A, M, B, N, C, N, M, N, K);
   else return fail(nullptr, XG_ERR_BAD_ARG, "xg_debug_gemm: layout must be 0 (NT), 1 (NN) or 2 (TN)");
+  if (engine == 2) {
+    // tcgen05 3xTF32 engine on a parameter-less scratch context (operands are split on the fly)
+    static xg_context* dbg = nullptr;
+    if (!dbg) {
+      dbg = new xg_context();
+      dbg->d = xg_dims{1, 1, 1, 1, 1, 1, 1, 1, XG_ACT_RELU, 0.f, 1e-5f, 0.1f};
+      for (int i = 0; i < XG_NUM_PARAMS; ++i) dbg->P[i] = nullptr;
+    }
+    cudaGetDevice(&dbg->device);
+    int s = gemm_tc(dbg, p, (cudaStream_t)stream);
+    if (s != XG_OK) g_last_error = dbg->es.msg;
+    return s;
+  }
   ErrorSink es;
   int s = gemm_simt(es, p, (cudaStream_t)stream);
   if (s != XG_OK) g_last_error = es.msg;

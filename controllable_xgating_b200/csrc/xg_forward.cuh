@@ -3,6 +3,7 @@
 #pragma once
 #include "xg_context.cuh"
 #include "xg_fwd_kernels.cuh"
+#include "xg_gemm_tc.cuh"
 
 namespace xg {
 
@@ -16,6 +17,7 @@ static inline int ew_grid(long n, int block = 256) {
 }
 
 static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) {
+  if (ctx->tc_mode && tc_eligible(p)) return gemm_tc(ctx, p, st);
   if (ctx->prof_on) {
     char tag[96];
     const char* lay = (p.sa_r == 1) ? (p.sb_r == 1 ? "nt" : "nn") : "tn";

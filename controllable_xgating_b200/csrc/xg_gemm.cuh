@@ -37,6 +37,27 @@ struct GemmP {
   Epilogue ep;
 };
 
+// element (i,j) of the logical output: bias, activation, dropout, aux store, cross gate, row
+// permutation, accumulate.  Shared by the SIMT and the tcgen05 engines.
+__device__ __forceinline__ void epilogue_store(const GemmP& p, int i, int j, float acc) {
+  const Epilogue& ep = p.ep;
+  float v = ep.alpha * acc;
+  if (ep.bias0) v += ep.bias0[j];
+  if (ep.bias1) v += ep.bias1[j];
+  if (ep.bias2) v += ep.bias2[j];
+  v = apply_act(v, ep.act);
+  if (ep.drop.on()) v *= ep.drop.factor((uint64_t)i * (uint64_t)p.N + (uint64_t)j);
+  if (ep.aux) ep.aux[(long)i * ep.ldaux + j] = v;
+  if (ep.tgt) {
+    const long trow = ep.tgt_div ? (i / ep.tgt_div) : (ep.tgt_mod ? (i % ep.tgt_mod) : i);
+    v = ep.tgt[trow * ep.ldt + j] * (1.f + v);
+  }
+  const long orow = p.perm_rb ? (long)(i % p.perm_rb) * p.perm_rs + i / p.perm_rb : (long)i;
+  float* c = p.C + orow * p.ldc + j;
+  if (ep.beta != 0.f) v += ep.beta * (*c);
+  *c = v;
+}
+
 template <int BM, int BN, int BK, int TM, int TN, bool A_RC, bool B_RC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(const GemmP p) {
@@ -144,28 +165,15 @@ gemm_simt_kernel(const GemmP p) {
   }
 
   // ---- fused epilogue ----
-  const Epilogue& ep = p.ep;
 #pragma unroll
   for (int m = 0; m < TM; ++m) {
     const int i = m0 + (m / VM) * (BM / CM) + ty * VM + (m % VM);
     if (i >= p.M) continue;
-    const long orow = p.perm_rb ? (long)(i % p.perm_rb) * p.perm_rs + i / p.perm_rb : (long)i;
-    const long trow = ep.tgt ? (ep.tgt_div ? (i / ep.tgt_div) : (ep.tgt_mod ? (i % ep.tgt_mod) : i)) : 0;
 #pragma unroll
     for (int n = 0; n < TN; ++n) {
       const int j = n0 + (n / VN) * (BN / CN) + tx * VN + (n % VN);
       if (j >= p.N) continue;
-      float v = ep.alpha * acc[m][n];
-      if (ep.bias0) v += ep.bias0[j];
-      if (ep.bias1) v += ep.bias1[j];
-      if (ep.bias2) v += ep.bias2[j];
-      v = apply_act(v, ep.act);
-      if (ep.drop.on()) v *= ep.drop.factor((uint64_t)i * (uint64_t)p.N + (uint64_t)j);
-      if (ep.aux) ep.aux[(long)i * ep.ldaux + j] = v;
-      if (ep.tgt) v = ep.tgt[trow * ep.ldt + j] * (1.f + v);
-      float* c = p.C + orow * p.ldc + j;
-      if (ep.beta != 0.f) v += ep.beta * (*c);
-      *c = v;
+      epilogue_store(p, i, j, acc[m][n]);
     }
   }
 }

@@ -1,0 +1,492 @@
+// tcgen05 GEMM engine with fp32-grade accuracy (3xTF32 split), sm_100a.
+//
+//   D[p, q] = sum_k P[p,k] * Q[q,k]       p < Pn (128 TMEM lanes per tile), q < Qn (BN TMEM columns)
+//
+// Both operands are K-major fp32 matrices that were split beforehand into a tf32-exact high part and
+// a tf32-rounded low part (x = hi + lo + O(2^-23 |x|)); the kernel accumulates  lo*hi + hi*lo + hi*hi
+// in the fp32 TMEM accumulator (the dropped lo*lo term is O(2^-22)), which is what makes greedy token
+// ids survive tensor-core math.  A plain tf32 or bf16 pass would flip ids.
+//
+// Pipeline (one 128 x BN output tile per CTA, 128 threads):
+//   warp 0 / lane 0 : TMA producer  — cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 32 floats x rows,
+//                     4 boxes (P_hi, P_lo, Q_hi, Q_lo) per stage, mbarrier complete_tx
+//   warp 1 / lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8, smem
+//                     descriptors (K-major, 128B swizzle, SBO = 1024 B), tcgen05.commit frees the stage
+//   warp 2          : TMEM allocator (BN fp32 columns)
+//   all 4 warps     : epilogue — tcgen05.ld 32x32b (lane = p), fused epilogue_store(), coalesced stores
+// No thread ever writes the operand tiles: they go global -> smem by TMA and smem -> tensor core by
+// UMMA, both in the async proxy, so no proxy fences are needed on the operand path.
+#pragma once
+#include <cuda.h>
+
+#include <unordered_map>
+
+#include "xg_context.cuh"
+
+namespace xg {
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte swizzle atoms, 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B  [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell) [46,48)
+  d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B      [61,64)
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------
+// split pre-pass: hi = rna_tf32(x), lo = rna_tf32(x - hi), written K-major with the K extent padded
+// to a multiple of 32 (zeros) so TMA boxes never leave the row.  src(r,k) = X[r*sr + k*sk] lets the
+// same kernel transpose (the NN / TN layouts of the backward pass become K-major here).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ X, long sr, long sk, int rows, int K, int Kp,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const bool k_contig = (sk == 1);
+  // load: threadIdx.x runs along the source-contiguous index
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = k_contig ? r0 + y : r0 + threadIdx.x;
+    int k = k_contig ? k0 + threadIdx.x : k0 + y;
+    float v = (r < rows && k < K) ? X[(long)r * sr + (long)k * sk] : 0.f;
+    if (k_contig) tile[y][threadIdx.x] = v; else tile[threadIdx.x][y] = v;   // tile[r - r0][k - k0]
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = r0 + y, k = k0 + threadIdx.x;
+    if (r < rows && k < Kp) {
+      const float v = tile[y][threadIdx.x];
+      const float h = tf32_rna(v);
+      hi[(long)r * Kp + k] = h;
+      lo[(long)r * Kp + k] = tf32_rna(v - h);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// the GEMM kernel
+//
+// Accuracy note (measured on B200): the tensor core adds into the fp32 TMEM accumulator with
+// truncation, so a chain of n dependent MMAs carries a one-sided error of ~n/2 ulp of the running sum
+// (3.6e-6 relative at K=512 with one accumulator).  Therefore
+//   * the large hi*hi products are accumulated in SHORT chains: KCH k-blocks (4*KCH MMAs) into one of
+//     two ping-pong TMEM accumulators, which the epilogue warps drain into fp32 REGISTER accumulators
+//     with round-to-nearest adds while the tensor core fills the other one;
+//   * the small cross terms lo*hi + hi*lo (2^-11 of the result) get their own TMEM accumulator for the
+//     whole K extent: truncation there is 2^-11 smaller and invisible.
+// Net error ~1e-7, the same class as an fp32 FFMA loop.
+// ------------------------------------------------------------------------------------
+struct TcParams {
+  int Pn, Qn, K;       // K = padded reduction extent (multiple of 32)
+  int swap_out;        // 1: logical (i,j) = (q,p)  [y = x W^T with W on the lane side]; 0: (i,j) = (p,q)
+  GemmP g;             // output pointer / leading dimension / epilogue (M,N = logical output extents)
+};
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStageBytes = 2 * 128 * 128 + 2 * BN * 128;
+  static constexpr int kStages = (BN == 64) ? 4 : 3;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (BN == 64) ? 256 : 512;   // 2 ping-pong + 1 small accumulator, power of 2
+  static constexpr int kChunk = 2;                            // k-blocks (of 32) per accumulation chain
+  static constexpr int kThreads = 192;                        // producer warp, MMA warp, 4 epilogue warps
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUtensorMap tmPl,
+               const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl, const TcParams prm) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* acc_full = empty_bar + Cfg::kStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint64_t* small_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(small_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * 128, q0 = blockIdx.y * BN;
+  const int num_kb = prm.K / 32;
+  const int num_chunks = (num_kb + Cfg::kChunk - 1) / Cfg::kChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    mbar_init(small_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmPh); tma_prefetch_desc(&tmPl); tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl);
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_small = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
+        tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * 32, p0);
+        tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
+        tma_load_2d(st + 2 * 128 * 128 + BN * 128, &tmQl, &full_bar[s], kb * 32, q0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+      for (int c = 0; c < num_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_main = tmem_base + b * BN;
+        for (int kk = 0; kk < Cfg::kChunk; ++kk) {
+          const int kb = c * Cfg::kChunk + kk;
+          if (kb >= num_kb) break;
+          const int s = kb % Cfg::kStages;
+          mbar_wait(&full_bar[s], (kb / Cfg::kStages) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * Cfg::kStageBytes);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {         // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
+            const uint64_t ph_d = umma_desc_sw128(base + k4 * 32);
+            const uint64_t pl_d = umma_desc_sw128(base + 128 * 128 + k4 * 32);
+            const uint64_t qh_d = umma_desc_sw128(base + 2 * 128 * 128 + k4 * 32);
+            const uint64_t ql_d = umma_desc_sw128(base + 2 * 128 * 128 + BN * 128 + k4 * 32);
+            umma_tf32(tmem_main, ph_d, qh_d, idesc, (kk | k4) != 0);
+            umma_tf32(tmem_small, pl_d, qh_d, idesc, (kb | k4) != 0);
+            umma_tf32(tmem_small, ph_d, ql_d, idesc, 1);
+          }
+          umma_commit(&empty_bar[s]);               // stage reusable once these MMAs have read it
+        }
+        umma_commit(&acc_full[b]);                  // this chain is complete
+      }
+      umma_commit(small_full);
+    }
+  } else {
+    // ===== epilogue warps: drain short chains into fp32 registers, then fused epilogue =====
+    const int quad = warp & 3;                      // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int p = p0 + quad * 32 + lane;            // TMEM lane == row p of the tile
+    float acc[BN];
+#pragma unroll
+    for (int u = 0; u < BN; ++u) acc[u] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(&acc_full[b], (c >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(b * BN + cc), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[b]);
+    }
+    mbar_wait(small_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < BN; cc += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_small + lane_base + (uint32_t)cc, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
+    }
+    if (p < prm.Pn) {
+#pragma unroll
+      for (int u = 0; u < BN; ++u) {
+        const int q = q0 + u;
+        if (q < prm.Qn) {
+          if (prm.swap_out) epilogue_store(prm.g, q, p, acc[u]);
+          else epilogue_store(prm.g, p, q, acc[u]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+  PFN_encodeTiled encode = nullptr;
+  bool attr_set[3] = {false, false, false};
+  // split copies of bound parameters: key = (param pointer, transposed?) -> {hi, lo, rows, Kp}
+  struct Split { float* hi; float* lo; int rows; int K; int Kp; };
+  std::unordered_map<uint64_t, Split> weight_cache;
+  // scratch for on-the-fly operand splits (grown on demand)
+  float* scratch[2] = {nullptr, nullptr};
+  size_t scratch_floats[2] = {0, 0};
+};
+
+inline TcState*& tc_state(xg_context* ctx) {
+  static std::unordered_map<xg_context*, TcState*> m;
+  return m[ctx];
+}
+
+static int tc_init(xg_context* ctx, TcState*& ts) {
+  ts = tc_state(ctx);
+  if (ts) return XG_OK;
+  ts = new TcState();
+  tc_state(ctx) = ts;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  XG_CUDA_TRY(ctx->es, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  XG_REQUIRE(ctx->es, fn != nullptr && qres == cudaDriverEntryPointSuccess, XG_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  ts->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return XG_OK;
+}
+
+static void tc_release(xg_context* ctx) {
+  TcState* ts = tc_state(ctx);
+  if (!ts) return;
+  for (auto& kv : ts->weight_cache) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+  for (int i = 0; i < 2; ++i) if (ts->scratch[i]) cudaFree(ts->scratch[i]);
+  delete ts;
+  tc_state(ctx) = nullptr;
+}
+
+static void tc_invalidate_weights(xg_context* ctx) {
+  TcState* ts = tc_state(ctx);
+  if (!ts) return;
+  for (auto& kv : ts->weight_cache) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+  ts->weight_cache.clear();
+}
+
+// 2-D map over a K-major fp32 matrix [rows][Kp] (pitch Kp floats): box = 32 floats x box_rows, 128B swizzle
+static int tc_make_map(xg_context* ctx, TcState* ts, const float* base, int rows, int Kp, int box_rows, CUtensorMap* out) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ts->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled failed", nullptr);
+    return XG_ERR_CUDA;
+  }
+  return XG_OK;
+}
+
+static int tc_split(xg_context* ctx, const float* X, long sr, long sk, int rows, int K, int Kp, float* hi, float* lo,
+                    cudaStream_t st) {
+  dim3 grid(Kp / 32, ceil_div(rows, 32));
+  ProfScope ps(ctx, "split_tf32", st);
+  split_tf32_kernel<<<grid, dim3(32, 8), 0, st>>>(X, sr, sk, rows, K, Kp, hi, lo);
+  XG_LAUNCH_CHECK(ctx->es);
+  return XG_OK;
+}
+
+// operand = logical matrix O[r][k] = X[r*sr + k*sk], r < rows, k < K.  Returns split K-major copies.
+// Bound parameters are split once and cached until xg_params_changed(); everything else goes to scratch.
+static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, long sr, long sk, int rows, int K,
+                      const float** hi, const float** lo, int* Kp_out, cudaStream_t st) {
+  const int Kp = (K + 31) / 32 * 32;
+  *Kp_out = Kp;
+  bool is_param = false;
+  for (int i = 0; i < XG_NUM_PARAMS && !is_param; ++i) {
+    int pr, pc;
+    param_shape(ctx->d, i, &pr, &pc);
+    const float* b = ctx->P[i];
+    if (b && X >= b && X < b + (long)pr * pc) is_param = true;
+  }
+  if (is_param) {
+    // key: pointer, orientation and extents (sub-views such as W_h2a[:, H:] get their own entry)
+    uint64_t key = reinterpret_cast<uint64_t>(X) ^ ((uint64_t)(sk == 1 ? 0x1 : 0x2) << 60) ^ ((uint64_t)rows << 40) ^
+                   ((uint64_t)K << 20);
+    auto it = ts->weight_cache.find(key);
+    if (it == ts->weight_cache.end()) {
+      TcState::Split sp{nullptr, nullptr, rows, K, Kp};
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.hi, sizeof(float) * (size_t)rows * Kp));
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.lo, sizeof(float) * (size_t)rows * Kp));
+      XG_TRY(tc_split(ctx, X, sr, sk, rows, K, Kp, sp.hi, sp.lo, st));
+      it = ts->weight_cache.emplace(key, sp).first;
+    }
+    *hi = it->second.hi;
+    *lo = it->second.lo;
+    return XG_OK;
+  }
+  const size_t need = (size_t)rows * Kp * 2;
+  if (ts->scratch_floats[slot] < need) {
+    XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+    if (ts->scratch[slot]) cudaFree(ts->scratch[slot]);
+    ts->scratch[slot] = nullptr;
+    ts->scratch_floats[slot] = 0;
+    XG_CUDA_TRY(ctx->es, cudaMalloc(&ts->scratch[slot], sizeof(float) * need));
+    ts->scratch_floats[slot] = need;
+  }
+  float* h = ts->scratch[slot];
+  float* l = h + (size_t)rows * Kp;
+  XG_TRY(tc_split(ctx, X, sr, sk, rows, K, Kp, h, l, st));
+  *hi = h;
+  *lo = l;
+  return XG_OK;
+}
+
+template <int BN>
+static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMap& a, const CUtensorMap& b,
+                     const CUtensorMap& c, const CUtensorMap& d, const TcParams& prm, cudaStream_t st) {
+  if (!ts->attr_set[cfg_idx]) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              TcCfg<BN>::kSmemBytes));
+    ts->attr_set[cfg_idx] = true;
+  }
+  dim3 grid(ceil_div(prm.Pn, 128), ceil_div(prm.Qn, BN));
+  gemm_tc_kernel<BN><<<grid, TcCfg<BN>::kThreads, TcCfg<BN>::kSmemBytes, st>>>(a, b, c, d, prm);
+  XG_LAUNCH_CHECK(ctx->es);
+  return XG_OK;
+}
+
+// shape gate: where the tensor-core engine pays (one 128-lane tile must not be mostly padding)
+static bool tc_eligible(const GemmP& p) {
+  return p.M >= 16 && p.N >= 64 && p.K >= 64 && (long)p.M * p.N * p.K >= (1L << 22);
+}
+
+// C (M,N) = epi( A . B ) in the GemmP convention (A(i,r), B(r,j), arbitrary strides).
+// Orientation: the side with more rows rides the 128 TMEM lanes unless it is the activation side of a
+// forward Linear (weights on the lanes => coalesced row-major stores and per-lane bias).
+static int gemm_tc(xg_context* ctx, const GemmP& p, cudaStream_t st) {
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  // operand "I" : rows i (M), reduction r ;  operand "J" : rows j (N), reduction r
+  const float *ih, *il, *jh, *jl;
+  int Kp = 0, Kp2 = 0;
+  XG_TRY(tc_operand(ctx, ts, 0, p.A, p.sa_i, p.sa_r, p.M, p.K, &ih, &il, &Kp, st));
+  XG_TRY(tc_operand(ctx, ts, 1, p.B, p.sb_j, p.sb_r, p.N, p.K, &jh, &jl, &Kp2, st));
+  TcParams prm;
+  prm.K = Kp;
+  prm.g = p;
+  // lanes <- J (output columns) so that stores are coalesced along j; columns <- I
+  prm.Pn = p.N;
+  prm.Qn = p.M;
+  prm.swap_out = 1;
+  const int BN = (p.M <= 64 || (long)ceil_div(p.N, 128) * ceil_div(p.M, 128) < 120) ? 64 : 128;
+  CUtensorMap mPh, mPl, mQh, mQl;
+  XG_TRY(tc_make_map(ctx, ts, jh, p.N, Kp, 128, &mPh));
+  XG_TRY(tc_make_map(ctx, ts, jl, p.N, Kp, 128, &mPl));
+  XG_TRY(tc_make_map(ctx, ts, ih, p.M, Kp, BN, &mQh));
+  XG_TRY(tc_make_map(ctx, ts, il, p.M, Kp, BN, &mQl));
+  char tag[96];
+  if (ctx->prof_on) {
+    const char* lay = (p.sa_r == 1) ? (p.sb_r == 1 ? "nt" : "nn") : "tn";
+    snprintf(tag, sizeof(tag), "gemmtc_%s_%dx%dx%d", lay, p.M, p.N, p.K);
+  } else {
+    tag[0] = 0;
+  }
+  ProfScope ps(ctx, std::string(tag), st);
+  if (BN == 64) return tc_launch<64>(ctx, ts, 0, mPh, mPl, mQh, mQl, prm, st);
+  return tc_launch<128>(ctx, ts, 1, mPh, mPl, mQh, mQl, prm, st);
+}
+
+}  // namespace xg

@@ -75,7 +75,14 @@ class Engine:
         self._bound_key = None
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._device = None
-        self._step = 0
+        self._param_version = None
+        self._tensor_cores = True
+
+    def set_engine(self, tensor_cores: bool):
+        """True (default): dense contractions above the size gate use the tcgen05 3xTF32 engine."""
+        self._tensor_cores = bool(tensor_cores)
+        if self.handle:
+            L.check(self.lib.xg_set_engine(self.handle, int(self._tensor_cores)), "xg_set_engine", self.handle)
 
     # ---- handle lifecycle -------------------------------------------------------------
     def _ensure_handle(self, device: torch.device):
@@ -92,6 +99,7 @@ class Engine:
                       L.XG_ACT[d["fusion_activity"]], float(d["drop_prob"]), 1e-5, 0.1)
         idx = device.index if device.index is not None else torch.cuda.current_device()
         L.check(self.lib.xg_create(ctypes.byref(xd), idx, ctypes.byref(self.handle)), "xg_create")
+        L.check(self.lib.xg_set_engine(self.handle, int(self._tensor_cores)), "xg_set_engine", self.handle)
         self._device = device
         self._bound_key = None
         self._ws.clear()
@@ -120,8 +128,17 @@ class Engine:
         dev = plist[0].device
         self._ensure_handle(dev)
         key = tuple(p.data_ptr() for p in plist) + tuple(b.data_ptr() for b in self._blist)
+        # in-place parameter updates (optimizer.step, load_state_dict, .data.copy_) bump Tensor._version:
+        # derived copies inside the library (tf32 hi/lo splits) must be dropped
+        ver = sum(p._version for p in plist)
         if key == self._bound_key:
+            if ver != self._param_version:
+                L.check(self.lib.xg_params_changed(self.handle), "xg_params_changed", self.handle)
+                self._param_version = ver
             return
+        self._param_version = ver
+        if self._bound_key is not None:
+            L.check(self.lib.xg_params_changed(self.handle), "xg_params_changed", self.handle)
         for n, p in zip(PARAM_NAMES, plist):
             if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("parameter %s must be contiguous fp32 on %s" % (n, dev))
