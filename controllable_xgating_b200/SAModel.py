@@ -21,7 +21,7 @@ from .sub_modules import (EncoderLstm_two_fc, Fusion, Gate, LSTMCore_two_layer_g
 __all__ = ["SAModel", "LanguageModelCriterion", "ClassiferCriterion", "RewardCriterion", "to_contiguous",
            "CaptionModel", "Gate", "Fusion", "EncoderLstm_two_fc", "LSTMCore_two_layer_gate", "two_inputs_lstmcell"]
 
-VERBOSE = True   # the reference prints 'sampling with greedy search' / '... beam search' (SAModel.py:131,177)
+VERBOSE = True   # default of SAModel.VERBOSE: the reference prints 'sampling with greedy search' / '... beam search' (SAModel.py:131,177)
 
 
 class _TrainForward(torch.autograd.Function):
@@ -55,6 +55,8 @@ class _TrainForward(torch.autograd.Function):
 
 
 class SAModel(CaptionModel):
+    VERBOSE = VERBOSE   # set SAModel.VERBOSE = False (or on an instance) to silence the reference-style prints
+
     def __init__(self, opt):
         super(SAModel, self).__init__()
         torch.manual_seed(opt.seed)                                  # SAModel.py:16
@@ -173,7 +175,7 @@ class SAModel(CaptionModel):
         """SAModel.py:129-161 (+ CaptionModel.beam_search), the whole batch in one device call.
         Returns CPU tensors like the reference (seq (m,T) int64, seqLogprobs (m,T) float)."""
         beam_size = opt.get("beam_size", 5)
-        if VERBOSE:
+        if self.VERBOSE:
             print("sampling with beam search ( beam_size = {} )".format(beam_size))
         assert beam_size <= self.vocab_size, ("lets assume this for now, otherwise this corner case causes a few headaches "
                                               "down the road. can be dealt with in future if needed")
@@ -195,7 +197,7 @@ class SAModel(CaptionModel):
         feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
         if beam_size > 1:
             return self.sample_beam(feats, feat_mask, pos_feats, opt)
-        if VERBOSE:
+        if self.VERBOSE:
             print("sampling with greedy search")
         seed = 0 if sample_max else self._engine.next_seed()
         with torch.no_grad():

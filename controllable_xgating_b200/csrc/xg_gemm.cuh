@@ -39,6 +39,28 @@ struct GemmP {
 
 // element (i,j) of the logical output: bias, activation, dropout, aux store, cross gate, row
 // permutation, accumulate.  Shared by the SIMT and the tcgen05 engines.
+__device__ __forceinline__ float epilogue_bias(const Epilogue& ep, int j) {
+  float b = 0.f;
+  if (ep.bias0) b += ep.bias0[j];
+  if (ep.bias1) b += ep.bias1[j];
+  if (ep.bias2) b += ep.bias2[j];
+  return b;
+}
+// v already holds alpha*acc + bias
+__device__ __forceinline__ void epilogue_finish(const GemmP& p, int i, int j, float v) {
+  const Epilogue& ep = p.ep;
+  v = apply_act(v, ep.act);
+  if (ep.drop.on()) v *= ep.drop.factor((uint64_t)i * (uint64_t)p.N + (uint64_t)j);
+  if (ep.aux) ep.aux[(long)i * ep.ldaux + j] = v;
+  if (ep.tgt) {
+    const long trow = ep.tgt_div ? (i / ep.tgt_div) : (ep.tgt_mod ? (i % ep.tgt_mod) : i);
+    v = ep.tgt[trow * ep.ldt + j] * (1.f + v);
+  }
+  const long orow = p.perm_rb ? (long)(i % p.perm_rb) * p.perm_rs + i / p.perm_rb : (long)i;
+  float* c = p.C + orow * p.ldc + j;
+  if (ep.beta != 0.f) v += ep.beta * (*c);
+  *c = v;
+}
 __device__ __forceinline__ void epilogue_store(const GemmP& p, int i, int j, float acc) {
   const Epilogue& ep = p.ep;
   float v = ep.alpha * acc;

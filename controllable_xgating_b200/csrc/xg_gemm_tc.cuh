@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <map>
+#include <tuple>
 #include <unordered_map>
 
 #include "xg_context.cuh"
@@ -295,14 +297,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
 #pragma unroll
       for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
     }
-    if (p < prm.Pn) {
+    // Stage the register accumulators through the pipeline buffers (idle now: every MMA has retired)
+    // so that ONE rolled copy of the generic epilogue serves all BN columns.  Unrolling it BN times
+    // produced an 84k-instruction kernel that was instruction-fetch bound (ncu, profiles/r1b).
+    float* stage_out = reinterpret_cast<float*>(smem);
+    const int pl = quad * 32 + lane;
 #pragma unroll
-      for (int u = 0; u < BN; ++u) {
+    for (int u = 0; u < BN; ++u) stage_out[u * 128 + pl] = acc[u];   // same thread reads it back: no barrier
+    if (p < prm.Pn) {
+      const float alpha = prm.g.ep.alpha;
+      const float bias_p = prm.swap_out ? epilogue_bias(prm.g.ep, p) : 0.f;   // j == p: per-lane constant
+      const int qn = min(BN, prm.Qn - q0);
+#pragma unroll 1
+      for (int u = 0; u < qn; ++u) {
+        const float a = stage_out[u * 128 + pl];
         const int q = q0 + u;
-        if (q < prm.Qn) {
-          if (prm.swap_out) epilogue_store(prm.g, q, p, acc[u]);
-          else epilogue_store(prm.g, p, q, acc[u]);
-        }
+        if (prm.swap_out) epilogue_finish(prm.g, q, p, alpha * a + bias_p);
+        else epilogue_finish(prm.g, p, q, alpha * a + epilogue_bias(prm.g.ep, q));
       }
     }
   }
@@ -323,7 +334,8 @@ struct TcState {
   bool attr_set[3] = {false, false, false};
   // split copies of bound parameters: key = (param pointer, transposed?) -> {hi, lo, rows, Kp}
   struct Split { float* hi; float* lo; int rows; int K; int Kp; };
-  std::unordered_map<uint64_t, Split> weight_cache;
+  typedef std::tuple<const float*, long, long, int, int> SplitKey;   // (pointer, row stride, k stride, rows, K)
+  std::map<SplitKey, Split> weight_cache;
   // scratch for on-the-fly operand splits (grown on demand)
   float* scratch[2] = {nullptr, nullptr};
   size_t scratch_floats[2] = {0, 0};
@@ -403,8 +415,7 @@ static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, lo
   }
   if (is_param) {
     // key: pointer, orientation and extents (sub-views such as W_h2a[:, H:] get their own entry)
-    uint64_t key = reinterpret_cast<uint64_t>(X) ^ ((uint64_t)(sk == 1 ? 0x1 : 0x2) << 60) ^ ((uint64_t)rows << 40) ^
-                   ((uint64_t)K << 20);
+    const TcState::SplitKey key(X, sr, sk, rows, K);
     auto it = ts->weight_cache.find(key);
     if (it == ts->weight_cache.end()) {
       TcState::Split sp{nullptr, nullptr, rows, K, Kp};
@@ -449,8 +460,13 @@ static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMa
 }
 
 // shape gate: where the tensor-core engine pays (one 128-lane tile must not be mostly padding)
+// One CTA streams a whole 128-row x K operand slab, so the engine only pays when the output has enough
+// 128 x 64 tiles to occupy a good part of the 148 SMs (measured: 64x2048x512 -> 16 tiles -> 77 us vs
+// 23 us on the SIMT engine).  Skinny recurrent products stay on the SIMT engine until the fused
+// split-K word-step kernel takes them over.
 static bool tc_eligible(const GemmP& p) {
-  return p.M >= 16 && p.N >= 64 && p.K >= 64 && (long)p.M * p.N * p.K >= (1L << 22);
+  const long tiles = (long)ceil_div(p.N, 128) * ceil_div(p.M, 64);
+  return p.K >= 64 && tiles >= 64 && (long)p.M * p.N * p.K >= (1L << 24);
 }
 
 // C (M,N) = epi( A . B ) in the GemmP convention (A(i,r), B(r,j), arbitrary strides).
