@@ -5,6 +5,7 @@
 #include "xg_backward.cuh"
 #include "xg_beam.cuh"
 #include "xg_forward.cuh"
+#include "xg_persist.cuh"
 
 using namespace xg;
 
@@ -137,6 +138,7 @@ int xg_destroy(xg_handle h) {
   if (!h) return XG_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  persist_release(h);
   tc_release(h);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
@@ -182,7 +184,8 @@ int xg_params_changed(xg_handle h) {
 
 int xg_set_engine(xg_handle h, int tensor_cores) {
   CHECK_HANDLE(h);
-  h->tc_mode = tensor_cores ? 1 : 0;
+  h->tc_mode = tensor_cores >= 1 ? 1 : 0;
+  h->persist_mode = tensor_cores >= 2 ? 1 : 0;
   return XG_OK;
 }
 
@@ -298,6 +301,8 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     XG_TRY(xg_attend_precompute(h, V, B, K, g.Uv, stream));
     Uv = g.Uv;
   }
+  if (sample_max && persist_eligible(h, B, K))   // fused persistent word loop (xg_persist.cuh)
+    return persist_greedy(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
   for (int q = 0; q < 4; ++q)
     XG_CUDA_TRY(h->es, cudaMemcpyAsync(g.st[q], state0[q], sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
   XG_CUDA_TRY(h->es, cudaMemsetAsync(g.tok, 0, sizeof(int64_t) * (size_t)B, st));          // <bos> (SAModel.py:184)

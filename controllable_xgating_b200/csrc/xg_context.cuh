@@ -20,6 +20,7 @@ struct xg_context {
   int* d_small = nullptr;    // matching device words
   // optional per-kernel timing with CUDA events on the launching stream (xg_profile_enable/_report)
   int tc_mode = 1;           // 1: dense contractions above the size gate run on the tcgen05 3xTF32 engine
+  int persist_mode = 1;      // 1: greedy decoding runs in the fused persistent word-step kernel when eligible
   bool prof_on = false;
   struct ProfRec { std::string name; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof_recs;

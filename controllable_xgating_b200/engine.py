@@ -76,13 +76,14 @@ class Engine:
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._device = None
         self._param_version = None
-        self._tensor_cores = True
+        self._engine_mode = 2
 
-    def set_engine(self, tensor_cores: bool):
-        """True (default): dense contractions above the size gate use the tcgen05 3xTF32 engine."""
-        self._tensor_cores = bool(tensor_cores)
+    def set_engine(self, tensor_cores: bool, persistent: bool = True):
+        """tensor_cores (default True): dense contractions above the size gate use the tcgen05 3xTF32 engine;
+        persistent (default True): greedy decoding runs in the fused persistent word-step kernel."""
+        self._engine_mode = (2 if persistent else 1) if tensor_cores else 0
         if self.handle:
-            L.check(self.lib.xg_set_engine(self.handle, int(self._tensor_cores)), "xg_set_engine", self.handle)
+            L.check(self.lib.xg_set_engine(self.handle, self._engine_mode), "xg_set_engine", self.handle)
 
     # ---- handle lifecycle -------------------------------------------------------------
     def _ensure_handle(self, device: torch.device):
@@ -99,7 +100,7 @@ class Engine:
                       L.XG_ACT[d["fusion_activity"]], float(d["drop_prob"]), 1e-5, 0.1)
         idx = device.index if device.index is not None else torch.cuda.current_device()
         L.check(self.lib.xg_create(ctypes.byref(xd), idx, ctypes.byref(self.handle)), "xg_create")
-        L.check(self.lib.xg_set_engine(self.handle, int(self._tensor_cores)), "xg_set_engine", self.handle)
+        L.check(self.lib.xg_set_engine(self.handle, self._engine_mode), "xg_set_engine", self.handle)
         self._device = device
         self._bound_key = None
         self._ws.clear()

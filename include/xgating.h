@@ -125,9 +125,10 @@ int xg_bind_params(xg_handle h, const float* const* params, int count);
 int xg_bind_bn_buffers(xg_handle h, float* rm_rgb, float* rv_rgb, float* rm_opfl, float* rv_opfl);
 /* call after the optimizer (or load_state_dict) rewrites parameter storage: drops derived copies. */
 int xg_params_changed(xg_handle h);
-/* tensor_cores != 0 (default): dense contractions above a size gate run on the tcgen05 3xTF32 engine
- * (fp32-grade accuracy); 0: everything on the SIMT fp32 engine.  Results agree to ~1e-6 relative. */
-int xg_set_engine(xg_handle h, int tensor_cores);
+/* mode 0: everything on the SIMT fp32 engine; 1: dense contractions above a size gate run on the
+ * tcgen05 3xTF32 engine (fp32-grade accuracy); 2 (default): 1 + greedy decoding in the fused persistent
+ * word-step kernel.  Results agree to ~1e-6 relative. */
+int xg_set_engine(xg_handle h, int mode);
 
 size_t xg_workspace_bytes(xg_handle h, int kind, int B, int K, int L_or_T, int beam);
 
