@@ -167,6 +167,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, long sr, long sk,
 struct TcParams {
   int Pn, Qn, K;       // K = padded reduction extent (multiple of 32)
   int swap_out;        // 1: logical (i,j) = (q,p)  [y = x W^T with W on the lane side]; 0: (i,j) = (p,q)
+  int dbg;             // diagnostics (XG_TC_DEBUG): 1 skip MMA issue, 2 one long chain (no promotion), 4 skip lo loads
   GemmP g;             // output pointer / leading dimension / epilogue (M,N = logical output extents)
 };
 
@@ -201,7 +202,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.x * 128, q0 = blockIdx.y * BN;
   const int num_kb = prm.K / 32;
-  const int num_chunks = (num_kb + Cfg::kChunk - 1) / Cfg::kChunk;
+  const int kchunk = (prm.dbg & 2) ? (1 << 20) : Cfg::kChunk;
+  const int num_chunks = (num_kb + kchunk - 1) / kchunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -225,6 +227,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
         const uint32_t ph = (kb / Cfg::kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * Cfg::kStageBytes;
+        if (prm.dbg & 4) {
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes / 2);
+          tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
+          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
+          continue;
+        }
         mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
         tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
         tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * 32, p0);
@@ -241,8 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
         mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_main = tmem_base + b * BN;
-        for (int kk = 0; kk < Cfg::kChunk; ++kk) {
-          const int kb = c * Cfg::kChunk + kk;
+        for (int kk = 0; kk < kchunk; ++kk) {
+          const int kb = c * kchunk + kk;
           if (kb >= num_kb) break;
           const int s = kb % Cfg::kStages;
           mbar_wait(&full_bar[s], (kb / Cfg::kStages) & 1);
@@ -254,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
             const uint64_t pl_d = umma_desc_sw128(base + 128 * 128 + k4 * 32);
             const uint64_t qh_d = umma_desc_sw128(base + 2 * 128 * 128 + k4 * 32);
             const uint64_t ql_d = umma_desc_sw128(base + 2 * 128 * 128 + BN * 128 + k4 * 32);
+            if (prm.dbg & 1) continue;
             umma_tf32(tmem_main, ph_d, qh_d, idesc, (kk | k4) != 0);
             umma_tf32(tmem_small, pl_d, qh_d, idesc, (kb | k4) != 0);
             umma_tf32(tmem_small, ph_d, ql_d, idesc, 1);
@@ -483,6 +492,7 @@ static int gemm_tc(xg_context* ctx, const GemmP& p, cudaStream_t st) {
   TcParams prm;
   prm.K = Kp;
   prm.g = p;
+  { const char* e = getenv("XG_TC_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
   // lanes <- J (output columns) so that stores are coalesced along j; columns <- I
   prm.Pn = p.N;
   prm.Qn = p.M;

@@ -39,8 +39,10 @@ struct GDesc {                 // one dense product  out[slot][n][r] = sum_k W[n
   float* out;                  // [slots][n_rows][R]
 };
 
+struct MapTable { CUtensorMap m[26]; };
+
 struct PersistParams {
-  const CUtensorMap* maps;
+  const CUtensorMap* maps;      // set on the device: points at the __grid_constant__ table
   GDesc ah, gate, z1x, z1h, z2h, z1g, z2x, z2a, logit;
   int B, R, K, H, E, Ep, A, V, T;
   // parameters (fp32, reference layouts)
@@ -58,11 +60,13 @@ struct PersistParams {
   float *hx;                            // [2H][R]
   float *c1, *c2;                       // [H][R]
   float *stats;                         // [tiles*4][R][4]  (max, argmax, sum-exp, -)
+  float *scores;                        // [R][K] attention scores of the current step
   float *unfinished;                    // [R]
   int64_t *tok;                         // [R]
   // outputs
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
+  long long* dbg_clock;                 // [T][9] SM-clock stamps of CTA 0 at phase boundaries (diagnostics), or NULL
 };
 
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -113,6 +117,9 @@ struct SmemView {
   uint64_t *full_bar, *empty_bar, *acc_full, *acc_empty, *small_full, *small_empty, *bulk_bar;
   uint32_t* tmem_slot;
 };
+
+__device__ __forceinline__ unsigned f2ord(float f);
+__device__ __forceinline__ float ord2f(unsigned o);
 
 // run all work items of `nd` products; item i of the phase goes to CTA (i % G)
 __device__ __noinline__ void gemm_phase(const PersistParams& P, const GDesc* const* descs, int nd, const SmemView& sv,
@@ -169,6 +176,7 @@ __device__ __noinline__ void gemm_phase(const PersistParams& P, const GDesc* con
               const int s = cnt % PS_STAGES;
               mbar_wait(&sv.full_bar[s], (cnt / PS_STAGES) & 1);
               tc_fence_after();
+              if (P.dbg_clock && cta == 0 && d.mode == 1 && kb < 16) P.dbg_clock[2048 * 17 + kb] = clock64();
               const uint32_t base = smem_u32(sv.stages + s * PS_STAGE_BYTES);
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
@@ -235,13 +243,10 @@ __device__ __noinline__ void gemm_phase(const PersistParams& P, const GDesc* con
 #pragma unroll
           for (int u = 0; u < PS_BN; ++u) {
             const float v = n < d.n_rows ? acc[u] + bias : -INFINITY;
-            float best = v; int bi = n;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
+            const unsigned ov = f2ord(v);
+            const unsigned mo = __reduce_max_sync(0xffffffffu, ov);
+            const float best = ord2f(mo);
+            const int bi = (int)__reduce_min_sync(0xffffffffu, ov == mo ? (unsigned)n : 0x7fffffffu);
             float e = (v == -INFINITY) ? 0.f : expf(v - best);
             e = warp_sum(e);
             if (lane == 0) {
@@ -266,10 +271,25 @@ __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, floa
   lo[idx] = tf32_rna(v - h);
 }
 
+// Sum of split-K partial slots.  All loads are issued before the first add: with 6 warps per SM and an
+// L1 that the grid barrier's fence leaves cold, a load->add->load chain costs one L2 round trip per slot
+// (measured: 50k cycles per cell phase); batched, the whole element costs one.
+template <int MAXS>
 __device__ __forceinline__ float sum_slots(const float* base, int slots, long slot_stride, long idx) {
+  float v[MAXS];
+#pragma unroll
+  for (int k = 0; k < MAXS; ++k) v[k] = k < slots ? __ldcg(base + (long)k * slot_stride + idx) : 0.f;
   float s = 0.f;
-  for (int k = 0; k < slots; ++k) s += base[(long)k * slot_stride + idx];   // fixed order
+#pragma unroll
+  for (int k = 0; k < MAXS; ++k) s += v[k];   // fixed order (unused slots add +0)
   return s;
+}
+__device__ __forceinline__ unsigned f2ord(float f) {      // order-preserving float -> uint (for redux.sync)
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
 // lstm cell (decoder order i,f,o,g) for all (unit j, row r); z = sum of partial slots + three biases
@@ -286,13 +306,17 @@ __device__ __forceinline__ void cell_phase(const PersistParams& P, int layer, co
   const long sstr = (long)4 * H * R;
   for (int e = gtid; e < H * R; e += gthreads) {
     const int j = e / R, r = e % R;
-    float z[4];
+    float z[4], za[4], zb[4], zc[4], zbias[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < 4; ++g) {            // issue every load of the element first
       const long idx = (long)(g * H + j) * R + r;
-      z[g] = sum_slots(da.out, da.slots, sstr, idx) + sum_slots(db.out, db.slots, sstr, idx) +
-             sum_slots(dc.out, dc.slots, sstr, idx) + (bi[g * H + j] + ba[g * H + j] + bh[g * H + j]);
+      za[g] = sum_slots<2>(da.out, da.slots, sstr, idx);
+      zb[g] = sum_slots<4>(db.out, db.slots, sstr, idx);
+      zc[g] = sum_slots<2>(dc.out, dc.slots, sstr, idx);
+      zbias[g] = __ldg(bi + g * H + j) + __ldg(ba + g * H + j) + __ldg(bh + g * H + j);
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) z[g] = za[g] + zb[g] + zc[g] + zbias[g];
     const float ig = sigmoid_f(z[0]), fg = sigmoid_f(z[1]), og = sigmoid_f(z[2]), gg = tanhf(z[3]);
     const float m = use_mask ? mask_rows[r] : 1.f;
     const float cp = cst[e];
@@ -307,8 +331,16 @@ __device__ __forceinline__ void cell_phase(const PersistParams& P, int layer, co
   }
 }
 
-__global__ void __launch_bounds__(PS_THREADS, 1) decode_persistent_kernel(const PersistParams* __restrict__ Pp) {
-  const PersistParams& P = *Pp;
+__global__ void __launch_bounds__(PS_THREADS, 1)
+decode_persistent_kernel(const PersistParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
+  // parameter block -> shared memory (the inline-asm memory clobbers force re-reads; keep them on-chip)
+  __shared__ PersistParams Psm;
+  for (int i = threadIdx.x; i < (int)(sizeof(PersistParams) / 4); i += PS_THREADS)
+    reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) Psm.maps = maps.m;
+  __syncthreads();
+  const PersistParams& P = Psm;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SmemView sv;
@@ -364,38 +396,73 @@ __global__ void __launch_bounds__(PS_THREADS, 1) decode_persistent_kernel(const 
   for (int r = gtid; r < R; r += gthreads) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
   grid_barrier(P.sync_counter, sync_target, G);
 
+#define PS_STAMP(i) do { if (P.dbg_clock && cta == 0 && threadIdx.x == 0) P.dbg_clock[t * 17 + (i)] = clock64(); } while (0)
   for (int t = 0; t < T; ++t) {
+    PS_STAMP(0);
     // ================= G1 =================
     {
       const GDesc* ds[5] = {&P.ah, &P.z1h, &P.z2h, &P.gate, &P.z1x};
       gemm_phase(P, ds, 5, sv, tmem_base, ps, cta, G);
     }
+    PS_STAMP(1);
     grid_barrier(P.sync_counter, sync_target, G);
-    // ================= P1: attention + POS gate =================
+    PS_STAMP(2);
+    // ================= P1: attention scores (all CTAs: caption x frame-group items) + POS gate =================
+    {
+      // s[r][k] = a2w . tanh(AH[r] + Uv[r,k,:]) + b      (sub_modules.py:677-678); softmax/context in P2
+      const int ng = max(1, min(K, G / max(B, 1)));
+      const int fpg = (K + ng - 1) / ng;            // frames per group
+      const int nge = (K + fpg - 1) / fpg;
+      const long sstr = (long)A * R;
+      float* ah = sv.scratch;                       // A floats
+      for (int it = cta; it < B * nge; it += G) {
+        const int r = it / nge, k0 = (it % nge) * fpg, k1 = min(K, k0 + fpg);
+        for (int a = threadIdx.x; a < A; a += PS_THREADS)
+          ah[a] = sum_slots<4>(P.ah.out, P.ah.slots, sstr, (long)a * R + r) + __ldg(P.b_h2a + a);
+        __syncthreads();
+        for (int k = k0 + warp; k < k1; k += PS_THREADS / 32) {
+          const float* u = P.Uv + ((long)r * K + k) * A;
+          float p = 0.f;
+#pragma unroll 4
+          for (int a = lane; a < A; a += 32) p += __ldg(P.w_a2w + a) * tanhf(ah[a] + __ldg(u + a));
+          p = warp_sum(p);
+          if (lane == 0) P.scores[(long)r * K + k] = p + __ldg(P.b_a2w);
+        }
+        __syncthreads();
+      }
+      const long gstr = (long)H * R;
+      for (int e = gtid; e < H * R; e += gthreads) {
+        const int j = e / R, r = e % R;
+        float g = sum_slots<2>(P.gate.out, P.gate.slots, gstr, (long)j * R + r) + __ldg(P.b_gate + j);
+        g = g > 0.f ? g : 0.f;
+        const float pv = r < B ? __ldg(P.pos + (long)r * H + j) : 0.f;
+        store_split(P.gp_hi, P.gp_lo, (long)r * H + j, pv * (1.f + g));
+      }
+    }
+    PS_STAMP(3);
+    grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(4);
+    // ================= G2 =================
+    {
+      const GDesc* ds[1] = {&P.z1g};
+      gemm_phase(P, ds, 1, sv, tmem_base, ps, cta, G);
+    }
+    PS_STAMP(5);
+    grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(6);
+    // ================= P2: softmax over ALL K frames + context (V[r] staged by a TMA bulk copy), lstm_1 =================
     for (int r = cta; r < B; r += G) {
-      float* ah = sv.scratch;          // A floats
-      float* sc = sv.scratch + A;      // K floats
-      float* vsm = reinterpret_cast<float*>(sv.stages);   // V[r] staged by TMA bulk copy (K*H floats)
+      float* sc = sv.scratch;                              // K floats
+      float* vsm = reinterpret_cast<float*>(sv.stages);    // K*H floats: the frame-feature matrix of caption r
       if (threadIdx.x == 0) {
         mbar_expect_tx(sv.bulk_bar, (uint32_t)(K * H * 4));
         bulk_g2s(vsm, P.Vf + (long)r * K * H, (uint32_t)(K * H * 4), sv.bulk_bar);
       }
-      const long sstr = (long)A * R;
-      for (int a = threadIdx.x; a < A; a += PS_THREADS)
-        ah[a] = sum_slots(P.ah.out, P.ah.slots, sstr, (long)a * R + r) + P.b_h2a[a];
-      __syncthreads();
-      for (int k = warp; k < K; k += PS_THREADS / 32) {
-        const float* u = P.Uv + ((long)r * K + k) * A;
-        float p = 0.f;
-        for (int a = lane; a < A; a += 32) p += P.w_a2w[a] * tanhf(ah[a] + u[a]);
-        p = warp_sum(p);
-        if (lane == 0) sc[k] = p + P.b_a2w[0];
-      }
-      __syncthreads();
-      if (warp == 0) {
+      if (warp == 1) {
         float mx = -INFINITY;
-        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, sc[k]);
+        for (int k = lane; k < K; k += 32) { const float v = __ldcg(P.scores + (long)r * K + k); sc[k] = v; mx = fmaxf(mx, v); }
         mx = warp_max(mx);
+        __syncwarp();
         float sum = 0.f;
         for (int k = lane; k < K; k += 32) { const float e = expf(sc[k] - mx); sc[k] = e; sum += e; }
         sum = warp_sum(sum);
@@ -405,50 +472,39 @@ __global__ void __launch_bounds__(PS_THREADS, 1) decode_persistent_kernel(const 
       mbar_wait(sv.bulk_bar, bulk_phase & 1);
       __syncthreads();
       for (int j = threadIdx.x; j < H; j += PS_THREADS) {
-        float s = 0.f;
-        for (int k = 0; k < K; ++k) s += sc[k] * vsm[k * H + j];
-        store_split(P.af_hi, P.af_lo, (long)r * H + j, s);
+        float a = 0.f;
+        for (int k = 0; k < K; ++k) a += sc[k] * vsm[k * H + j];
+        store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
       }
       bulk_phase++;
       __syncthreads();
     }
-    {
-      const long sstr = (long)H * R;
-      for (int e = gtid; e < H * R; e += gthreads) {
-        const int j = e / R, r = e % R;
-        float g = sum_slots(P.gate.out, P.gate.slots, sstr, (long)j * R + r) + P.b_gate[j];
-        g = g > 0.f ? g : 0.f;
-        const float pv = r < B ? P.pos[(long)r * H + j] : 0.f;
-        store_split(P.gp_hi, P.gp_lo, (long)r * H + j, pv * (1.f + g));
-      }
-    }
-    // the stage buffers were read through the generic proxy (vsm): order before the next TMA writes
-    fence_proxy_async_smem();
-    grid_barrier(P.sync_counter, sync_target, G);
-    // ================= G2 =================
-    {
-      const GDesc* ds[1] = {&P.z1g};
-      gemm_phase(P, ds, 1, sv, tmem_base, ps, cta, G);
-    }
-    grid_barrier(P.sync_counter, sync_target, G);
-    // ================= P2: lstm_1 =================
+    fence_proxy_async_smem();      // vsm was read through the generic proxy: order before the next TMA writes
     cell_phase(P, 0, P.unfinished, t > 0, gtid, gthreads);
+    PS_STAMP(7);
     grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(8);
     // ================= G3 =================
     {
       const GDesc* ds[2] = {&P.z2x, &P.z2a};
       gemm_phase(P, ds, 2, sv, tmem_base, ps, cta, G);
     }
+    PS_STAMP(9);
     grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(10);
     // ================= P3: lstm_2 =================
     cell_phase(P, 1, P.unfinished, t > 0, gtid, gthreads);
+    PS_STAMP(11);
     grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(12);
     // ================= G4: logits statistics =================
     {
       const GDesc* ds[1] = {&P.logit};
       gemm_phase(P, ds, 1, sv, tmem_base, ps, cta, G);
     }
+    PS_STAMP(13);
     grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(14);
     // ================= P4: greedy bookkeeping + next embedding (SAModel.py:185-210) =================
     {
       const int nrec = ((P.V + 127) / 128) * 4;
@@ -491,7 +547,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) decode_persistent_kernel(const 
         __syncthreads();
       }
     }
+    PS_STAMP(15);
     grid_barrier(P.sync_counter, sync_target, G);
+    PS_STAMP(16);
   }
 
   tc_fence_before();
@@ -510,6 +568,7 @@ struct PersistState {
   PersistParams* d_params = nullptr;
   unsigned int* d_counter = nullptr;
   int* d_flags = nullptr;
+  long long* d_dbg = nullptr;
   PersistParams hp;              // host copy (pointers into the pool)
   bool attr_set = false;
 };
@@ -565,6 +624,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_params = a.take<PersistParams>(1);
       S->d_counter = a.take<unsigned int>(64);
       S->d_flags = a.take<int>(2048);
+      S->d_dbg = a.take<long long>(2048 * 17 + 64);
       hp.xt_hi = a.take<float>((long)R * Ep); hp.xt_lo = a.take<float>((long)R * Ep);
       hp.hh_hi = a.take<float>((long)R * 2 * H); hp.hh_lo = a.take<float>((long)R * 2 * H);
       hp.gp_hi = a.take<float>((long)R * H); hp.gp_lo = a.take<float>((long)R * H);
@@ -573,6 +633,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       hp.c1 = a.take<float>((long)H * R); hp.c2 = a.take<float>((long)H * R);
       hp.stats = a.take<float>((long)((V + 127) / 128) * 4 * R * 4);
       hp.unfinished = a.take<float>(R);
+      hp.scores = a.take<float>((long)R * K);
       hp.tok = a.take<int64_t>(R);
       hp.ah.out = a.take<float>((long)slots_of(2 * kbH, per_g1) * A * R);
       hp.gate.out = a.take<float>((long)slots_of(kbE, per_g1) * H * R);
@@ -594,7 +655,8 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   if (T > 2048) { ctx->es.msg = "persist_greedy: seq_length too large"; return XG_ERR_BAD_SHAPE; }
 
   // ---- tensor maps: 9 weights x (hi,lo) = 0..17 ; activations xt 18,19  hh 20,21  gp 22,23  af 24,25 ----
-  CUtensorMap maps[32];
+  MapTable mt;
+  CUtensorMap* maps = mt.m;
   for (int i = 0; i < 9; ++i) {
     XG_TRY(tc_make_map(ctx, ts, whi[i], wspec[i].rows, wkp[i], 128, &maps[2 * i]));
     XG_TRY(tc_make_map(ctx, ts, wlo[i], wspec[i].rows, wkp[i], 128, &maps[2 * i + 1]));
@@ -603,7 +665,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_TRY(tc_make_map(ctx, ts, hp.hh_hi, R, 2 * H, PS_BN, &maps[20])); XG_TRY(tc_make_map(ctx, ts, hp.hh_lo, R, 2 * H, PS_BN, &maps[21]));
   XG_TRY(tc_make_map(ctx, ts, hp.gp_hi, R, H, PS_BN, &maps[22])); XG_TRY(tc_make_map(ctx, ts, hp.gp_lo, R, H, PS_BN, &maps[23]));
   XG_TRY(tc_make_map(ctx, ts, hp.af_hi, R, H, PS_BN, &maps[24])); XG_TRY(tc_make_map(ctx, ts, hp.af_lo, R, H, PS_BN, &maps[25]));
-  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_maps, maps, sizeof(CUtensorMap) * 26, cudaMemcpyHostToDevice, st));
 
   auto mk = [&](GDesc& g, int widx, int xmap, int xkb0, int n_rows, int nkb, int per, int mode) {
     g.w_hi = 2 * widx; g.w_lo = 2 * widx + 1; g.x_hi = xmap; g.x_lo = xmap + 1;
@@ -628,6 +689,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int q = 0; q < 4; ++q) hp.state0[q] = state0[q];
   hp.seq = seq_out; hp.seqlogp = logp_out; hp.flags = S->d_flags;
   hp.sync_counter = S->d_counter;
+  hp.dbg_clock = getenv("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(PersistParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * 64, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
@@ -644,7 +706,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   {
     ProfScope ps(ctx, "decode_persistent", st);
     const PersistParams* dp = S->d_params;
-    void* args[1] = {(void*)&dp};
+    void* args[2] = {(void*)&dp, (void*)&mt};
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(ctx->sm_count), dim3(PS_THREADS), args,
                                                      PS_SMEM_BYTES, st));
   }
@@ -653,6 +715,28 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   int steps = 0;
   while (steps < T && ctx->h_pinned[steps] != 0) ++steps;
   *steps_out = steps;
+  if (hp.dbg_clock) {   // XG_PERSIST_TRACE=1: average SM cycles per phase (CTA 0), printed to stderr
+    std::vector<long long> h((size_t)T * 17);
+    cudaMemcpy(h.data(), S->d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    const char* names[8] = {"G1", "P1", "G2", "P2", "G3", "P3", "G4", "P4"};
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) {
+      double w = 0, b = 0;
+      for (int t = 1; t < T; ++t) {
+        w += (double)(h[t * 17 + 2 * i + 1] - h[t * 17 + 2 * i]);
+        b += (double)(h[t * 17 + 2 * i + 2] - h[t * 17 + 2 * i + 1]);
+      }
+      w /= (T > 1 ? T - 1 : 1); b /= (T > 1 ? T - 1 : 1);
+      tot += w + b;
+      fprintf(stderr, "[xg persist trace] %s  own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
+    }
+    fprintf(stderr, "[xg persist trace] step %.0f cycles\n", tot);
+    std::vector<long long> kbt(64);
+    cudaMemcpy(kbt.data(), S->d_dbg + 2048 * 17, sizeof(long long) * 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[xg persist trace] logits item of CTA 0, cycles between consecutive 'stage full' events:");
+    for (int i = 1; i < 16; ++i) fprintf(stderr, " %lld", kbt[i] - kbt[i - 1]);
+    fprintf(stderr, "\n");
+  }
   return XG_OK;
 }
 
