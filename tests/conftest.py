@@ -8,7 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_library():
+    """The package refuses to import without libxgating.so; build it (nvcc, ~1 min) when a fresh checkout has none."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_xg_build", os.path.join(ROOT, "controllable_xgating_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build(force=False, verbose=False)
+
+
 def pytest_configure(config):
+    _ensure_library()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
