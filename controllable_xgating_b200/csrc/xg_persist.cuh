@@ -310,9 +310,9 @@ __device__ __forceinline__ void cell_phase(const PersistParams& P, int layer, co
 #pragma unroll
     for (int g = 0; g < 4; ++g) {            // issue every load of the element first
       const long idx = (long)(g * H + j) * R + r;
-      za[g] = sum_slots<2>(da.out, da.slots, sstr, idx);
+      za[g] = sum_slots<4>(da.out, da.slots, sstr, idx);
       zb[g] = sum_slots<4>(db.out, db.slots, sstr, idx);
-      zc[g] = sum_slots<2>(dc.out, dc.slots, sstr, idx);
+      zc[g] = sum_slots<4>(dc.out, dc.slots, sstr, idx);
       zbias[g] = __ldg(bi + g * H + j) + __ldg(ba + g * H + j) + __ldg(bh + g * H + j);
     }
 #pragma unroll
@@ -433,7 +433,7 @@ decode_persistent_kernel(const PersistParams* __restrict__ Pp, const __grid_cons
       const long gstr = (long)H * R;
       for (int e = gtid; e < H * R; e += gthreads) {
         const int j = e / R, r = e % R;
-        float g = sum_slots<2>(P.gate.out, P.gate.slots, gstr, (long)j * R + r) + __ldg(P.b_gate + j);
+        float g = sum_slots<4>(P.gate.out, P.gate.slots, gstr, (long)j * R + r) + __ldg(P.b_gate + j);
         g = g > 0.f ? g : 0.f;
         const float pv = r < B ? __ldg(P.pos + (long)r * H + j) : 0.f;
         store_split(P.gp_hi, P.gp_lo, (long)r * H + j, pv * (1.f + g));
@@ -587,7 +587,7 @@ static void persist_release(xg_context* ctx) {
 
 static bool persist_eligible(const xg_context* ctx, int B, int K) {
   const xg_dims& d = ctx->d;
-  return ctx->persist_mode && d.rnn % 32 == 0 && B <= 64 && d.att + K <= PS_SCRATCH_FLOATS &&
+  return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= 1024 && B <= 64 && d.att + K <= PS_SCRATCH_FLOATS &&
          (long)K * d.rnn * 4 <= (long)PS_STAGES * PS_STAGE_BYTES && ((long)K * d.rnn * 4) % 16 == 0 && d.vocab >= 2;
 }
 
@@ -679,6 +679,8 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   mk(hp.z2a, 6, 24, 0, 4 * H, kbH, per_g3, 0);
   mk(hp.z2h, 7, 20, kbH, 4 * H, kbH, per_g1, 0);
   mk(hp.logit, 8, 20, kbH, V, kbH, kbH, 1);
+  for (const GDesc* g : {&hp.ah, &hp.gate, &hp.z1x, &hp.z1g, &hp.z1h, &hp.z2x, &hp.z2a, &hp.z2h})
+    XG_REQUIRE(ctx->es, g->slots <= 4, XG_ERR_UNSUPPORTED, "persistent decoder: more than 4 split-K slots");
   hp.maps = S->d_maps;
   hp.B = B; hp.R = R; hp.K = K; hp.H = H; hp.E = E; hp.Ep = Ep; hp.A = A; hp.V = V; hp.T = T;
   hp.b_h2a = ctx->P[XG_P_H2A_B]; hp.w_a2w = ctx->P[XG_P_A2W_W]; hp.b_a2w = ctx->P[XG_P_A2W_B]; hp.b_gate = ctx->P[XG_P_DGATE_B];
