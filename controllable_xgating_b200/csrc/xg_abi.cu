@@ -130,6 +130,14 @@ int xg_create(const xg_dims* dims, int device, xg_handle* out) {
     delete ctx;
     return fail(nullptr, XG_ERR_CUDA, "xg_create: cannot allocate staging words");
   }
+  ctx->splitk.ws_floats = (size_t)320 * 64 * 64;   // 296 CTAs x one 64x64 partial tile (5 MB)
+  ctx->splitk.ctr_count = 128;
+  if (cudaMalloc(&ctx->splitk.ws, sizeof(float) * ctx->splitk.ws_floats) != cudaSuccess ||
+      cudaMalloc(&ctx->splitk.ctr, sizeof(unsigned int) * ctx->splitk.ctr_count) != cudaSuccess ||
+      cudaMemset(ctx->splitk.ctr, 0, sizeof(unsigned int) * ctx->splitk.ctr_count) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, XG_ERR_CUDA, "xg_create: cannot allocate split-K scratch");
+  }
   *out = ctx;
   return XG_OK;
 }
@@ -144,6 +152,8 @@ int xg_destroy(xg_handle h) {
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->d_small) cudaFree(h->d_small);
+  if (h->splitk.ws) cudaFree(h->splitk.ws);
+  if (h->splitk.ctr) cudaFree(h->splitk.ctr);
   delete h;
   return XG_OK;
 }
@@ -505,7 +515,15 @@ int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float*
     return s;
   }
   ErrorSink es;
-  int s = gemm_simt(es, p, (cudaStream_t)stream);
+  static SplitKScratch dbg_sk;     // engine 3: SIMT engine with split-K enabled
+  if (engine == 3 && !dbg_sk.ws) {
+    dbg_sk.ws_floats = (size_t)320 * 64 * 64; dbg_sk.ctr_count = 128;
+    if (cudaMalloc(&dbg_sk.ws, sizeof(float) * dbg_sk.ws_floats) != cudaSuccess ||
+        cudaMalloc(&dbg_sk.ctr, sizeof(unsigned int) * dbg_sk.ctr_count) != cudaSuccess ||
+        cudaMemset(dbg_sk.ctr, 0, sizeof(unsigned int) * dbg_sk.ctr_count) != cudaSuccess)
+      return fail(nullptr, XG_ERR_CUDA, "xg_debug_gemm: cannot allocate split-K scratch");
+  }
+  int s = gemm_simt(es, p, (cudaStream_t)stream, engine == 3 ? &dbg_sk : nullptr);
   if (s != XG_OK) g_last_error = es.msg;
   return s;
 }

@@ -18,6 +18,7 @@ struct xg_context {
   xg::ErrorSink es;
   int* h_pinned = nullptr;   // small pinned staging area for SYNC read-backs
   int* d_small = nullptr;    // matching device words
+  xg::SplitKScratch splitk;  // partial tiles + tile counters of the split-K SIMT GEMM
   // optional per-kernel timing with CUDA events on the launching stream (xg_profile_enable/_report)
   int tc_mode = 1;           // 1: dense contractions above the size gate run on the tcgen05 3xTF32 engine
   int persist_mode = 1;      // 1: greedy decoding runs in the fused persistent word-step kernel when eligible

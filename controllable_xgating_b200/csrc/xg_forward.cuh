@@ -23,9 +23,9 @@ static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) {
     const char* lay = (p.sa_r == 1) ? (p.sb_r == 1 ? "nt" : "nn") : "tn";
     snprintf(tag, sizeof(tag), "gemm_%s_%dx%dx%d", lay, p.M, p.N, p.K);
     ProfScope ps(ctx, std::string(tag), st);
-    return gemm_simt(ctx->es, p, st);
+    return gemm_simt(ctx->es, p, st, &ctx->splitk);
   }
-  return gemm_simt(ctx->es, p, st);
+  return gemm_simt(ctx->es, p, st, &ctx->splitk);
 }
 
 // ------------------------------------------------------------------------------------

@@ -35,6 +35,19 @@ struct GemmP {
   int M, N, K;
   int perm_rb = 0, perm_rs = 0;  // row(i) = perm_rb ? (i % perm_rb) * perm_rs + i / perm_rb : i
   Epilogue ep;
+  // split-K (skinny products, M = batch): blockIdx.z owns k in [z*kchunk, (z+1)*kchunk); partial tiles go
+  // to `ws`, the last CTA to arrive at a tile (counter `ctr`) adds them in split order (deterministic)
+  // and runs the epilogue.  ksplit <= 1: plain single-pass GEMM.
+  int ksplit = 1, kchunk = 0;
+  float* ws = nullptr;
+  unsigned int* ctr = nullptr;
+};
+
+struct SplitKScratch {           // owned by the handle (xg_context); one stream at a time
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  unsigned int* ctr = nullptr;   // zero-initialised; every launch leaves it zero again
+  int ctr_count = 0;
 };
 
 // element (i,j) of the logical output: bias, activation, dropout, aux store, cross gate, row
@@ -109,6 +122,8 @@ gemm_simt_kernel(const GemmP p) {
     for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
 
   float ra[LA], rb[LB];
+  const int kbeg = p.ksplit > 1 ? blockIdx.z * p.kchunk : 0;
+  const int kend = p.ksplit > 1 ? min(p.K, kbeg + p.kchunk) : p.K;
 
   auto load_tile = [&](int k0) {
 #pragma unroll
@@ -117,7 +132,7 @@ gemm_simt_kernel(const GemmP p) {
       int rr = A_RC ? (e % BK) : (e / BM);
       int ii = A_RC ? (e / BK) : (e % BM);
       int gi = m0 + ii, gr = k0 + rr;
-      ra[l] = (gi < p.M && gr < p.K) ? __ldg(p.A + (long)gi * p.sa_i + (long)gr * p.sa_r) : 0.f;
+      ra[l] = (gi < p.M && gr < kend) ? __ldg(p.A + (long)gi * p.sa_i + (long)gr * p.sa_r) : 0.f;
     }
 #pragma unroll
     for (int l = 0; l < LB; ++l) {
@@ -125,7 +140,7 @@ gemm_simt_kernel(const GemmP p) {
       int rr = B_RC ? (e % BK) : (e / BN);
       int jj = B_RC ? (e / BK) : (e % BN);
       int gj = n0 + jj, gr = k0 + rr;
-      rb[l] = (gj < p.N && gr < p.K) ? __ldg(p.B + (long)gr * p.sb_r + (long)gj * p.sb_j) : 0.f;
+      rb[l] = (gj < p.N && gr < kend) ? __ldg(p.B + (long)gr * p.sb_r + (long)gj * p.sb_j) : 0.f;
     }
   };
   auto store_tile = [&](int buf) {
@@ -145,13 +160,13 @@ gemm_simt_kernel(const GemmP p) {
     }
   };
 
-  const int ntiles = (p.K + BK - 1) / BK;
-  load_tile(0);
+  const int ntiles = (kend - kbeg + BK - 1) / BK;
+  load_tile(kbeg);
   store_tile(0);
   __syncthreads();
   for (int t = 0; t < ntiles; ++t) {
     const int buf = t & 1;
-    if (t + 1 < ntiles) load_tile((t + 1) * BK);
+    if (t + 1 < ntiles) load_tile(kbeg + (t + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
@@ -186,6 +201,40 @@ gemm_simt_kernel(const GemmP p) {
     __syncthreads();
   }
 
+  // ---- split-K: publish the partial tile; the last CTA of the tile reduces in split order ----
+  if (p.ksplit > 1) {
+    __shared__ int s_last;
+    const long tile = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = p.ws + ((long)blockIdx.z * gridDim.x * gridDim.y + tile) * (BM * BN);
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) __stcg(mine + (m * TN + n) * NT + tid, acc[m][n]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(p.ctr + tile, 1u);
+      s_last = (prev == (unsigned)p.ksplit - 1u);
+      if (s_last) p.ctr[tile] = 0u;          // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
+    const long zstride = (long)gridDim.x * gridDim.y * (BM * BN);
+    const float* base = p.ws + tile * (BM * BN);
+    for (int z = 0; z < p.ksplit; ++z) {
+      float v[TM * TN];
+#pragma unroll
+      for (int e = 0; e < TM * TN; ++e) v[e] = __ldcg(base + (long)z * zstride + e * NT + tid);
+#pragma unroll
+      for (int e = 0; e < TM * TN; ++e) acc[e / TN][e % TN] += v[e];
+    }
+  }
+
   // ---- fused epilogue ----
 #pragma unroll
   for (int m = 0; m < TM; ++m) {
@@ -202,7 +251,7 @@ gemm_simt_kernel(const GemmP p) {
 
 template <int BM, int BN, int BK, int TM, int TN>
 static int gemm_launch_cfg(ErrorSink& es, const GemmP& p, cudaStream_t st) {
-  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), p.ksplit > 1 ? p.ksplit : 1);
   dim3 block((BM / TM) * (BN / TN));
   const bool arc = (p.sa_r == 1), brc = (p.sb_r == 1);
   if (arc && brc) gemm_simt_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, st>>>(p);
@@ -213,12 +262,27 @@ static int gemm_launch_cfg(ErrorSink& es, const GemmP& p, cudaStream_t st) {
   return XG_OK;
 }
 
-// Tile choice: keep >= ~120 CTAs in flight on the 148 SMs where the shape allows it.
-static int gemm_simt(ErrorSink& es, const GemmP& p, cudaStream_t st) {
+// Tile choice: keep >= ~120 CTAs in flight on the 148 SMs where the shape allows it; skinny products
+// (few output tiles, long K: the M = batch recurrent GEMMs) are cut along K instead.
+static int gemm_simt(ErrorSink& es, const GemmP& p_in, cudaStream_t st, const SplitKScratch* sk = nullptr) {
+  GemmP p = p_in;
   if (p.M <= 0 || p.N <= 0) return XG_OK;
   XG_REQUIRE(es, p.K >= 0 && p.A && p.B && p.C, XG_ERR_BAD_ARG, "gemm_simt: bad arguments");
   const long big = (long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
   const long med = (long)ceil_div(p.M, 64) * ceil_div(p.N, 64);
+  if (sk && sk->ws && med < 120 && p.K >= 128 && (double)p.M * p.N * p.K >= (double)(1 << 21)) {
+    int S = (int)(296 / med);
+    if (S > 16) S = 16;
+    if (S > p.K / 64) S = p.K / 64;
+    if (S >= 2) {
+      const int kchunk = ceil_div(ceil_div(p.K, S), 32) * 32;
+      S = ceil_div(p.K, kchunk);
+      if (S >= 2 && med <= sk->ctr_count && (size_t)med * S * 64 * 64 <= sk->ws_floats) {
+        p.ksplit = S; p.kchunk = kchunk; p.ws = sk->ws; p.ctr = sk->ctr;
+        return gemm_launch_cfg<64, 64, 32, 4, 4>(es, p, st);
+      }
+    }
+  }
   if (big >= 120) return gemm_launch_cfg<128, 128, 8, 8, 8>(es, p, st);
   if (med >= 120) return gemm_launch_cfg<64, 64, 16, 4, 4>(es, p, st);
   return gemm_launch_cfg<32, 32, 32, 2, 2>(es, p, st);

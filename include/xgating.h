@@ -244,7 +244,8 @@ int xg_debug_dropout_mask(uint64_t seed, int site, size_t n, float p, float* out
 
 /* C (M,N) = A . B with the library's GEMM kernels; layout: 0 = NT (A (M,K), B (N,K)),
  * 1 = NN (A (M,K), B (K,N)), 2 = TN (A (K,M), B (K,N)).  engine: 0 = auto, 1 = SIMT fp32,
- * 2 = tcgen05 3xTF32 (XG_ERR_UNSUPPORTED if the shape is not eligible). */
+ * 2 = tcgen05 3xTF32 (XG_ERR_UNSUPPORTED if the shape is not eligible), 3 = SIMT fp32 with the
+ * deterministic split-K path enabled for skinny shapes (what the handle-bound path uses). */
 int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float* C,
                   int M, int N, int K, void* stream);
 

@@ -64,6 +64,27 @@ def test_gemm_engine(layout, shape):
     assert rel_err(C.numpy(), ref.numpy()) < 2e-6
 
 
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(64, 2048, 512), (64, 512, 2048), (64, 1024, 1536), (64, 1536, 1024), (2, 2048, 512),
+                                   (37, 130, 1000), (256, 512, 2048), (64, 468, 2048)])
+def test_gemm_split_k(layout, shape):
+    """skinny recurrent products: split-K SIMT path (engine 3) is deterministic and fp32-exact-grade."""
+    from controllable_xgating_b200.engine import debug_gemm
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 5 + N * 11 + K + layout)
+    a_shape = (M, K) if layout in (0, 1) else (K, M)
+    b_shape = (N, K) if layout == 0 else (K, N)
+    A = torch.rand(a_shape, generator=g) - 0.5
+    B = torch.rand(b_shape, generator=g) - 0.5
+    Ad, Bd = A.double(), B.double()
+    ref = (Ad if layout != 2 else Ad.t()) @ (Bd.t() if layout == 0 else Bd)
+    Ac, Bc = A.cuda(), B.cuda()
+    C = debug_gemm(layout, 3, Ac, Bc, M, N, K)
+    assert rel_err(C.cpu().numpy(), ref.numpy()) < 2e-6
+    for _ in range(3):      # fixed-order reduction: bit-identical from launch to launch
+        assert torch.equal(debug_gemm(layout, 3, Ac, Bc, M, N, K), C)
+
+
 def test_dropout_mask_properties():
     from controllable_xgating_b200.engine import dropout_mask
     n, p = 1 << 20, 0.5
