@@ -173,6 +173,7 @@ int xg_bind_params(xg_handle h, const float* const* params, int count) {
     if (!params[i]) return fail(h, XG_ERR_NULL_POINTER, "xg_bind_params: null parameter pointer");
   for (int i = 0; i < count; ++i) h->P[i] = params[i];
   h->bound = true;
+  h->param_epoch++;
   return XG_OK;
 }
 
@@ -189,6 +190,7 @@ int xg_params_changed(xg_handle h) {
   XG_TRY(set_device(h));
   XG_CUDA_TRY(h->es, cudaDeviceSynchronize());
   tc_invalidate_weights(h);   // tf32 hi/lo splits of the bound parameters
+  h->param_epoch++;           // POS-gate token table of the persistent decoder
   return XG_OK;
 }
 
@@ -311,8 +313,10 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     XG_TRY(xg_attend_precompute(h, V, B, K, g.Uv, stream));
     Uv = g.Uv;
   }
-  if (sample_max && persist_eligible(h, B, K))   // fused persistent word loop (xg_persist.cuh)
-    return persist_greedy(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
+  if (sample_max && persist_eligible(h, B, K)) {   // fused persistent word loop (xg_persist.cuh)
+    const int ps = persist_greedy(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
+    if (ps != PK_FALLBACK) return ps;
+  }
   for (int q = 0; q < 4; ++q)
     XG_CUDA_TRY(h->es, cudaMemcpyAsync(g.st[q], state0[q], sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
   XG_CUDA_TRY(h->es, cudaMemsetAsync(g.tok, 0, sizeof(int64_t) * (size_t)B, st));          // <bos> (SAModel.py:184)

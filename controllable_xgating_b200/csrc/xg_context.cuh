@@ -13,6 +13,7 @@ struct xg_context {
   int sm_count = 148;
   const float* P[XG_NUM_PARAMS];
   bool bound = false;
+  unsigned long long param_epoch = 0;   // bumped by xg_bind_params / xg_params_changed: derived tables are stale
   float* bn[4] = {nullptr, nullptr, nullptr, nullptr};  // rm_rgb, rv_rgb, rm_opfl, rv_opfl
   bool bn_bound = false;
   xg::ErrorSink es;

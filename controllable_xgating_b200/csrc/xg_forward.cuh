@@ -4,6 +4,7 @@
 #include "xg_context.cuh"
 #include "xg_fwd_kernels.cuh"
 #include "xg_gemm_tc.cuh"
+#include "xg_persist.cuh"
 
 namespace xg {
 
@@ -66,8 +67,11 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
     gi.ep.bias1 = P_(ctx, plstm[s] + 3);
     XG_TRY(gemm_run(ctx, gi, st));
   }
-  // recurrence over frames (:132-147); the two streams are independent
-  for (int t = 0; t < K; ++t) {
+  // recurrence over frames (:132-147); the two streams are independent: one persistent cooperative
+  // kernel for all frames of both streams when the shape allows it (xg_persist.cuh)
+  const int pst = persist_encode(ctx, fmask, B, K, eb, st);
+  if (pst != PK_FALLBACK) XG_TRY(pst);
+  for (int t = 0; t < K && pst == PK_FALLBACK; ++t) {
     for (int s = 0; s < 2; ++s) {
       float* Zt = eb.G[s] + (long)t * B * 4 * H;
       if (t > 0) {
