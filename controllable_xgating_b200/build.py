@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libxgating.so (there is no CPU fallback)")
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + SOURCES
+    extra = os.environ.get("XG_EXTRA_NVCC_FLAGS", "").split()     # diagnostics builds only (e.g. -DPK_FINE_TRACE)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp] + SOURCES
     if verbose:
         print("[xgating build]", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -46,26 +46,66 @@ constexpr int PK_BULK_CHUNKS = 4;
 constexpr int PK_STAMPS = 16;
 
 struct PItem { short desc, slot, rt, cb, kb0, nkb; };
-struct PSched { int n; PItem it[PK_MAX_ITEMS]; };
+struct PSched { short n, tot_kb, tot_chunks, pad; PItem it[PK_MAX_ITEMS]; };   // 80 bytes
 
 struct GDesc {                   // out[slot][r][n] = sum_k W[n,k] * X[r, 32*xkb0 + k]
   int w_map, x_hi, x_lo;         // indices into the tensor-map table
   int xkb0, n_rows, nkb;
-  float* out;                    // [slots][R][n_rows]
-  const unsigned char* nslots;   // [row tiles][column blocks]: slots written for that strip
+  float* out;                    // [slots][R][n_rows]; slots a strip never writes stay zero (pool is zero-filled
+  int ns;                        //   once and the schedule is static), so every consumer adds `ns` slots
 };
 
 struct MapTable { CUtensorMap m[16]; };
 
+// CODE SIZE IS THE FIRST-ORDER COST HERE: every phase runs once per word step, so its instructions are
+// fetched cold unless the whole step fits the 32 KB L1.5 instruction cache (measured: the first version,
+// 12.3k instructions, ran at ~13 cycles per instruction in every phase).  Hence: rolled loops, shared
+// __noinline__ helpers, ex2/rcp-based activations, descriptors advanced by adds.
+
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// mbarrier wait: one try_wait inline (it suspends in hardware), the bounded spin lives out of line
+__device__ __noinline__ void pk_wait_spin(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void pk_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  if (!done) pk_wait_spin(addr, parity);
+}
+__device__ __forceinline__ void pk_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void pk_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pk_tma_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void pk_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, %1;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
 }
 
 // grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int G) {
+__device__ __noinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int G) {
   fence_proxy_async_global();          // generic-proxy global writes -> visible to later TMA reads
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -89,10 +129,12 @@ struct PipeState {       // running counters, identical in every thread by const
   uint32_t item_count;   // items processed so far (small-accumulator handshake)
 };
 
+// shared-memory map (32-bit shared-window addresses; the barriers are 8 bytes apart)
 struct SmemView {
   uint8_t* stages;
   float* scratch;
-  uint64_t *full_bar, *empty_bar, *split_bar, *acc_full, *acc_empty, *small_full, *small_empty, *bulk_bar;
+  uint32_t stages_u32;
+  uint32_t full_bar, empty_bar, split_bar, acc_full, acc_empty, small_full, small_empty, bulk_bar;
   uint32_t* tmem_slot;
 };
 
@@ -100,29 +142,35 @@ __device__ __forceinline__ SmemView carve_smem(uint8_t* smem_raw) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SmemView sv;
   sv.stages = smem;
+  sv.stages_u32 = smem_u32(smem);
   sv.scratch = reinterpret_cast<float*>(smem + PK_STAGES * PK_STAGE_BYTES);
-  sv.full_bar = reinterpret_cast<uint64_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4);
-  sv.empty_bar = sv.full_bar + PK_STAGES;
-  sv.split_bar = sv.empty_bar + PK_STAGES;
-  sv.acc_full = sv.split_bar + PK_STAGES;
-  sv.acc_empty = sv.acc_full + 2;
-  sv.small_full = sv.acc_empty + 2;
-  sv.small_empty = sv.small_full + 1;
-  sv.bulk_bar = sv.small_empty + 1;
-  sv.tmem_slot = reinterpret_cast<uint32_t*>(sv.bulk_bar + PK_BULK_CHUNKS);
+  const uint32_t bars = smem_u32(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4);
+  sv.full_bar = bars;
+  sv.empty_bar = sv.full_bar + 8 * PK_STAGES;
+  sv.split_bar = sv.empty_bar + 8 * PK_STAGES;
+  sv.acc_full = sv.split_bar + 8 * PK_STAGES;
+  sv.acc_empty = sv.acc_full + 16;
+  sv.small_full = sv.acc_empty + 16;
+  sv.small_empty = sv.small_full + 8;
+  sv.bulk_bar = sv.small_empty + 8;
+  sv.tmem_slot = reinterpret_cast<uint32_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4 + 8 * (3 * PK_STAGES + 6 + PK_BULK_CHUNKS));
   return sv;
 }
 
-__device__ __forceinline__ uint32_t pipeline_setup(const SmemView& sv) {
+__device__ __forceinline__ void pk_mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
+}
+
+__device__ __noinline__ uint32_t pipeline_setup(const SmemView& sv) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < PK_STAGES; ++s) {
-      mbar_init(&sv.full_bar[s], 1); mbar_init(&sv.empty_bar[s], 1); mbar_init(&sv.split_bar[s], 128);
+      pk_mbar_init(sv.full_bar + 8 * s, 1); pk_mbar_init(sv.empty_bar + 8 * s, 1); pk_mbar_init(sv.split_bar + 8 * s, 128);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sv.acc_full[b], 1); mbar_init(&sv.acc_empty[b], 128); }
-    mbar_init(sv.small_full, 1);
-    mbar_init(sv.small_empty, 128);
-    for (int c = 0; c < PK_BULK_CHUNKS; ++c) mbar_init(&sv.bulk_bar[c], 1);
+    for (int b = 0; b < 2; ++b) { pk_mbar_init(sv.acc_full + 8 * b, 1); pk_mbar_init(sv.acc_empty + 8 * b, 128); }
+    pk_mbar_init(sv.small_full, 1);
+    pk_mbar_init(sv.small_empty, 128);
+    for (int c = 0; c < PK_BULK_CHUNKS; ++c) pk_mbar_init(sv.bulk_bar + 8 * c, 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<256>(sv.tmem_slot);
@@ -132,140 +180,186 @@ __device__ __forceinline__ uint32_t pipeline_setup(const SmemView& sv) {
   return *sv.tmem_slot;
 }
 
-__device__ __forceinline__ void pipeline_teardown(uint32_t tmem_base) {
+__device__ __noinline__ void pipeline_teardown(uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 2) tmem_dealloc<256>(tmem_base);
 }
 
-// all work items of this CTA for one GEMM phase
-__device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, const CUtensorMap* maps, int R, int hi_inplace,
-                                        const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = sc->n;
-  for (int ii = 0; ii < n_items; ++ii) {
-    const PItem it = sc->it[ii];
-    const GDesc& d = descs[it.desc];
-    const int nkb = it.nkb, kb0 = it.kb0;
-    const int n_chunks = (nkb + PK_CHUNK - 1) / PK_CHUNK;
-    if (warp == 0) {
-      if (lane == 0) {
-        const CUtensorMap* mw = maps + d.w_map; const CUtensorMap* mxh = maps + d.x_hi; const CUtensorMap* mxl = maps + d.x_lo;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint32_t cnt = ps.kb_count + kb;
-          const int s = cnt % PK_STAGES;
-          mbar_wait(&sv.empty_bar[s], ((cnt / PK_STAGES) & 1) ^ 1);
-          uint8_t* st = sv.stages + s * PK_STAGE_BYTES;
-          mbar_expect_tx(&sv.full_bar[s], PK_TX_BYTES);
-          tma_load_2d(st, mw, &sv.full_bar[s], (kb0 + kb) * 32, it.rt * 128);
-          tma_load_2d(st + 2 * PK_W_BYTES, mxh, &sv.full_bar[s], (d.xkb0 + kb0 + kb) * 32, it.cb * PK_BN);
-          tma_load_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, &sv.full_bar[s], (d.xkb0 + kb0 + kb) * 32, it.cb * PK_BN);
+#ifdef PK_FINE_TRACE
+#define PK_FINE(i) do { if (g_fine) g_fine[(i)] = clock64(); } while (0)
+#else
+#define PK_FINE(i) do { } while (0)
+#endif
+
+// all work items of this CTA for one GEMM phase (sc lives in shared memory)
+__device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, const CUtensorMap* maps, int R,
+                                        const SmemView& sv, uint32_t tmem_base, PipeState& ps, long long* g_fine = nullptr) {
+  // warp-uniform role dispatch: the broadcast makes the warp index (and every counter derived below)
+  // provably uniform, so descriptors / coordinates live in uniform registers and each UTCHMMA / UTMALDG
+  // issues directly instead of through a per-lane waterfall (ELECT + R2UR.BROADCAST loop, ~90 cycles each)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
+  if (threadIdx.x == 0) PK_FINE(0);
+  if (warp == 0) {            // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
+    const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
+    const uint32_t full_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii) {
+      const PItem it = sc->it[ii];
+      const GDesc& d = descs[it.desc];
+      const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, d.w_map, 0);
+      const CUtensorMap* mxh = maps + __shfl_sync(0xffffffffu, d.x_hi, 0);
+      const CUtensorMap* mxl = maps + __shfl_sync(0xffffffffu, d.x_lo, 0);
+      int wk = __shfl_sync(0xffffffffu, it.kb0 * 32, 0), xk = __shfl_sync(0xffffffffu, (d.xkb0 + it.kb0) * 32, 0);
+      const int row = __shfl_sync(0xffffffffu, it.rt * 128, 0), col = __shfl_sync(0xffffffffu, it.cb * PK_BN, 0);
+      const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += 32, xk += 32) {
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+        const uint32_t st = stages_u32 + s * PK_STAGE_BYTES, fb = full_bar + 8 * s;
+        if (elect_one_sync()) {
+          pk_expect_tx(fb, PK_TX_BYTES);
+          pk_tma_2d(st, mw, fb, wk, row);
+          pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
+          pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
+          if (ii == 0 && kb < 4) PK_FINE(1 + kb);
         }
+        __syncwarp();
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(128, PK_BN);
-        const uint32_t tmem_small = tmem_base + 2 * PK_BN;
-        mbar_wait(sv.small_empty, (ps.item_count & 1) ^ 1);   // previous item's cross-term accumulator read out
-        tc_fence_after();
-        for (int c = 0; c < n_chunks; ++c) {
-          const uint32_t cc = ps.chunk_count + c;
-          const int b = cc & 1;
-          mbar_wait(&sv.acc_empty[b], ((cc >> 1) & 1) ^ 1);
+    }
+  } else if (warp == 1) {     // ===== MMA issuer (same discipline) =====
+    constexpr uint32_t idesc = umma_idesc_tf32(128, PK_BN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tmem_small = tb + 2 * PK_BN;
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0),
+             ic = __shfl_sync(0xffffffffu, ps.item_count, 0);
+    const uint32_t split_bar = __shfl_sync(0xffffffffu, sv.split_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+    const uint32_t acc_full = __shfl_sync(0xffffffffu, sv.acc_full, 0), acc_empty = __shfl_sync(0xffffffffu, sv.acc_empty, 0);
+    const uint32_t small_full = __shfl_sync(0xffffffffu, sv.small_full, 0), small_empty = __shfl_sync(0xffffffffu, sv.small_empty, 0);
+    // descriptor of byte offset 0 of the stage ring; everything else is an add on the address field
+    const uint32_t desc_lo0 = __shfl_sync(0xffffffffu, (uint32_t)umma_desc_sw128(sv.stages_u32), 0);
+    const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii, ++ic) {
+      const int nkb = __shfl_sync(0xffffffffu, (int)sc->it[ii].nkb, 0);
+      pk_wait(small_empty, (ic & 1) ^ 1);      // previous item's cross-term accumulator read out
+      tc_fence_after();
+      uint32_t tmem_main = tb, b = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        if ((kb & 1) == 0) {
+          b = cc & 1;
+          pk_wait(acc_empty + 8 * b, ((cc >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tmem_main = tmem_base + b * PK_BN;
-          for (int kk = 0; kk < PK_CHUNK; ++kk) {
-            const int kb = c * PK_CHUNK + kk;
-            if (kb >= nkb) break;
-            const uint32_t cnt = ps.kb_count + kb;
-            const int s = cnt % PK_STAGES;
-            mbar_wait(&sv.split_bar[s], (cnt / PK_STAGES) & 1);     // TMA landed AND lo tile written
-            tc_fence_after();
-            const uint32_t base = smem_u32(sv.stages + s * PK_STAGE_BYTES);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t wh = umma_desc_sw128(base + k4 * 32);
-              const uint64_t wl = umma_desc_sw128(base + PK_W_BYTES + k4 * 32);
-              const uint64_t xh = umma_desc_sw128(base + 2 * PK_W_BYTES + k4 * 32);
-              const uint64_t xl = umma_desc_sw128(base + 2 * PK_W_BYTES + PK_X_BYTES + k4 * 32);
-              umma_tf32(tmem_main, wh, xh, idesc, (kk | k4) != 0);
-              umma_tf32(tmem_small, wl, xh, idesc, (kb | k4) != 0);
-              umma_tf32(tmem_small, wh, xl, idesc, 1);
-            }
-            umma_commit(&sv.empty_bar[s]);
-          }
-          umma_commit(&sv.acc_full[b]);
+          tmem_main = tb + b * PK_BN;
         }
-        umma_commit(sv.small_full);
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        pk_wait(split_bar + 8 * s, (cnt / PK_STAGES) & 1);     // TMA landed AND lo tile written
+        tc_fence_after();
+        const uint32_t dlo = desc_lo0 + ((s * PK_STAGE_BYTES) >> 4);
+        if (elect_one_sync()) {
+          if (ii == 0 && kb < 4) PK_FINE(13 + kb);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t wh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2);
+            const uint64_t wl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (PK_W_BYTES >> 4));
+            const uint64_t xh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES) >> 4));
+            const uint64_t xl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES + PK_X_BYTES) >> 4));
+            umma_tf32(tmem_main, wh, xh, idesc, ((kb & 1) | k4) != 0);
+            umma_tf32(tmem_small, wl, xh, idesc, (kb | k4) != 0);
+            umma_tf32(tmem_small, wh, xl, idesc, 1);
+          }
+          pk_commit(empty_bar + 8 * s);
+          if (ii == 0 && kb < 4) PK_FINE(17 + kb);
+          if ((kb & 1) || kb == nkb - 1) pk_commit(acc_full + 8 * b);
+          if (kb == nkb - 1) { pk_commit(small_full); if (ii == 0) PK_FINE(21); }
+        }
+        __syncwarp();
+        if ((kb & 1) || kb == nkb - 1) ++cc;
       }
-    } else if (warp < 6) {
-      const int quad = warp & 3;
-      const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    }
+  } else if (warp < 6) {      // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
+    const int quad = warp & 3;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t cc = ps.chunk_count, ic = ps.item_count;
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii, ++ic) {
+      const PItem it = sc->it[ii];
+      const GDesc& d = descs[it.desc];
+      const int n_chunks = (it.nkb + PK_CHUNK - 1) / PK_CHUNK;
       float acc[PK_BN];
 #pragma unroll
       for (int u = 0; u < PK_BN; ++u) acc[u] = 0.f;
-      for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t cc = ps.chunk_count + c;
-        const int b = cc & 1;
-        mbar_wait(&sv.acc_full[b], (cc >> 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c <= n_chunks; ++c) {        // last round: the cross-term accumulator
+        uint32_t col;
+        if (c < n_chunks) {
+          const uint32_t b = cc & 1;
+          pk_wait(sv.acc_full + 8 * b, (cc >> 1) & 1);
+          col = b * PK_BN;
+        } else {
+          pk_wait(sv.small_full, ic & 1);
+          col = 2 * PK_BN;
+        }
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < PK_BN; q += 32) {
+        if (ii == 0 && threadIdx.x == 64) { if (c < n_chunks) { if (c < 2) PK_FINE(22 + c); } else PK_FINE(24); }
+        {
           uint32_t r[32];
-          tmem_ld32(tmem_base + lane_base + (uint32_t)(b * PK_BN + q), r);
+          tmem_ld32(taddr + col, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 32; ++u) acc[q + u] += __uint_as_float(r[u]);
+          for (int u = 0; u < 32; ++u) acc[u] += __uint_as_float(r[u]);
+          tmem_ld32(taddr + col + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc[32 + u] += __uint_as_float(r[u]);
         }
         tc_fence_before();
-        mbar_arrive(&sv.acc_empty[b]);
+        if (c < n_chunks) { pk_arrive(sv.acc_empty + 8 * (cc & 1)); ++cc; }
+        else pk_arrive(sv.small_empty);
       }
-      mbar_wait(sv.small_full, ps.item_count & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < PK_BN; q += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + 2 * PK_BN + lane_base + (uint32_t)q, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 32; ++u) acc[q + u] += __uint_as_float(r[u]);
-      }
-      tc_fence_before();
-      mbar_arrive(sv.small_empty);
       const int n = it.rt * 128 + quad * 32 + lane;        // weight row held by this thread
       if (n < d.n_rows) {
         float* o = d.out + ((long)it.slot * R + it.cb * PK_BN) * d.n_rows + n;   // lanes -> consecutive n
+        const long str = d.n_rows;
 #pragma unroll
-        for (int u = 0; u < PK_BN; ++u) __stcg(o + (long)u * d.n_rows, acc[u]);
+        for (int u = 0; u < PK_BN; ++u) { __stcg(o, acc[u]); o += str; }
       }
-    } else {
-      // weight split: lo = rna_tf32(w - trunc_tf32(w)); the tensor core itself truncates the raw tile to hi
-      const int t = threadIdx.x - 6 * 32;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t cnt = ps.kb_count + kb;
-        const int s = cnt % PK_STAGES;
-        mbar_wait(&sv.full_bar[s], (cnt / PK_STAGES) & 1);
-        float4* src = reinterpret_cast<float4*>(sv.stages + s * PK_STAGE_BYTES);
-        float4* dst = reinterpret_cast<float4*>(sv.stages + s * PK_STAGE_BYTES + PK_W_BYTES);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = src[t + 128 * q];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = tf32_rna(v.x - h.x);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = tf32_rna(v.y - h.y);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = tf32_rna(v.z - h.z);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = tf32_rna(v.w - h.w);
-          dst[t + 128 * q] = l;
-          if (hi_inplace) src[t + 128 * q] = h;
-        }
-        fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
-        mbar_arrive(&sv.split_bar[s]);
-      }
+      if (ii == 0 && threadIdx.x == 64) PK_FINE(25);
     }
-    ps.kb_count += nkb;
-    ps.chunk_count += n_chunks;
-    ps.item_count += 1;
+  } else {                    // ===== weight split: lo = rna_tf32(w - trunc_tf32(w)); the tensor core truncates the raw tile =====
+    const int t = threadIdx.x - 6 * 32;
+    uint32_t cnt = ps.kb_count;
+    const int tot = sc->tot_kb;
+#pragma unroll 1
+    for (int q0 = 0; q0 < tot; ++q0, ++cnt) {
+      const uint32_t s = cnt & (PK_STAGES - 1);
+      pk_wait(sv.full_bar + 8 * s, (cnt / PK_STAGES) & 1);
+      if (q0 < 4 && t == 0) PK_FINE(5 + q0);
+      const float4* src = reinterpret_cast<const float4*>(sv.stages + s * PK_STAGE_BYTES) + t;
+      float4* dst = reinterpret_cast<float4*>(sv.stages + s * PK_STAGE_BYTES + PK_W_BYTES) + t;
+#pragma unroll 4
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[128 * q];
+        float4 l;
+        l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+        l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+        l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+        l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+        dst[128 * q] = l;
+      }
+      fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
+      pk_arrive(sv.split_bar + 8 * s);
+      if (q0 < 4 && t == 0) PK_FINE(9 + q0);
+    }
   }
+  ps.kb_count += sc->tot_kb;
+  ps.chunk_count += sc->tot_chunks;
+  ps.item_count += n_items;
 }
 
 __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, float v) {
@@ -274,16 +368,16 @@ __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, floa
   lo[idx] = tf32_rna(v - h);
 }
 
-// sum of the split-K partial slots of element (r, n), in slot order.  All loads are issued before the
-// first add (one L2 round trip per element instead of one per slot).
-__device__ __forceinline__ float zsum(const GDesc& d, int R, int r, int n) {
-  const int ncb = R / PK_BN;
-  const int ns = d.nslots[(n >> 7) * ncb + r / PK_BN];
+// split-K partial slots of element (r, n): zload issues every load (one L2 round trip for the whole
+// batch a caller builds), zadd adds them in slot order.
+__device__ __forceinline__ void zload(const GDesc& d, int R, int r, int n, float (&v)[PK_MAX_SLOTS]) {
   const float* p = d.out + (long)r * d.n_rows + n;
   const long sstr = (long)R * d.n_rows;
-  float v[PK_MAX_SLOTS];
+  const int ns = d.ns;
 #pragma unroll
-  for (int k = 0; k < PK_MAX_SLOTS; ++k) v[k] = k < ns ? __ldcg(p + k * sstr) : 0.f;
+  for (int k = 0; k < PK_MAX_SLOTS; ++k) { v[k] = k < ns ? __ldcg(p) : 0.f; p += sstr; }
+}
+__device__ __forceinline__ float zadd(const float (&v)[PK_MAX_SLOTS]) {
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < PK_MAX_SLOTS; ++k) s += v[k];
@@ -297,8 +391,9 @@ __device__ __forceinline__ unsigned f2ord(float f) {      // order-preserving fl
 __device__ __forceinline__ float ord2f(unsigned o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
-// tanh via one ex2.approx and one fast division: |error| ~1e-7 absolute (the attention scores only)
+// ex2/rcp-based activations: |error| ~1e-7 absolute, a handful of instructions each
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ====================================================================================
 // decoder
@@ -308,9 +403,10 @@ enum { DD_AH = 0, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G, DD_Z2X, DD_Z2A, DD_LOGIT, DD_C
 struct DecParams {
   GDesc d[PK_MAX_DESCS];
   const PSched* sched;          // [3][G]
-  int B, R, K, H, E, Ep, A, V, T, hi_inplace;
+  int B, R, K, H, E, Ep, A, V, T;
   const float *b_h2a, *w_a2w, *b_a2w;
-  const float *b1_i2h, *b1_a2h, *b1_h2h, *b2_i2h, *b2_a2h, *b2_h2h, *b_logit, *embed;
+  const float* bias[2][3];      // lstm_1 / lstm_2: i2h, a2h, h2h biases
+  const float *b_logit, *embed;
   const float* tgate;           // (V, H)  relu(embed . W_gate^T + b): the POS-gate pre-factor of every token
   const float *Vf, *Uv, *pos;   // (B,K,H), (B,K,A), (B,H)
   const float* state0[4];       // h1,c1,h2,c2 each (B,H)
@@ -319,138 +415,268 @@ struct DecParams {
   float *gp_hi, *gp_lo;         // [R][H]
   float *af_hi, *af_lo;         // [R][H]
   float *hx;                    // [R][2H] exact states
-  float *c1, *c2;               // [R][H]
+  float *cx;                    // [2][R][H]
   float *stats;                 // [vocab blocks][R][4]  (max, argmax, sum-exp, -)
   float *unfinished;            // [R]
   int64_t *tok;                 // [R]
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
-  long long* dbg_clock;         // [T][PK_STAMPS] SM-clock stamps of CTA 0 at phase boundaries, or NULL
+  long long* dbg_clock;         // diagnostics, or NULL
 };
 
-constexpr int DEC_VBLOCK = 1024;   // vocabulary rows per statistics record
+constexpr int DEC_VBLOCK = 256;    // vocabulary rows per statistics record (8 per lane)
+constexpr int DEC_NA = 5;          // attention units per thread: att <= 5 * 320
 
 // lstm cell (decoder gate order i,f,o,g), elements (r, j) with j fastest
-__device__ __forceinline__ void dec_cell_phase(const DecParams& P, int layer, bool use_mask, int part, int nparts) {
+__device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int use_mask, int part, int nparts) {
   const int H = P.H, R = P.R;
-  const GDesc& da = layer == 0 ? P.d[DD_Z1X] : P.d[DD_Z2X];
-  const GDesc& db = layer == 0 ? P.d[DD_Z1G] : P.d[DD_Z2A];
-  const GDesc& dc = layer == 0 ? P.d[DD_Z1H] : P.d[DD_Z2H];
-  const float* bi = layer == 0 ? P.b1_i2h : P.b2_i2h;
-  const float* ba = layer == 0 ? P.b1_a2h : P.b2_a2h;
-  const float* bh = layer == 0 ? P.b1_h2h : P.b2_h2h;
-  float* cst = layer == 0 ? P.c1 : P.c2;
+  const GDesc& da = P.d[layer == 0 ? DD_Z1X : DD_Z2X];
+  const GDesc& db = P.d[layer == 0 ? DD_Z1G : DD_Z2A];
+  const GDesc& dc = P.d[layer == 0 ? DD_Z1H : DD_Z2H];
+  const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
+  float* cst = P.cx + (long)layer * R * H;
+#pragma unroll 1
   for (int e = part * PK_THREADS + threadIdx.x; e < P.B * H; e += nparts * PK_THREADS) {
     const int r = e / H, j = e % H;
-    float z[4];
+    float va[4][PK_MAX_SLOTS], vb[4][PK_MAX_SLOTS], vc[4][PK_MAX_SLOTS], bias[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < 4; ++g) {              // every load of the element is in flight before the first add
       const int n = g * H + j;
-      z[g] = zsum(da, R, r, n) + zsum(db, R, r, n) + zsum(dc, R, r, n) + (__ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n));
+      zload(da, R, r, n, va[g]); zload(db, R, r, n, vb[g]); zload(dc, R, r, n, vc[g]);
+      bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n);
     }
-    const float ig = sigmoid_f(z[0]), fg = sigmoid_f(z[1]), og = sigmoid_f(z[2]), gg = tanhf(z[3]);
     const float m = use_mask ? __ldcg(P.unfinished + r) : 1.f;
     const float cp = cst[e];
-    const float hp = P.hx[(long)r * 2 * H + layer * H + j];
+    float* hxp = P.hx + (long)r * 2 * H + layer * H + j;
+    const float hp = *hxp;
+    float z[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) z[g] = zadd(va[g]) + zadd(vb[g]) + zadd(vc[g]) + bias[g];
+    const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
     float c = fg * cp + ig * gg;
     c = c * m + cp * (1.f - m);
-    float h = og * tanhf(c);
+    float h = og * tanh_fast(c);
     h = h * m + hp * (1.f - m);
     cst[e] = c;
-    P.hx[(long)r * 2 * H + layer * H + j] = h;
+    *hxp = h;
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + layer * H + j, h);
   }
 }
 
-// temporal attention of caption r on one CTA: Uv[r] arrives by four bulk copies into the (idle) pipeline
-// stages while ah is assembled; scores -> softmax over ALL K frames -> context (sub_modules.py:677-680)
-__device__ __forceinline__ void dec_attention(const DecParams& P, int r, const SmemView& sv, uint32_t& bulk_phase) {
+// temporal attention of caption r on one CTA (sub_modules.py:677-680).  Uv[r] arrives by four bulk copies
+// into the (idle) pipeline stages; every thread owns the attention units a = tid + 320 i (ah[a], w[a] in
+// registers) and walks all K frames, so the 43k tanh of a caption are spread over all ten warps; frame
+// scores are reduced warp -> CTA in a fixed order; softmax over ALL K frames; context from V[r].
+__device__ __noinline__ void dec_attention(const DecParams& P, int r, const SmemView& sv, uint32_t& bulk_phase) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = P.K, A = P.A, H = P.H;
-  float* ah = sv.scratch;                       // A floats
-  float* sc = sv.scratch + A;                   // K floats
-  float* uv = reinterpret_cast<float*>(sv.stages);
+  float* red = sv.scratch;                      // [PK_WARPS][K] per-warp partial scores
+  float* sc = sv.scratch + PK_WARPS * K;        // K floats
+  const float* uv = reinterpret_cast<const float*>(sv.stages);
   const int fpc = (K + PK_BULK_CHUNKS - 1) / PK_BULK_CHUNKS;
   if (threadIdx.x == 0) {
+#pragma unroll 1
     for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
       const int k0 = c * fpc, k1 = min(K, k0 + fpc);
       if (k0 >= k1) break;
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
-      mbar_expect_tx(&sv.bulk_bar[c], nb);
-      bulk_g2s(uv + (long)k0 * A, P.Uv + ((long)r * K + k0) * A, nb, &sv.bulk_bar[c]);
+      pk_expect_tx(sv.bulk_bar + 8 * c, nb);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
     }
   }
-  for (int a = threadIdx.x; a < A; a += PK_THREADS) ah[a] = zsum(P.d[DD_AH], P.R, r, a) + __ldg(P.b_h2a + a);
-  __syncthreads();
-  const float ba = __ldg(P.b_a2w);
+  float ahr[DEC_NA], wr[DEC_NA];
+  {
+    float v[DEC_NA][PK_MAX_SLOTS];
+#pragma unroll
+    for (int i = 0; i < DEC_NA; ++i) {
+      const int a = min(threadIdx.x + PK_THREADS * i, A - 1);
+      zload(P.d[DD_AH], P.R, r, a, v[i]);
+      ahr[i] = __ldg(P.b_h2a + a);
+      wr[i] = (threadIdx.x + PK_THREADS * i < A) ? __ldg(P.w_a2w + a) : 0.f;     // out-of-range units weigh 0
+    }
+#pragma unroll
+    for (int i = 0; i < DEC_NA; ++i) ahr[i] += zadd(v[i]);
+  }
+  int k = 0;
+#pragma unroll 1
   for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-    const int k0 = c * fpc, k1 = min(K, k0 + fpc);
-    if (k0 >= k1) break;
-    mbar_wait(&sv.bulk_bar[c], bulk_phase & 1);
-    for (int k = k0 + warp; k < k1; k += PK_WARPS) {
+    const int k1 = min(K, (c + 1) * fpc);
+    if (k >= k1) break;
+    pk_wait(sv.bulk_bar + 8 * c, bulk_phase & 1);
+#pragma unroll 1
+    for (; k < k1; ++k) {
       const float* u = uv + (long)k * A;
       float p = 0.f;
-#pragma unroll 4
-      for (int a = lane; a < A; a += 32) p += __ldg(P.w_a2w + a) * tanh_fast(ah[a] + u[a]);
+#pragma unroll
+      for (int i = 0; i < DEC_NA; ++i) p += wr[i] * tanh_fast(ahr[i] + u[min(threadIdx.x + PK_THREADS * i, A - 1)]);
       p = warp_sum(p);
-      if (lane == 0) sc[k] = p + ba;
+      if (lane == 0) red[warp * K + k] = p;
     }
   }
   bulk_phase++;
   __syncthreads();
   if (warp == 0) {
+    const float ba = __ldg(P.b_a2w);
     float mx = -INFINITY;
-    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, sc[k]);
+#pragma unroll 1
+    for (int kk = lane; kk < K; kk += 32) {
+      float p = 0.f;
+#pragma unroll
+      for (int w = 0; w < PK_WARPS; ++w) p += red[w * K + kk];
+      p += ba;
+      sc[kk] = p;
+      mx = fmaxf(mx, p);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int k = lane; k < K; k += 32) { const float e = expf(sc[k] - mx); sc[k] = e; sum += e; }
+#pragma unroll 1
+    for (int kk = lane; kk < K; kk += 32) { const float e = __expf(sc[kk] - mx); sc[kk] = e; sum += e; }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int k = lane; k < K; k += 32) sc[k] *= inv;
+#pragma unroll 1
+    for (int kk = lane; kk < K; kk += 32) sc[kk] *= inv;
   }
   __syncthreads();
+#pragma unroll 1
   for (int j = threadIdx.x; j < H; j += PK_THREADS) {
     const float* v = P.Vf + (long)r * K * H + j;
     float a = 0.f;
-    int k = 0;
-    for (; k + 4 <= K; k += 4) {
-      const float v0 = __ldg(v + (long)k * H), v1 = __ldg(v + (long)(k + 1) * H), v2 = __ldg(v + (long)(k + 2) * H),
-                  v3 = __ldg(v + (long)(k + 3) * H);
-      a += sc[k] * v0; a += sc[k + 1] * v1; a += sc[k + 2] * v2; a += sc[k + 3] * v3;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float vv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) vv[q] = __ldg(v + (long)min(k0 + q, K - 1) * H);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a += (k0 + q < K ? sc[k0 + q] : 0.f) * vv[q];
     }
-    for (; k < K; ++k) a += sc[k] * __ldg(v + (long)k * H);
     store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
   __syncthreads();
 }
 
 // next-step inputs of caption r for token `tokv`: xt = embed[tok] and gp = pos * (1 + tgate[tok])
-__device__ __forceinline__ void dec_token_inputs(const DecParams& P, int r, int tokv) {
+__device__ __noinline__ void dec_token_inputs(const DecParams& P, int r, int tokv) {
   const float* src = P.embed + (long)tokv * P.E;
+#pragma unroll 1
   for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS)
     store_split(P.xt_hi, P.xt_lo, (long)r * P.Ep + k, k < P.E ? __ldg(src + k) : 0.f);
   const float* tg = P.tgate + (long)tokv * P.H;
+#pragma unroll 1
   for (int j = threadIdx.x; j < P.H; j += PK_THREADS)
     store_split(P.gp_hi, P.gp_lo, (long)r * P.H + j, __ldg(P.pos + (long)r * P.H + j) * (1.f + __ldcg(tg + j)));
+}
+
+// per (caption, block of 256 vocabulary rows): max / lowest argmax / sum-exp of the logits
+__device__ __noinline__ void dec_logit_stats(const DecParams& P, int cta, int G) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int V = P.V, R = P.R;
+  const int nvb = (V + DEC_VBLOCK - 1) / DEC_VBLOCK;
+  const GDesc& dl = P.d[DD_LOGIT];
+  const long sstr = (long)R * dl.n_rows;
+  constexpr int NI = DEC_VBLOCK / 32;
+#pragma unroll 1
+  for (int item = cta * PK_WARPS + warp; item < P.B * nvb; item += G * PK_WARPS) {
+    const int r = item / nvb, vb = item % nvb;
+    const int n0 = vb * DEC_VBLOCK + lane;
+    float v[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) v[i] = 0.f;
+    const float* lp = dl.out + (long)r * dl.n_rows;
+#pragma unroll 1
+    for (int k = 0; k < dl.ns; ++k, lp += sstr) {        // slot-major: NI independent loads in flight per slot
+      float tl[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) tl[i] = __ldcg(lp + min(n0 + i * 32, V - 1));
+#pragma unroll
+      for (int i = 0; i < NI; ++i) v[i] += tl[i];
+    }
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int n = n0 + i * 32;
+      v[i] = n < V ? v[i] + __ldg(P.b_logit + min(n, V - 1)) : -INFINITY;
+      if (v[i] > best) { best = v[i]; bi = n; }
+    }
+    const unsigned mo = __reduce_max_sync(0xffffffffu, f2ord(best));
+    const float wbest = ord2f(mo);
+    const int wbi = (int)__reduce_min_sync(0xffffffffu, (f2ord(best) == mo && best != -INFINITY) ? (unsigned)bi : 0x7fffffffu);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) s += __expf(v[i] - wbest);      // exp(-inf) = 0 for the padding rows
+    s = warp_sum(s);
+    if (lane == 0) *reinterpret_cast<float4*>(P.stats + ((long)vb * R + r) * 4) = make_float4(wbest, __int_as_float(wbi), s, 0.f);
+  }
+}
+
+// greedy bookkeeping of caption r at step t (SAModel.py:185-210); returns the raw argmax token
+__device__ __noinline__ int dec_pick(const DecParams& P, int r, int t) {
+  const int lane = threadIdx.x & 31;
+  const int nvb = (P.V + DEC_VBLOCK - 1) / DEC_VBLOCK;
+  float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
+  for (int q = lane; q < nvb; q += 32) {
+    const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * P.R + r) * 4));
+    const int vi = __float_as_int(rec.y);
+    if (rec.x > best || (rec.x == best && vi < bi)) { best = rec.x; bi = vi; }
+  }
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  float s = 0.f;
+#pragma unroll 1
+  for (int q = lane; q < nvb; q += 32) {
+    const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * P.R + r) * 4));
+    s += rec.z * __expf(rec.x - best);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
+    unf = (unf != 0.f && bi > 0) ? 1.f : 0.f;
+    P.unfinished[r] = unf;
+    P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)bi : 0;
+    P.seqlogp[(long)r * P.T + t] = -logf(s);
+    P.tok[r] = bi;
+    if (unf != 0.f) P.flags[t] = 1;
+  }
+  return bi;
+}
+
+// diagnostics (XG_PERSIST_TRACE): SM-clock stamps of CTA 0 for every step + globaltimer stamps of EVERY CTA for step 3
+__device__ __noinline__ void pk_stamp(long long* dbg, int cta, int t, int i) {
+  if (dbg == nullptr || threadIdx.x != 0) return;
+  if (cta == 0) dbg[t * PK_STAMPS + i] = clock64();
+  if (t == 3) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[(2048 + cta) * PK_STAMPS + i] = (long long)gt;
+  }
 }
 
 __global__ void __launch_bounds__(PK_THREADS, 1)
 decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
   __shared__ DecParams Psm;
+  __shared__ PSched s_sched[3];
+  const int cta = blockIdx.x, G = gridDim.x;
   for (int i = threadIdx.x; i < (int)(sizeof(DecParams) / 4); i += PK_THREADS)
     reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
   __syncthreads();
   const DecParams& P = Psm;
+  for (int i = threadIdx.x; i < (int)(3 * sizeof(PSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(PSched) / 4), w = i % (int)(sizeof(PSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(P.sched + (long)ph * G + cta)[w];
+  }
   extern __shared__ uint8_t smem_raw[];
   const SmemView sv = carve_smem(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cta = blockIdx.x, G = gridDim.x;
-  const int H = P.H, R = P.R, B = P.B, T = P.T, V = P.V;
+  const int warp = threadIdx.x >> 5;
+  const int H = P.H, R = P.R, B = P.B, T = P.T;
   const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 16) tma_prefetch_desc(&maps.m[threadIdx.x]);
   PipeState ps{0, 0, 0};
   unsigned int sync_target = 0;
   uint32_t bulk_phase = 0;
-  const PSched* my_sched = P.sched + cta;
 
   // ---- prologue: states, <bos> inputs, bookkeeping ----
   for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
@@ -458,7 +684,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     const float h1 = r < B ? P.state0[0][e] : 0.f, c1 = r < B ? P.state0[1][e] : 0.f;
     const float h2 = r < B ? P.state0[2][e] : 0.f, c2 = r < B ? P.state0[3][e] : 0.f;
     P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
-    P.c1[e] = c1; P.c2[e] = c2;
+    P.cx[e] = c1; P.cx[(long)R * H + e] = c2;
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + j, h1);
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + H + j, h2);
   }
@@ -476,117 +702,72 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
   }
   grid_barrier(P.sync_counter, sync_target, G);
 
-#define PK_STAMP(i) do { if (P.dbg_clock && cta == 0 && threadIdx.x == 0) P.dbg_clock[t * PK_STAMPS + (i)] = clock64(); } while (0)
+#pragma unroll 1
   for (int t = 0; t < T; ++t) {
-    PK_STAMP(0);
+    pk_stamp(P.dbg_clock, cta, t, 0);
     // ===== G1: everything that needs only the previous state and the current token =====
     //   AH = W_h2a.[h1|h2]   Z1h = W_h2h1.h1   Z2h = W_h2h2.h2   Z1x = W_i2h1.xt   Z1g = W_a2h1.gp
-    gemm_phase(P.d, my_sched, maps.m, R, P.hi_inplace, sv, tmem_base, ps);
-    PK_STAMP(1);
+    gemm_phase(P.d, &s_sched[0], maps.m, R, sv, tmem_base, ps);
+    pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(2);
+    pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
     if (G > B) {
       if (cta < B) dec_attention(P, cta, sv, bulk_phase);
-      else dec_cell_phase(P, 0, t > 0, cta - B, G - B);
     } else {
+#pragma unroll 1
       for (int r = cta; r < B; r += G) dec_attention(P, r, sv, bulk_phase);
-      dec_cell_phase(P, 0, t > 0, cta, G);
     }
+    if (G <= B || cta >= B) dec_cell_phase(P, 0, t > 0, G > B ? cta - B : cta, G > B ? G - B : G);
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
-    PK_STAMP(3);
+    pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(4);
+    pk_stamp(P.dbg_clock, cta, t, 4);
     // ===== G3: Z2x = W_i2h2.h1'   Z2a = W_a2h2.af =====
-    gemm_phase(P.d, my_sched + G, maps.m, R, P.hi_inplace, sv, tmem_base, ps);
-    PK_STAMP(5);
+#ifdef PK_FINE_TRACE
+    {
+      long long* fine = (P.dbg_clock && t == 3 && (cta == 0 || cta == 100)) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + (cta ? 32 : 0) : nullptr;
+      gemm_phase(P.d, &s_sched[1], maps.m, R, sv, tmem_base, ps, fine);
+      if (fine && threadIdx.x == 0) fine[26] = clock64();
+      grid_barrier(P.sync_counter, sync_target, G);
+      if (fine && threadIdx.x == 0) fine[27] = clock64();
+    }
+#else
+    gemm_phase(P.d, &s_sched[1], maps.m, R, sv, tmem_base, ps);
+    pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(6);
+#endif
+    pk_stamp(P.dbg_clock, cta, t, 6);
     // ===== P3: lstm_2 cell =====
     dec_cell_phase(P, 1, t > 0, cta, G);
-    PK_STAMP(7);
+    pk_stamp(P.dbg_clock, cta, t, 7);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(8);
+    pk_stamp(P.dbg_clock, cta, t, 8);
     // ===== G4: logits (split-K partial tiles) =====
-    gemm_phase(P.d, my_sched + 2 * G, maps.m, R, P.hi_inplace, sv, tmem_base, ps);
-    PK_STAMP(9);
+    gemm_phase(P.d, &s_sched[2], maps.m, R, sv, tmem_base, ps);
+    pk_stamp(P.dbg_clock, cta, t, 9);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(10);
-    // ===== P4a: per (caption, block of 1024 vocabulary rows): max / lowest argmax / sum-exp =====
-    {
-      const int nvb = (V + DEC_VBLOCK - 1) / DEC_VBLOCK;
-      const GDesc& dl = P.d[DD_LOGIT];
-      for (int item = cta * PK_WARPS + warp; item < B * nvb; item += G * PK_WARPS) {
-        const int r = item / nvb, vb = item % nvb;
-        float v[DEC_VBLOCK / 32];
-#pragma unroll
-        for (int i = 0; i < DEC_VBLOCK / 32; ++i) {
-          const int n = vb * DEC_VBLOCK + i * 32 + lane;
-          v[i] = n < V ? zsum(dl, R, r, n) + __ldg(P.b_logit + n) : -INFINITY;
-        }
-        float best = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < DEC_VBLOCK / 32; ++i)
-          if (v[i] > best) { best = v[i]; bi = vb * DEC_VBLOCK + i * 32 + lane; }
-        const unsigned mo = __reduce_max_sync(0xffffffffu, f2ord(best));
-        const float wbest = ord2f(mo);
-        const int wbi = (int)__reduce_min_sync(0xffffffffu, (f2ord(best) == mo && best != -INFINITY) ? (unsigned)bi : 0x7fffffffu);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < DEC_VBLOCK / 32; ++i) s += (v[i] == -INFINITY) ? 0.f : expf(v[i] - wbest);
-        s = warp_sum(s);
-        if (lane == 0) {
-          float4 rec = make_float4(wbest, __int_as_float(wbi), s, 0.f);
-          *reinterpret_cast<float4*>(P.stats + ((long)vb * R + r) * 4) = rec;
-        }
+    pk_stamp(P.dbg_clock, cta, t, 10);
+    // ===== P4a: logit statistics =====
+    dec_logit_stats(P, cta, G);
+    pk_stamp(P.dbg_clock, cta, t, 11);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 12);
+    // ===== P4b: greedy bookkeeping + inputs of the next step =====
+#pragma unroll 1
+    for (int r = cta; r < B; r += G) {
+      if (warp == 0) {
+        const int bi = dec_pick(P, r, t);
+        if ((threadIdx.x & 31) == 0) reinterpret_cast<int*>(sv.scratch)[0] = bi;
       }
+      __syncthreads();
+      const int tokv = reinterpret_cast<int*>(sv.scratch)[0];
+      dec_token_inputs(P, r, tokv);
+      __syncthreads();
     }
-    PK_STAMP(11);
+    pk_stamp(P.dbg_clock, cta, t, 13);
     grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(12);
-    // ===== P4b: greedy bookkeeping + inputs of the next step (SAModel.py:185-210) =====
-    {
-      const int nvb = (V + DEC_VBLOCK - 1) / DEC_VBLOCK;
-      for (int r = cta; r < B; r += G) {
-        if (warp == 0) {
-          float best = -INFINITY; int bi = 0x7fffffff;
-          for (int q = lane; q < nvb; q += 32) {
-            const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * R + r) * 4));
-            const int vi = __float_as_int(rec.y);
-            if (rec.x > best || (rec.x == best && vi < bi)) { best = rec.x; bi = vi; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-          }
-          float s = 0.f;
-          for (int q = lane; q < nvb; q += 32) {
-            const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * R + r) * 4));
-            if (rec.x != -INFINITY) s += rec.z * expf(rec.x - best);
-          }
-          s = warp_sum(s);
-          if (lane == 0) {
-            float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
-            unf = (unf != 0.f && bi > 0) ? 1.f : 0.f;
-            P.unfinished[r] = unf;
-            P.seq[(long)r * T + t] = unf != 0.f ? (int64_t)bi : 0;
-            P.seqlogp[(long)r * T + t] = -logf(s);
-            P.tok[r] = bi;
-            if (unf != 0.f) P.flags[t] = 1;
-            reinterpret_cast<int*>(sv.scratch)[0] = bi;
-          }
-        }
-        __syncthreads();
-        const int tokv = reinterpret_cast<int*>(sv.scratch)[0];
-        dec_token_inputs(P, r, tokv);
-        __syncthreads();
-      }
-    }
-    PK_STAMP(13);
-    grid_barrier(P.sync_counter, sync_target, G);
-    PK_STAMP(14);
+    pk_stamp(P.dbg_clock, cta, t, 14);
     if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
   pipeline_teardown(tmem_base);
@@ -598,7 +779,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
 struct EncParams {
   GDesc d[2];                   // rgb, opfl recurrent products
   const PSched* sched;          // [G]
-  int B, R, K, H, hi_inplace;
+  int B, R, K, H;
   float* Gt[2];                 // (K,B,4H) input projections + biases  ->  activated gates (in place)
   float* Hs[2];                 // (K,B,H)
   float* Cs[2];                 // (K,B,H)
@@ -610,40 +791,51 @@ struct EncParams {
 __global__ void __launch_bounds__(PK_THREADS, 1)
 encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
   __shared__ EncParams Psm;
+  __shared__ PSched s_sched;
+  const int cta = blockIdx.x, G = gridDim.x;
   for (int i = threadIdx.x; i < (int)(sizeof(EncParams) / 4); i += PK_THREADS)
     reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
   __syncthreads();
   const EncParams& P = Psm;
+  for (int i = threadIdx.x; i < (int)(sizeof(PSched) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&s_sched)[i] = reinterpret_cast<const uint32_t*>(P.sched + cta)[i];
   extern __shared__ uint8_t smem_raw[];
   const SmemView sv = carve_smem(smem_raw);
-  const int cta = blockIdx.x, G = gridDim.x;
   const int H = P.H, R = P.R, B = P.B, K = P.K;
   const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 4) tma_prefetch_desc(&maps.m[threadIdx.x]);
   PipeState ps{0, 0, 0};
   unsigned int sync_target = 0;
 
   for (int e = cta * PK_THREADS + threadIdx.x; e < (R - B) * 2 * H; e += G * PK_THREADS) {   // padding rows
     P.hh_hi[(long)B * 2 * H + e] = 0.f; P.hh_lo[(long)B * 2 * H + e] = 0.f;
   }
+#pragma unroll 1
   for (int t = 0; t < K; ++t) {
     if (t > 0) {
-      gemm_phase(P.d, P.sched + cta, maps.m, R, P.hi_inplace, sv, tmem_base, ps);
+      gemm_phase(P.d, &s_sched, maps.m, R, sv, tmem_base, ps);
       grid_barrier(P.sync_counter, sync_target, G);
     }
+#pragma unroll 1
     for (int e = cta * PK_THREADS + threadIdx.x; e < 2 * B * H; e += G * PK_THREADS) {
       const int s = e / (B * H), b = (e / H) % B, j = e % H;
-      float* z = P.Gt[s] + ((long)t * B + b) * 4 * H;
-      float zz[4];
+      float* z = P.Gt[s] + ((long)t * B + b) * 4 * H + j;
+      float zz[4], vs[4][PK_MAX_SLOTS];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) zz[g] = z[g * H + j] + (t > 0 ? zsum(P.d[s], R, b, g * H + j) : 0.f);
-      const float ig = sigmoid_f(zz[0]), fg = sigmoid_f(zz[1]), gg = tanhf(zz[2]), og = sigmoid_f(zz[3]);
+      for (int g = 0; g < 4; ++g) {
+        zz[g] = z[g * H];
+        if (t > 0) zload(P.d[s], R, b, g * H + j, vs[g]);
+      }
       const float m = __ldg(P.fmask + (long)b * K + t);
       const long o = ((long)t * B + b) * H + j;
       const float cp = t > 0 ? P.Cs[s][o - (long)B * H] : 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) if (t > 0) zz[g] += zadd(vs[g]);
+      const float ig = sigmoid_fast(zz[0]), fg = sigmoid_fast(zz[1]), gg = tanh_fast(zz[2]), og = sigmoid_fast(zz[3]);
       const float c2 = fg * cp + ig * gg;
-      const float h = og * tanhf(c2) * m;      // h' *= mask (sub_modules.py:139,146)
+      const float h = og * tanh_fast(c2) * m;  // h' *= mask (sub_modules.py:139,146)
       const float c = c2 * m;                  // c' *= mask (:140,147)
-      z[j] = ig; z[H + j] = fg; z[2 * H + j] = gg; z[3 * H + j] = og;
+      z[0] = ig; z[H] = fg; z[2 * H] = gg; z[3 * H] = og;
       P.Cs[s][o] = c;
       P.Hs[s][o] = h;
       if (t + 1 < K) store_split(P.hh_hi, P.hh_lo, (long)b * 2 * H + s * H + j, h);
@@ -658,7 +850,7 @@ encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant
 // ------------------------------------------------------------------------------------
 struct PhaseSchedule {
   std::vector<PSched> per_cta;                         // [G]
-  std::vector<std::vector<unsigned char>> nslots;      // per desc (phase-local order): [rts * ncb]
+  std::vector<int> ns;                                 // per desc (phase-local order): max slots of a strip
   bool ok = true;
 };
 
@@ -683,17 +875,18 @@ static PhaseSchedule build_phase(const std::vector<int>& desc_ids, const GDesc* 
       const int take = (int)std::min<long>(need, s.nkb - off);
       if (sc.n >= PK_MAX_ITEMS || s.slots >= PK_MAX_SLOTS) { ph.ok = false; return ph; }
       sc.it[sc.n++] = PItem{(short)s.desc, (short)s.slots, (short)s.rt, (short)s.cb, (short)off, (short)take};
+      sc.tot_kb += (short)take;
+      sc.tot_chunks += (short)((take + PK_CHUNK - 1) / PK_CHUNK);
       s.slots++;
       off += take; need -= take;
       if (off == s.nkb) { ++si; off = 0; }
     }
   }
-  ph.nslots.resize(desc_ids.size());
+  ph.ns.assign(desc_ids.size(), 0);
   size_t k = 0;
   for (size_t i = 0; i < desc_ids.size(); ++i) {
     const int rts = (descs[desc_ids[i]].n_rows + 127) / 128;
-    ph.nslots[i].resize((size_t)rts * ncb);
-    for (size_t q = 0; q < (size_t)rts * ncb; ++q) ph.nslots[i][q] = (unsigned char)strips[k++].slots;
+    for (size_t q = 0; q < (size_t)rts * ncb; ++q) ph.ns[i] = std::max(ph.ns[i], strips[k++].slots);
   }
   return ph;
 }
@@ -739,19 +932,18 @@ static inline int env_flag(const char* name) { const char* e = getenv(name); ret
 static bool persist_eligible(const xg_context* ctx, int B, int K) {
   const xg_dims& d = ctx->d;
   return ctx->persist_mode && d.rnn % 32 == 0 && d.embed % 4 == 0 && d.att % 4 == 0 && B <= 64 &&
-         d.att + K + 8 <= PK_SCRATCH_FLOATS && (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 &&
+         (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS && (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 &&
          d.vocab < 32000 && d.att < 32000 && d.rnn <= 4096;
 }
 
 // schedule of one kernel (phases laid one after the other, [phase][G]); false if a phase cannot be scheduled
-static bool persist_plan(const std::vector<std::vector<int>>& phases, GDesc* descs, int ncb, int G, std::vector<PSched>& sched,
-                         std::vector<std::vector<unsigned char>>& nslots_by_desc) {
+static bool persist_plan(const std::vector<std::vector<int>>& phases, GDesc* descs, int ncb, int G, std::vector<PSched>& sched) {
   sched.clear();
   for (const auto& ids : phases) {
     PhaseSchedule ph = build_phase(ids, descs, ncb, G);
     if (!ph.ok) return false;
     sched.insert(sched.end(), ph.per_cta.begin(), ph.per_cta.end());
-    for (size_t i = 0; i < ids.size(); ++i) nslots_by_desc[ids[i]] = ph.nslots[i];
+    for (size_t i = 0; i < ids.size(); ++i) descs[ids[i]].ns = ph.ns[i];
   }
   return true;
 }
@@ -788,8 +980,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   mk(DD_LOGIT, 7, 10, kbH, V, kbH);
   const std::vector<std::vector<int>> phases = {{DD_AH, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT}};
   std::vector<PSched> sched;
-  std::vector<std::vector<unsigned char>> nslots(DD_COUNT);
-  if (!persist_plan(phases, hp.d, R / PK_BN, G, sched, nslots)) return PK_FALLBACK;
+  if (!persist_plan(phases, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
 
   // ---- device pool ----
   if (S->R != R || S->K != K) {
@@ -799,18 +990,15 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_params = a.take<DecParams>(1);
       S->d_counter = a.take<unsigned int>(64);
       S->d_flags = a.take<int>(2048);
-      S->d_dbg = a.take<long long>(2048 * PK_STAMPS);
+      S->d_dbg = a.take<long long>((2048 + 256 + 8) * PK_STAMPS);
       hp.sched = a.take<PSched>(sched.size());
-      for (int i = 0; i < DD_COUNT; ++i) {
-        hp.d[i].nslots = a.take<unsigned char>(nslots[i].size());
-        hp.d[i].out = a.take<float>((size_t)PK_MAX_SLOTS * R * hp.d[i].n_rows);
-      }
+      for (int i = 0; i < DD_COUNT; ++i) hp.d[i].out = a.take<float>((size_t)hp.d[i].ns * R * hp.d[i].n_rows);
       hp.xt_hi = a.take<float>((long)R * Ep); hp.xt_lo = a.take<float>((long)R * Ep);
       hp.hh_hi = a.take<float>((long)R * 2 * H); hp.hh_lo = a.take<float>((long)R * 2 * H);
       hp.gp_hi = a.take<float>((long)R * H); hp.gp_lo = a.take<float>((long)R * H);
       hp.af_hi = a.take<float>((long)R * H); hp.af_lo = a.take<float>((long)R * H);
       hp.hx = a.take<float>((long)R * 2 * H);
-      hp.c1 = a.take<float>((long)R * H); hp.c2 = a.take<float>((long)R * H);
+      hp.cx = a.take<float>((long)2 * R * H);
       hp.stats = a.take<float>((long)nvb * R * 4);
       hp.unfinished = a.take<float>(R);
       hp.tok = a.take<int64_t>(R);
@@ -826,9 +1014,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(hp.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
-  for (int i = 0; i < DD_COUNT; ++i)
-    XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<unsigned char*>(hp.d[i].nslots), nslots[i].data(), nslots[i].size(),
-                                         cudaMemcpyHostToDevice, st));
 
   // ---- POS-gate table of every token: tgate = relu(embed . W_gate^T + b)  (sub_modules.py:29-32 applied to
   //      SAModel.py:198's embedding rows); rebuilt whenever the bound parameters change ----
@@ -855,10 +1040,9 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_TRY(tc_make_map(ctx, ts, hp.af_hi, R, H, PK_BN, &maps[14])); XG_TRY(tc_make_map(ctx, ts, hp.af_lo, R, H, PK_BN, &maps[15]));
 
   hp.B = B; hp.R = R; hp.K = K; hp.H = H; hp.E = E; hp.Ep = Ep; hp.A = A; hp.V = V; hp.T = T;
-  hp.hi_inplace = env_flag("XG_PERSIST_HI_INPLACE");
   hp.b_h2a = ctx->P[XG_P_H2A_B]; hp.w_a2w = ctx->P[XG_P_A2W_W]; hp.b_a2w = ctx->P[XG_P_A2W_B];
-  hp.b1_i2h = ctx->P[XG_P_L1_I2H_B]; hp.b1_a2h = ctx->P[XG_P_L1_A2H_B]; hp.b1_h2h = ctx->P[XG_P_L1_H2H_B];
-  hp.b2_i2h = ctx->P[XG_P_L2_I2H_B]; hp.b2_a2h = ctx->P[XG_P_L2_A2H_B]; hp.b2_h2h = ctx->P[XG_P_L2_H2H_B];
+  hp.bias[0][0] = ctx->P[XG_P_L1_I2H_B]; hp.bias[0][1] = ctx->P[XG_P_L1_A2H_B]; hp.bias[0][2] = ctx->P[XG_P_L1_H2H_B];
+  hp.bias[1][0] = ctx->P[XG_P_L2_I2H_B]; hp.bias[1][1] = ctx->P[XG_P_L2_A2H_B]; hp.bias[1][2] = ctx->P[XG_P_L2_H2H_B];
   hp.b_logit = ctx->P[XG_P_LOGIT_B]; hp.embed = ctx->P[XG_P_EMBED_W];
   hp.tgate = S->tgate;
   hp.Vf = Vf; hp.Uv = Uv; hp.pos = pos;
@@ -871,7 +1055,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
-  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * 2048 * PK_STAMPS, st));
+  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256 + 8) * PK_STAMPS, st));
 
   if (!S->attr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
@@ -910,6 +1094,37 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       fprintf(stderr, "[xg persist trace] %-26s own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
     }
     fprintf(stderr, "[xg persist trace] step %.0f cycles\n", tot);
+#ifdef PK_FINE_TRACE
+    if (steps > 3) {   // step 3, phase G3, first item of CTA 0 and CTA 100: pipeline events in SM cycles after phase entry
+      const char* ev[28] = {"entry", "tma0", "tma1", "tma2", "tma3", "full0", "full1", "full2", "full3", "split0", "split1", "split2", "split3",
+                            "mma_go0", "mma_go1", "mma_go2", "mma_go3", "mma_iss0", "mma_iss1", "mma_iss2", "mma_iss3", "small_commit",
+                            "acc_full0", "acc_full1", "small_full", "stored", "barrier_in", "barrier_out"};
+      for (int w = 0; w < 2; ++w) {
+        long long f[32];
+        cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + w * 32, sizeof(f), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[xg persist trace] G3 item 0 of cta %d:", w ? 100 : 0);
+        for (int i = 1; i < 28; ++i) if (f[i]) fprintf(stderr, " %s=%lld", ev[i], f[i] - f[0]);
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
+    if (steps > 3 && G <= 256) {   // step 3, all CTAs: when does each CTA finish its share of a phase (ns after the phase opened)?
+      std::vector<long long> ga((size_t)G * PK_STAMPS);
+      cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < 7; ++i) {
+        long long open = 0;
+        for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);   // last CTA through the previous barrier
+        std::vector<long long> fin(G);
+        for (int c = 0; c < G; ++c) fin[c] = ga[(size_t)c * PK_STAMPS + 2 * i + 1] - open;
+        std::vector<long long> srt = fin;
+        std::sort(srt.begin(), srt.end());
+        long long close = 0;
+        for (int c = 0; c < G; ++c) close = std::max(close, ga[(size_t)c * PK_STAMPS + 2 * i + 2]);
+        int worst = (int)(std::max_element(fin.begin(), fin.end()) - fin.begin());
+        fprintf(stderr, "[xg persist trace] step 3 %-26s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
+                names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, close - open);
+      }
+    }
   }
   return XG_OK;
 }
@@ -932,8 +1147,7 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
     g.w_map = s; g.x_hi = 2; g.x_lo = 3; g.xkb0 = s * kbH; g.n_rows = 4 * H; g.nkb = kbH;
   }
   std::vector<PSched> sched;
-  std::vector<std::vector<unsigned char>> nslots(2);
-  if (!persist_plan({{0, 1}}, ep.d, R / PK_BN, G, sched, nslots)) return PK_FALLBACK;
+  if (!persist_plan({{0, 1}}, ep.d, R / PK_BN, G, sched)) return PK_FALLBACK;
   if (S->eB != B) {
     if (S->epool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->epool); S->epool = nullptr; }
     for (int pass = 0; pass < 2; ++pass) {
@@ -941,10 +1155,7 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
       S->d_eparams = a.take<EncParams>(1);
       S->d_ecounter = a.take<unsigned int>(64);
       ep.sched = a.take<PSched>(sched.size());
-      for (int s = 0; s < 2; ++s) {
-        ep.d[s].nslots = a.take<unsigned char>(nslots[s].size());
-        ep.d[s].out = a.take<float>((size_t)PK_MAX_SLOTS * R * 4 * H);
-      }
+      for (int s = 0; s < 2; ++s) ep.d[s].out = a.take<float>((size_t)ep.d[s].ns * R * 4 * H);
       ep.hh_hi = a.take<float>((long)R * 2 * H); ep.hh_lo = a.take<float>((long)R * 2 * H);
       if (pass == 0) {
         S->epool_bytes = a.off + 1024;
@@ -956,16 +1167,13 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(ep.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
-  for (int s = 0; s < 2; ++s)
-    XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<unsigned char*>(ep.d[s].nslots), nslots[s].data(), nslots[s].size(),
-                                         cudaMemcpyHostToDevice, st));
   MapTable mt;
   XG_TRY(tc_make_map(ctx, ts, ctx->P[XG_P_LSTM_RGB_WHH], 4 * H, H, 128, &mt.m[0]));
   XG_TRY(tc_make_map(ctx, ts, ctx->P[XG_P_LSTM_OPFL_WHH], 4 * H, H, 128, &mt.m[1]));
   XG_TRY(tc_make_map(ctx, ts, ep.hh_hi, R, 2 * H, PK_BN, &mt.m[2]));
   XG_TRY(tc_make_map(ctx, ts, ep.hh_lo, R, 2 * H, PK_BN, &mt.m[3]));
   for (int i = 4; i < 16; ++i) mt.m[i] = mt.m[0];
-  ep.B = B; ep.R = R; ep.K = K; ep.H = H; ep.hi_inplace = env_flag("XG_PERSIST_HI_INPLACE");
+  ep.B = B; ep.R = R; ep.K = K; ep.H = H;
   for (int s = 0; s < 2; ++s) { ep.Gt[s] = eb.G[s]; ep.Hs[s] = eb.Hs[s]; ep.Cs[s] = eb.Cs[s]; }
   ep.fmask = fmask;
   ep.sync_counter = S->d_ecounter;
