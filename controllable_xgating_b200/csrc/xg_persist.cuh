@@ -42,7 +42,7 @@ constexpr int PK_SMEM_BYTES = PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4
 constexpr int PK_MAX_ITEMS = 6;
 constexpr int PK_MAX_SLOTS = 6;
 constexpr int PK_MAX_DESCS = 8;
-constexpr int PK_BULK_CHUNKS = 4;
+constexpr int PK_BULK_CHUNKS = 4;     // Uv chunks (+1 barrier for V)
 constexpr int PK_STAMPS = 16;
 
 struct PItem { short desc, slot, rt, cb, kb0, nkb; };
@@ -55,7 +55,7 @@ struct GDesc {                   // out[slot][r][n] = sum_k W[n,k] * X[r, 32*xkb
   int ns;                        //   once and the schedule is static), so every consumer adds `ns` slots
 };
 
-struct MapTable { CUtensorMap m[16]; };
+struct MapTable { CUtensorMap m[18]; };   // 0-15 GEMM operands, 16: V as [B*K][H] (box H/2 x K, no swizzle)
 
 // CODE SIZE IS THE FIRST-ORDER COST HERE: every phase runs once per word step, so its instructions are
 // fetched cold unless the whole step fits the 32 KB L1.5 instruction cache (measured: the first version,
@@ -86,6 +86,9 @@ __device__ __forceinline__ void pk_wait(uint32_t addr, uint32_t parity) {
                : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   if (!done) pk_wait_spin(addr, parity);
 }
+__device__ __forceinline__ void pk_expect_tx_noarrive(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void pk_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
 __device__ __forceinline__ void pk_expect_tx(uint32_t addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
@@ -104,7 +107,8 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-// grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency)
+// grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency).
+// (A variant with one release flag per CTA written by the last arriver measured slower: 2.2 vs 1.8 us.)
 __device__ __noinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int G) {
   fence_proxy_async_global();          // generic-proxy global writes -> visible to later TMA reads
   __syncthreads();
@@ -127,6 +131,7 @@ struct PipeState {       // running counters, identical in every thread by const
   uint32_t kb_count;     // k-blocks issued so far (stage ring position)
   uint32_t chunk_count;  // accumulation chains issued so far (ping-pong accumulator position)
   uint32_t item_count;   // items processed so far (small-accumulator handshake)
+  uint32_t npre;         // leading k-blocks of the NEXT GEMM phase whose weight tiles are already in flight
 };
 
 // shared-memory map (32-bit shared-window addresses; the barriers are 8 bytes apart)
@@ -153,7 +158,7 @@ __device__ __forceinline__ SmemView carve_smem(uint8_t* smem_raw) {
   sv.small_full = sv.acc_empty + 16;
   sv.small_empty = sv.small_full + 8;
   sv.bulk_bar = sv.small_empty + 8;
-  sv.tmem_slot = reinterpret_cast<uint32_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4 + 8 * (3 * PK_STAGES + 6 + PK_BULK_CHUNKS));
+  sv.tmem_slot = reinterpret_cast<uint32_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4 + 8 * (3 * PK_STAGES + 6 + PK_BULK_CHUNKS + 1));
   return sv;
 }
 
@@ -170,7 +175,7 @@ __device__ __noinline__ uint32_t pipeline_setup(const SmemView& sv) {
     for (int b = 0; b < 2; ++b) { pk_mbar_init(sv.acc_full + 8 * b, 1); pk_mbar_init(sv.acc_empty + 8 * b, 128); }
     pk_mbar_init(sv.small_full, 1);
     pk_mbar_init(sv.small_empty, 128);
-    for (int c = 0; c < PK_BULK_CHUNKS; ++c) pk_mbar_init(sv.bulk_bar + 8 * c, 1);
+    for (int c = 0; c <= PK_BULK_CHUNKS; ++c) pk_mbar_init(sv.bulk_bar + 8 * c, 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<256>(sv.tmem_slot);
@@ -204,6 +209,7 @@ __device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, co
   if (threadIdx.x == 0) PK_FINE(0);
   if (warp == 0) {            // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
+    int npre = (int)__shfl_sync(0xffffffffu, ps.npre, 0);      // weight tiles of the first npre k-blocks were prefetched
     const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
     const uint32_t full_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
 #pragma unroll 1
@@ -219,14 +225,23 @@ __device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, co
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += 32, xk += 32) {
         const uint32_t s = cnt & (PK_STAGES - 1);
-        pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
         const uint32_t st = stages_u32 + s * PK_STAGE_BYTES, fb = full_bar + 8 * s;
-        if (elect_one_sync()) {
-          pk_expect_tx(fb, PK_TX_BYTES);
-          pk_tma_2d(st, mw, fb, wk, row);
-          pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
-          pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
-          if (ii == 0 && kb < 4) PK_FINE(1 + kb);
+        if (npre > 0) {         // weights already on their way (gemm_prefetch): only the activation tiles remain
+          --npre;
+          if (elect_one_sync()) {
+            pk_expect_tx(fb, 2 * PK_X_BYTES);
+            pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
+            pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
+          }
+        } else {
+          pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            pk_expect_tx(fb, PK_TX_BYTES);
+            pk_tma_2d(st, mw, fb, wk, row);
+            pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
+            pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
+            if (ii == 0 && kb < 4) PK_FINE(1 + kb);
+          }
         }
         __syncwarp();
       }
@@ -360,6 +375,57 @@ __device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, co
   ps.kb_count += sc->tot_kb;
   ps.chunk_count += sc->tot_chunks;
   ps.item_count += n_items;
+  ps.npre = 0;
+}
+
+// Issued at the END of a pointwise phase, before its grid barrier: the weight tiles of the first k-blocks of
+// the next GEMM phase do not depend on anything the barrier protects, so their TMA latency hides behind it.
+// (tx bytes are announced without an arrival; the producer's arrive.expect_tx for the activation tiles
+// completes the stage.)
+__device__ __noinline__ void gemm_prefetch(const GDesc* descs, const PSched* sc, const CUtensorMap* maps, const SmemView& sv,
+                                           PipeState& ps) {
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
+  int npre = 0;
+  if (warp == 0) {
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
+    const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
+    const uint32_t full_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items && npre < PK_STAGES; ++ii) {
+      const PItem it = sc->it[ii];
+      const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, descs[it.desc].w_map, 0);
+      int wk = __shfl_sync(0xffffffffu, it.kb0 * 32, 0);
+      const int row = __shfl_sync(0xffffffffu, it.rt * 128, 0);
+      const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+#pragma unroll 1
+      for (int kb = 0; kb < nkb && npre < PK_STAGES; ++kb, ++cnt, wk += 32, ++npre) {
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+        if (elect_one_sync()) {
+          pk_expect_tx_noarrive(full_bar + 8 * s, PK_W_BYTES);
+          pk_tma_2d(stages_u32 + s * PK_STAGE_BYTES, mw, full_bar + 8 * s, wk, row);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // every thread must agree on npre: recompute it from the schedule
+  const int tot = sc->tot_kb;
+  ps.npre = (uint32_t)(tot < PK_STAGES ? tot : PK_STAGES);
+}
+
+// leaving the loop with prefetched weight tiles in flight: complete their stages and wait for the data
+__device__ __noinline__ void gemm_prefetch_drain(const SmemView& sv, PipeState& ps) {
+  if (threadIdx.x == 0) {
+    for (uint32_t q = 0; q < ps.npre; ++q) {
+      const uint32_t cnt = ps.kb_count + q, s = cnt & (PK_STAGES - 1);
+      pk_arrive(sv.full_bar + 8 * s);
+      pk_wait(sv.full_bar + 8 * s, (cnt / PK_STAGES) & 1);
+    }
+  }
+  ps.npre = 0;
+  __syncthreads();
 }
 
 __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, float v) {
@@ -416,19 +482,20 @@ struct DecParams {
   float *af_hi, *af_lo;         // [R][H]
   float *hx;                    // [R][2H] exact states
   float *cx;                    // [2][R][H]
-  float *stats;                 // [vocab blocks][R][4]  (max, argmax, sum-exp, -)
   float *unfinished;            // [R]
+  float *scores;                // [R][K] attention scores of the current step (exchanged inside a CTA pair)
+  unsigned int* att_flag;       // [2R] step stamps of the pair exchange
   int64_t *tok;                 // [R]
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
   long long* dbg_clock;         // diagnostics, or NULL
 };
 
-constexpr int DEC_VBLOCK = 256;    // vocabulary rows per statistics record (8 per lane)
 constexpr int DEC_NA = 5;          // attention units per thread: att <= 5 * 320
 
 // lstm cell (decoder gate order i,f,o,g), elements (r, j) with j fastest
-__device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int use_mask, int part, int nparts) {
+__device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int use_mask, int part, int nparts, long long* g_fine = nullptr) {
+  if (threadIdx.x == 0) PK_FINE(0);
   const int H = P.H, R = P.R;
   const GDesc& da = P.d[layer == 0 ? DD_Z1X : DD_Z2X];
   const GDesc& db = P.d[layer == 0 ? DD_Z1G : DD_Z2A];
@@ -452,6 +519,7 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int u
     float z[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) z[g] = zadd(va[g]) + zadd(vb[g]) + zadd(vc[g]) + bias[g];
+    if (threadIdx.x == 0 && z[0] != 12345.f) PK_FINE(1);
     const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
     float c = fg * cp + ig * gg;
     c = c * m + cp * (1.f - m);
@@ -460,36 +528,51 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int u
     cst[e] = c;
     *hxp = h;
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + layer * H + j, h);
+    if (threadIdx.x == 0) PK_FINE(2);
   }
+  if (threadIdx.x == 0) PK_FINE(3);
 }
 
-// temporal attention of caption r on one CTA (sub_modules.py:677-680).  Uv[r] arrives by four bulk copies
-// into the (idle) pipeline stages; every thread owns the attention units a = tid + 320 i (ah[a], w[a] in
-// registers) and walks all K frames, so the 43k tanh of a caption are spread over all ten warps; frame
-// scores are reduced warp -> CTA in a fixed order; softmax over ALL K frames; context from V[r].
-__device__ __noinline__ void dec_attention(const DecParams& P, int r, const SmemView& sv, uint32_t& bulk_phase) {
+// temporal attention of caption r on a PAIR of CTAs (sub_modules.py:677-680); the 43k tanh of a caption are
+// MUFU-bound on one SM, so the frames are halved: CTA (r, half) bulk-copies its frames of Uv[r] and its
+// half of the columns of V[r] into the (idle) pipeline stages, computes the scores of its frames (every
+// thread owns the attention units a = tid + 320 i, the frames of a chunk run with independent accumulators),
+// publishes them, exchanges with its partner through a release/acquire flag, and then both CTAs take the
+// softmax over ALL K frames and each produces its half of the context vector.
+constexpr int DEC_FPC = 8;         // frames per Uv chunk (frames per CTA <= 32)
+__device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, int half, int t, const SmemView& sv,
+                                           uint32_t& bulk_phase, long long* g_fine = nullptr) {
+  if (threadIdx.x == 0) PK_FINE(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = P.K, A = P.A, H = P.H;
-  float* red = sv.scratch;                      // [PK_WARPS][K] per-warp partial scores
-  float* sc = sv.scratch + PK_WARPS * K;        // K floats
+  const int kh = (K + 1) / 2, kb = half * kh, nk = max(0, min(K, kb + kh) - kb);   // my frames [kb, kb + nk)
+  const int Hh = H / 2, jb = half * Hh;                                            // my context columns [jb, jb + Hh)
+  float* red = sv.scratch;                      // [PK_WARPS][kh] per-warp partial scores
+  float* sc = sv.scratch + PK_WARPS * kh;       // K floats
   const float* uv = reinterpret_cast<const float*>(sv.stages);
-  const int fpc = (K + PK_BULK_CHUNKS - 1) / PK_BULK_CHUNKS;
+  const uint32_t v_off = (uint32_t)kh * A * 4u;
+  const float* vs = reinterpret_cast<const float*>(sv.stages + v_off);            // [K][Hh]
+  constexpr int fpc = DEC_FPC;
   if (threadIdx.x == 0) {
 #pragma unroll 1
     for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-      const int k0 = c * fpc, k1 = min(K, k0 + fpc);
+      const int k0 = c * fpc, k1 = min(nk, k0 + fpc);
       if (k0 >= k1) break;
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
       pk_expect_tx(sv.bulk_bar + 8 * c, nb);
-      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + kb + k0) * A, nb, sv.bulk_bar + 8 * c);
     }
+    pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * Hh * 4u);
+    pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, jb, r * K);
   }
   float ahr[DEC_NA], wr[DEC_NA];
+  int aoff[DEC_NA];
   {
     float v[DEC_NA][PK_MAX_SLOTS];
 #pragma unroll
     for (int i = 0; i < DEC_NA; ++i) {
       const int a = min(threadIdx.x + PK_THREADS * i, A - 1);
+      aoff[i] = a;
       zload(P.d[DD_AH], P.R, r, a, v[i]);
       ahr[i] = __ldg(P.b_h2a + a);
       wr[i] = (threadIdx.x + PK_THREADS * i < A) ? __ldg(P.w_a2w + a) : 0.f;     // out-of-range units weigh 0
@@ -497,36 +580,60 @@ __device__ __noinline__ void dec_attention(const DecParams& P, int r, const Smem
 #pragma unroll
     for (int i = 0; i < DEC_NA; ++i) ahr[i] += zadd(v[i]);
   }
-  int k = 0;
+  if (threadIdx.x == 0) PK_FINE(1);
 #pragma unroll 1
   for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-    const int k1 = min(K, (c + 1) * fpc);
-    if (k >= k1) break;
+    const int k0 = c * fpc, k1 = min(nk, k0 + fpc);
+    if (k0 >= k1) break;
     pk_wait(sv.bulk_bar + 8 * c, bulk_phase & 1);
-#pragma unroll 1
-    for (; k < k1; ++k) {
-      const float* u = uv + (long)k * A;
-      float p = 0.f;
+    if (threadIdx.x == 0) PK_FINE(2 + 2 * c);
+    float p[DEC_FPC];
 #pragma unroll
-      for (int i = 0; i < DEC_NA; ++i) p += wr[i] * tanh_fast(ahr[i] + u[min(threadIdx.x + PK_THREADS * i, A - 1)]);
-      p = warp_sum(p);
-      if (lane == 0) red[warp * K + k] = p;
+    for (int f = 0; f < DEC_FPC; ++f) {
+      p[f] = 0.f;
+      const float* u = uv + (long)min(k0 + f, nk - 1) * A;
+#pragma unroll
+      for (int i = 0; i < DEC_NA; ++i) p[f] += wr[i] * tanh_fast(ahr[i] + u[aoff[i]]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int f = 0; f < DEC_FPC; ++f) p[f] += __shfl_xor_sync(0xffffffffu, p[f], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int f = 0; f < DEC_FPC; ++f) if (k0 + f < k1) red[warp * kh + k0 + f] = p[f];
+    }
+    if (threadIdx.x == 0) PK_FINE(3 + 2 * c);
   }
-  bulk_phase++;
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 0) {              // publish my scores, swap with the partner CTA
     const float ba = __ldg(P.b_a2w);
+#pragma unroll 1
+    for (int kk = lane; kk < nk; kk += 32) {
+      float q = 0.f;
+#pragma unroll
+      for (int w = 0; w < PK_WARPS; ++w) q += red[w * kh + kk];
+      __stcg(P.scores + (long)r * K + kb + kk, q + ba);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned want = (unsigned)t + 1u;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.att_flag + 2 * r + half), "r"(want) : "memory");
+      const unsigned int* other = P.att_flag + 2 * r + (half ^ 1);
+      const long long t0 = clock64();
+      while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(other) : "memory");
+        if (v >= want) break;
+        if (clock64() - t0 > 8000000000LL) __trap();
+      }
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) PK_FINE(10);
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int kk = lane; kk < K; kk += 32) {
-      float p = 0.f;
-#pragma unroll
-      for (int w = 0; w < PK_WARPS; ++w) p += red[w * K + kk];
-      p += ba;
-      sc[kk] = p;
-      mx = fmaxf(mx, p);
-    }
+    for (int kk = lane; kk < K; kk += 32) { const float q = __ldcg(P.scores + (long)r * K + kk); sc[kk] = q; mx = fmaxf(mx, q); }
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll 1
@@ -536,110 +643,119 @@ __device__ __noinline__ void dec_attention(const DecParams& P, int r, const Smem
 #pragma unroll 1
     for (int kk = lane; kk < K; kk += 32) sc[kk] *= inv;
   }
+  pk_wait(sv.bulk_bar + 8 * PK_BULK_CHUNKS, bulk_phase & 1);
+  bulk_phase++;
   __syncthreads();
+  if (threadIdx.x == 0) PK_FINE(11);
 #pragma unroll 1
-  for (int j = threadIdx.x; j < H; j += PK_THREADS) {
-    const float* v = P.Vf + (long)r * K * H + j;
+  for (int j = threadIdx.x; j < Hh; j += PK_THREADS) {
     float a = 0.f;
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      float vv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) vv[q] = __ldg(v + (long)min(k0 + q, K - 1) * H);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) a += (k0 + q < K ? sc[k0 + q] : 0.f) * vv[q];
-    }
-    store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) a += sc[k] * vs[k * Hh + j];
+    store_split(P.af_hi, P.af_lo, (long)r * H + jb + j, a);
   }
+  if (threadIdx.x == 0) PK_FINE(12);
   __syncthreads();
 }
 
 // next-step inputs of caption r for token `tokv`: xt = embed[tok] and gp = pos * (1 + tgate[tok])
+// (all loads of a thread are issued before the first store: one L2 round trip)
+constexpr int DEC_TI = 2;          // columns per thread: embed (padded) and rnn <= 2 * 320
 __device__ __noinline__ void dec_token_inputs(const DecParams& P, int r, int tokv) {
   const float* src = P.embed + (long)tokv * P.E;
-#pragma unroll 1
-  for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS)
-    store_split(P.xt_hi, P.xt_lo, (long)r * P.Ep + k, k < P.E ? __ldg(src + k) : 0.f);
   const float* tg = P.tgate + (long)tokv * P.H;
-#pragma unroll 1
-  for (int j = threadIdx.x; j < P.H; j += PK_THREADS)
-    store_split(P.gp_hi, P.gp_lo, (long)r * P.H + j, __ldg(P.pos + (long)r * P.H + j) * (1.f + __ldcg(tg + j)));
+  const float* ps = P.pos + (long)r * P.H;
+  float x[DEC_TI], g[DEC_TI], q[DEC_TI];
+#pragma unroll
+  for (int i = 0; i < DEC_TI; ++i) {
+    const int k = threadIdx.x + i * PK_THREADS;
+    x[i] = k < P.E ? __ldg(src + k) : 0.f;
+    g[i] = k < P.H ? __ldcg(tg + k) : 0.f;
+    q[i] = k < P.H ? __ldg(ps + k) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < DEC_TI; ++i) {
+    const int k = threadIdx.x + i * PK_THREADS;
+    if (k < P.Ep) store_split(P.xt_hi, P.xt_lo, (long)r * P.Ep + k, x[i]);
+    if (k < P.H) store_split(P.gp_hi, P.gp_lo, (long)r * P.H + k, q[i] * (1.f + g[i]));
+  }
 }
 
-// per (caption, block of 256 vocabulary rows): max / lowest argmax / sum-exp of the logits
-__device__ __noinline__ void dec_logit_stats(const DecParams& P, int cta, int G) {
+// greedy pick of caption r at step t on one CTA (SAModel.py:185-210): logits = sum of the split-K slots + bias,
+// staged in shared memory (the pipeline stages are idle); max / lowest argmax, then log-sum-exp; returns the
+// raw argmax token to every thread.
+constexpr int DEC_PB = 32;         // logits per thread per batch of loads
+__device__ __noinline__ int dec_pick(const DecParams& P, int r, int t, const SmemView& sv, long long* g_fine = nullptr) {
+  if (threadIdx.x == 0) PK_FINE(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int V = P.V, R = P.R;
-  const int nvb = (V + DEC_VBLOCK - 1) / DEC_VBLOCK;
   const GDesc& dl = P.d[DD_LOGIT];
   const long sstr = (long)R * dl.n_rows;
-  constexpr int NI = DEC_VBLOCK / 32;
-#pragma unroll 1
-  for (int item = cta * PK_WARPS + warp; item < P.B * nvb; item += G * PK_WARPS) {
-    const int r = item / nvb, vb = item % nvb;
-    const int n0 = vb * DEC_VBLOCK + lane;
-    float v[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) v[i] = 0.f;
-    const float* lp = dl.out + (long)r * dl.n_rows;
-#pragma unroll 1
-    for (int k = 0; k < dl.ns; ++k, lp += sstr) {        // slot-major: NI independent loads in flight per slot
-      float tl[NI];
-#pragma unroll
-      for (int i = 0; i < NI; ++i) tl[i] = __ldcg(lp + min(n0 + i * 32, V - 1));
-#pragma unroll
-      for (int i = 0; i < NI; ++i) v[i] += tl[i];
-    }
-    float best = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int n = n0 + i * 32;
-      v[i] = n < V ? v[i] + __ldg(P.b_logit + min(n, V - 1)) : -INFINITY;
-      if (v[i] > best) { best = v[i]; bi = n; }
-    }
-    const unsigned mo = __reduce_max_sync(0xffffffffu, f2ord(best));
-    const float wbest = ord2f(mo);
-    const int wbi = (int)__reduce_min_sync(0xffffffffu, (f2ord(best) == mo && best != -INFINITY) ? (unsigned)bi : 0x7fffffffu);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NI; ++i) s += __expf(v[i] - wbest);      // exp(-inf) = 0 for the padding rows
-    s = warp_sum(s);
-    if (lane == 0) *reinterpret_cast<float4*>(P.stats + ((long)vb * R + r) * 4) = make_float4(wbest, __int_as_float(wbi), s, 0.f);
-  }
-}
-
-// greedy bookkeeping of caption r at step t (SAModel.py:185-210); returns the raw argmax token
-__device__ __noinline__ int dec_pick(const DecParams& P, int r, int t) {
-  const int lane = threadIdx.x & 31;
-  const int nvb = (P.V + DEC_VBLOCK - 1) / DEC_VBLOCK;
+  float* lg = reinterpret_cast<float*>(sv.stages);            // V floats
+  float* redf = sv.scratch;                                   // [PK_WARPS]
+  int* redi = reinterpret_cast<int*>(sv.scratch + 16);        // [PK_WARPS]
+  const float* lp0 = dl.out + (long)r * dl.n_rows;
   float best = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 1
-  for (int q = lane; q < nvb; q += 32) {
-    const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * P.R + r) * 4));
-    const int vi = __float_as_int(rec.y);
-    if (rec.x > best || (rec.x == best && vi < bi)) { best = rec.x; bi = vi; }
-  }
+  for (int n0 = threadIdx.x; n0 < V; n0 += PK_THREADS * DEC_PB) {
+    float v[DEC_PB];
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) v[i] = 0.f;
+    const float* lp = lp0;
 #pragma unroll 1
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    for (int k = 0; k < dl.ns; ++k, lp += sstr) {        // slot-major: DEC_PB independent loads in flight per slot
+      float tl[DEC_PB];
+#pragma unroll
+      for (int i = 0; i < DEC_PB; ++i) tl[i] = __ldcg(lp + min(n0 + i * PK_THREADS, V - 1));
+#pragma unroll
+      for (int i = 0; i < DEC_PB; ++i) v[i] += tl[i];
+      if (threadIdx.x == 0 && v[0] != 12345.f && n0 < PK_THREADS) PK_FINE(1 + k);
+    }
+    float bl[DEC_PB];
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) bl[i] = __ldg(P.b_logit + min(n0 + i * PK_THREADS, V - 1));
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) {
+      const int n = n0 + i * PK_THREADS;
+      const float x = v[i] + bl[i];
+      if (n < V) {
+        lg[n] = x;
+        if (x > best) { best = x; bi = n; }              // ascending n per thread: first maximum kept
+      }
+    }
+  }
+  {
+    const unsigned mo = __reduce_max_sync(0xffffffffu, f2ord(best));
+    const int wbi = (int)__reduce_min_sync(0xffffffffu, (f2ord(best) == mo) ? (unsigned)bi : 0x7fffffffu);
+    if (lane == 0) { redf[warp] = ord2f(mo); redi[warp] = wbi; }
+  }
+  if (threadIdx.x == 0) PK_FINE(6);
+  __syncthreads();
+  best = redf[0]; bi = redi[0];
+#pragma unroll
+  for (int w = 1; w < PK_WARPS; ++w) {
+    const float ov = redf[w]; const int oi = redi[w];
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
   float s = 0.f;
-#pragma unroll 1
-  for (int q = lane; q < nvb; q += 32) {
-    const float4 rec = __ldcg(reinterpret_cast<const float4*>(P.stats + ((long)q * P.R + r) * 4));
-    s += rec.z * __expf(rec.x - best);
-  }
+#pragma unroll 4
+  for (int n = threadIdx.x; n < V; n += PK_THREADS) s += __expf(lg[n] - best);
   s = warp_sum(s);
-  if (lane == 0) {
+  __syncthreads();                                            // redf is reused
+  if (lane == 0) redf[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < PK_WARPS; ++w) tot += redf[w];
     float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
     unf = (unf != 0.f && bi > 0) ? 1.f : 0.f;
     P.unfinished[r] = unf;
     P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)bi : 0;
-    P.seqlogp[(long)r * P.T + t] = -logf(s);
+    P.seqlogp[(long)r * P.T + t] = -logf(tot);
     P.tok[r] = bi;
     if (unf != 0.f) P.flags[t] = 1;
+    PK_FINE(7);
   }
   return bi;
 }
@@ -670,11 +786,10 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
   }
   extern __shared__ uint8_t smem_raw[];
   const SmemView sv = carve_smem(smem_raw);
-  const int warp = threadIdx.x >> 5;
   const int H = P.H, R = P.R, B = P.B, T = P.T;
   const uint32_t tmem_base = pipeline_setup(sv);
-  if (threadIdx.x < 16) tma_prefetch_desc(&maps.m[threadIdx.x]);
-  PipeState ps{0, 0, 0};
+  if (threadIdx.x < 17) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
   unsigned int sync_target = 0;
   uint32_t bulk_phase = 0;
 
@@ -700,6 +815,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     }
     if (threadIdx.x == 0) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
   }
+  gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
 
 #pragma unroll 1
@@ -711,15 +827,18 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
-    // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (G > B) {
-      if (cta < B) dec_attention(P, cta, sv, bulk_phase);
+    // ===== P1: attention (a CTA pair per caption)  ||  lstm_1 cell (the other CTAs) =====
+    if (cta < 2 * B) {
+#ifdef PK_FINE_TRACE
+      dec_attention(P, &maps.m[16], cta >> 1, cta & 1, t, sv, bulk_phase, (P.dbg_clock && t == 3 && cta == 5) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 64 : nullptr);
+#else
+      dec_attention(P, &maps.m[16], cta >> 1, cta & 1, t, sv, bulk_phase);
+#endif
     } else {
-#pragma unroll 1
-      for (int r = cta; r < B; r += G) dec_attention(P, r, sv, bulk_phase);
+      dec_cell_phase(P, 0, t > 0, cta - 2 * B, G - 2 * B);
     }
-    if (G <= B || cta >= B) dec_cell_phase(P, 0, t > 0, G > B ? cta - B : cta, G > B ? G - B : G);
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
+    gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 4);
@@ -739,37 +858,50 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
 #endif
     pk_stamp(P.dbg_clock, cta, t, 6);
     // ===== P3: lstm_2 cell =====
+#ifdef PK_FINE_TRACE
+    {
+      long long* fine = (P.dbg_clock && t == 3 && cta == 7) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 96 : nullptr;
+      dec_cell_phase(P, 1, t > 0, cta, G, fine);
+      gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
+      if (fine && threadIdx.x == 0) fine[4] = clock64();
+      grid_barrier(P.sync_counter, sync_target, G);
+      if (fine && threadIdx.x == 0) fine[5] = clock64();
+    }
+#else
     dec_cell_phase(P, 1, t > 0, cta, G);
+    gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 7);
     grid_barrier(P.sync_counter, sync_target, G);
+#endif
     pk_stamp(P.dbg_clock, cta, t, 8);
     // ===== G4: logits (split-K partial tiles) =====
     gemm_phase(P.d, &s_sched[2], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 9);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 10);
-    // ===== P4a: logit statistics =====
-    dec_logit_stats(P, cta, G);
+    // ===== P4: greedy pick + inputs of the next step (one CTA per caption) =====
+#pragma unroll 1
+    for (int r = cta; r < B; r += G) {
+#ifdef PK_FINE_TRACE
+      long long* g_fine = (P.dbg_clock && t == 3 && cta == 9) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 112 : nullptr;
+      const int tokv = dec_pick(P, r, t, sv, g_fine);
+      dec_token_inputs(P, r, tokv);
+      __syncthreads();
+      if (threadIdx.x == 0) PK_FINE(8);
+#else
+      const int tokv = dec_pick(P, r, t, sv);
+      dec_token_inputs(P, r, tokv);
+      __syncthreads();
+#endif
+    }
+    fence_proxy_async_smem();
+    if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 11);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 12);
-    // ===== P4b: greedy bookkeeping + inputs of the next step =====
-#pragma unroll 1
-    for (int r = cta; r < B; r += G) {
-      if (warp == 0) {
-        const int bi = dec_pick(P, r, t);
-        if ((threadIdx.x & 31) == 0) reinterpret_cast<int*>(sv.scratch)[0] = bi;
-      }
-      __syncthreads();
-      const int tokv = reinterpret_cast<int*>(sv.scratch)[0];
-      dec_token_inputs(P, r, tokv);
-      __syncthreads();
-    }
-    pk_stamp(P.dbg_clock, cta, t, 13);
-    grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 14);
     if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
+  gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
   pipeline_teardown(tmem_base);
 }
 
@@ -804,7 +936,7 @@ encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant
   const int H = P.H, R = P.R, B = P.B, K = P.K;
   const uint32_t tmem_base = pipeline_setup(sv);
   if (threadIdx.x < 4) tma_prefetch_desc(&maps.m[threadIdx.x]);
-  PipeState ps{0, 0, 0};
+  PipeState ps{0, 0, 0, 0};
   unsigned int sync_target = 0;
 
   for (int e = cta * PK_THREADS + threadIdx.x; e < (R - B) * 2 * H; e += G * PK_THREADS) {   // padding rows
@@ -840,7 +972,10 @@ encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant
       P.Hs[s][o] = h;
       if (t + 1 < K) store_split(P.hh_hi, P.hh_lo, (long)b * 2 * H + s * H + j, h);
     }
-    if (t + 1 < K) grid_barrier(P.sync_counter, sync_target, G);
+    if (t + 1 < K) {
+      gemm_prefetch(P.d, &s_sched, maps.m, sv, ps);
+      grid_barrier(P.sync_counter, sync_target, G);
+    }
   }
   pipeline_teardown(tmem_base);
 }
@@ -931,9 +1066,13 @@ static inline int env_flag(const char* name) { const char* e = getenv(name); ret
 
 static bool persist_eligible(const xg_context* ctx, int B, int K) {
   const xg_dims& d = ctx->d;
-  return ctx->persist_mode && d.rnn % 32 == 0 && d.embed % 4 == 0 && d.att % 4 == 0 && B <= 64 &&
-         (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS && (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 &&
-         d.vocab < 32000 && d.att < 32000 && d.rnn <= 4096;
+  const int kh = (K + 1) / 2;
+  return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
+         d.att % 32 == 0 && B <= 64 && K >= 2 && K <= 256 &&
+         ctx->sm_count >= 2 * B + 8 && ctx->sm_count <= 256 &&
+         (PK_WARPS * kh + K) + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS && kh <= PK_BULK_CHUNKS * DEC_FPC &&
+         ((long)kh * d.att + (long)K * (d.rnn / 2)) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES &&
+         (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000 && d.rnn <= 4096;
 }
 
 // schedule of one kernel (phases laid one after the other, [phase][G]); false if a phase cannot be scheduled
@@ -962,7 +1101,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   if (!S) S = new PersistState();
   DecParams& hp = S->hp;
   const int kbH = H / 32, kbE = Ep / 32;
-  const int nvb = (V + DEC_VBLOCK - 1) / DEC_VBLOCK;
 
   // ---- products ----
   auto mk = [&](int id, int wmap, int xmap, int xkb0, int n_rows, int nkb) {
@@ -988,9 +1126,9 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
     for (int pass = 0; pass < 2; ++pass) {
       Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
       S->d_params = a.take<DecParams>(1);
-      S->d_counter = a.take<unsigned int>(64);
+      S->d_counter = a.take<unsigned int>(32 * 258 + 256);
       S->d_flags = a.take<int>(2048);
-      S->d_dbg = a.take<long long>((2048 + 256 + 8) * PK_STAMPS);
+      S->d_dbg = a.take<long long>((2048 + 256 + 16) * PK_STAMPS);
       hp.sched = a.take<PSched>(sched.size());
       for (int i = 0; i < DD_COUNT; ++i) hp.d[i].out = a.take<float>((size_t)hp.d[i].ns * R * hp.d[i].n_rows);
       hp.xt_hi = a.take<float>((long)R * Ep); hp.xt_lo = a.take<float>((long)R * Ep);
@@ -999,8 +1137,8 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       hp.af_hi = a.take<float>((long)R * H); hp.af_lo = a.take<float>((long)R * H);
       hp.hx = a.take<float>((long)R * 2 * H);
       hp.cx = a.take<float>((long)2 * R * H);
-      hp.stats = a.take<float>((long)nvb * R * 4);
       hp.unfinished = a.take<float>(R);
+      hp.scores = a.take<float>((long)R * K);
       hp.tok = a.take<int64_t>(R);
       S->tgate = a.take<float>((long)V * H);
       if (pass == 0) {
@@ -1038,6 +1176,17 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_TRY(tc_make_map(ctx, ts, hp.hh_hi, R, 2 * H, PK_BN, &maps[10])); XG_TRY(tc_make_map(ctx, ts, hp.hh_lo, R, 2 * H, PK_BN, &maps[11]));
   XG_TRY(tc_make_map(ctx, ts, hp.gp_hi, R, H, PK_BN, &maps[12])); XG_TRY(tc_make_map(ctx, ts, hp.gp_lo, R, H, PK_BN, &maps[13]));
   XG_TRY(tc_make_map(ctx, ts, hp.af_hi, R, H, PK_BN, &maps[14])); XG_TRY(tc_make_map(ctx, ts, hp.af_lo, R, H, PK_BN, &maps[15]));
+  {   // V as [B*K][H]: one box = (H/2 columns) x (K frames) of a caption, dense in shared memory
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)B * K};
+    cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)(H / 2), (cuuint32_t)K};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = ts->encode(&maps[16], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vf), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (V) failed", nullptr); return XG_ERR_CUDA; }
+    maps[17] = maps[16];
+  }
 
   hp.B = B; hp.R = R; hp.K = K; hp.H = H; hp.E = E; hp.Ep = Ep; hp.A = A; hp.V = V; hp.T = T;
   hp.b_h2a = ctx->P[XG_P_H2A_B]; hp.w_a2w = ctx->P[XG_P_A2W_W]; hp.b_a2w = ctx->P[XG_P_A2W_B];
@@ -1049,13 +1198,14 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int q = 0; q < 4; ++q) hp.state0[q] = state0[q];
   hp.seq = seq_out; hp.seqlogp = logp_out; hp.flags = S->d_flags;
   hp.sync_counter = S->d_counter;
+  hp.att_flag = S->d_counter + 32 * 258;
   hp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * 64, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
-  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256 + 8) * PK_STAMPS, st));
+  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256 + 16) * PK_STAMPS, st));
 
   if (!S->attr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
@@ -1079,11 +1229,11 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   if (hp.dbg_clock) {   // XG_PERSIST_TRACE=1: average SM cycles per phase (CTA 0), printed to stderr
     std::vector<long long> h((size_t)T * PK_STAMPS);
     cudaMemcpy(h.data(), S->d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-    const char* names[7] = {"G1 (ah,z1h,z2h,z1x,z1g)", "P1 (attention || cell1)", "G3 (z2x,z2a)", "P3 (cell2)", "G4 (logits)",
-                            "P4a (logit stats)", "P4b (pick, next inputs)"};
+    const char* names[6] = {"G1 (ah,z1h,z2h,z1x,z1g)", "P1 (attention || cell1)", "G3 (z2x,z2a)", "P3 (cell2)", "G4 (logits)",
+                            "P4 (pick, next inputs)"};
     double tot = 0;
     const int n = steps > 1 ? steps - 1 : 1;
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 6; ++i) {
       double w = 0, b = 0;
       for (int t = 1; t < std::max(steps, 2); ++t) {
         w += (double)(h[t * PK_STAMPS + 2 * i + 1] - h[t * PK_STAMPS + 2 * i]);
@@ -1106,12 +1256,23 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
         for (int i = 1; i < 28; ++i) if (f[i]) fprintf(stderr, " %s=%lld", ev[i], f[i] - f[0]);
         fprintf(stderr, "\n");
       }
+      long long f[16];
+      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 64, sizeof(f), cudaMemcpyDeviceToHost);
+      const char* ea[13] = {"entry", "ah_ready", "chunk0_in", "chunk0_done", "chunk1_in", "chunk1_done", "chunk2_in", "chunk2_done", "chunk3_in",
+                            "chunk3_done", "scores_synced", "softmax_done", "context_done"};
+      fprintf(stderr, "[xg persist trace] attention of cta 5:");
+      for (int i = 1; i < 13; ++i) fprintf(stderr, " %s=%lld", ea[i], f[i] - f[0]);
+      fprintf(stderr, "\n");
+      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 96, sizeof(f), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[xg persist trace] cell2 of cta 7: loads_done=%lld stored=%lld end=%lld barrier_in=%lld barrier_out=%lld\n", f[1] - f[0], f[2] - f[0], f[3] - f[0], f[4] - f[0], f[5] - f[0]);
+      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 112, sizeof(f), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[xg persist trace] pick of cta 9: slot0=%lld slot1=%lld slot2=%lld reduce_in=%lld booked=%lld inputs_done=%lld\n", f[1] - f[0], f[2] - f[0], f[3] - f[0], f[6] - f[0], f[7] - f[0], f[8] - f[0]);
     }
 #endif
     if (steps > 3 && G <= 256) {   // step 3, all CTAs: when does each CTA finish its share of a phase (ns after the phase opened)?
       std::vector<long long> ga((size_t)G * PK_STAMPS);
       cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
-      for (int i = 0; i < 7; ++i) {
+      for (int i = 0; i < 6; ++i) {
         long long open = 0;
         for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);   // last CTA through the previous barrier
         std::vector<long long> fin(G);
@@ -1133,7 +1294,7 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
 static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, EncBufs& eb, cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, G = ctx->sm_count;
-  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || K < 2) return PK_FALLBACK;
+  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || K < 2 || G > 256) return PK_FALLBACK;
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
   if (R / PK_BN > 32) return PK_FALLBACK;
   TcState* ts = nullptr;
@@ -1153,7 +1314,7 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
     for (int pass = 0; pass < 2; ++pass) {
       Arena a(pass == 0 ? nullptr : S->epool, pass == 0 ? 0 : S->epool_bytes);
       S->d_eparams = a.take<EncParams>(1);
-      S->d_ecounter = a.take<unsigned int>(64);
+      S->d_ecounter = a.take<unsigned int>(32 * 258);
       ep.sched = a.take<PSched>(sched.size());
       for (int s = 0; s < 2; ++s) ep.d[s].out = a.take<float>((size_t)ep.d[s].ns * R * 4 * H);
       ep.hh_hi = a.take<float>((long)R * 2 * H); ep.hh_lo = a.take<float>((long)R * 2 * H);
@@ -1172,13 +1333,13 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
   XG_TRY(tc_make_map(ctx, ts, ctx->P[XG_P_LSTM_OPFL_WHH], 4 * H, H, 128, &mt.m[1]));
   XG_TRY(tc_make_map(ctx, ts, ep.hh_hi, R, 2 * H, PK_BN, &mt.m[2]));
   XG_TRY(tc_make_map(ctx, ts, ep.hh_lo, R, 2 * H, PK_BN, &mt.m[3]));
-  for (int i = 4; i < 16; ++i) mt.m[i] = mt.m[0];
+  for (int i = 4; i < 18; ++i) mt.m[i] = mt.m[0];
   ep.B = B; ep.R = R; ep.K = K; ep.H = H;
   for (int s = 0; s < 2; ++s) { ep.Gt[s] = eb.G[s]; ep.Hs[s] = eb.Hs[s]; ep.Cs[s] = eb.Cs[s]; }
   ep.fmask = fmask;
   ep.sync_counter = S->d_ecounter;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_eparams, &ep, sizeof(EncParams), cudaMemcpyHostToDevice, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_ecounter, 0, sizeof(unsigned int) * 64, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_ecounter, 0, sizeof(unsigned int) * 32 * 258, st));
   if (!S->eattr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(encode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
     int nb = 0;
