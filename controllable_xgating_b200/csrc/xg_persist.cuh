@@ -97,6 +97,9 @@ __device__ __forceinline__ void pk_tma_2d(uint32_t dst, const CUtensorMap* tm, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void pk_tma_prefetch_l2(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void pk_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -197,8 +200,16 @@ __device__ __noinline__ void pipeline_teardown(uint32_t tmem_base) {
 #define PK_FINE(i) do { } while (0)
 #endif
 
+// lo part of the in-kernel weight split: residual of the truncation the tensor core applies to the raw word,
+// rounded to tf32 (nearest, ties away) with integer ops — cvt.rna.tf32 runs on the 16-lane conversion pipe and
+// made the split warps the slowest stage of the pipeline (1100 cycles per 16 KB tile)
+__device__ __forceinline__ float tf32_lo(float w) {
+  const float r = w - __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+  return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
+}
+
 // all work items of this CTA for one GEMM phase (sc lives in shared memory)
-__device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, const CUtensorMap* maps, int R,
+__device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, const PSched* sc_next, const CUtensorMap* maps, int R,
                                         const SmemView& sv, uint32_t tmem_base, PipeState& ps, long long* g_fine = nullptr) {
   // warp-uniform role dispatch: the broadcast makes the warp index (and every counter derived below)
   // provably uniform, so descriptors / coordinates live in uniform registers and each UTCHMMA / UTMALDG
@@ -244,6 +255,23 @@ __device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, co
           }
         }
         __syncwarp();
+      }
+    }
+    // the weight tiles of the NEXT GEMM phase go to L2 now (HBM has slack; their TMA loads then see L2 latency)
+    if (sc_next != nullptr) {
+      const int nn = __shfl_sync(0xffffffffu, (int)sc_next->n, 0);
+#pragma unroll 1
+      for (int ii = 0; ii < nn; ++ii) {
+        const PItem it = sc_next->it[ii];
+        const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, descs[it.desc].w_map, 0);
+        int wk = __shfl_sync(0xffffffffu, it.kb0 * 32, 0);
+        const int row = __shfl_sync(0xffffffffu, it.rt * 128, 0);
+        const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb, wk += 32) {
+          if (elect_one_sync()) pk_tma_prefetch_l2(mw, wk, row);
+          __syncwarp();
+        }
       }
     }
   } else if (warp == 1) {     // ===== MMA issuer (same discipline) =====
@@ -361,10 +389,7 @@ __device__ __noinline__ void gemm_phase(const GDesc* descs, const PSched* sc, co
       for (int q = 0; q < 8; ++q) {
         const float4 v = src[128 * q];
         float4 l;
-        l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-        l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-        l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-        l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+        l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
         dst[128 * q] = l;
       }
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
@@ -483,8 +508,6 @@ struct DecParams {
   float *hx;                    // [R][2H] exact states
   float *cx;                    // [2][R][H]
   float *unfinished;            // [R]
-  float *scores;                // [R][K] attention scores of the current step (exchanged inside a CTA pair)
-  unsigned int* att_flag;       // [2R] step stamps of the pair exchange
   int64_t *tok;                 // [R]
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
@@ -533,37 +556,38 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int u
   if (threadIdx.x == 0) PK_FINE(3);
 }
 
-// temporal attention of caption r on a PAIR of CTAs (sub_modules.py:677-680); the 43k tanh of a caption are
-// MUFU-bound on one SM, so the frames are halved: CTA (r, half) bulk-copies its frames of Uv[r] and its
-// half of the columns of V[r] into the (idle) pipeline stages, computes the scores of its frames (every
-// thread owns the attention units a = tid + 320 i, the frames of a chunk run with independent accumulators),
-// publishes them, exchanges with its partner through a release/acquire flag, and then both CTAs take the
-// softmax over ALL K frames and each produces its half of the context vector.
-constexpr int DEC_FPC = 8;         // frames per Uv chunk (frames per CTA <= 32)
-__device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, int half, int t, const SmemView& sv,
+// temporal attention of caption r on one CTA (sub_modules.py:677-680).  Uv[r] arrives in 8-frame chunks by bulk
+// copies into the (idle) pipeline stages; every thread owns the attention units a = tid + 320 i (ah[a], w[a]
+// in registers) and runs the frames of a chunk with independent accumulators (their warp reductions
+// interleave); frame scores are reduced warp -> CTA in a fixed order; softmax over ALL K frames; V[r] is
+// fetched by TMA (two H/2-column panels) behind Uv when both fit, else over the first two consumed chunks.
+// (A CTA pair per caption was tried: the score exchange costs what halving the frames saves.)
+constexpr int DEC_FPC = 8;         // frames per Uv chunk (K <= 32)
+__device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, const SmemView& sv,
                                            uint32_t& bulk_phase, long long* g_fine = nullptr) {
   if (threadIdx.x == 0) PK_FINE(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int K = P.K, A = P.A, H = P.H;
-  const int kh = (K + 1) / 2, kb = half * kh, nk = max(0, min(K, kb + kh) - kb);   // my frames [kb, kb + nk)
-  const int Hh = H / 2, jb = half * Hh;                                            // my context columns [jb, jb + Hh)
-  float* red = sv.scratch;                      // [PK_WARPS][kh] per-warp partial scores
-  float* sc = sv.scratch + PK_WARPS * kh;       // K floats
+  const int K = P.K, A = P.A, H = P.H, Hh = H / 2;
+  float* red = sv.scratch;                      // [PK_WARPS][K] per-warp partial scores
+  float* sc = sv.scratch + PK_WARPS * K;        // K floats
   const float* uv = reinterpret_cast<const float*>(sv.stages);
-  const uint32_t v_off = (uint32_t)kh * A * 4u;
-  const float* vs = reinterpret_cast<const float*>(sv.stages + v_off);            // [K][Hh]
   constexpr int fpc = DEC_FPC;
+  const bool v_behind = (long)K * (A + H) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
+  const uint32_t v_off = v_behind ? (uint32_t)K * A * 4u : 0u;
   if (threadIdx.x == 0) {
 #pragma unroll 1
     for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-      const int k0 = c * fpc, k1 = min(nk, k0 + fpc);
+      const int k0 = c * fpc, k1 = min(K, k0 + fpc);
       if (k0 >= k1) break;
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
       pk_expect_tx(sv.bulk_bar + 8 * c, nb);
-      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + kb + k0) * A, nb, sv.bulk_bar + 8 * c);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
     }
-    pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * Hh * 4u);
-    pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, jb, r * K);
+    if (v_behind) {
+      pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
+      pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, r * K);
+      pk_tma_2d(sv.stages_u32 + v_off + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, r * K);
+    }
   }
   float ahr[DEC_NA], wr[DEC_NA];
   int aoff[DEC_NA];
@@ -583,7 +607,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   if (threadIdx.x == 0) PK_FINE(1);
 #pragma unroll 1
   for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-    const int k0 = c * fpc, k1 = min(nk, k0 + fpc);
+    const int k0 = c * fpc, k1 = min(K, k0 + fpc);
     if (k0 >= k1) break;
     pk_wait(sv.bulk_bar + 8 * c, bulk_phase & 1);
     if (threadIdx.x == 0) PK_FINE(2 + 2 * c);
@@ -591,7 +615,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
 #pragma unroll
     for (int f = 0; f < DEC_FPC; ++f) {
       p[f] = 0.f;
-      const float* u = uv + (long)min(k0 + f, nk - 1) * A;
+      const float* u = uv + (long)min(k0 + f, K - 1) * A;
 #pragma unroll
       for (int i = 0; i < DEC_NA; ++i) p[f] += wr[i] * tanh_fast(ahr[i] + u[aoff[i]]);
     }
@@ -602,38 +626,33 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     }
     if (lane == 0) {
 #pragma unroll
-      for (int f = 0; f < DEC_FPC; ++f) if (k0 + f < k1) red[warp * kh + k0 + f] = p[f];
+      for (int f = 0; f < DEC_FPC; ++f) if (k0 + f < k1) red[warp * K + k0 + f] = p[f];
     }
     if (threadIdx.x == 0) PK_FINE(3 + 2 * c);
-  }
-  __syncthreads();
-  if (warp == 0) {              // publish my scores, swap with the partner CTA
-    const float ba = __ldg(P.b_a2w);
-#pragma unroll 1
-    for (int kk = lane; kk < nk; kk += 32) {
-      float q = 0.f;
-#pragma unroll
-      for (int w = 0; w < PK_WARPS; ++w) q += red[w * kh + kk];
-      __stcg(P.scores + (long)r * K + kb + kk, q + ba);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const unsigned want = (unsigned)t + 1u;
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.att_flag + 2 * r + half), "r"(want) : "memory");
-      const unsigned int* other = P.att_flag + 2 * r + (half ^ 1);
-      const long long t0 = clock64();
-      while (true) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(other) : "memory");
-        if (v >= want) break;
-        if (clock64() - t0 > 8000000000LL) __trap();
+    if (!v_behind && (c == 1 || k1 == K)) {   // the first chunks are consumed by every warp: V[r] goes over them
+      __syncthreads();
+      if (threadIdx.x == 0 && (c == 1 || (c == 0 && k1 == K))) {
+        fence_proxy_async_smem();
+        pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
+        pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, r * K);
+        pk_tma_2d(sv.stages_u32 + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, r * K);
       }
     }
-    __syncwarp();
-    if (threadIdx.x == 0) PK_FINE(10);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) PK_FINE(10);
+  if (warp == 0) {
+    const float ba = __ldg(P.b_a2w);
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int kk = lane; kk < K; kk += 32) { const float q = __ldcg(P.scores + (long)r * K + kk); sc[kk] = q; mx = fmaxf(mx, q); }
+    for (int kk = lane; kk < K; kk += 32) {
+      float q = 0.f;
+#pragma unroll
+      for (int w = 0; w < PK_WARPS; ++w) q += red[w * K + kk];
+      q += ba;
+      sc[kk] = q;
+      mx = fmaxf(mx, q);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll 1
@@ -647,12 +666,14 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   bulk_phase++;
   __syncthreads();
   if (threadIdx.x == 0) PK_FINE(11);
+  const float* vs = reinterpret_cast<const float*>(sv.stages + v_off);            // two panels [K][Hh]
 #pragma unroll 1
-  for (int j = threadIdx.x; j < Hh; j += PK_THREADS) {
+  for (int j = threadIdx.x; j < H; j += PK_THREADS) {
+    const float* vp = vs + (j >= Hh ? K * Hh + (j - Hh) : j);
     float a = 0.f;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) a += sc[k] * vs[k * Hh + j];
-    store_split(P.af_hi, P.af_lo, (long)r * H + jb + j, a);
+    for (int k = 0; k < K; ++k) a += sc[k] * vp[k * Hh];
+    store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
   if (threadIdx.x == 0) PK_FINE(12);
   __syncthreads();
@@ -823,19 +844,19 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     pk_stamp(P.dbg_clock, cta, t, 0);
     // ===== G1: everything that needs only the previous state and the current token =====
     //   AH = W_h2a.[h1|h2]   Z1h = W_h2h1.h1   Z2h = W_h2h2.h2   Z1x = W_i2h1.xt   Z1g = W_a2h1.gp
-    gemm_phase(P.d, &s_sched[0], maps.m, R, sv, tmem_base, ps);
+    gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
-    // ===== P1: attention (a CTA pair per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (cta < 2 * B) {
+    // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
+    if (cta < B) {
 #ifdef PK_FINE_TRACE
-      dec_attention(P, &maps.m[16], cta >> 1, cta & 1, t, sv, bulk_phase, (P.dbg_clock && t == 3 && cta == 5) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 64 : nullptr);
+      dec_attention(P, &maps.m[16], cta, sv, bulk_phase, (P.dbg_clock && t == 3 && cta == 5) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 64 : nullptr);
 #else
-      dec_attention(P, &maps.m[16], cta >> 1, cta & 1, t, sv, bulk_phase);
+      dec_attention(P, &maps.m[16], cta, sv, bulk_phase);
 #endif
     } else {
-      dec_cell_phase(P, 0, t > 0, cta - 2 * B, G - 2 * B);
+      dec_cell_phase(P, 0, t > 0, cta - B, G - B);
     }
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
@@ -846,13 +867,13 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
 #ifdef PK_FINE_TRACE
     {
       long long* fine = (P.dbg_clock && t == 3 && (cta == 0 || cta == 100)) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + (cta ? 32 : 0) : nullptr;
-      gemm_phase(P.d, &s_sched[1], maps.m, R, sv, tmem_base, ps, fine);
+      gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps, fine);
       if (fine && threadIdx.x == 0) fine[26] = clock64();
       grid_barrier(P.sync_counter, sync_target, G);
       if (fine && threadIdx.x == 0) fine[27] = clock64();
     }
 #else
-    gemm_phase(P.d, &s_sched[1], maps.m, R, sv, tmem_base, ps);
+    gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
 #endif
@@ -875,7 +896,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
 #endif
     pk_stamp(P.dbg_clock, cta, t, 8);
     // ===== G4: logits (split-K partial tiles) =====
-    gemm_phase(P.d, &s_sched[2], maps.m, R, sv, tmem_base, ps);
+    gemm_phase(P.d, &s_sched[2], &s_sched[0], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 9);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 10);
@@ -945,7 +966,7 @@ encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant
 #pragma unroll 1
   for (int t = 0; t < K; ++t) {
     if (t > 0) {
-      gemm_phase(P.d, &s_sched, maps.m, R, sv, tmem_base, ps);
+      gemm_phase(P.d, &s_sched, nullptr, maps.m, R, sv, tmem_base, ps);
       grid_barrier(P.sync_counter, sync_target, G);
     }
 #pragma unroll 1
@@ -1066,13 +1087,13 @@ static inline int env_flag(const char* name) { const char* e = getenv(name); ret
 
 static bool persist_eligible(const xg_context* ctx, int B, int K) {
   const xg_dims& d = ctx->d;
-  const int kh = (K + 1) / 2;
+  const bool v_behind = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
+  const bool v_over = (long)K * d.rnn <= (long)std::min(K, 2 * DEC_FPC) * d.att;
   return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
-         d.att % 32 == 0 && B <= 64 && K >= 2 && K <= 256 &&
-         ctx->sm_count >= 2 * B + 8 && ctx->sm_count <= 256 &&
-         (PK_WARPS * kh + K) + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS && kh <= PK_BULK_CHUNKS * DEC_FPC &&
-         ((long)kh * d.att + (long)K * (d.rnn / 2)) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES &&
-         (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000 && d.rnn <= 4096;
+         d.att % 32 == 0 && B <= 64 && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= B + 8 &&
+         (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS &&
+         (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && (v_behind || v_over) &&
+         (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000;
 }
 
 // schedule of one kernel (phases laid one after the other, [phase][G]); false if a phase cannot be scheduled
@@ -1138,7 +1159,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       hp.hx = a.take<float>((long)R * 2 * H);
       hp.cx = a.take<float>((long)2 * R * H);
       hp.unfinished = a.take<float>(R);
-      hp.scores = a.take<float>((long)R * K);
       hp.tok = a.take<int64_t>(R);
       S->tgate = a.take<float>((long)V * H);
       if (pass == 0) {
@@ -1198,7 +1218,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int q = 0; q < 4; ++q) hp.state0[q] = state0[q];
   hp.seq = seq_out; hp.seqlogp = logp_out; hp.flags = S->d_flags;
   hp.sync_counter = S->d_counter;
-  hp.att_flag = S->d_counter + 32 * 258;
   hp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
