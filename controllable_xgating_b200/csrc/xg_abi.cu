@@ -131,10 +131,10 @@ int xg_create(const xg_dims* dims, int device, xg_handle* out) {
     return fail(nullptr, XG_ERR_CUDA, "xg_create: cannot allocate staging words");
   }
   ctx->splitk.ws_floats = (size_t)320 * 64 * 64;   // 296 CTAs x one 64x64 partial tile (5 MB)
-  ctx->splitk.ctr_count = 128;
+  ctx->splitk.ctr_count = 128;     // + 128 completion counters of the skinny kernel
   if (cudaMalloc(&ctx->splitk.ws, sizeof(float) * ctx->splitk.ws_floats) != cudaSuccess ||
-      cudaMalloc(&ctx->splitk.ctr, sizeof(unsigned int) * ctx->splitk.ctr_count) != cudaSuccess ||
-      cudaMemset(ctx->splitk.ctr, 0, sizeof(unsigned int) * ctx->splitk.ctr_count) != cudaSuccess) {
+      cudaMalloc(&ctx->splitk.ctr, sizeof(unsigned int) * 2 * ctx->splitk.ctr_count) != cudaSuccess ||
+      cudaMemset(ctx->splitk.ctr, 0, sizeof(unsigned int) * 2 * ctx->splitk.ctr_count) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, XG_ERR_CUDA, "xg_create: cannot allocate split-K scratch");
   }
@@ -523,8 +523,8 @@ int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float*
   if (engine == 3 && !dbg_sk.ws) {
     dbg_sk.ws_floats = (size_t)320 * 64 * 64; dbg_sk.ctr_count = 128;
     if (cudaMalloc(&dbg_sk.ws, sizeof(float) * dbg_sk.ws_floats) != cudaSuccess ||
-        cudaMalloc(&dbg_sk.ctr, sizeof(unsigned int) * dbg_sk.ctr_count) != cudaSuccess ||
-        cudaMemset(dbg_sk.ctr, 0, sizeof(unsigned int) * dbg_sk.ctr_count) != cudaSuccess)
+        cudaMalloc(&dbg_sk.ctr, sizeof(unsigned int) * 2 * dbg_sk.ctr_count) != cudaSuccess ||
+        cudaMemset(dbg_sk.ctr, 0, sizeof(unsigned int) * 2 * dbg_sk.ctr_count) != cudaSuccess)
       return fail(nullptr, XG_ERR_CUDA, "xg_debug_gemm: cannot allocate split-K scratch");
   }
   int s = gemm_simt(es, p, (cudaStream_t)stream, engine == 3 ? &dbg_sk : nullptr);

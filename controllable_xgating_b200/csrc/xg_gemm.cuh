@@ -226,12 +226,16 @@ gemm_simt_kernel(const GemmP p) {
       for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
     const long zstride = (long)gridDim.x * gridDim.y * (BM * BN);
     const float* base = p.ws + tile * (BM * BN);
-    for (int z = 0; z < p.ksplit; ++z) {
-      float v[TM * TN];
+    for (int z0 = 0; z0 < p.ksplit; z0 += 2) {     // two splits' loads in flight, added in split order
+      float v[2][TM * TN];
 #pragma unroll
-      for (int e = 0; e < TM * TN; ++e) v[e] = __ldcg(base + (long)z * zstride + e * NT + tid);
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int e = 0; e < TM * TN; ++e) acc[e / TN][e % TN] += v[e];
+        for (int e = 0; e < TM * TN; ++e) v[q][e] = (z0 + q < p.ksplit) ? __ldcg(base + (long)(z0 + q) * zstride + e * NT + tid) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < TM * TN; ++e) acc[e / TN][e % TN] += v[q][e];
     }
   }
 
@@ -247,6 +251,179 @@ gemm_simt_kernel(const GemmP p) {
       epilogue_store(p, i, j, acc[m][n]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// Skinny split-K kernel (M = batch rows, long K): the whole K-chunk of both operand tiles is fetched in
+// ONE shot with 16-byte cp.async (zero-filled past the edges), so a CTA pays one memory round trip instead
+// of one per k-tile (the tiled kernel above measured 29-34 us on 64x512x2048, all of it load latency).
+//   A: (M,K) K-contiguous.   B_KMAJOR: B is (N,K) K-contiguous [y = x W^T];  else B is (K,N) N-contiguous
+//   [dx = dy W].  Thread (tx, ty) of 16x16 owns rows ty + 16a and columns tx + 16b (K-major B, conflict-free
+//   float4 reads along k) or 4tx + b (N-major B, one float4 per k).  Split-K publish / fixed-order reduce as above.
+// ------------------------------------------------------------------------------------
+constexpr int SK_KC = 128;                       // max K-chunk per CTA
+constexpr int SK_PA = SK_KC + 4;                 // A / K-major B row pitch (floats): 33 x 16 B -> conflict-free
+constexpr int SK_PB = 64 + 4;                    // N-major B row pitch
+constexpr int SK_SMEM = (64 * SK_PA + (64 * SK_PA > SK_KC * SK_PB ? 64 * SK_PA : SK_KC * SK_PB)) * 4;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <bool B_KMAJOR>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmP p) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* As = sk_smem;                 // [64][SK_PA]
+  float* Bs = sk_smem + 64 * SK_PA;    // K-major: [64][SK_PA]   N-major: [SK_KC][SK_PB]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kbeg = blockIdx.z * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
+  const int kc = kend - kbeg;                       // <= SK_KC, multiple of 4 except possibly at the very end of K
+  const int kc4 = (kc + 3) >> 2;
+  // ---- one-shot fetch ----
+  for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {          // A: 64 rows x 32 chunks of 4 floats
+    const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
+    const int gi = m0 + row, gk = kbeg + c4 * 4;
+    int nb = (gi < p.M && gk < kend) ? min(16, (kend - gk) * 4) : 0;
+    const float* src = nb ? p.A + (long)gi * p.sa_i + gk : p.A;
+    if (c4 < kc4) cp_async16(As + row * SK_PA + c4 * 4, src, nb);
+  }
+  if (B_KMAJOR) {
+    for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {
+      const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
+      const int gj = n0 + row, gk = kbeg + c4 * 4;
+      int nb = (gj < p.N && gk < kend) ? min(16, (kend - gk) * 4) : 0;
+      const float* src = nb ? p.B + (long)gj * p.sb_j + gk : p.B;
+      if (c4 < kc4) cp_async16(Bs + row * SK_PA + c4 * 4, src, nb);
+    }
+  } else {
+    for (int e = tid; e < SK_KC * 16; e += 256) {               // B: kc rows x 16 chunks of 4 columns
+      const int kr = e >> 4, c4 = e & 15;
+      const int gk = kbeg + kr, gj = n0 + c4 * 4;
+      int nb = (gk < kend && gj < p.N) ? min(16, (p.N - gj) * 4) : 0;
+      const float* src = nb ? p.B + (long)gk * p.sb_r + gj : p.B;
+      if (kr < kc4 * 4) cp_async16(Bs + kr * SK_PB + c4 * 4, src, nb);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+  for (int k4 = 0; k4 < kc4; ++k4) {
+    float4 av[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(As + (ty + 16 * a) * SK_PA + k4 * 4);
+    if (B_KMAJOR) {
+      float4 bv[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(Bs + (tx + 16 * b) * SK_PA + k4 * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]); acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]); acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+        }
+    } else {
+      float4 bk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bk[q] = *reinterpret_cast<const float4*>(Bs + (k4 * 4 + q) * SK_PB + tx * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float ak[4] = {av[a].x, av[a].y, av[a].z, av[a].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[a][0] = fmaf(ak[q], bk[q].x, acc[a][0]); acc[a][1] = fmaf(ak[q], bk[q].y, acc[a][1]);
+          acc[a][2] = fmaf(ak[q], bk[q].z, acc[a][2]); acc[a][3] = fmaf(ak[q], bk[q].w, acc[a][3]);
+        }
+      }
+    }
+  }
+
+  // ---- split-K: publish the partial tile, wait until all S splits of the tile are published (the whole grid is
+  //      co-resident: <= 2 CTAs per SM), then EVERY split CTA reduces its 1/S slice of the tile in split order
+  //      and runs the epilogue on it — a single last-arriver reducing the whole tile cost a 20k-cycle tail ----
+  if (p.ksplit > 1) {
+    const int S = p.ksplit;
+    const long tile = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    const long zstride = (long)gridDim.x * gridDim.y * 4096;
+    float* mine = p.ws + (long)blockIdx.z * zstride + tile * 4096;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) __stcg(mine + e * 256 + tid, acc[e >> 2][e & 3]);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(p.ctr + tile, 1u);
+      const long long t0 = clock64();
+      while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ctr + tile) : "memory");
+        if (v >= (unsigned)S) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __syncthreads();
+    const float* base = p.ws + tile * 4096;
+    for (int q = blockIdx.z * 256 + tid; q < 4096; q += S * 256) {
+      float v[32];
+#pragma unroll
+      for (int z = 0; z < 32; ++z) v[z] = z < S ? __ldcg(base + (long)z * zstride + q) : 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int z = 0; z < 32; ++z) sum += v[z];
+      const int e = q >> 8, t = q & 255, ea = e >> 2, eb = e & 3, qx = t & 15, qy = t >> 4;
+      const int i = m0 + qy + 16 * ea;
+      const int j = n0 + (B_KMAJOR ? qx + 16 * eb : qx * 4 + eb);
+      if (i < p.M && j < p.N) epilogue_store(p, i, j, sum);
+    }
+    __syncthreads();
+    if (tid == 0) {                                   // the last CTA to finish re-arms the tile's counters
+      const unsigned prev = atomicAdd(p.ctr + 128 + tile, 1u);
+      if (prev == (unsigned)S - 1u) { p.ctr[128 + tile] = 0u; __threadfence(); p.ctr[tile] = 0u; }
+    }
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = m0 + ty + 16 * a;
+    if (i >= p.M) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = n0 + (B_KMAJOR ? tx + 16 * b : tx * 4 + b);
+      if (j < p.N) epilogue_store(p, i, j, acc[a][b]);
+    }
+  }
+}
+
+static inline bool skinny_ok(const GemmP& p) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (p.sa_r != 1 || (p.sa_i & 3) || !al16(p.A) || !al16(p.B)) return false;
+  if (p.sb_r == 1) return (p.sb_j & 3) == 0;            // K-major B
+  if (p.sb_j == 1) return (p.sb_r & 3) == 0;            // N-major B
+  return false;
+}
+
+static int gemm_skinny_launch(ErrorSink& es, const GemmP& p, cudaStream_t st) {
+  static bool attr[2] = {false, false};
+  const bool kmaj = (p.sb_r == 1);
+  if (!attr[kmaj]) {
+    cudaError_t e = kmaj ? cudaFuncSetAttribute(gemm_skinny_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM)
+                         : cudaFuncSetAttribute(gemm_skinny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
+    if (e != cudaSuccess) { es.set(__FILE__, __LINE__, "cudaFuncSetAttribute(gemm_skinny)", cudaGetErrorString(e)); return XG_ERR_CUDA; }
+    attr[kmaj] = true;
+  }
+  dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), p.ksplit > 1 ? p.ksplit : 1);
+  if (kmaj) gemm_skinny_kernel<true><<<grid, 256, SK_SMEM, st>>>(p);
+  else gemm_skinny_kernel<false><<<grid, 256, SK_SMEM, st>>>(p);
+  XG_LAUNCH_CHECK(es);
+  return XG_OK;
 }
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -275,10 +452,18 @@ static int gemm_simt(ErrorSink& es, const GemmP& p_in, cudaStream_t st, const Sp
     if (S > 16) S = 16;
     if (S > p.K / 64) S = p.K / 64;
     if (S >= 2) {
-      const int kchunk = ceil_div(ceil_div(p.K, S), 32) * 32;
+      int kchunk = ceil_div(ceil_div(p.K, S), 32) * 32;
       S = ceil_div(p.K, kchunk);
       if (S >= 2 && med <= sk->ctr_count && (size_t)med * S * 64 * 64 <= sk->ws_floats) {
         p.ksplit = S; p.kchunk = kchunk; p.ws = sk->ws; p.ctr = sk->ctr;
+        if (skinny_ok(p) && med <= 128) {
+          if (kchunk > SK_KC) {                       // one-shot fetch holds at most SK_KC of K per CTA
+            kchunk = SK_KC; S = ceil_div(p.K, kchunk);
+            if ((size_t)med * S * 64 * 64 > sk->ws_floats || S > 32 || med * S > 296) return gemm_launch_cfg<64, 64, 32, 4, 4>(es, p, st);
+            p.ksplit = S; p.kchunk = kchunk;
+          }
+          return gemm_skinny_launch(es, p, st);
+        }
         return gemm_launch_cfg<64, 64, 32, 4, 4>(es, p, st);
       }
     }
