@@ -151,7 +151,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     gd.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gd, st));
     // (e) attention backward
-    XG_TRY(launch(ctx, "att_bwd", att_bwd_kernel, B, 256, att_smem, st, W.dAF, S.AH + (long)i * B * A, S.Uv, S.V, P_(ctx, XG_P_A2W_W),
+    XG_TRY(launch(ctx, "att_bwd", att_bwd_kernel, dim3(B, ATT_BWD_SPLITS), 256, att_smem, st, W.dAF, S.AH + (long)i * B * A, S.Uv, S.V, P_(ctx, XG_P_A2W_W),
                                             S.ALPHA + (long)i * B * K, K, A, H, W.dV, W.dUv,
                                             W.DAH + (long)i * B * A, W.dwa_part, W.dba_part));
     // (f) lstm_1 cell backward on dh1_new

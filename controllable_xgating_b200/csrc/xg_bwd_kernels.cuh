@@ -80,54 +80,86 @@ __global__ void dec_cell_bwd_kernel(float* __restrict__ G, const float* __restri
 //   dpre[k,a] = ds_k * wa[a] * (1 - tanh^2(AH[a] + Uv[k,a])) ; dUv += dpre ; dAH[a] = sum_k dpre ;
 //   dwa_part[b,a] += sum_k ds_k * tanh(.) ; dba_part[b] += sum_k ds_k
 // dynamic smem: A + 2K + H floats.
+constexpr int ATT_BWD_SPLITS = 4;
 __global__ void att_bwd_kernel(const float* __restrict__ dAF, const float* __restrict__ AH,
                                const float* __restrict__ Uv, const float* __restrict__ V,
                                const float* __restrict__ wa, const float* __restrict__ alpha,
                                int K, int A, int H, float* __restrict__ dV, float* __restrict__ dUv,
                                float* __restrict__ dAH, float* __restrict__ dwa_part, float* __restrict__ dba_part) {
+  // grid (B, S): every CTA of a caption recomputes the K softmax-gradient terms (K dot products with V[b],
+  // cheap), then takes 1/S of the frames for the dV update and 1/S of the attention units for the
+  // dUv / dAH / dwa terms.  Loads are batched ahead of their first use (was 75 us per launch on 64 CTAs).
   extern __shared__ float sm[];
-  float* ah = sm;            // A
-  float* al = ah + A;        // K
+  float* al = sm;            // K
   float* ds = al + K;        // K
   float* daf = ds + K;       // H
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, sp = blockIdx.y, S = gridDim.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int a = threadIdx.x; a < A; a += blockDim.x) ah[a] = AH[(long)b * A + a];
   for (int k = threadIdx.x; k < K; k += blockDim.x) al[k] = alpha[(long)b * K + k];
   for (int j = threadIdx.x; j < H; j += blockDim.x) daf[j] = dAF[(long)b * H + j];
   __syncthreads();
   for (int k = warp; k < K; k += nwarp) {
     const float* v = V + ((long)b * K + k) * H;
     float p = 0.f;
-    for (int j = lane; j < H; j += 32) p += daf[j] * v[j];
+    for (int j0 = lane; j0 < H; j0 += 32 * 8) {
+      float vv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) vv[q] = __ldg(v + min(j0 + 32 * q, H - 1));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p += (j0 + 32 * q < H ? daf[min(j0 + 32 * q, H - 1)] : 0.f) * vv[q];
+    }
     p = warp_sum(p);
     if (lane == 0) ds[k] = p;   // dal_k for now
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < K * H; e += blockDim.x) {
-    const int k = e / H, j = e % H;
-    dV[((long)b * K + k) * H + j] += al[k] * daf[j];
+  {   // dV[b, k, :] += alpha_k * dAF[b, :]   for this CTA's frames
+    const int kper = (K + S - 1) / S, kb0 = sp * kper, kb1 = min(K, kb0 + kper);
+    const int n = max(0, kb1 - kb0) * H;
+    float* dv = dV + ((long)b * K + kb0) * H;
+    for (int e0 = threadIdx.x; e0 < n; e0 += blockDim.x * 8) {
+      float old[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) old[q] = dv[min(e0 + (int)blockDim.x * q, n - 1)];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + (int)blockDim.x * q;
+        if (e < n) dv[e] = old[q] + al[kb0 + e / H] * daf[e % H];
+      }
+    }
   }
   float dot = 0.f;
   for (int k = 0; k < K; ++k) dot += al[k] * ds[k];   // every thread computes the same fixed-order sum
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x) ds[k] = al[k] * (ds[k] - dot);
   __syncthreads();
-  for (int a = threadIdx.x; a < A; a += blockDim.x) {
-    const float w = wa[a], h0 = ah[a];
+  const int aper = (A + S - 1) / S, a0 = sp * aper, a1 = min(A, a0 + aper);
+  for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    const float w = wa[a], h0 = AH[(long)b * A + a];
     float acc_ah = 0.f, acc_wa = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const long idx = ((long)b * K + k) * A + a;
-      const float th = tanhf(h0 + Uv[idx]);
-      const float dp = ds[k] * w * (1.f - th * th);
-      dUv[idx] += dp;
-      acc_ah += dp;
-      acc_wa += ds[k] * th;
+    const long base = (long)b * K * A + a;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float uu[8], dd[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long idx = base + (long)min(k0 + q, K - 1) * A;
+        uu[q] = __ldg(Uv + idx);
+        dd[q] = dUv[idx];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (k0 + q < K) {
+          const float th = tanhf(h0 + uu[q]);
+          const float dp = ds[k0 + q] * w * (1.f - th * th);
+          dUv[base + (long)(k0 + q) * A] = dd[q] + dp;
+          acc_ah += dp;
+          acc_wa += ds[k0 + q] * th;
+        }
+      }
     }
     dAH[(long)b * A + a] = acc_ah;
     dwa_part[(long)b * A + a] += acc_wa;
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && sp == 0) {
     float s = 0.f;
     for (int k = 0; k < K; ++k) s += ds[k];
     dba_part[b] += s;
