@@ -314,7 +314,7 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     Uv = g.Uv;
   }
   if (sample_max && persist_eligible(h, B, K)) {   // fused persistent word loop (xg_persist.cuh)
-    const int ps = persist_greedy(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
+    const int ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
     if (ps != PK_FALLBACK) return ps;
   }
   for (int q = 0; q < 4; ++q)

@@ -246,7 +246,18 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     ga.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, ga, st));
   }
-  for (int i = 0; i < Lp; ++i) {
+  // the word loop: one persistent cooperative kernel for all L' steps when the shape allows it (xg_persist.cuh)
+  int pst = PK_FALLBACK;
+  if (persist_eligible(ctx, B, K) && Lp >= 1) {
+    PersistTrainIO io;
+    io.seq_mask = seq_mask; io.L = L;
+    io.G1 = S.G1; io.G2 = S.G2; io.C1 = S.C1; io.C2 = S.C2; io.H12 = S.H12; io.AH = S.AH; io.ALPHA = S.ALPHA; io.AF = S.AF;
+    io.drop1 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1);
+    io.drop2 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2);
+    pst = persist_decode(ctx, S.V, S.Uv, pos, nullptr, B, K, Lp, nullptr, nullptr, nullptr, &io, st);
+    if (pst != PK_FALLBACK) XG_TRY(pst);
+  }
+  for (int i = 0; i < Lp && pst == PK_FALLBACK; ++i) {
     const float* h12p = S.H12 + (long)i * B * 2 * H;
     float* h12n = S.H12 + (long)(i + 1) * B * 2 * H;
     float* AHi = S.AH + (long)i * B * A;

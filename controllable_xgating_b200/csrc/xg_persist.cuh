@@ -512,44 +512,76 @@ struct DecParams {
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
   long long* dbg_clock;         // diagnostics, or NULL
+  // mode 1: teacher-forced training forward (SAModel.forward, SAModel.py:88-111) — no logit / pick phases; the
+  // input parts of lstm_1 are hoisted (G1s holds them + all three biases on entry); every activation the
+  // hand-written backward needs is stored in the step-major layouts of TrainSaved
+  int mode, L;
+  const float* seq_mask;        // (B, L)
+  float *G1s, *G2s;             // (T, B, 4H)   pre-activations -> activated gates (i,f,o,g)
+  float *C1s, *C2s;             // (T+1, B, H)
+  float *H12s;                  // (T+1, B, 2H) [h1 | h2] entering each step (after dropout)
+  float *AHs, *ALPHAs, *AFs;    // (T,B,A), (T,B,K), (T,B,H)
+  DropSpec drop1, drop2;        // dropout on the carried h of lstm_1 / lstm_2 (index = t*B*H + b*H + j)
 };
 
 constexpr int DEC_NA = 5;          // attention units per thread: att <= 5 * 320
 
 // lstm cell (decoder gate order i,f,o,g), elements (r, j) with j fastest
-__device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int use_mask, int part, int nparts, long long* g_fine = nullptr) {
+__device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int t, int part, int nparts, long long* g_fine = nullptr) {
   if (threadIdx.x == 0) PK_FINE(0);
-  const int H = P.H, R = P.R;
+  const int H = P.H, R = P.R, B = P.B;
+  const int train = P.mode;
   const GDesc& da = P.d[layer == 0 ? DD_Z1X : DD_Z2X];
   const GDesc& db = P.d[layer == 0 ? DD_Z1G : DD_Z2A];
   const GDesc& dc = P.d[layer == 0 ? DD_Z1H : DD_Z2H];
   const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
   float* cst = P.cx + (long)layer * R * H;
+  const bool hoisted = train && layer == 0;      // lstm_1 in training: x / gp parts + biases already sit in G1s
 #pragma unroll 1
-  for (int e = part * PK_THREADS + threadIdx.x; e < P.B * H; e += nparts * PK_THREADS) {
+  for (int e = part * PK_THREADS + threadIdx.x; e < B * H; e += nparts * PK_THREADS) {
     const int r = e / H, j = e % H;
     float va[4][PK_MAX_SLOTS], vb[4][PK_MAX_SLOTS], vc[4][PK_MAX_SLOTS], bias[4];
+    float* gsave = train ? (layer == 0 ? P.G1s : P.G2s) + ((long)t * B + r) * 4 * H + j : nullptr;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {              // every load of the element is in flight before the first add
       const int n = g * H + j;
-      zload(da, R, r, n, va[g]); zload(db, R, r, n, vb[g]); zload(dc, R, r, n, vc[g]);
-      bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n);
+      zload(dc, R, r, n, vc[g]);
+      if (hoisted) {
+        bias[g] = gsave[g * H];
+      } else {
+        zload(da, R, r, n, va[g]); zload(db, R, r, n, vb[g]);
+        bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n);
+      }
     }
-    const float m = use_mask ? __ldcg(P.unfinished + r) : 1.f;
-    const float cp = cst[e];
+    float m, cp, hp;
     float* hxp = P.hx + (long)r * 2 * H + layer * H + j;
-    const float hp = *hxp;
+    if (train) {
+      m = __ldg(P.seq_mask + (long)r * P.L + t);
+      cp = (layer == 0 ? P.C1s : P.C2s)[((long)t * B + r) * H + j];
+      hp = P.H12s[((long)t * B + r) * 2 * H + layer * H + j];
+    } else {
+      m = t > 0 ? __ldcg(P.unfinished + r) : 1.f;
+      cp = cst[e];
+      hp = *hxp;
+    }
     float z[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) z[g] = zadd(va[g]) + zadd(vb[g]) + zadd(vc[g]) + bias[g];
+    for (int g = 0; g < 4; ++g) z[g] = hoisted ? bias[g] + zadd(vc[g]) : zadd(va[g]) + zadd(vb[g]) + zadd(vc[g]) + bias[g];
     if (threadIdx.x == 0 && z[0] != 12345.f) PK_FINE(1);
     const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
     float c = fg * cp + ig * gg;
     c = c * m + cp * (1.f - m);
     float h = og * tanh_fast(c);
     h = h * m + hp * (1.f - m);
-    cst[e] = c;
-    *hxp = h;
+    if (train) {
+      h *= (layer == 0 ? P.drop1 : P.drop2).factor((uint64_t)t * B * H + (uint64_t)e);
+      gsave[0] = ig; gsave[H] = fg; gsave[2 * H] = og; gsave[3 * H] = gg;
+      (layer == 0 ? P.C1s : P.C2s)[((long)(t + 1) * B + r) * H + j] = c;
+      P.H12s[((long)(t + 1) * B + r) * 2 * H + layer * H + j] = h;
+    } else {
+      cst[e] = c;
+      *hxp = h;
+    }
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + layer * H + j, h);
     if (threadIdx.x == 0) PK_FINE(2);
   }
@@ -563,7 +595,7 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int u
 // fetched by TMA (two H/2-column panels) behind Uv when both fit, else over the first two consumed chunks.
 // (A CTA pair per caption was tried: the score exchange costs what halving the frames saves.)
 constexpr int DEC_FPC = 8;         // frames per Uv chunk (K <= 32)
-__device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, const SmemView& sv,
+__device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, int t, const SmemView& sv,
                                            uint32_t& bulk_phase, long long* g_fine = nullptr) {
   if (threadIdx.x == 0) PK_FINE(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -603,6 +635,11 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     }
 #pragma unroll
     for (int i = 0; i < DEC_NA; ++i) ahr[i] += zadd(v[i]);
+    if (P.mode) {
+#pragma unroll
+      for (int i = 0; i < DEC_NA; ++i)
+        if (threadIdx.x + PK_THREADS * i < A) P.AHs[((long)t * P.B + r) * A + aoff[i]] = ahr[i];
+    }
   }
   if (threadIdx.x == 0) PK_FINE(1);
 #pragma unroll 1
@@ -660,7 +697,10 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
 #pragma unroll 1
-    for (int kk = lane; kk < K; kk += 32) sc[kk] *= inv;
+    for (int kk = lane; kk < K; kk += 32) {
+      sc[kk] *= inv;
+      if (P.mode) P.ALPHAs[((long)t * P.B + r) * K + kk] = sc[kk];
+    }
   }
   pk_wait(sv.bulk_bar + 8 * PK_BULK_CHUNKS, bulk_phase & 1);
   bulk_phase++;
@@ -673,6 +713,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     float a = 0.f;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) a += sc[k] * vp[k * Hh];
+    if (P.mode) P.AFs[((long)t * P.B + r) * H + j] = a;
     store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
   if (threadIdx.x == 0) PK_FINE(12);
@@ -814,20 +855,27 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
   unsigned int sync_target = 0;
   uint32_t bulk_phase = 0;
 
+  const int train = P.mode;
   // ---- prologue: states, <bos> inputs, bookkeeping ----
   for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
     const int r = e / H, j = e % H;
-    const float h1 = r < B ? P.state0[0][e] : 0.f, c1 = r < B ? P.state0[1][e] : 0.f;
-    const float h2 = r < B ? P.state0[2][e] : 0.f, c2 = r < B ? P.state0[3][e] : 0.f;
+    float h1 = 0.f, h2 = 0.f;
+    if (r < B) {
+      if (train) {                                    // init_hidden wrote H12s[0] / C1s[0] / C2s[0]
+        h1 = P.H12s[(long)r * 2 * H + j]; h2 = P.H12s[(long)r * 2 * H + H + j];
+      } else {
+        h1 = P.state0[0][e]; h2 = P.state0[2][e];
+        P.cx[e] = P.state0[1][e]; P.cx[(long)R * H + e] = P.state0[3][e];
+      }
+    }
     P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
-    P.cx[e] = c1; P.cx[(long)R * H + e] = c2;
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + j, h1);
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + H + j, h2);
   }
   for (int r = cta; r < R; r += G) {
-    if (r < B) {
+    if (r < B && !train) {
       dec_token_inputs(P, r, 0);                      // token 0 = <bos> (SAModel.py:184)
-    } else {                                          // padding rows of the 64-wide operand tiles
+    } else if (r >= B) {                              // padding rows of the 64-wide operand tiles
       for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { P.xt_hi[(long)r * P.Ep + k] = 0.f; P.xt_lo[(long)r * P.Ep + k] = 0.f; }
       for (int j = threadIdx.x; j < H; j += PK_THREADS) {
         P.gp_hi[(long)r * H + j] = 0.f; P.gp_lo[(long)r * H + j] = 0.f;
@@ -842,59 +890,33 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     pk_stamp(P.dbg_clock, cta, t, 0);
-    // ===== G1: everything that needs only the previous state and the current token =====
-    //   AH = W_h2a.[h1|h2]   Z1h = W_h2h1.h1   Z2h = W_h2h2.h2   Z1x = W_i2h1.xt   Z1g = W_a2h1.gp
+    // ===== G1: everything that needs only the previous state (and, when decoding, the current token) =====
+    //   AH = W_h2a.[h1|h2]   Z1h = W_h2h1.h1   Z2h = W_h2h2.h2   [decode: Z1x = W_i2h1.xt   Z1g = W_a2h1.gp]
     gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (cta < B) {
-#ifdef PK_FINE_TRACE
-      dec_attention(P, &maps.m[16], cta, sv, bulk_phase, (P.dbg_clock && t == 3 && cta == 5) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 64 : nullptr);
-#else
-      dec_attention(P, &maps.m[16], cta, sv, bulk_phase);
-#endif
-    } else {
-      dec_cell_phase(P, 0, t > 0, cta - B, G - B);
-    }
+    if (cta < B) dec_attention(P, &maps.m[16], cta, t, sv, bulk_phase);
+    else dec_cell_phase(P, 0, t, cta - B, G - B);
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 4);
     // ===== G3: Z2x = W_i2h2.h1'   Z2a = W_a2h2.af =====
-#ifdef PK_FINE_TRACE
-    {
-      long long* fine = (P.dbg_clock && t == 3 && (cta == 0 || cta == 100)) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + (cta ? 32 : 0) : nullptr;
-      gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps, fine);
-      if (fine && threadIdx.x == 0) fine[26] = clock64();
-      grid_barrier(P.sync_counter, sync_target, G);
-      if (fine && threadIdx.x == 0) fine[27] = clock64();
-    }
-#else
-    gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps);
+    gemm_phase(P.d, &s_sched[1], train ? &s_sched[0] : &s_sched[2], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
-#endif
     pk_stamp(P.dbg_clock, cta, t, 6);
     // ===== P3: lstm_2 cell =====
-#ifdef PK_FINE_TRACE
-    {
-      long long* fine = (P.dbg_clock && t == 3 && cta == 7) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 96 : nullptr;
-      dec_cell_phase(P, 1, t > 0, cta, G, fine);
-      gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
-      if (fine && threadIdx.x == 0) fine[4] = clock64();
-      grid_barrier(P.sync_counter, sync_target, G);
-      if (fine && threadIdx.x == 0) fine[5] = clock64();
-    }
-#else
-    dec_cell_phase(P, 1, t > 0, cta, G);
-    gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
+    dec_cell_phase(P, 1, t, cta, G);
+    if (!train) gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
+    else if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 7);
     grid_barrier(P.sync_counter, sync_target, G);
-#endif
     pk_stamp(P.dbg_clock, cta, t, 8);
+    if (train) continue;           // the heads are batched over all steps after the loop (SAModel.py:109-110)
     // ===== G4: logits (split-K partial tiles) =====
     gemm_phase(P.d, &s_sched[2], &s_sched[0], maps.m, R, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 9);
@@ -903,17 +925,9 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     // ===== P4: greedy pick + inputs of the next step (one CTA per caption) =====
 #pragma unroll 1
     for (int r = cta; r < B; r += G) {
-#ifdef PK_FINE_TRACE
-      long long* g_fine = (P.dbg_clock && t == 3 && cta == 9) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 112 : nullptr;
-      const int tokv = dec_pick(P, r, t, sv, g_fine);
-      dec_token_inputs(P, r, tokv);
-      __syncthreads();
-      if (threadIdx.x == 0) PK_FINE(8);
-#else
       const int tokv = dec_pick(P, r, t, sv);
       dec_token_inputs(P, r, tokv);
       __syncthreads();
-#endif
     }
     fence_proxy_async_smem();
     if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
@@ -1059,6 +1073,7 @@ struct PersistState {
   long long* d_dbg = nullptr;
   float* tgate = nullptr;
   unsigned long long tgate_epoch = ~0ull;
+  int sched_mode = -1;           // schedule the slot buffers were last written under (0 decode, 1 training)
   bool attr_set = false;
   // encoder
   int eB = 0;
@@ -1110,8 +1125,17 @@ static bool persist_plan(const std::vector<std::vector<int>>& phases, GDesc* des
 
 static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st);   // xg_forward.cuh
 
-static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
-                          int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st) {
+// teacher-forced training forward: the step-major saved buffers of TrainSaved (xg_context.cuh)
+struct PersistTrainIO {
+  const float* seq_mask; int L;
+  float *G1, *G2, *C1, *C2, *H12, *AH, *ALPHA, *AF;
+  DropSpec drop1, drop2;
+};
+
+// mode 0 (tr == nullptr): greedy decoding, T = seq_length.  mode 1: teacher-forced forward over T = L' steps.
+static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
+                          int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, const PersistTrainIO* tr,
+                          cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
   const int R = 64, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
@@ -1137,9 +1161,16 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   mk(DD_Z2X, 5, 10, 0, 4 * H, kbH);
   mk(DD_Z2A, 6, 14, 0, 4 * H, kbH);
   mk(DD_LOGIT, 7, 10, kbH, V, kbH);
-  const std::vector<std::vector<int>> phases = {{DD_AH, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT}};
+  // both schedules are planned: the slot buffers (shared by the two modes) are sized by the larger slot count
+  const std::vector<std::vector<int>> phases_dec = {{DD_AH, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT}};
+  const std::vector<std::vector<int>> phases_trn = {{DD_AH, DD_Z1H, DD_Z2H}, {DD_Z2X, DD_Z2A}, {}};
   std::vector<PSched> sched;
-  if (!persist_plan(phases, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
+  int ns_cap[DD_COUNT];
+  for (int i = 0; i < DD_COUNT; ++i) hp.d[i].ns = 0;
+  if (!persist_plan(tr ? phases_dec : phases_trn, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
+  for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = hp.d[i].ns;
+  if (!persist_plan(tr ? phases_trn : phases_dec, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;   // the one that runs
+  for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = std::max(ns_cap[i], hp.d[i].ns);
 
   // ---- device pool ----
   if (S->R != R || S->K != K) {
@@ -1149,9 +1180,9 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_params = a.take<DecParams>(1);
       S->d_counter = a.take<unsigned int>(32 * 258 + 256);
       S->d_flags = a.take<int>(2048);
-      S->d_dbg = a.take<long long>((2048 + 256 + 16) * PK_STAMPS);
+      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS);
       hp.sched = a.take<PSched>(sched.size());
-      for (int i = 0; i < DD_COUNT; ++i) hp.d[i].out = a.take<float>((size_t)hp.d[i].ns * R * hp.d[i].n_rows);
+      for (int i = 0; i < DD_COUNT; ++i) hp.d[i].out = a.take<float>((size_t)ns_cap[i] * R * hp.d[i].n_rows);
       hp.xt_hi = a.take<float>((long)R * Ep); hp.xt_lo = a.take<float>((long)R * Ep);
       hp.hh_hi = a.take<float>((long)R * 2 * H); hp.hh_lo = a.take<float>((long)R * 2 * H);
       hp.gp_hi = a.take<float>((long)R * H); hp.gp_lo = a.take<float>((long)R * H);
@@ -1169,13 +1200,24 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
     }
     S->R = R; S->K = K;
     S->tgate_epoch = ~0ull;
+    S->sched_mode = -1;
+  }
+  // consumers add every slot up to the per-product maximum and rely on never-written slots being zero: that
+  // holds per schedule, so the slot buffers are cleared when the schedule changes (decode <-> training)
+  if (S->sched_mode != (tr ? 1 : 0)) {
+    if (S->sched_mode != -1) {
+      char* lo = reinterpret_cast<char*>(hp.d[0].out);
+      char* hi = reinterpret_cast<char*>(hp.d[DD_COUNT - 1].out) + sizeof(float) * (size_t)ns_cap[DD_COUNT - 1] * R * hp.d[DD_COUNT - 1].n_rows;
+      XG_CUDA_TRY(ctx->es, cudaMemsetAsync(lo, 0, (size_t)(hi - lo), st));
+    }
+    S->sched_mode = tr ? 1 : 0;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(hp.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
   // ---- POS-gate table of every token: tgate = relu(embed . W_gate^T + b)  (sub_modules.py:29-32 applied to
   //      SAModel.py:198's embedding rows); rebuilt whenever the bound parameters change ----
-  if (S->tgate_epoch != ctx->param_epoch) {
+  if (!tr && S->tgate_epoch != ctx->param_epoch) {
     GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], E, ctx->P[XG_P_DGATE_W], E, S->tgate, H, V, H, E);
     g.ep.bias0 = ctx->P[XG_P_DGATE_B];
     g.ep.act = XG_ACT_RELU;
@@ -1215,16 +1257,25 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.b_logit = ctx->P[XG_P_LOGIT_B]; hp.embed = ctx->P[XG_P_EMBED_W];
   hp.tgate = S->tgate;
   hp.Vf = Vf; hp.Uv = Uv; hp.pos = pos;
-  for (int q = 0; q < 4; ++q) hp.state0[q] = state0[q];
+  for (int q = 0; q < 4; ++q) hp.state0[q] = state0 ? state0[q] : nullptr;
+  hp.mode = tr ? 1 : 0;
+  if (tr) {
+    hp.L = tr->L; hp.seq_mask = tr->seq_mask;
+    hp.G1s = tr->G1; hp.G2s = tr->G2; hp.C1s = tr->C1; hp.C2s = tr->C2; hp.H12s = tr->H12;
+    hp.AHs = tr->AH; hp.ALPHAs = tr->ALPHA; hp.AFs = tr->AF;
+    hp.drop1 = tr->drop1; hp.drop2 = tr->drop2;
+  }
   hp.seq = seq_out; hp.seqlogp = logp_out; hp.flags = S->d_flags;
   hp.sync_counter = S->d_counter;
   hp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
-  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256 + 16) * PK_STAMPS, st));
+  if (!tr) {
+    XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
+    XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
+  }
+  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256) * PK_STAMPS, st));
 
   if (!S->attr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
@@ -1234,12 +1285,13 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
     S->attr_set = true;
   }
   {
-    ProfScope ps(ctx, "decode_persistent", st);
+    ProfScope ps(ctx, tr ? "train_decode_persistent" : "decode_persistent", st);
     const DecParams* dp = S->d_params;
     void* args[2] = {(void*)&dp, (void*)&mt};
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(G), dim3(PK_THREADS), args,
                                                      PK_SMEM_BYTES, st));
   }
+  if (tr) return XG_OK;            // asynchronous: the batched heads follow on the same stream
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
   int steps = 0;
@@ -1263,31 +1315,6 @@ static int persist_greedy(xg_context* ctx, const float* Vf, const float* Uv, con
       fprintf(stderr, "[xg persist trace] %-26s own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
     }
     fprintf(stderr, "[xg persist trace] step %.0f cycles\n", tot);
-#ifdef PK_FINE_TRACE
-    if (steps > 3) {   // step 3, phase G3, first item of CTA 0 and CTA 100: pipeline events in SM cycles after phase entry
-      const char* ev[28] = {"entry", "tma0", "tma1", "tma2", "tma3", "full0", "full1", "full2", "full3", "split0", "split1", "split2", "split3",
-                            "mma_go0", "mma_go1", "mma_go2", "mma_go3", "mma_iss0", "mma_iss1", "mma_iss2", "mma_iss3", "small_commit",
-                            "acc_full0", "acc_full1", "small_full", "stored", "barrier_in", "barrier_out"};
-      for (int w = 0; w < 2; ++w) {
-        long long f[32];
-        cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + w * 32, sizeof(f), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[xg persist trace] G3 item 0 of cta %d:", w ? 100 : 0);
-        for (int i = 1; i < 28; ++i) if (f[i]) fprintf(stderr, " %s=%lld", ev[i], f[i] - f[0]);
-        fprintf(stderr, "\n");
-      }
-      long long f[16];
-      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 64, sizeof(f), cudaMemcpyDeviceToHost);
-      const char* ea[13] = {"entry", "ah_ready", "chunk0_in", "chunk0_done", "chunk1_in", "chunk1_done", "chunk2_in", "chunk2_done", "chunk3_in",
-                            "chunk3_done", "scores_synced", "softmax_done", "context_done"};
-      fprintf(stderr, "[xg persist trace] attention of cta 5:");
-      for (int i = 1; i < 13; ++i) fprintf(stderr, " %s=%lld", ea[i], f[i] - f[0]);
-      fprintf(stderr, "\n");
-      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 96, sizeof(f), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[xg persist trace] cell2 of cta 7: loads_done=%lld stored=%lld end=%lld barrier_in=%lld barrier_out=%lld\n", f[1] - f[0], f[2] - f[0], f[3] - f[0], f[4] - f[0], f[5] - f[0]);
-      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS + 112, sizeof(f), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[xg persist trace] pick of cta 9: slot0=%lld slot1=%lld slot2=%lld reduce_in=%lld booked=%lld inputs_done=%lld\n", f[1] - f[0], f[2] - f[0], f[3] - f[0], f[6] - f[0], f[7] - f[0], f[8] - f[0]);
-    }
-#endif
     if (steps > 3 && G <= 256) {   // step 3, all CTAs: when does each CTA finish its share of a phase (ns after the phase opened)?
       std::vector<long long> ga((size_t)G * PK_STAMPS);
       cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
