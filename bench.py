@@ -268,19 +268,40 @@ def main():
     peak, peak_src = peaks()
 
     def algorithmic_bytes(name):
-        # DESIGN.md "algorithmic bytes": a GEMM launch must read both operands once and write C once
-        if name.startswith("gemm_"):
+        """DESIGN.md section 4 / SURVEY.md 8(d): bytes a launch must move once, whatever the implementation."""
+        H, E, A, V, R, F = DIMS["H"], DIMS["E"], DIMS["A"], DIMS["V"], DIMS["R"], DIMS["F"]
+        if name == "decode_persistent":
+            # per word step: every decoder weight once (52.5 MB fp32 incl. the logit matrix) + V and Uv of every caption
+            w = 4.0 * (A * 2 * H + H * E + 4 * H * E + 5 * 4 * H * H + V * H)
+            act = 4.0 * BATCH * K_FRAMES * (H + A)
+            return T_SEQ * (w + act)
+        if name == "encode_persistent":
+            # per frame step (27 of them): both recurrent matrices once (16.8 MB with the input halves hoisted: 8.4 MB)
+            return (K_FRAMES - 1) * 4.0 * 2 * 4 * H * H
+        # a GEMM launch must read both operands once and write C once
+        if name.startswith("gemm"):
             m, n, k = (int(x) for x in name.split("_")[2].split("x"))
             return 4.0 * (m * k + n * k + m * n)
         if name == "att_fwd":      # AH + Uv + V read, alpha + context written, per caption row
-            return 4.0 * BATCH * (DIMS["A"] + K_FRAMES * DIMS["A"] + K_FRAMES * DIMS["H"] + K_FRAMES + DIMS["H"])
+            return 4.0 * BATCH * (A + K_FRAMES * A + K_FRAMES * H + K_FRAMES + H)
+        return None
+
+    def measured_traffic(name):
+        """dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (per launch),
+        recorded under profiles/ by the round's profiling run; None if no capture is committed."""
+        pth = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(pth):
+            try:
+                return json.load(open(pth)).get(name, {}).get("dram_bytes_per_launch")
+            except Exception:
+                return None
         return None
 
     ab = algorithmic_bytes(top["name"])
     avg_ms = top["ms"] / top["launches"]
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": (ab / (avg_ms * 1e-3) / 1e9) if ab else None,
                 "peak": peak, "unit": "GB/s", "frac": (ab / (avg_ms * 1e-3) / 1e9 / peak) if ab else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                "traffic": measured_traffic(top["name"]), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                 "avg_launch_us": avg_ms * 1e3, "share_of_step": top["ms"] / tot_prof_ms,
                 "top5": [{"name": p["name"], "launches_per_step": p["launches"] / prof_steps,
                           "us_per_launch": p["ms"] / p["launches"] * 1e3, "share": p["ms"] / tot_prof_ms} for p in prof[:5]]}

@@ -410,19 +410,32 @@ static inline bool skinny_ok(const GemmP& p) {
   return false;
 }
 
-static int gemm_skinny_launch(ErrorSink& es, const GemmP& p, cudaStream_t st) {
-  static bool attr[2] = {false, false};
+// The split CTAs of a tile wait for one another, so the whole grid must be co-resident: the kernel is launched
+// cooperatively (all-or-nothing scheduling — e.g. next to an NCCL kernel that holds a few SMs) and only for
+// grids the device can hold (checked against the occupancy calculator, >= 2 CTAs per SM expected).
+static int gemm_skinny_launch(ErrorSink& es, const GemmP& p, cudaStream_t st, bool* too_large) {
+  static int max_ctas[2] = {-1, -1};
   const bool kmaj = (p.sb_r == 1);
-  if (!attr[kmaj]) {
+  *too_large = false;
+  if (max_ctas[kmaj] < 0) {
     cudaError_t e = kmaj ? cudaFuncSetAttribute(gemm_skinny_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM)
                          : cudaFuncSetAttribute(gemm_skinny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM);
     if (e != cudaSuccess) { es.set(__FILE__, __LINE__, "cudaFuncSetAttribute(gemm_skinny)", cudaGetErrorString(e)); return XG_ERR_CUDA; }
-    attr[kmaj] = true;
+    int per_sm = 0, dev = 0, sms = 0;
+    e = kmaj ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_skinny_kernel<true>, 256, SK_SMEM)
+             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_skinny_kernel<false>, 256, SK_SMEM);
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { es.set(__FILE__, __LINE__, "occupancy query (gemm_skinny)", cudaGetErrorString(e)); return XG_ERR_CUDA; }
+    max_ctas[kmaj] = per_sm * sms;
   }
   dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), p.ksplit > 1 ? p.ksplit : 1);
-  if (kmaj) gemm_skinny_kernel<true><<<grid, 256, SK_SMEM, st>>>(p);
-  else gemm_skinny_kernel<false><<<grid, 256, SK_SMEM, st>>>(p);
-  XG_LAUNCH_CHECK(es);
+  if ((long)grid.x * grid.y * grid.z > max_ctas[kmaj]) { *too_large = true; return XG_OK; }
+  GemmP pc = p;
+  void* args[1] = {(void*)&pc};
+  cudaError_t e = cudaLaunchCooperativeKernel(kmaj ? (void*)gemm_skinny_kernel<true> : (void*)gemm_skinny_kernel<false>, grid,
+                                              dim3(256), args, SK_SMEM, st);
+  if (e != cudaSuccess) { es.set(__FILE__, __LINE__, "cudaLaunchCooperativeKernel(gemm_skinny)", cudaGetErrorString(e)); return XG_ERR_CUDA; }
   return XG_OK;
 }
 
@@ -462,7 +475,9 @@ static int gemm_simt(ErrorSink& es, const GemmP& p_in, cudaStream_t st, const Sp
             if ((size_t)med * S * 64 * 64 > sk->ws_floats || S > 32 || med * S > 296) return gemm_launch_cfg<64, 64, 32, 4, 4>(es, p, st);
             p.ksplit = S; p.kchunk = kchunk;
           }
-          return gemm_skinny_launch(es, p, st);
+          bool too_large = false;
+          const int rc = gemm_skinny_launch(es, p, st, &too_large);
+          if (rc != XG_OK || !too_large) return rc;
         }
         return gemm_launch_cfg<64, 64, 32, 4, 4>(es, p, st);
       }

@@ -527,10 +527,11 @@ struct DecParams {
 constexpr int DEC_NA = 5;          // attention units per thread: att <= 5 * 320
 
 // lstm cell (decoder gate order i,f,o,g), elements (r, j) with j fastest
+template <int TRAIN>
 __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int t, int part, int nparts, long long* g_fine = nullptr) {
   if (threadIdx.x == 0) PK_FINE(0);
   const int H = P.H, R = P.R, B = P.B;
-  const int train = P.mode;
+  constexpr bool train = TRAIN != 0;
   const GDesc& da = P.d[layer == 0 ? DD_Z1X : DD_Z2X];
   const GDesc& db = P.d[layer == 0 ? DD_Z1G : DD_Z2A];
   const GDesc& dc = P.d[layer == 0 ? DD_Z1H : DD_Z2H];
@@ -595,6 +596,7 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int t
 // fetched by TMA (two H/2-column panels) behind Uv when both fit, else over the first two consumed chunks.
 // (A CTA pair per caption was tried: the score exchange costs what halving the frames saves.)
 constexpr int DEC_FPC = 8;         // frames per Uv chunk (K <= 32)
+template <int TRAIN>
 __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, int t, const SmemView& sv,
                                            uint32_t& bulk_phase, long long* g_fine = nullptr) {
   if (threadIdx.x == 0) PK_FINE(0);
@@ -635,7 +637,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     }
 #pragma unroll
     for (int i = 0; i < DEC_NA; ++i) ahr[i] += zadd(v[i]);
-    if (P.mode) {
+    if (TRAIN) {
 #pragma unroll
       for (int i = 0; i < DEC_NA; ++i)
         if (threadIdx.x + PK_THREADS * i < A) P.AHs[((long)t * P.B + r) * A + aoff[i]] = ahr[i];
@@ -699,7 +701,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
 #pragma unroll 1
     for (int kk = lane; kk < K; kk += 32) {
       sc[kk] *= inv;
-      if (P.mode) P.ALPHAs[((long)t * P.B + r) * K + kk] = sc[kk];
+      if (TRAIN) P.ALPHAs[((long)t * P.B + r) * K + kk] = sc[kk];
     }
   }
   pk_wait(sv.bulk_bar + 8 * PK_BULK_CHUNKS, bulk_phase & 1);
@@ -713,7 +715,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     float a = 0.f;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) a += sc[k] * vp[k * Hh];
-    if (P.mode) P.AFs[((long)t * P.B + r) * H + j] = a;
+    if (TRAIN) P.AFs[((long)t * P.B + r) * H + j] = a;
     store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
   if (threadIdx.x == 0) PK_FINE(12);
@@ -833,6 +835,7 @@ __device__ __noinline__ void pk_stamp(long long* dbg, int cta, int t, int i) {
   }
 }
 
+template <int TRAIN>
 __global__ void __launch_bounds__(PK_THREADS, 1)
 decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
   __shared__ DecParams Psm;
@@ -855,7 +858,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
   unsigned int sync_target = 0;
   uint32_t bulk_phase = 0;
 
-  const int train = P.mode;
+  constexpr bool train = TRAIN != 0;
   // ---- prologue: states, <bos> inputs, bookkeeping ----
   for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
     const int r = e / H, j = e % H;
@@ -897,8 +900,8 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (cta < B) dec_attention(P, &maps.m[16], cta, t, sv, bulk_phase);
-    else dec_cell_phase(P, 0, t, cta - B, G - B);
+    if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, t, sv, bulk_phase);
+    else dec_cell_phase<TRAIN>(P, 0, t, cta - B, G - B);
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
@@ -910,7 +913,7 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 6);
     // ===== P3: lstm_2 cell =====
-    dec_cell_phase(P, 1, t, cta, G);
+    dec_cell_phase<TRAIN>(P, 1, t, cta, G);
     if (!train) gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
     else if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 7);
@@ -1278,18 +1281,20 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256) * PK_STAMPS, st));
 
   if (!S->attr_set) {
-    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
-    int nb = 0;
-    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_persistent_kernel, PK_THREADS, PK_SMEM_BYTES));
-    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "persistent decoder does not fit on an SM");
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0, nb1 = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_persistent_kernel<0>, PK_THREADS, PK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, decode_persistent_kernel<1>, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1 && nb1 >= 1, XG_ERR_CUDA, "persistent decoder does not fit on an SM");
     S->attr_set = true;
   }
   {
     ProfScope ps(ctx, tr ? "train_decode_persistent" : "decode_persistent", st);
     const DecParams* dp = S->d_params;
     void* args[2] = {(void*)&dp, (void*)&mt};
-    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(G), dim3(PK_THREADS), args,
-                                                     PK_SMEM_BYTES, st));
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(tr ? (void*)decode_persistent_kernel<1> : (void*)decode_persistent_kernel<0>, dim3(G),
+                                                     dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   }
   if (tr) return XG_OK;            // asynchronous: the batched heads follow on the same stream
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
