@@ -92,9 +92,15 @@ def test_persistent_schedule_switch_keeps_results():
     P["logit.bias"][0] = -1e4
     m = build_model(cfg, P, drop=0.0)
     opt = {"sample_max": 1, "beam_size": 1}
+    bn0 = {k: v.clone() for k, v in m.named_buffers()}        # train-mode BatchNorm moves the running statistics
+
+    def restore_bn():
+        with torch.no_grad():
+            for k, v in m.named_buffers():
+                v.copy_(bn0[k])
     m.eval(); seq_a, lp_a = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], opt)
-    m.train(); lp1, l1, _ = _train_grads(m, d, X)
+    m.train(); lp1, l1, _ = _train_grads(m, d, X); restore_bn()
     m.eval(); seq_b, lp_b = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], opt)
-    m.train(); lp2, l2, _ = _train_grads(m, d, X)
+    m.train(); lp2, l2, _ = _train_grads(m, d, X); restore_bn()
     assert torch.equal(seq_a, seq_b) and torch.equal(lp_a, lp_b)
     assert torch.equal(lp1, lp2) and l1 == l2
