@@ -13,6 +13,8 @@ from .CaptionModel import CaptionModel  # noqa: E402
 from .SAModel import (ClassiferCriterion, LanguageModelCriterion, RewardCriterion, SAModel,  # noqa: E402
                       to_contiguous)
 
+from .optim import FusedAdam  # noqa: E402
+
 __all__ = ["SAModel", "CaptionModel", "LanguageModelCriterion", "ClassiferCriterion", "RewardCriterion",
-           "to_contiguous"]
+           "to_contiguous", "FusedAdam"]
 __version__ = "0.1.0"

@@ -29,6 +29,10 @@ class XgDims(ctypes.Structure):
                 ("drop_prob", c_float), ("bn_eps", c_float), ("bn_momentum", c_float)]
 
 
+class XgAdamTensor(ctypes.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_int64)]
+
+
 PtrTable = c_void_p * XG_NUM_PARAMS
 Ptr4 = c_void_p * 4
 
@@ -72,6 +76,8 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "xg_profile_enable": (c_int, [c_void_p, c_int]),
     "xg_profile_report": (c_int, [c_void_p, c_char_p, c_size_t]),
+    "xg_adam_step": (c_int, [POINTER(XgAdamTensor), c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int,
+                             c_int, c_void_p]),
     "xg_debug_dropout_mask": (c_int, [c_uint64, c_int, c_size_t, c_float, c_void_p, c_void_p]),
     "xg_debug_gemm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

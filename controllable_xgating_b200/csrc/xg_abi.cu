@@ -5,6 +5,7 @@
 #include "xg_backward.cuh"
 #include "xg_beam.cuh"
 #include "xg_forward.cuh"
+#include "xg_optim.cuh"
 #include "xg_persist.cuh"
 
 using namespace xg;
@@ -485,6 +486,15 @@ int xg_profile_report(xg_handle h, char* buf, size_t buf_bytes) {
 __global__ void dropout_mask_kernel(uint64_t seed, uint32_t site, size_t n, float p, float keep, float* out) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
     out[e] = p > 0.f ? drop_factor(seed, site, e, p, keep) : 1.f;
+}
+
+int xg_adam_step(const xg_adam_tensor* tensors, int count, int step, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float grad_clip, int eps_mode, int write_clamped_grad, void* stream) {
+  ErrorSink es;
+  const int s = adam_step(es, tensors, count, step, lr, beta1, beta2, eps, weight_decay, grad_clip, eps_mode,
+                          write_clamped_grad, (cudaStream_t)stream);
+  if (s != XG_OK) g_last_error = es.msg;
+  return s;
 }
 
 int xg_debug_dropout_mask(uint64_t seed, int site, size_t n, float p, float* out, void* stream) {

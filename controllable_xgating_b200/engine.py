@@ -66,6 +66,12 @@ def _req(t: torch.Tensor, shape: Sequence[int], dtype, name: str) -> torch.Tenso
 
 class Engine:
     """One per SAModel instance."""
+    _live = None        # weak set of engines (FusedAdam notifies them after rewriting parameter storage)
+
+    @classmethod
+    def notify_params_changed(cls):
+        for e in list(cls._live or ()):
+            e._force_changed = True
 
     def __init__(self, module: torch.nn.Module, dims: dict):
         self.module = module
@@ -77,6 +83,11 @@ class Engine:
         self._device = None
         self._param_version = None
         self._engine_mode = 2
+        self._force_changed = False
+        if Engine._live is None:
+            import weakref
+            Engine._live = weakref.WeakSet()
+        Engine._live.add(self)
 
     def set_engine(self, tensor_cores: bool, persistent: bool = True):
         """tensor_cores (default True): dense contractions above the size gate use the tcgen05 3xTF32 engine;
@@ -133,7 +144,8 @@ class Engine:
         # derived copies inside the library (tf32 hi/lo splits) must be dropped
         ver = sum(p._version for p in plist)
         if key == self._bound_key:
-            if ver != self._param_version:
+            if ver != self._param_version or self._force_changed:
+                self._force_changed = False
                 L.check(self.lib.xg_params_changed(self.handle), "xg_params_changed", self.handle)
                 self._param_version = ver
             return

@@ -237,6 +237,24 @@ int xg_nll_criterion_bwd(int N, const int64_t* target, const float* mask, const 
 int xg_profile_enable(xg_handle h, int on);
 int xg_profile_report(xg_handle h, char* buf, size_t buf_bytes);
 
+/* ---- optimizer step (the step right after the hot path: starttrain.py:134-137) --------- */
+/* One launch over all parameter tensors: elementwise clamp of the gradient to +-grad_clip
+ * (myutils.clip_gradient, myutils.py:79-85; grad_clip <= 0 disables; write_clamped_grad != 0 stores the
+ * clamped value back like clamp_ does) followed by Adam (optim.Adam(model.parameters(), lr, weight_decay),
+ * starttrain.py:76: L2 weight decay added to the gradient, no amsgrad).  eps_mode 0 = the PyTorch 0.3.1
+ * formula the reference pins (denom = sqrt(v) + eps), 1 = PyTorch >= 1.0 (denom = sqrt(v)/sqrt(1-beta2^t) + eps).
+ * step is 1-based.  Up to 64 tensors per call; exp_avg / exp_avg_sq are caller-owned fp32 state buffers.
+ * Callers that go on using a handle bound to these parameters must call xg_params_changed(). */
+typedef struct xg_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} xg_adam_tensor;
+int xg_adam_step(const xg_adam_tensor* tensors, int count, int step, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, float grad_clip, int eps_mode, int write_clamped_grad, void* stream);
+
 /* ---- test / diagnostics hooks -------------------------------------------------------- */
 /* the dropout mask (0 or 1/(1-p)) the kernels apply at `site` for logical element indices
  * [0,n) under `seed`, so a train-mode run can be replayed in the CPU oracle. */
