@@ -242,17 +242,22 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   const int plstm[2] = {XG_P_LSTM_RGB_WIH, XG_P_LSTM_OPFL_WIH};
   const uint32_t site_emb[2] = {XG_DROP_ENC_EMB_RGB, XG_DROP_ENC_EMB_OPFL};
   const int RS = bn_row_splits(KB);
+  // frame recurrence of both streams: one persistent cooperative kernel when the shape allows it (xg_persist.cuh)
+  const int pbw = persist_encode_bwd(ctx, fmask, B, K, eb, W.dH, st);
+  if (pbw != PK_FALLBACK) XG_TRY(pbw);
   for (int s = 0; s < 2; ++s) {
     float* DZ = eb.G[s];   // gates -> dz in place
-    XG_CUDA_TRY(ctx->es, cudaMemsetAsync(W.dcc, 0, sizeof(float) * (size_t)B * H, st));
-    for (int t = K - 1; t >= 0; --t) {
-      float* dzt = DZ + (long)t * B * 4 * H;
-      XG_TRY(launch(ctx, "enc_cell_bwd", enc_cell_bwd_kernel, ceil_div(B * H, 256), 256, 0, st, 
-          dzt, eb.Cs[s] + (long)t * B * H, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
-          W.dH[s] + (long)t * B * H, t < K - 1 ? W.dhc : nullptr, W.dcc, fmask, K, t, B, H));
-      if (t > 0) {
-        GemmP g = gemm_nn(dzt, 4 * H, P_(ctx, plstm[s] + 1), H, W.dhc, H, B, H, 4 * H);
-        XG_TRY(gemm_run(ctx, g, st));
+    if (pbw == PK_FALLBACK) {
+      XG_CUDA_TRY(ctx->es, cudaMemsetAsync(W.dcc, 0, sizeof(float) * (size_t)B * H, st));
+      for (int t = K - 1; t >= 0; --t) {
+        float* dzt = DZ + (long)t * B * 4 * H;
+        XG_TRY(launch(ctx, "enc_cell_bwd", enc_cell_bwd_kernel, ceil_div(B * H, 256), 256, 0, st,
+            dzt, eb.Cs[s] + (long)t * B * H, t > 0 ? eb.Cs[s] + (long)(t - 1) * B * H : nullptr,
+            W.dH[s] + (long)t * B * H, t < K - 1 ? W.dhc : nullptr, W.dcc, fmask, K, t, B, H));
+        if (t > 0) {
+          GemmP g = gemm_nn(dzt, 4 * H, P_(ctx, plstm[s] + 1), H, W.dhc, H, B, H, 4 * H);
+          XG_TRY(gemm_run(ctx, g, st));
+        }
       }
     }
     // weight_hh: rows t>=1 of dz pair with h[t-1]

@@ -461,19 +461,22 @@ __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, floa
 
 // split-K partial slots of element (r, n): zload issues every load (one L2 round trip for the whole
 // batch a caller builds), zadd adds them in slot order.
-__device__ __forceinline__ void zload(const GDesc& d, int R, int r, int n, float (&v)[PK_MAX_SLOTS]) {
+template <int MAXS>
+__device__ __forceinline__ void zload(const GDesc& d, int R, int r, int n, float (&v)[MAXS]) {
   const float* p = d.out + (long)r * d.n_rows + n;
   const long sstr = (long)R * d.n_rows;
   const int ns = d.ns;
 #pragma unroll
-  for (int k = 0; k < PK_MAX_SLOTS; ++k) { v[k] = k < ns ? __ldcg(p) : 0.f; p += sstr; }
+  for (int k = 0; k < MAXS; ++k) { v[k] = k < ns ? __ldcg(p) : 0.f; p += sstr; }
 }
-__device__ __forceinline__ float zadd(const float (&v)[PK_MAX_SLOTS]) {
+template <int MAXS>
+__device__ __forceinline__ float zadd(const float (&v)[MAXS]) {
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < PK_MAX_SLOTS; ++k) s += v[k];
+  for (int k = 0; k < MAXS; ++k) s += v[k];
   return s;
 }
+constexpr int ENCB_MAX_SLOTS = 24;     // encoder backward: 8 strips of 64 k-blocks over 148 CTAs
 
 __device__ __forceinline__ unsigned f2ord(float f) {      // order-preserving float -> uint (for redux.sync)
   const unsigned u = __float_as_uint(f);
@@ -1018,6 +1021,103 @@ encode_persistent_kernel(const EncParams* __restrict__ Pp, const __grid_constant
   pipeline_teardown(tmem_base);
 }
 
+// ====================================================================================
+// encoder recurrence, BACKWARD (both streams), t = K-1..0 (autograd of sub_modules.py:132-147):
+//   dh_t = (dH_t + W_hh^T-product of dz_{t+1}) * m_t ;  LSTMCell backward -> dz_t (in place over the saved gates)
+//   dh carried to t-1:  dz_t . W_hh   [weights: the TRANSPOSED recurrent matrices, (H, 4H) K-major]
+// ====================================================================================
+struct EncBwdParams {
+  GDesc d[2];                   // rgb, opfl:  dhc = W_hh^T . dz
+  const PSched* sched;          // [G]
+  int B, R, K, H;
+  float* Gt[2];                 // (K,B,4H) activated gates (i,f,g,o) -> dz (in place)
+  const float* Cs[2];           // (K,B,H)
+  const float* dHs[2];          // (K,B,H) direct gradient of every h_t (cross gates)
+  const float* fmask;           // (B,K)
+  float* dcc;                   // [2][B][H] carried dc
+  float *dz_hi, *dz_lo;         // [R][8H]  [dz_rgb | dz_opfl] of the frame just processed
+  unsigned int* sync_counter;
+};
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+encode_bwd_persistent_kernel(const EncBwdParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
+  __shared__ EncBwdParams Psm;
+  __shared__ PSched s_sched;
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(EncBwdParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
+  __syncthreads();
+  const EncBwdParams& P = Psm;
+  for (int i = threadIdx.x; i < (int)(sizeof(PSched) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&s_sched)[i] = reinterpret_cast<const uint32_t*>(P.sched + cta)[i];
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B, K = P.K;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 4) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+
+  for (int e = cta * PK_THREADS + threadIdx.x; e < (R - B) * 8 * H; e += G * PK_THREADS) {   // padding rows
+    P.dz_hi[(long)B * 8 * H + e] = 0.f; P.dz_lo[(long)B * 8 * H + e] = 0.f;
+  }
+#pragma unroll 1
+  for (int t = K - 1; t >= 0; --t) {
+#pragma unroll 1
+    for (int e = cta * PK_THREADS + threadIdx.x; e < 2 * B * H; e += G * PK_THREADS) {
+      const int s = e / (B * H), b = (e / H) % B, j = e % H;
+      float* g4 = P.Gt[s] + ((long)t * B + b) * 4 * H + j;
+      float vs[ENCB_MAX_SLOTS];
+      const bool carry = t < K - 1;
+      if (carry) zload(P.d[s], R, b, j, vs);
+      const float gi = g4[0], gf = g4[H], gg = g4[2 * H], go = g4[3 * H];
+      const float m = __ldg(P.fmask + (long)b * K + t);
+      const long o = ((long)t * B + b) * H + j;
+      float dh = P.dHs[s][o];
+      const float ccur = P.Cs[s][o];
+      const float cp = t > 0 ? P.Cs[s][o - (long)B * H] : 0.f;
+      float* dccp = P.dcc + (long)s * B * H + (long)b * H + j;
+      const float dcin = carry ? *dccp : 0.f;
+      if (carry) dh += zadd(vs);
+      dh *= m;
+      const float tc = tanhf(ccur);
+      const float d_o = dh * tc;
+      const float dc = dcin * m + dh * go * (1.f - tc * tc);
+      const float di = dc * gg, dg = dc * gi, df = dc * cp;
+      *dccp = dc * gf;
+      const float z0 = di * gi * (1.f - gi), z1 = df * gf * (1.f - gf), z2 = dg * (1.f - gg * gg), z3 = d_o * go * (1.f - go);
+      g4[0] = z0; g4[H] = z1; g4[2 * H] = z2; g4[3 * H] = z3;
+      if (t > 0) {
+        const long xb = (long)b * 8 * H + (long)s * 4 * H + j;
+        store_split(P.dz_hi, P.dz_lo, xb, z0); store_split(P.dz_hi, P.dz_lo, xb + H, z1);
+        store_split(P.dz_hi, P.dz_lo, xb + 2 * H, z2); store_split(P.dz_hi, P.dz_lo, xb + 3 * H, z3);
+      }
+    }
+    if (t > 0) {
+      gemm_prefetch(P.d, &s_sched, maps.m, sv, ps);
+      grid_barrier(P.sync_counter, sync_target, G);
+      gemm_phase(P.d, &s_sched, nullptr, maps.m, R, sv, tmem_base, ps);
+      grid_barrier(P.sync_counter, sync_target, G);
+    }
+  }
+  pipeline_teardown(tmem_base);
+}
+
+// WT[c][r] = W[r][c]   (rows x cols -> cols x rows), 32x32 tiles through shared memory
+__global__ void transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ WT) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = r0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < rows && c < cols) ? W[(long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int c = c0 + y, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) WT[(long)c * rows + r] = tile[threadIdx.x][y];
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
@@ -1028,7 +1128,7 @@ struct PhaseSchedule {
 };
 
 // lay the k-blocks of all strips (desc, row tile, column block) end to end; CTA c gets units [cU/G, (c+1)U/G)
-static PhaseSchedule build_phase(const std::vector<int>& desc_ids, const GDesc* descs, int ncb, int G) {
+static PhaseSchedule build_phase(const std::vector<int>& desc_ids, const GDesc* descs, int ncb, int G, int max_slots) {
   PhaseSchedule ph;
   ph.per_cta.assign(G, PSched{});
   struct Strip { int desc, rt, cb, nkb, slots; };
@@ -1046,7 +1146,7 @@ static PhaseSchedule build_phase(const std::vector<int>& desc_ids, const GDesc* 
     while (need > 0 && si < strips.size()) {
       Strip& s = strips[si];
       const int take = (int)std::min<long>(need, s.nkb - off);
-      if (sc.n >= PK_MAX_ITEMS || s.slots >= PK_MAX_SLOTS) { ph.ok = false; return ph; }
+      if (sc.n >= PK_MAX_ITEMS || s.slots >= max_slots) { ph.ok = false; return ph; }
       sc.it[sc.n++] = PItem{(short)s.desc, (short)s.slots, (short)s.rt, (short)s.cb, (short)off, (short)take};
       sc.tot_kb += (short)take;
       sc.tot_chunks += (short)((take + PK_CHUNK - 1) / PK_CHUNK);
@@ -1078,6 +1178,15 @@ struct PersistState {
   unsigned long long tgate_epoch = ~0ull;
   int sched_mode = -1;           // schedule the slot buffers were last written under (0 decode, 1 training)
   bool attr_set = false;
+  // encoder backward
+  int bB = 0;
+  char* bpool = nullptr;
+  size_t bpool_bytes = 0;
+  EncBwdParams bp;
+  EncBwdParams* d_bparams = nullptr;
+  unsigned int* d_bcounter = nullptr;
+  float* wT[2] = {nullptr, nullptr};
+  bool battr_set = false;
   // encoder
   int eB = 0;
   char* epool = nullptr;
@@ -1097,6 +1206,7 @@ static void persist_release(xg_context* ctx) {
   if (!s) return;
   if (s->pool) cudaFree(s->pool);
   if (s->epool) cudaFree(s->epool);
+  if (s->bpool) cudaFree(s->bpool);
   delete s;
   persist_state(ctx) = nullptr;
 }
@@ -1115,10 +1225,11 @@ static bool persist_eligible(const xg_context* ctx, int B, int K) {
 }
 
 // schedule of one kernel (phases laid one after the other, [phase][G]); false if a phase cannot be scheduled
-static bool persist_plan(const std::vector<std::vector<int>>& phases, GDesc* descs, int ncb, int G, std::vector<PSched>& sched) {
+static bool persist_plan(const std::vector<std::vector<int>>& phases, GDesc* descs, int ncb, int G, std::vector<PSched>& sched,
+                         int max_slots = PK_MAX_SLOTS) {
   sched.clear();
   for (const auto& ids : phases) {
-    PhaseSchedule ph = build_phase(ids, descs, ncb, G);
+    PhaseSchedule ph = build_phase(ids, descs, ncb, G, max_slots);
     if (!ph.ok) return false;
     sched.insert(sched.end(), ph.per_cta.begin(), ph.per_cta.end());
     for (size_t i = 0; i < ids.size(); ++i) descs[ids[i]].ns = ph.ns[i];
@@ -1402,6 +1513,79 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
   const EncParams* dp = S->d_eparams;
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  return XG_OK;
+}
+
+// backward frame recurrence of both encoder streams: eb.G holds the activated gates (-> dz in place), dH the direct
+// gradients of every h_t; dz of all frames is left in eb.G for the batched weight gradients that follow
+static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K, const EncBufs& eb, float* const* dH, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, G = ctx->sm_count;
+  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || K < 2 || G > 256) return PK_FALLBACK;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
+  if (R / PK_BN > 32) return PK_FALLBACK;
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  PersistState*& S = persist_state(ctx);
+  if (!S) S = new PersistState();
+  EncBwdParams& bp = S->bp;
+  const int kb4H = 4 * H / 32;
+  for (int s = 0; s < 2; ++s) {
+    GDesc& g = bp.d[s];
+    g.w_map = s; g.x_hi = 2; g.x_lo = 3; g.xkb0 = s * kb4H; g.n_rows = H; g.nkb = kb4H;
+  }
+  std::vector<PSched> sched;
+  if (!persist_plan({{0, 1}}, bp.d, R / PK_BN, G, sched, ENCB_MAX_SLOTS)) return PK_FALLBACK;
+  if (S->bB != B) {
+    if (S->bpool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->bpool); S->bpool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->bpool, pass == 0 ? 0 : S->bpool_bytes);
+      S->d_bparams = a.take<EncBwdParams>(1);
+      S->d_bcounter = a.take<unsigned int>(64);
+      bp.sched = a.take<PSched>(sched.size());
+      for (int s = 0; s < 2; ++s) bp.d[s].out = a.take<float>((size_t)bp.d[s].ns * R * H);
+      bp.dz_hi = a.take<float>((long)R * 8 * H); bp.dz_lo = a.take<float>((long)R * 8 * H);
+      bp.dcc = a.take<float>((long)2 * B * H);
+      S->wT[0] = a.take<float>((long)4 * H * H); S->wT[1] = a.take<float>((long)4 * H * H);
+      if (pass == 0) {
+        S->bpool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->bpool, S->bpool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->bpool, 0, S->bpool_bytes, st));
+      }
+    }
+    S->bB = B;
+  }
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(bp.sched), sched.data(), sizeof(PSched) * sched.size(),
+                                       cudaMemcpyHostToDevice, st));
+  const int whh[2] = {XG_P_LSTM_RGB_WHH, XG_P_LSTM_OPFL_WHH};
+  for (int s = 0; s < 2; ++s) {    // the recurrent matrices change every optimizer step: transpose per call (2 x 4 MB)
+    ProfScope ps(ctx, "transpose", st);
+    transpose_kernel<<<dim3(ceil_div(H, 32), ceil_div(4 * H, 32)), dim3(32, 8), 0, st>>>(ctx->P[whh[s]], 4 * H, H, S->wT[s]);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  MapTable mt;
+  XG_TRY(tc_make_map(ctx, ts, S->wT[0], H, 4 * H, 128, &mt.m[0]));
+  XG_TRY(tc_make_map(ctx, ts, S->wT[1], H, 4 * H, 128, &mt.m[1]));
+  XG_TRY(tc_make_map(ctx, ts, bp.dz_hi, R, 8 * H, PK_BN, &mt.m[2]));
+  XG_TRY(tc_make_map(ctx, ts, bp.dz_lo, R, 8 * H, PK_BN, &mt.m[3]));
+  for (int i = 4; i < 18; ++i) mt.m[i] = mt.m[0];
+  bp.B = B; bp.R = R; bp.K = K; bp.H = H;
+  for (int s = 0; s < 2; ++s) { bp.Gt[s] = eb.G[s]; bp.Cs[s] = eb.Cs[s]; bp.dHs[s] = dH[s]; }
+  bp.fmask = fmask;
+  bp.sync_counter = S->d_bcounter;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_bparams, &bp, sizeof(EncBwdParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_bcounter, 0, sizeof(unsigned int) * 64, st));
+  if (!S->battr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(encode_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_bwd_persistent_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "persistent encoder backward does not fit on an SM");
+    S->battr_set = true;
+  }
+  ProfScope ps(ctx, "encode_bwd_persistent", st);
+  const EncBwdParams* dp = S->d_bparams;
+  void* args[2] = {(void*)&dp, (void*)&mt};
+  XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   return XG_OK;
 }
 
