@@ -133,7 +133,20 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   float* G1 = S.G1;   // gates are overwritten by dz in place (the saved block is consumed by backward)
   float* G2 = S.G2;
   const size_t att_smem = (size_t)(A + 2 * K + H) * sizeof(float);
-  for (int i = Lp - 1; i >= 0; --i) {
+  // the word loop: one persistent cooperative kernel for all L' steps when the shape allows it (xg_persist.cuh)
+  int pdb = PK_FALLBACK;
+  {
+    PersistBwdIO io;
+    io.seq_mask = seq_mask; io.L = L; io.dOUT = W.dOUT;
+    io.G1 = G1; io.G2 = G2; io.C1 = S.C1; io.C2 = S.C2; io.AH = S.AH; io.ALPHA = S.ALPHA;
+    io.DAH = W.DAH; io.dV = W.dV; io.dUv = W.dUv; io.dwa_part = W.dwa_part; io.dba_part = W.dba_part;
+    io.dHcar = W.dHcar; io.dC1 = W.dC1; io.dC2 = W.dC2;
+    io.drop1 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1);
+    io.drop2 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2);
+    pdb = persist_decode_bwd(ctx, S.V, S.Uv, B, K, Lp, io, st);
+    if (pdb != PK_FALLBACK) XG_TRY(pdb);
+  }
+  for (int i = Lp - 1; i >= 0 && pdb == PK_FALLBACK; --i) {
     const float* m = seq_mask + i;
     float* dz2 = G2 + (long)i * B * 4 * H;
     float* dz1 = G1 + (long)i * B * 4 * H;

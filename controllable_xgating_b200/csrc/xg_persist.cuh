@@ -1118,6 +1118,223 @@ __global__ void transpose_kernel(const float* __restrict__ W, int rows, int cols
   }
 }
 
+// ====================================================================================
+// decoder word loop, BACKWARD (hand-derived BPTT of LSTMCore_two_layer_gate, oracle/manual_bptt.py), i = T-1..0:
+//   Pa  lstm_2 cell backward:  dh2 = dOUT_i + carried  ->  dz2 (in place over the saved gates)
+//   Gb  dh1' += dz2.W_i2h2    dAF = dz2.W_a2h2    dh2_prev += dz2.W_h2h2           [transposed weights, K = 4H]
+//   Pc  attention backward on a CTA pair per caption (dV, dUv, dAH, dw_a2w, db_a2w)  ||  lstm_1 cell backward
+//   Gd  dh1_prev += dz1.W_h2h1        d[h1|h2]_prev += dAH.W_h2a
+// "carried" gradients are never materialised between steps: the cell phases add the split-K slots of the
+// products that feed them (plus the masked pass-through part kept in dHcar); dHcar / dC1 / dC2 hold the
+// gradients of the initial state when the loop ends.
+// ====================================================================================
+enum { DB_GB = 0, DB_GC, DB_GD, DB_GG, DB_GH, DB_COUNT };
+constexpr int DECB_MAX_SLOTS = 20;
+
+struct DecBwdParams {
+  GDesc d[DB_COUNT];
+  const PSched* sched;          // [2][G]
+  int B, R, K, H, A, T, L;
+  const float* seq_mask;        // (B, L)
+  const float* dOUT;            // (T, B, H)
+  float *G1s, *G2s;             // (T, B, 4H) activated gates (i,f,o,g) -> dz in place
+  const float *C1s, *C2s;       // (T+1, B, H)
+  const float *AHs, *ALPHAs;    // (T,B,A), (T,B,K)
+  const float *Uv, *Vf, *w_a2w;
+  float* DAH;                   // (T, B, A)
+  float *dV, *dUv;              // (B,K,H), (B,K,A)   accumulated over the steps
+  float *dwa_part, *dba_part;   // (B,A), (B)
+  float *dz2_hi, *dz2_lo, *dz1_hi, *dz1_lo;   // [R][4H]
+  float *dah_hi, *dah_lo;       // [R][A]
+  float* dHcar;                 // (B, 2H) masked pass-through parts during the loop; final d[h1|h2]_0 at the end
+  float* dC[2];                 // (B, H) carried dc of lstm_1 / lstm_2
+  DropSpec drop1, drop2;
+  unsigned int* sync_counter;
+};
+
+// lstm cell backward of `layer` at step i for the elements of this partition
+__device__ __noinline__ void decb_cell_phase(const DecBwdParams& P, int layer, int i, int part, int nparts) {
+  const int H = P.H, R = P.R, B = P.B, T = P.T;
+  float* gs = layer == 0 ? P.G1s : P.G2s;
+  const float* cs = layer == 0 ? P.C1s : P.C2s;
+  float* dcx = P.dC[layer];
+  float* xhi = layer == 0 ? P.dz1_hi : P.dz2_hi;
+  float* xlo = layer == 0 ? P.dz1_lo : P.dz2_lo;
+  const bool carry = i < T - 1;
+#pragma unroll 1
+  for (int e = part * PK_THREADS + threadIdx.x; e < B * H; e += nparts * PK_THREADS) {
+    const int b = e / H, j = e % H;
+    float va[DECB_MAX_SLOTS], vb[DECB_MAX_SLOTS], vc[DECB_MAX_SLOTS];
+    // lstm_2: carried = dz2_{i+1}.W_h2h2 + dAH_{i+1}.W_h2a[:, H:]        lstm_1: dz1_{i+1}.W_h2h1 + dAH_{i+1}.W_h2a[:, :H]
+    if (carry) {
+      zload(P.d[layer == 0 ? DB_GG : DB_GD], R, b, j, va);
+      zload(P.d[DB_GH], R, b, layer * H + j, vb);
+    }
+    if (layer == 0) zload(P.d[DB_GB], R, b, j, vc);            // this step's dz2.W_i2h2
+    float* g4 = gs + ((long)i * B + b) * 4 * H + j;
+    const float gi = g4[0], gf = g4[H], go = g4[2 * H], gg = g4[3 * H];
+    const float m = __ldg(P.seq_mask + (long)b * P.L + i);
+    float* dhp = P.dHcar + (long)b * 2 * H + layer * H + j;
+    float dh = *dhp;
+    if (layer == 1) dh += P.dOUT[((long)i * B + b) * H + j];
+    const float cn = cs[((long)(i + 1) * B + b) * H + j], cp = cs[((long)i * B + b) * H + j];
+    const float dcin = dcx[e];
+    if (carry) dh += zadd(va) + zadd(vb);
+    if (layer == 0) dh += zadd(vc);
+    const float dhd = dh * (layer == 0 ? P.drop1 : P.drop2).factor((uint64_t)i * B * H + (uint64_t)e);
+    const float dh_t = dhd * m;
+    const float tc = tanhf(cn);
+    const float d_o = dh_t * tc;
+    const float dcn = dcin + dh_t * go * (1.f - tc * tc);
+    const float dc_t = dcn * m;
+    dcx[e] = dcn * (1.f - m) + dc_t * gf;
+    const float di = dc_t * gg, dg = dc_t * gi, df = dc_t * cp;
+    const float z0 = di * gi * (1.f - gi), z1 = df * gf * (1.f - gf), z2 = d_o * go * (1.f - go), z3 = dg * (1.f - gg * gg);
+    g4[0] = z0; g4[H] = z1; g4[2 * H] = z2; g4[3 * H] = z3;
+    *dhp = dhd * (1.f - m);
+    const long xb = (long)b * 4 * H + j;
+    store_split(xhi, xlo, xb, z0); store_split(xhi, xlo, xb + H, z1);
+    store_split(xhi, xlo, xb + 2 * H, z2); store_split(xhi, xlo, xb + 3 * H, z3);
+  }
+}
+
+// attention backward of caption r at step i, split `sp` of 2 (attention units and frames are halved)
+__device__ __noinline__ void decb_attention(const DecBwdParams& P, int r, int sp, int i, const SmemView& sv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = P.K, A = P.A, H = P.H, B = P.B;
+  float* al = sv.scratch;           // K
+  float* ds = al + K;               // K
+  float* daf = ds + K;              // H
+  for (int k = threadIdx.x; k < K; k += PK_THREADS) al[k] = P.ALPHAs[((long)i * B + r) * K + k];
+#pragma unroll 1
+  for (int j = threadIdx.x; j < H; j += PK_THREADS) {
+    float v[DECB_MAX_SLOTS];
+    zload(P.d[DB_GC], P.R, r, j, v);
+    daf[j] = zadd(v);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int k = warp; k < K; k += PK_WARPS) {
+    const float* v = P.Vf + ((long)r * K + k) * H;
+    float p = 0.f;
+#pragma unroll 1
+    for (int j0 = lane; j0 < H; j0 += 32 * 8) {
+      float vv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) vv[q] = __ldg(v + min(j0 + 32 * q, H - 1));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p += (j0 + 32 * q < H ? daf[min(j0 + 32 * q, H - 1)] : 0.f) * vv[q];
+    }
+    p = warp_sum(p);
+    if (lane == 0) ds[k] = p;
+  }
+  __syncthreads();
+  {   // dV[r, k, :] += alpha_k * dAF[r, :]  for this split's frames
+    const int kper = (K + 1) / 2, kb0 = sp * kper, kb1 = min(K, kb0 + kper);
+    const int n = max(0, kb1 - kb0) * H;
+    float* dv = P.dV + ((long)r * K + kb0) * H;
+#pragma unroll 1
+    for (int e0 = threadIdx.x; e0 < n; e0 += PK_THREADS * 8) {
+      float old[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) old[q] = dv[min(e0 + PK_THREADS * q, n - 1)];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + PK_THREADS * q;
+        if (e < n) dv[e] = old[q] + al[kb0 + e / H] * daf[e % H];
+      }
+    }
+  }
+  float dot = 0.f;
+  for (int k = 0; k < K; ++k) dot += al[k] * ds[k];   // every thread computes the same fixed-order sum
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += PK_THREADS) ds[k] = al[k] * (ds[k] - dot);
+  __syncthreads();
+  const int aper = (A + 1) / 2, a0 = sp * aper, a1 = min(A, a0 + aper);
+#pragma unroll 1
+  for (int a = a0 + threadIdx.x; a < a1; a += PK_THREADS) {
+    const float w = __ldg(P.w_a2w + a), h0 = P.AHs[((long)i * B + r) * A + a];
+    float acc_ah = 0.f, acc_wa = 0.f;
+    const long base = (long)r * K * A + a;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float uu[8], dd[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long idx = base + (long)min(k0 + q, K - 1) * A;
+        uu[q] = __ldg(P.Uv + idx);
+        dd[q] = P.dUv[idx];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (k0 + q < K) {
+          const float th = tanh_fast(h0 + uu[q]);
+          const float dp = ds[k0 + q] * w * (1.f - th * th);
+          P.dUv[base + (long)(k0 + q) * A] = dd[q] + dp;
+          acc_ah += dp;
+          acc_wa += ds[k0 + q] * th;
+        }
+      }
+    }
+    P.DAH[((long)i * B + r) * A + a] = acc_ah;
+    store_split(P.dah_hi, P.dah_lo, (long)r * A + a, acc_ah);
+    P.dwa_part[(long)r * A + a] += acc_wa;
+  }
+  if (threadIdx.x == 0 && sp == 0) {
+    float sdb = 0.f;
+    for (int k = 0; k < K; ++k) sdb += ds[k];
+    P.dba_part[r] += sdb;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+decode_bwd_persistent_kernel(const DecBwdParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
+  __shared__ DecBwdParams Psm;
+  __shared__ PSched s_sched[2];
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(DecBwdParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
+  __syncthreads();
+  const DecBwdParams& P = Psm;
+  for (int i = threadIdx.x; i < (int)(2 * sizeof(PSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(PSched) / 4), w = i % (int)(sizeof(PSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(P.sched + (long)ph * G + cta)[w];
+  }
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B, T = P.T;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 11) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+
+#pragma unroll 1
+  for (int i = T - 1; i >= 0; --i) {
+    decb_cell_phase(P, 1, i, cta, G);                                            // Pa
+    gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+    grid_barrier(P.sync_counter, sync_target, G);
+    gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);     // Gb
+    grid_barrier(P.sync_counter, sync_target, G);
+    if (cta < 2 * B) decb_attention(P, cta >> 1, cta & 1, i, sv);                // Pc
+    else decb_cell_phase(P, 0, i, cta - 2 * B, G - 2 * B);
+    gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
+    grid_barrier(P.sync_counter, sync_target, G);
+    gemm_phase(P.d, &s_sched[1], &s_sched[0], maps.m, R, sv, tmem_base, ps);     // Gd
+    grid_barrier(P.sync_counter, sync_target, G);
+  }
+  // gradients of the initial state: pass-through parts + the products of step 0
+#pragma unroll 1
+  for (int e = cta * PK_THREADS + threadIdx.x; e < B * 2 * H; e += G * PK_THREADS) {
+    const int b = e / (2 * H), c = e % (2 * H), layer = c / H, j = c % H;
+    float va[DECB_MAX_SLOTS], vb[DECB_MAX_SLOTS];
+    zload(P.d[layer == 0 ? DB_GG : DB_GD], R, b, j, va);
+    zload(P.d[DB_GH], R, b, c, vb);
+    P.dHcar[e] += zadd(va) + zadd(vb);
+  }
+  pipeline_teardown(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
@@ -1178,6 +1395,15 @@ struct PersistState {
   unsigned long long tgate_epoch = ~0ull;
   int sched_mode = -1;           // schedule the slot buffers were last written under (0 decode, 1 training)
   bool attr_set = false;
+  // decoder backward
+  int dbB = 0, dbK = 0;
+  char* dbpool = nullptr;
+  size_t dbpool_bytes = 0;
+  DecBwdParams dbp;
+  DecBwdParams* d_dbparams = nullptr;
+  unsigned int* d_dbcounter = nullptr;
+  float* dbwT[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool dbattr_set = false;
   // encoder backward
   int bB = 0;
   char* bpool = nullptr;
@@ -1207,6 +1433,7 @@ static void persist_release(xg_context* ctx) {
   if (s->pool) cudaFree(s->pool);
   if (s->epool) cudaFree(s->epool);
   if (s->bpool) cudaFree(s->bpool);
+  if (s->dbpool) cudaFree(s->dbpool);
   delete s;
   persist_state(ctx) = nullptr;
 }
@@ -1586,6 +1813,104 @@ static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K,
   const EncBwdParams* dp = S->d_bparams;
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  return XG_OK;
+}
+
+// backward word loop of the decoder; io = the saved step-major buffers (G1 / G2 become dz in place)
+struct PersistBwdIO {
+  const float* seq_mask; int L;
+  const float* dOUT;
+  float *G1, *G2; const float *C1, *C2, *AH, *ALPHA;
+  float *DAH, *dV, *dUv, *dwa_part, *dba_part, *dHcar, *dC1, *dC2;
+  DropSpec drop1, drop2;
+};
+
+static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv, int B, int K, int T, const PersistBwdIO& io,
+                              cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, A = d.att, G = ctx->sm_count;
+  if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > 64 || G < 2 * B + 8 || G > 256 || T < 1 ||
+      2 * K + H + 8 > PK_SCRATCH_FLOATS)
+    return PK_FALLBACK;
+  const int R = 64;
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  PersistState*& S = persist_state(ctx);
+  if (!S) S = new PersistState();
+  DecBwdParams& bp = S->dbp;
+  const int kb4H = 4 * H / 32, kbA = A / 32;
+  auto mk = [&](int id, int wmap, int xmap, int n_rows, int nkb) {
+    GDesc& g = bp.d[id];
+    g.w_map = wmap; g.x_hi = xmap; g.x_lo = xmap + 1; g.xkb0 = 0; g.n_rows = n_rows; g.nkb = nkb;
+  };
+  // maps: 0..4 transposed weights (i2h2, a2h2, h2h2, h2h1: (H,4H); h2a: (2H,A)); dz2 5,6  dz1 7,8  dah 9,10
+  mk(DB_GB, 0, 5, H, kb4H);
+  mk(DB_GC, 1, 5, H, kb4H);
+  mk(DB_GD, 2, 5, H, kb4H);
+  mk(DB_GG, 3, 7, H, kb4H);
+  mk(DB_GH, 4, 9, 2 * H, kbA);
+  std::vector<PSched> sched;
+  if (!persist_plan({{DB_GB, DB_GC, DB_GD}, {DB_GG, DB_GH}}, bp.d, R / PK_BN, G, sched, DECB_MAX_SLOTS)) return PK_FALLBACK;
+  if (S->dbB != R || S->dbK != K) {
+    if (S->dbpool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->dbpool); S->dbpool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->dbpool, pass == 0 ? 0 : S->dbpool_bytes);
+      S->d_dbparams = a.take<DecBwdParams>(1);
+      S->d_dbcounter = a.take<unsigned int>(64);
+      bp.sched = a.take<PSched>(sched.size());
+      for (int i = 0; i < DB_COUNT; ++i) bp.d[i].out = a.take<float>((size_t)bp.d[i].ns * R * bp.d[i].n_rows);
+      bp.dz2_hi = a.take<float>((long)R * 4 * H); bp.dz2_lo = a.take<float>((long)R * 4 * H);
+      bp.dz1_hi = a.take<float>((long)R * 4 * H); bp.dz1_lo = a.take<float>((long)R * 4 * H);
+      bp.dah_hi = a.take<float>((long)R * A); bp.dah_lo = a.take<float>((long)R * A);
+      for (int w = 0; w < 4; ++w) S->dbwT[w] = a.take<float>((long)4 * H * H);
+      S->dbwT[4] = a.take<float>((long)2 * H * A);
+      if (pass == 0) {
+        S->dbpool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->dbpool, S->dbpool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->dbpool, 0, S->dbpool_bytes, st));
+      }
+    }
+    S->dbB = R; S->dbK = K;
+  }
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(bp.sched), sched.data(), sizeof(PSched) * sched.size(),
+                                       cudaMemcpyHostToDevice, st));
+  // the weights change every optimizer step: transposed copies per call (4 x 4 MB + 6 MB)
+  const int wsrc[5] = {XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W, XG_P_L1_H2H_W, XG_P_H2A_W};
+  for (int w = 0; w < 5; ++w) {
+    int rows, cols;
+    param_shape(d, wsrc[w], &rows, &cols);
+    ProfScope ps(ctx, "transpose", st);
+    transpose_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, st>>>(ctx->P[wsrc[w]], rows, cols, S->dbwT[w]);
+    XG_LAUNCH_CHECK(ctx->es);
+  }
+  MapTable mt;
+  for (int w = 0; w < 4; ++w) XG_TRY(tc_make_map(ctx, ts, S->dbwT[w], H, 4 * H, 128, &mt.m[w]));
+  XG_TRY(tc_make_map(ctx, ts, S->dbwT[4], 2 * H, A, 128, &mt.m[4]));
+  XG_TRY(tc_make_map(ctx, ts, bp.dz2_hi, R, 4 * H, PK_BN, &mt.m[5])); XG_TRY(tc_make_map(ctx, ts, bp.dz2_lo, R, 4 * H, PK_BN, &mt.m[6]));
+  XG_TRY(tc_make_map(ctx, ts, bp.dz1_hi, R, 4 * H, PK_BN, &mt.m[7])); XG_TRY(tc_make_map(ctx, ts, bp.dz1_lo, R, 4 * H, PK_BN, &mt.m[8]));
+  XG_TRY(tc_make_map(ctx, ts, bp.dah_hi, R, A, PK_BN, &mt.m[9])); XG_TRY(tc_make_map(ctx, ts, bp.dah_lo, R, A, PK_BN, &mt.m[10]));
+  for (int i = 11; i < 18; ++i) mt.m[i] = mt.m[0];
+  bp.B = B; bp.R = R; bp.K = K; bp.H = H; bp.A = A; bp.T = T; bp.L = io.L;
+  bp.seq_mask = io.seq_mask; bp.dOUT = io.dOUT;
+  bp.G1s = io.G1; bp.G2s = io.G2; bp.C1s = io.C1; bp.C2s = io.C2; bp.AHs = io.AH; bp.ALPHAs = io.ALPHA;
+  bp.Uv = Uv; bp.Vf = Vf; bp.w_a2w = ctx->P[XG_P_A2W_W];
+  bp.DAH = io.DAH; bp.dV = io.dV; bp.dUv = io.dUv; bp.dwa_part = io.dwa_part; bp.dba_part = io.dba_part;
+  bp.dHcar = io.dHcar; bp.dC[0] = io.dC1; bp.dC[1] = io.dC2;
+  bp.drop1 = io.drop1; bp.drop2 = io.drop2;
+  bp.sync_counter = S->d_dbcounter;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_dbparams, &bp, sizeof(DecBwdParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbcounter, 0, sizeof(unsigned int) * 64, st));
+  if (!S->dbattr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_bwd_persistent_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "persistent decoder backward does not fit on an SM");
+    S->dbattr_set = true;
+  }
+  ProfScope ps(ctx, "decode_bwd_persistent", st);
+  const DecBwdParams* dp = S->d_dbparams;
+  void* args[2] = {(void*)&dp, (void*)&mt};
+  XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   return XG_OK;
 }
 
