@@ -503,6 +503,7 @@ struct DecParams {
   const float *b_logit, *embed;
   const float* tgate;           // (V, H)  relu(embed . W_gate^T + b): the POS-gate pre-factor of every token
   const float *Vf, *Uv, *pos;   // (B,K,H), (B,K,A), (B,H)
+  float* EUv;                   // (B,K,A) exp(2 Uv), built in the prologue: tanh(ah + uv) = 1 - 2 / (e^{2ah} e^{2uv} + 1)
   const float* state0[4];       // h1,c1,h2,c2 each (B,H)
   float *xt_hi, *xt_lo;         // [R][Ep]
   float *hh_hi, *hh_lo;         // [R][2H]   [h1 | h2]
@@ -618,7 +619,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
       if (k0 >= k1) break;
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
       pk_expect_tx(sv.bulk_bar + 8 * c, nb);
-      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.Uv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
     }
     if (v_behind) {
       pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
@@ -646,6 +647,15 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
         if (threadIdx.x + PK_THREADS * i < A) P.AHs[((long)t * P.B + r) * A + aoff[i]] = ahr[i];
     }
   }
+  // tanh(ah + uv) = 1 - 2 / (e^{2 ah} e^{2 uv} + 1): e^{2 uv} is step-invariant (EUv), so each of the 43k
+  // evaluations costs one MUFU (rcp) instead of two; the constant sum of the weights is added once
+  float wsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < DEC_NA; ++i) {
+    wsum += wr[i];
+    ahr[i] = __expf(2.f * fminf(fmaxf(ahr[i], -40.f), 40.f));
+    wr[i] *= -2.f;
+  }
   if (threadIdx.x == 0) PK_FINE(1);
 #pragma unroll 1
   for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
@@ -656,10 +666,10 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     float p[DEC_FPC];
 #pragma unroll
     for (int f = 0; f < DEC_FPC; ++f) {
-      p[f] = 0.f;
+      p[f] = wsum;
       const float* u = uv + (long)min(k0 + f, K - 1) * A;
 #pragma unroll
-      for (int i = 0; i < DEC_NA; ++i) p[f] += wr[i] * tanh_fast(ahr[i] + u[aoff[i]]);
+      for (int i = 0; i < DEC_NA; ++i) p[f] = fmaf(wr[i], __fdividef(1.f, fmaf(ahr[i], u[aoff[i]], 1.f)), p[f]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -890,6 +900,11 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     }
     if (threadIdx.x == 0) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
   }
+  {   // EUv = exp(2 Uv), clamped like the per-step factor
+    const long n = (long)B * P.K * P.A;
+    for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
+      P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
+  }
   gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
 
@@ -903,8 +918,14 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, t, sv, bulk_phase);
-    else dec_cell_phase<TRAIN>(P, 0, t, cta - B, G - B);
+    if (G >= B + 8) {              // enough SMs: captions and cell elements on disjoint CTAs
+      if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, t, sv, bulk_phase);
+      else dec_cell_phase<TRAIN>(P, 0, t, cta - B, G - B);
+    } else {                       // large batches: every CTA walks its captions, then its cell elements
+#pragma unroll 1
+      for (int r = cta; r < B; r += G) dec_attention<TRAIN>(P, &maps.m[16], r, t, sv, bulk_phase);
+      dec_cell_phase<TRAIN>(P, 0, t, cta, G);
+    }
     fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
@@ -1445,7 +1466,7 @@ static bool persist_eligible(const xg_context* ctx, int B, int K) {
   const bool v_behind = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
   const bool v_over = (long)K * d.rnn <= (long)std::min(K, 2 * DEC_FPC) * d.att;
   return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
-         d.att % 32 == 0 && B <= 64 && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= B + 8 &&
+         d.att % 32 == 0 && B <= 256 && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
          (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS &&
          (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && (v_behind || v_over) &&
          (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000;
@@ -1479,7 +1500,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
                           cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
-  const int R = 64, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
   if (T > 2048) return PK_FALLBACK;
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
@@ -1533,6 +1554,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       hp.unfinished = a.take<float>(R);
       hp.tok = a.take<int64_t>(R);
       S->tgate = a.take<float>((long)V * H);
+      hp.EUv = a.take<float>((long)R * K * A);
       if (pass == 0) {
         S->pool_bytes = a.off + 1024;
         XG_CUDA_TRY(ctx->es, cudaMalloc(&S->pool, S->pool_bytes));

@@ -40,7 +40,7 @@ def test_persistent_full_size_with_eos():
     assert rel_err(lps.cpu().numpy(), lps_o.numpy()) < RTOL
 
 
-@pytest.mark.parametrize("B", [1, 7, 33])
+@pytest.mark.parametrize("B", [1, 7, 33, 100, 200])
 def test_persistent_partial_batches(B):
     cfg, P, b = _full_case(B, seed=B); d = dev(b)
     P = {k: v.clone() for k, v in P.items()}
@@ -62,7 +62,7 @@ def _train_grads(m, d, X):
     return logp.detach().cpu(), float(loss), {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("B", [64, 21])
+@pytest.mark.parametrize("B", [64, 21, 150])
 def test_persistent_training_forward_matches_unfused(B):
     """teacher-forced word loop in the persistent kernel (mode 1) vs the per-step launches: same log-probs,
     loss and gradients (the backward consumes the activations the kernel saved), with dropout 0.5."""
