@@ -566,8 +566,8 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int t
       hp = P.H12s[((long)t * B + r) * 2 * H + layer * H + j];
     } else {
       m = t > 0 ? __ldcg(P.unfinished + r) : 1.f;
-      cp = cst[e];
-      hp = *hxp;
+      cp = __ldcg(cst + e);
+      hp = __ldcg(hxp);
     }
     float z[4];
 #pragma unroll
@@ -905,63 +905,114 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
       P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
   }
-  gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
-  grid_barrier(P.sync_counter, sync_target, G);
-
+  if constexpr (train) {
+    // ---------------- teacher-forced word loop: G1 {ah, z1h, z2h} -> P1 -> G3 -> P3 ----------------
+    gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+    grid_barrier(P.sync_counter, sync_target, G);
 #pragma unroll 1
-  for (int t = 0; t < T; ++t) {
-    pk_stamp(P.dbg_clock, cta, t, 0);
-    // ===== G1: everything that needs only the previous state (and, when decoding, the current token) =====
-    //   AH = W_h2a.[h1|h2]   Z1h = W_h2h1.h1   Z2h = W_h2h2.h2   [decode: Z1x = W_i2h1.xt   Z1g = W_a2h1.gp]
-    gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);
-    pk_stamp(P.dbg_clock, cta, t, 1);
-    grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 2);
-    // ===== P1: attention (one CTA per caption)  ||  lstm_1 cell (the other CTAs) =====
-    if (G >= B + 8) {              // enough SMs: captions and cell elements on disjoint CTAs
-      if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, t, sv, bulk_phase);
-      else dec_cell_phase<TRAIN>(P, 0, t, cta - B, G - B);
-    } else {                       // large batches: every CTA walks its captions, then its cell elements
+    for (int t = 0; t < T; ++t) {
+      gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);          // AH, Z1h, Z2h
+      grid_barrier(P.sync_counter, sync_target, G);
+      if (G >= B + 8) {              // enough SMs: captions and cell elements on disjoint CTAs
+        if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, t, sv, bulk_phase);
+        else dec_cell_phase<TRAIN>(P, 0, t, cta - B, G - B);
+      } else {                       // large batches: every CTA walks its captions, then its cell elements
 #pragma unroll 1
-      for (int r = cta; r < B; r += G) dec_attention<TRAIN>(P, &maps.m[16], r, t, sv, bulk_phase);
-      dec_cell_phase<TRAIN>(P, 0, t, cta, G);
-    }
-    fence_proxy_async_smem();      // stages were read/written through the generic + bulk paths: order before TMA reuse
-    gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
-    pk_stamp(P.dbg_clock, cta, t, 3);
+        for (int r = cta; r < B; r += G) dec_attention<TRAIN>(P, &maps.m[16], r, t, sv, bulk_phase);
+        dec_cell_phase<TRAIN>(P, 0, t, cta, G);
+      }
+      fence_proxy_async_smem();      // stages were used through the generic + bulk paths: order before TMA reuse
+      gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
+      grid_barrier(P.sync_counter, sync_target, G);
+      gemm_phase(P.d, &s_sched[1], &s_sched[0], maps.m, R, sv, tmem_base, ps);          // Z2x, Z2a
+      grid_barrier(P.sync_counter, sync_target, G);
+      dec_cell_phase<TRAIN>(P, 1, t, cta, G);
+      if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+      grid_barrier(P.sync_counter, sync_target, G);
+    }                                // the heads are batched over all steps after the loop (SAModel.py:109-110)
+  } else {
+    // ---------------- greedy word loop ----------------
+    // The products that need only the states — AH, Z1h, Z2h of step t+1 — ride in the logits phase of step t, so
+    // the attention of step t+1 runs NEXT TO the pick of step t (both are one-CTA-per-caption phases) and the
+    // token-dependent phase G1 shrinks to Z1x, Z1g.  Before the loop the same schedule runs once on the initial
+    // state (its logits are ignored; same schedule = same slot layout).
+    gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
     grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 4);
-    // ===== G3: Z2x = W_i2h2.h1'   Z2a = W_a2h2.af =====
-    gemm_phase(P.d, &s_sched[1], train ? &s_sched[0] : &s_sched[2], maps.m, R, sv, tmem_base, ps);
-    pk_stamp(P.dbg_clock, cta, t, 5);
-    grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 6);
-    // ===== P3: lstm_2 cell =====
-    dec_cell_phase<TRAIN>(P, 1, t, cta, G);
-    if (!train) gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
-    else if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
-    pk_stamp(P.dbg_clock, cta, t, 7);
-    grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 8);
-    if (train) continue;           // the heads are batched over all steps after the loop (SAModel.py:109-110)
-    // ===== G4: logits (split-K partial tiles) =====
     gemm_phase(P.d, &s_sched[2], &s_sched[0], maps.m, R, sv, tmem_base, ps);
-    pk_stamp(P.dbg_clock, cta, t, 9);
+    gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
     grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 10);
-    // ===== P4: greedy pick + inputs of the next step (one CTA per caption) =====
+    const bool split_roles = G >= 2 * B;
 #pragma unroll 1
-    for (int r = cta; r < B; r += G) {
-      const int tokv = dec_pick(P, r, t, sv);
-      dec_token_inputs(P, r, tokv);
-      __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      pk_stamp(P.dbg_clock, cta, t, 0);
+      // ===== G1: Z1x = W_i2h1.xt   Z1g = W_a2h1.gp =====
+      gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);
+      pk_stamp(P.dbg_clock, cta, t, 1);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 2);
+      // ===== P1: lstm_1 cell (step 0 also runs the attention of step 0) =====
+      if (t == 0) {
+        if (G >= B + 8) {
+          if (cta < B) dec_attention<TRAIN>(P, &maps.m[16], cta, 0, sv, bulk_phase);
+          else dec_cell_phase<TRAIN>(P, 0, 0, cta - B, G - B);
+        } else {
+#pragma unroll 1
+          for (int r = cta; r < B; r += G) dec_attention<TRAIN>(P, &maps.m[16], r, 0, sv, bulk_phase);
+          dec_cell_phase<TRAIN>(P, 0, 0, cta, G);
+        }
+        fence_proxy_async_smem();
+      } else {
+        dec_cell_phase<TRAIN>(P, 0, t, cta, G);
+      }
+      gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
+      pk_stamp(P.dbg_clock, cta, t, 3);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 4);
+      // ===== G3: Z2x = W_i2h2.h1'   Z2a = W_a2h2.af =====
+      gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps);
+      pk_stamp(P.dbg_clock, cta, t, 5);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 6);
+      // ===== P3: lstm_2 cell =====
+      dec_cell_phase<TRAIN>(P, 1, t, cta, G);
+      gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
+      pk_stamp(P.dbg_clock, cta, t, 7);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 8);
+      // ===== G4: logits of step t  +  AH, Z1h, Z2h of step t+1 =====
+      gemm_phase(P.d, &s_sched[2], &s_sched[0], maps.m, R, sv, tmem_base, ps);
+      pk_stamp(P.dbg_clock, cta, t, 9);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 10);
+      // ===== P4: greedy pick + next-step inputs (CTAs < B)  ||  attention of step t+1 (CTAs B..2B-1) =====
+      if (split_roles) {
+        if (cta < B) {
+          const int tokv = dec_pick(P, cta, t, sv);
+          dec_token_inputs(P, cta, tokv);
+          __syncthreads();
+        } else if (cta < 2 * B && t + 1 < T) {
+          dec_attention<TRAIN>(P, &maps.m[16], cta - B, t + 1, sv, bulk_phase);
+        }
+      } else {
+#pragma unroll 1
+        for (int r = cta; r < B; r += G) {
+          const int tokv = dec_pick(P, r, t, sv);
+          dec_token_inputs(P, r, tokv);
+          __syncthreads();
+        }
+        if (t + 1 < T) {
+          fence_proxy_async_smem();
+#pragma unroll 1
+          for (int r = cta; r < B; r += G) dec_attention<TRAIN>(P, &maps.m[16], r, t + 1, sv, bulk_phase);
+        }
+      }
+      fence_proxy_async_smem();
+      if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+      pk_stamp(P.dbg_clock, cta, t, 11);
+      grid_barrier(P.sync_counter, sync_target, G);
+      pk_stamp(P.dbg_clock, cta, t, 12);
+      if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
     }
-    fence_proxy_async_smem();
-    if (t + 1 < T) gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
-    pk_stamp(P.dbg_clock, cta, t, 11);
-    grid_barrier(P.sync_counter, sync_target, G);
-    pk_stamp(P.dbg_clock, cta, t, 12);
-    if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
   gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
   pipeline_teardown(tmem_base);
@@ -1524,7 +1575,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   mk(DD_Z2A, 6, 14, 0, 4 * H, kbH);
   mk(DD_LOGIT, 7, 10, kbH, V, kbH);
   // both schedules are planned: the slot buffers (shared by the two modes) are sized by the larger slot count
-  const std::vector<std::vector<int>> phases_dec = {{DD_AH, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT}};
+  const std::vector<std::vector<int>> phases_dec = {{DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT, DD_AH, DD_Z1H, DD_Z2H}};
   const std::vector<std::vector<int>> phases_trn = {{DD_AH, DD_Z1H, DD_Z2H}, {DD_Z2X, DD_Z2A}, {}};
   std::vector<PSched> sched;
   int ns_cap[DD_COUNT];
@@ -1665,8 +1716,8 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   if (hp.dbg_clock) {   // XG_PERSIST_TRACE=1: average SM cycles per phase (CTA 0), printed to stderr
     std::vector<long long> h((size_t)T * PK_STAMPS);
     cudaMemcpy(h.data(), S->d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-    const char* names[6] = {"G1 (ah,z1h,z2h,z1x,z1g)", "P1 (attention || cell1)", "G3 (z2x,z2a)", "P3 (cell2)", "G4 (logits)",
-                            "P4 (pick, next inputs)"};
+    const char* names[6] = {"G1 (z1x,z1g)", "P1 (cell1)", "G3 (z2x,z2a)", "P3 (cell2)", "G4 (logits,ah,z1h,z2h)",
+                            "P4 (pick || attention t+1)"};
     double tot = 0;
     const int n = steps > 1 ? steps - 1 : 1;
     for (int i = 0; i < 6; ++i) {
