@@ -30,7 +30,7 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, rgb, opfl, fmask, pos, seq, smask, seed, *params):
         eng = model._engine
-        logp, cat, c = eng.train_fwd(rgb, opfl, fmask, pos, seq, smask, model.training, seed, keep=True)
+        logp, cat, c = eng.train_fwd(rgb, opfl, fmask, pos, seq, smask, model._train_flags(), seed, keep=True)
         ctx.model = model
         ctx.c = c
         ctx.save_for_backward(logp, cat)
@@ -123,6 +123,11 @@ class SAModel(CaptionModel):
             self._bump_bn_counters()
         return V, Uv, st
 
+    def _train_flags(self):
+        """`train` argument of xg_train_fwd: bit 0 training mode, bit 1 keep the BatchNorm running statistics
+        (set while sample() replays a batch it has already encoded in training mode)."""
+        return (1 if self.training else 0) | (2 if getattr(self, "_bn_frozen", False) else 0)
+
     def _bump_bn_counters(self):
         enc = self.two_spatial_encoder
         enc.visual_emb_rgb[1].num_batches_tracked += 1
@@ -152,17 +157,19 @@ class SAModel(CaptionModel):
 
     def forward(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):
         """SAModel.py:67-115 -> (word log-probs (m,L',V), category log-probs (m,L',C))."""
-        if self.training and self.ss_prob > 0.0:
+        if self.training and self.ss_prob > 0.0 and not getattr(self, "_bn_frozen", False):
             raise NotImplementedError("scheduled sampling (ss_prob > 0, SAModel.py:89-99) is not implemented yet in the "
                                       "fused training path; set scheduled_sampling_start=-1")
-        seed = self._engine.next_seed() if (self.training and self.drop_prob_lm > 0) else 0
+        seed = getattr(self, "_forced_seed", None)
+        if seed is None:
+            seed = self._engine.next_seed() if (self.training and self.drop_prob_lm > 0) else 0
         plist = self._engine.params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in plist):
             logp, cat = _TrainForward.apply(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask, seed, *plist)
         else:
             logp, cat, _ = self._engine.train_fwd(feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask,
-                                                  self.training, seed, keep=False)
-        if self.training:
+                                                  self._train_flags(), seed, keep=False)
+        if self.training and not getattr(self, "_bn_frozen", False):
             self._bump_bn_counters()
         return logp, cat
 
@@ -191,9 +198,10 @@ class SAModel(CaptionModel):
         sample_max = opt.get("sample_max", 1)
         beam_size = opt.get("beam_size", 1)
         temperature = opt.get("temperature", 1.0)
-        if self.training and self.drop_prob_lm > 0:
-            raise NotImplementedError("sample() in train mode with dropout (the SCST path, starttrain.py:131) is not "
-                                      "implemented yet; call model.eval() first")
+        if self.training:
+            if beam_size > 1:
+                raise NotImplementedError("sample_beam() under model.train() is not supported; call model.eval() first")
+            return self._sample_training(feats_rgb, feats_opfl, feat_mask, pos_feats, sample_max, temperature)
         feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
         if beam_size > 1:
             return self.sample_beam(feats, feat_mask, pos_feats, opt)
@@ -207,6 +215,43 @@ class SAModel(CaptionModel):
             # the reference crashes here (torch.cat of an empty list, SAModel.py:219)
             raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
         return seq[:, :steps], lps[:, :steps]
+
+
+    def _sample_training(self, feats_rgb, feats_opfl, feat_mask, pos_feats, sample_max, temperature):
+        """sample() under model.train() — the self-critical path (starttrain.py:131, myutils.py:41-77): tokens are
+        drawn with dropout and batch-statistics BatchNorm active, and the returned log-probs carry gradients.
+
+        1. the encoder runs ONCE in training mode (running statistics updated once, like the reference);
+        2. the word loop samples with the training dropout of the step (Philox seed s);
+        3. a teacher-forced forward on the sampled tokens with the SAME seed (running statistics frozen) reproduces
+           those activations and provides the autograd graph: seqLogprobs = gather(logp, seq)."""
+        eng = self._engine
+        seed = eng.next_seed()
+        with torch.no_grad():
+            feats, Uv, st = eng.encode(feats_rgb, feats_opfl, feat_mask, True, seed, True)
+            self._bump_bn_counters()
+            sseed = 0 if sample_max else eng.next_seed()
+            seq, lps, steps = eng.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max, temperature, sseed,
+                                                drop_seed=seed)
+        if steps == 0:
+            raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
+        seq = seq[:, :steps]
+        B = seq.size(0)
+        # inputs of the steps: <bos>, then the tokens just sampled; the state mask of step t >= 1 is `unfinished`
+        seq_in = torch.cat([seq.new_zeros(B, 1), seq[:, :steps - 1]], 1)
+        mask = torch.cat([torch.ones(B, 1, device=seq.device), (seq[:, :steps - 1] > 0).float()], 1)
+        self._forced_seed, self._bn_frozen = seed, True
+        try:
+            logp, _ = self.forward(feats_rgb, feats_opfl, feat_mask, pos_feats, seq_in, mask)
+        finally:
+            self._forced_seed, self._bn_frozen = None, False
+        lps = lps[:, :steps]
+        self._last_sample_logprobs = lps                 # from the sampling pass itself (diagnostics / tests)
+        gathered = logp[:, :steps].gather(2, seq.unsqueeze(2)).squeeze(2)
+        # a caption that finished before step t keeps recording the log-prob of its RAW sample (SAModel.py:209-210)
+        # while seq holds 0 there; those positions are exactly the ones RewardCriterion masks out (SAModel.py:262)
+        live = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=seq.device), seq[:, :steps - 1] > 0], 1)
+        return seq, torch.where(live, gathered, lps)
 
 
 # ------------------------------------------------------------------------------------------

@@ -195,6 +195,13 @@ int xg_params_changed(xg_handle h) {
   return XG_OK;
 }
 
+int xg_set_decode_dropout(xg_handle h, int on, uint64_t seed) {
+  CHECK_HANDLE(h);
+  h->dec_drop_on = on ? 1 : 0;
+  h->dec_drop_seed = seed;
+  return XG_OK;
+}
+
 int xg_set_engine(xg_handle h, int tensor_cores) {
   CHECK_HANDLE(h);
   h->tc_mode = tensor_cores >= 1 ? 1 : 0;
@@ -314,7 +321,8 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     XG_TRY(xg_attend_precompute(h, V, B, K, g.Uv, stream));
     Uv = g.Uv;
   }
-  if (sample_max && persist_eligible(h, B, K)) {   // fused persistent word loop (xg_persist.cuh)
+  const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;     // training-mode sampling (self-critical path)
+  if (sample_max && !step_drop && persist_eligible(h, B, K)) {   // fused persistent word loop (xg_persist.cuh)
     const int ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
     if (ps != PK_FALLBACK) return ps;
   }
@@ -332,7 +340,15 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     }
     if (t == T) break;   // the reference runs one more (unused) word step here (SAModel.py:216-217)
     XG_TRY(launch(h, "gather_rows", gather_rows_kernel, B, 128, 0, st, h->P[XG_P_EMBED_W], g.tok, 1, 0, B, B, d.embed, d.vocab, g.step.XT));
-    XG_TRY(decode_step_core(h, g.step.XT, t == 0 ? nullptr : g.unfinished, 1, V, Uv, pos, s, g.step, nullptr, B, K, 1, st));
+    DropSpec drops[3];
+    if (step_drop) {
+      const uint64_t base = (uint64_t)t * B * H;
+      drops[0] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_GATE, base);
+      drops[1] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_H1, base);
+      drops[2] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_H2, base);
+    }
+    XG_TRY(decode_step_core(h, g.step.XT, t == 0 ? nullptr : g.unfinished, 1, V, Uv, pos, s, g.step, nullptr, B, K, 1, st,
+                            step_drop ? drops : nullptr));
     XG_TRY(logits_core(h, g.st[2], H, B, g.logits, st));
   }
   XG_CUDA_TRY(h->es, cudaMemcpyAsync(h->h_pinned, g.flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,8 @@ struct xg_context {
   // optional per-kernel timing with CUDA events on the launching stream (xg_profile_enable/_report)
   int tc_mode = 1;           // 1: dense contractions above the size gate run on the tcgen05 3xTF32 engine
   int persist_mode = 1;      // 1: greedy decoding runs in the fused persistent word-step kernel when eligible
+  int dec_drop_on = 0;       // xg_set_decode_dropout: xg_sample_greedy applies the TRAINING dropout of the word step
+  unsigned long long dec_drop_seed = 0;   //   (same Philox sites / indices as xg_train_fwd with this seed)
   bool prof_on = false;
   struct ProfRec { std::string name; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof_recs;

@@ -33,8 +33,11 @@ static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) {
 // EncoderLstm_two_fc.forward (sub_modules.py:118-159)
 // ------------------------------------------------------------------------------------
 static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, const float* fmask, int B, int K,
-                       int train, uint64_t seed, EncBufs& eb, float* V_out, float* Uv_out,
+                       int train_flags, uint64_t seed, EncBufs& eb, float* V_out, float* Uv_out,
                        float* const* state_out, cudaStream_t st) {
+  // train_flags: bit 0 = training mode (batch statistics, dropout); bit 1 = do NOT update the BatchNorm running
+  // statistics (second pass over the same batch: the teacher-forced pass of the self-critical path)
+  const int train = train_flags & 1, bn_update = (train_flags & 2) ? 0 : 1;
   const xg_dims& d = ctx->d;
   const int H = d.rnn;
   const int BK = B * K;
@@ -56,7 +59,7 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
     }
     XG_TRY(launch(ctx, "bn_finalize", bn_finalize_kernel, ceil_div(H, 128), 128, 0, st, eb.part, RS, BK, H, train, P_(ctx, pw[s] + 2),
                                                         P_(ctx, pw[s] + 3), ctx->bn[2 * s], ctx->bn[2 * s + 1],
-                                                        d.bn_eps, d.bn_momentum, train ? 1 : 0, eb.scale[s],
+                                                        d.bn_eps, d.bn_momentum, (train && bn_update) ? 1 : 0, eb.scale[s],
                                                         eb.shift[s], eb.mean[s], eb.invstd[s]));
     // ReLU, dropout, frame mask; output frame-major (:123,128)
     XG_TRY(launch(ctx, "bn_apply", bn_apply_kernel, ew_grid((long)BK * H), 256, 0, st, eb.Y[s], eb.scale[s], eb.shift[s], fmask, B, K, H,
@@ -151,7 +154,8 @@ struct StepState {
 
 static int decode_step_core(xg_context* ctx, const float* xt, const float* mask, long mask_stride, const float* V,
                             const float* Uv, const float* pos, const StepState& s, StepBufs& sb, float* alpha_out,
-                            int B, int K, int feat_div, cudaStream_t st) {
+                            int B, int K, int feat_div, cudaStream_t st, const DropSpec* drops = nullptr) {
+  // drops (optional): training dropout of the step {POS gate relu, lstm_1 h, lstm_2 h} with per-step index bases
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att;
   // attention on the PREVIOUS states
@@ -173,6 +177,7 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     g.ep.tgt = pos;
     g.ep.ldt = H;
     g.ep.tgt_div = feat_div > 1 ? feat_div : 0;
+    if (drops) g.ep.drop = drops[0];
     XG_TRY(gemm_run(ctx, g, st));
   }
   // lstm_1
@@ -187,7 +192,7 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     gh.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gh, st));
     XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, sb.Z1, s.c1p, s.h1p, s.ld_h1p, mask, mask_stride, B, H,
-                                                         make_drop(false, 0.f, 0, 0), s.c1n, s.h1n, s.ld_h1n, nullptr, 0));
+                                                         drops ? drops[1] : make_drop(false, 0.f, 0, 0), s.c1n, s.h1n, s.ld_h1n, nullptr, 0));
   }
   // lstm_2
   {
@@ -201,7 +206,7 @@ static int decode_step_core(xg_context* ctx, const float* xt, const float* mask,
     gh.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gh, st));
     XG_TRY(launch(ctx, "dec_cell", dec_cell_kernel, ceil_div(B * H, 256), 256, 0, st, sb.Z2, s.c2p, s.h2p, s.ld_h2p, mask, mask_stride, B, H,
-                                                         make_drop(false, 0.f, 0, 0), s.c2n, s.h2n, s.ld_h2n, nullptr, 0));
+                                                         drops ? drops[2] : make_drop(false, 0.f, 0, 0), s.c2n, s.h2n, s.ld_h2n, nullptr, 0));
   }
   return XG_OK;
 }
@@ -228,6 +233,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   float* st0[4] = {S.H12, S.C1, S.H12 + H, S.C2};   // h1 | h2 interleaved in H12[0] with ld 2H
   // encoder + Uv; the init state goes straight into H12[0] / C1[0] / C2[0]
   XG_TRY(encode_core(ctx, rgb, opfl, fmask, B, K, train, seed, S.enc, S.V, S.Uv, nullptr, st));
+  train &= 1;      // bit 1 (no running-statistics update) only concerns the encoder's BatchNorm
   XG_TRY(init_hidden_core(ctx, S.V, fmask, B, K, S.enc.meanV, st0, 2 * H, st));
   // hoisted over all steps: embedding, POS gate, input parts of lstm_1
   XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, (int)LB, 128, 0, st, P_(ctx, XG_P_EMBED_W), seq, L, 1, B, (int)LB, E, V, S.XT));

@@ -256,8 +256,16 @@ class Engine:
                                         _stream()), "xg_decode_step", self.handle)
         return st_out[2], logp, st_out
 
-    def sample_greedy(self, V, Uv, pos, state, T: int, sample_max: int, temperature: float, seed: int):
+    def sample_greedy(self, V, Uv, pos, state, T: int, sample_max: int, temperature: float, seed: int,
+                      drop_seed: Optional[int] = None):
+        """drop_seed: apply the TRAINING dropout of the word step with this Philox seed (self-critical sampling)."""
         self.bind()
+        if drop_seed is not None:
+            L.check(self.lib.xg_set_decode_dropout(self.handle, 1, drop_seed), "xg_set_decode_dropout", self.handle)
+            try:
+                return self.sample_greedy(V, Uv, pos, state, T, sample_max, temperature, seed)
+            finally:
+                L.check(self.lib.xg_set_decode_dropout(self.handle, 0, 0), "xg_set_decode_dropout", self.handle)
         d = self.dims
         B, K = int(V.shape[0]), int(V.shape[1])
         pos = _req(pos, (B, d["H"]), torch.float32, "pos_feats")

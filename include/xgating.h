@@ -163,6 +163,14 @@ int xg_decode_step(xg_handle h, const int64_t* tokens, const float* xt, const fl
                    float* out, float* logp, int B, int K,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* Training-mode sampling (the self-critical path, starttrain.py:131: model.sample() under model.train()):
+ * while `on`, xg_sample_greedy applies the dropout of the training word step (POS gate, lstm_1 / lstm_2 hidden
+ * states) with the Philox sites and indices xg_train_fwd uses for `seed`, so that a teacher-forced xg_train_fwd on
+ * the sampled tokens with the same seed reproduces the sampled log-probs and provides their gradients.
+ * For xg_train_fwd / xg_encode_fwd, bit 1 of `train` (train = 3) keeps training-mode statistics and dropout but
+ * does not update the BatchNorm running statistics (second pass over the same batch). */
+int xg_set_decode_dropout(xg_handle h, int on, uint64_t seed);
+
 /* ---- decoding ---------------------------------------------------------------------- */
 /* SAModel.sample, beam_size == 1 (SAModel.py:176-219), word loop only (encoder via xg_encode_fwd).
  *   sample_max != 0: greedy (torch.max, :186).  sample_max == 0: multinomial with `temperature`

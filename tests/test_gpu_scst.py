@@ -1,0 +1,71 @@
+"""sample() under model.train() — the self-critical path (starttrain.py:131, SAModel.py:163-219,
+255-267): tokens drawn with dropout + batch-statistics BatchNorm active, returned log-probs carry gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import xgating_oracle as O
+from tests.common import RTOL, make_case, rel_err
+from tests.test_gpu_parity import _grad_check, build_model, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _masks(seed, p, B, K, H, L):
+    from controllable_xgating_b200.engine import dropout_mask
+
+    def mk(site, shape):
+        return dropout_mask(seed, site, int(np.prod(shape)), p, "cuda").cpu().view(*shape)
+    return {"enc_emb_rgb": mk("enc_emb_rgb", (B, K, H)), "enc_emb_opfl": mk("enc_emb_opfl", (B, K, H)),
+            "enc_gate_rgb": mk("enc_gate_rgb", (K, B, H)).transpose(0, 1).contiguous(),
+            "enc_gate_opfl": mk("enc_gate_opfl", (K, B, H)).transpose(0, 1).contiguous(),
+            "enc_fusion": mk("enc_fusion", (K, B, H)).transpose(0, 1).contiguous(),
+            "dec_gate": mk("dec_gate", (L, B, H)), "dec_h1": mk("dec_h1", (L, B, H)), "dec_h2": mk("dec_h2", (L, B, H)),
+            "cls": mk("cls", (L, B, 128))}
+
+
+@pytest.mark.parametrize("name,sample_max", [("mid", 0), ("mid", 1), ("tiny", 0)])
+def test_training_mode_sample_matches_oracle_and_backpropagates(name, sample_max):
+    import controllable_xgating_b200 as X
+    cfg, P, b = make_case(name); d = dev(b)
+    dims, B, K = cfg["dims"], cfg["B"], cfg["K"]
+    p = 0.5
+    m = build_model(cfg, P, drop=p).train()
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # the dropout seed Engine.next_seed() will draw first
+    torch.manual_seed(77)
+    seq, lp = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": sample_max, "beam_size": 1})
+    assert lp.requires_grad and tuple(lp.shape) == tuple(seq.shape)
+    steps = seq.shape[1]
+    # (1) the teacher-forced replay reproduces the log-probs of the sampling pass itself (same masks, same BatchNorm)
+    assert rel_err(lp.detach().cpu().numpy(), m._last_sample_logprobs.cpu().numpy()) < 1e-4
+    # (2) oracle: training-mode forward on the sampled tokens with the kernels' dropout masks replayed
+    seq_c = seq.cpu()
+    seq_in = torch.cat([torch.zeros(B, 1, dtype=torch.long), seq_c[:, :steps - 1]], 1)
+    mask = torch.cat([torch.ones(B, 1), (seq_c[:, :steps - 1] > 0).float()], 1)
+    masks = _masks(seed, p, B, K, dims["H"], steps)
+    Pg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in P.items()}
+    logp_o, _ = O.forward(Pg, b["rgb"], b["opfl"], b["feat_mask"], b["pos"], seq_in, mask, train=True, masks=masks)
+    lp_o = logp_o[:, :steps].gather(2, seq_c.unsqueeze(2)).squeeze(2)
+    live = torch.cat([torch.ones(B, 1, dtype=torch.bool), seq_c[:, :steps - 1] > 0], 1)   # positions RewardCriterion keeps
+    assert rel_err((lp.detach().cpu() * live).numpy(), (lp_o.detach() * live).numpy()) < RTOL
+    # (3) RewardCriterion (SAModel.py:255-267) and its gradients
+    g = torch.Generator().manual_seed(5)
+    reward = torch.rand(B, steps, generator=g) - 0.3
+    loss = X.RewardCriterion()(lp, seq, reward.cuda())
+    loss.backward()
+    loss_o = O.reward_criterion(lp_o, seq_c, reward)
+    assert abs(float(loss) - float(loss_o)) < 1e-4 * max(abs(float(loss_o)), 1e-3)
+    names = [k for k, v in Pg.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss_o, [Pg[k] for k in names], allow_unused=True)
+    _grad_check(m, {k: (gr.numpy() if gr is not None else np.zeros(tuple(Pg[k].shape), np.float32)) for k, gr in zip(names, grads)})
+
+
+def test_training_mode_sample_updates_batchnorm_once():
+    cfg, P, b = make_case("mid"); d = dev(b)
+    m1 = build_model(cfg, P, drop=0.5).train()
+    m2 = build_model(cfg, P, drop=0.5).train()
+    m1.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 0, "beam_size": 1})
+    m2(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
+    for (k1, v1), (k2, v2) in zip(m1.named_buffers(), m2.named_buffers()):
+        assert torch.equal(v1, v2), k1
