@@ -30,7 +30,8 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, rgb, opfl, fmask, pos, seq, smask, seed, *params):
         eng = model._engine
-        logp, cat, c = eng.train_fwd(rgb, opfl, fmask, pos, seq, smask, model._train_flags(), seed, keep=True)
+        logp, cat, c = eng.train_fwd(rgb, opfl, fmask, pos, seq, smask, model._train_flags(), seed, keep=True,
+                                     steps=getattr(model, "_forced_steps", None))
         ctx.model = model
         ctx.c = c
         ctx.save_for_backward(logp, cat)
@@ -158,8 +159,7 @@ class SAModel(CaptionModel):
     def forward(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):
         """SAModel.py:67-115 -> (word log-probs (m,L',V), category log-probs (m,L',C))."""
         if self.training and self.ss_prob > 0.0 and not getattr(self, "_bn_frozen", False):
-            raise NotImplementedError("scheduled sampling (ss_prob > 0, SAModel.py:89-99) is not implemented yet in the "
-                                      "fused training path; set scheduled_sampling_start=-1")
+            return self._forward_scheduled(feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask)
         seed = getattr(self, "_forced_seed", None)
         if seed is None:
             seed = self._engine.next_seed() if (self.training and self.drop_prob_lm > 0) else 0
@@ -168,7 +168,8 @@ class SAModel(CaptionModel):
             logp, cat = _TrainForward.apply(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask, seed, *plist)
         else:
             logp, cat, _ = self._engine.train_fwd(feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask,
-                                                  self._train_flags(), seed, keep=False)
+                                                  self._train_flags(), seed, keep=False,
+                                                  steps=getattr(self, "_forced_steps", None))
         if self.training and not getattr(self, "_bn_frozen", False):
             self._bump_bn_counters()
         return logp, cat
@@ -216,6 +217,26 @@ class SAModel(CaptionModel):
             raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
         return seq[:, :steps], lps[:, :steps]
 
+
+    def _forward_scheduled(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):
+        """forward() with scheduled sampling (ss_prob > 0, SAModel.py:89-99).  The sampled inputs carry no gradient
+        in the reference either, so: (1) encoder once in training mode; (2) a token pass walks the word loop
+        without gradients and decides every step's input token (ground truth, or a draw from the previous step's
+        distribution with probability ss_prob); (3) the teacher-forced forward on THOSE tokens with the same
+        dropout seed and frozen running statistics gives the log-probs and their graph."""
+        eng = self._engine
+        seed = eng.next_seed()
+        ss_seed = eng.next_seed()
+        with torch.no_grad():
+            feats, Uv, st = eng.encode(feats_rgb, feats_opfl, feat_mask, True, seed, True)
+            self._bump_bn_counters()
+            used, Lp = eng.scheduled_tokens(feats, Uv, pos_feats, st, seq, seq_mask, self.ss_prob, ss_seed, drop_seed=seed)
+        self._last_ss_tokens = used                       # diagnostics / tests
+        self._forced_seed, self._bn_frozen, self._forced_steps = seed, True, Lp
+        try:
+            return self.forward(feats_rgb, feats_opfl, feat_mask, pos_feats, used, seq_mask)
+        finally:
+            self._forced_seed, self._bn_frozen, self._forced_steps = None, False, None
 
     def _sample_training(self, feats_rgb, feats_opfl, feat_mask, pos_feats, sample_max, temperature):
         """sample() under model.train() — the self-critical path (starttrain.py:131, myutils.py:41-77): tokens are

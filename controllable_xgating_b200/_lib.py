@@ -61,6 +61,8 @@ SIGNATURES = {
     "xg_sample_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int,
                                  c_int, c_float, c_uint64, c_void_p, c_void_p, POINTER(c_int),
                                  c_void_p, c_size_t, c_void_p]),
+    "xg_scheduled_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_int, c_float, c_uint64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xg_sample_beam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),

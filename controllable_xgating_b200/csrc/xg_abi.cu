@@ -359,6 +359,52 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
   return XG_OK;
 }
 
+int xg_scheduled_tokens(xg_handle h, const float* V, const float* Uv, const float* pos, const float* const* state0,
+                        const int64_t* seq, const float* seq_mask, int B, int K, int L, int Lp, float ss_prob,
+                        uint64_t ss_seed, int64_t* tokens_out, void* ws, size_t ws_bytes, void* stream) {
+  CHECK_HANDLE(h); CHECK_BOUND(h);
+  CHECK_PTR(h, V); CHECK_PTR(h, pos); CHECK_PTR(h, state0); CHECK_PTR(h, seq); CHECK_PTR(h, seq_mask);
+  CHECK_PTR(h, tokens_out); CHECK_PTR(h, ws);
+  CHECK_POS(h, B); CHECK_POS(h, K); CHECK_POS(h, L); CHECK_POS(h, Lp);
+  if (Lp > L) return fail(h, XG_ERR_BAD_SHAPE, "xg_scheduled_tokens: Lp > L");
+  if (!(ss_prob >= 0.f && ss_prob <= 1.f)) return fail(h, XG_ERR_BAD_ARG, "xg_scheduled_tokens: ss_prob must be in [0,1]");
+  for (int q = 0; q < 4; ++q) CHECK_PTR(h, state0[q]);
+  XG_TRY(set_device(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const xg_dims& d = h->d;
+  const int H = d.rnn;
+  Arena a(ws, ws_bytes);
+  GreedyBufs g; carve_greedy(a, d, B, K, L, g);
+  if (a.overflow) return fail(h, XG_ERR_WORKSPACE, "xg_scheduled_tokens: workspace too small");
+  if (!Uv) {
+    XG_TRY(xg_attend_precompute(h, V, B, K, g.Uv, stream));
+    Uv = g.Uv;
+  }
+  const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;
+  for (int q = 0; q < 4; ++q)
+    XG_CUDA_TRY(h->es, cudaMemcpyAsync(g.st[q], state0[q], sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
+  XG_CUDA_TRY(h->es, cudaMemcpyAsync(tokens_out, seq, sizeof(int64_t) * (size_t)B * L, cudaMemcpyDeviceToDevice, st));
+  StepState s{g.st[0], H, g.st[1], g.st[2], H, g.st[3], g.st[0], H, g.st[1], g.st[2], H, g.st[3]};
+  for (int i = 0; i < Lp; ++i) {
+    if (i == 0 || ss_prob <= 0.f) {      // step 0 always takes the ground truth (SAModel.py:89: i >= 1)
+      XG_TRY(launch(h, "gather_rows", gather_rows_kernel, B, 128, 0, st, h->P[XG_P_EMBED_W], seq + i, L, 0, B, B, d.embed, d.vocab, g.step.XT));
+    } else {
+      XG_TRY(launch(h, "ss_pick", ss_pick_kernel, B, 256, 0, st, g.logits, d.vocab, i, L, ss_prob, ss_seed, seq, g.tok, tokens_out));
+      XG_TRY(launch(h, "gather_rows", gather_rows_kernel, B, 128, 0, st, h->P[XG_P_EMBED_W], g.tok, 1, 0, B, B, d.embed, d.vocab, g.step.XT));
+    }
+    DropSpec drops[3];
+    if (step_drop) {
+      const uint64_t base = (uint64_t)i * B * H;
+      drops[0] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_GATE, base);
+      drops[1] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_H1, base);
+      drops[2] = make_drop(true, d.drop_prob, h->dec_drop_seed, XG_DROP_DEC_H2, base);
+    }
+    XG_TRY(decode_step_core(h, g.step.XT, seq_mask + i, L, V, Uv, pos, s, g.step, nullptr, B, K, 1, st, step_drop ? drops : nullptr));
+    if (i + 1 < Lp && ss_prob > 0.f) XG_TRY(logits_core(h, g.st[2], H, B, g.logits, st));
+  }
+  return XG_OK;
+}
+
 int xg_sample_beam(xg_handle h, const float* V, const float* feat_mask, const float* pos, int B, int K, int T, int beam,
                    int64_t* seq_out, float* logp_out, int64_t* done_seq, float* done_logps, float* done_p,
                    int32_t* done_count, void* ws, size_t ws_bytes, void* stream) {

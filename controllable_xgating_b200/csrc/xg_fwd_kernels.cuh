@@ -363,6 +363,43 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, int 
   }
 }
 
+// scheduled sampling (SAModel.py:89-99): with probability ss_prob the input token of step i is drawn from the
+// previous step's word distribution exp(log_softmax(logits)), else it is the ground-truth token seq[b, i].
+// One CTA per caption; one Philox uniform decides, a second one drives the inverse-CDF scan (fixed order).
+__global__ void ss_pick_kernel(const float* __restrict__ logits, int V, int i, int L, float ss_prob, uint64_t seed,
+                               const int64_t* __restrict__ seq, int64_t* __restrict__ tok, int64_t* __restrict__ used) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const int64_t gt = seq[(long)b * L + i];
+  const float coin = philox_uniform(seed, 0x53530000u + (uint32_t)i, (uint64_t)b);
+  if (coin >= ss_prob) {           // uniform for the whole CTA
+    if (threadIdx.x == 0) { tok[b] = gt; used[(long)b * L + i] = gt; }
+    return;
+  }
+  const float* x = logits + (long)b * V;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, x[j]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(x[j] - mx);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float u = philox_uniform(seed, 0x53540000u + (uint32_t)i, (uint64_t)b) * s;
+    float acc = 0.f; int sel = V - 1;
+    for (int j = 0; j < V; ++j) {
+      acc += expf(x[j] - mx);
+      if (acc > u) { sel = j; break; }
+    }
+    tok[b] = (int64_t)sel;
+    used[(long)b * L + i] = (int64_t)sel;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, long n, float v) {
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }

@@ -256,6 +256,30 @@ class Engine:
                                         _stream()), "xg_decode_step", self.handle)
         return st_out[2], logp, st_out
 
+    def scheduled_tokens(self, V, Uv, pos, state, seq, smask, ss_prob: float, ss_seed: int, drop_seed: Optional[int]):
+        """input tokens of every step under scheduled sampling (SAModel.py:89-99); no gradients."""
+        self.bind()
+        d = self.dims
+        B, K = int(V.shape[0]), int(V.shape[1])
+        Lmax = int(seq.shape[1])
+        pos = _req(pos, (B, d["H"]), torch.float32, "pos_feats")
+        seq = _req(seq, (B, Lmax), torch.int64, "seq")
+        smask = _req(smask, (B, Lmax), torch.float32, "seq_mask")
+        Lp = self.seq_steps(seq)
+        out = torch.empty(B, Lmax, dtype=torch.int64, device=V.device)
+        ws = self.workspace(L.XG_WS_GREEDY, B, K, Lmax)
+        stp = (c_void_p * 4)(*[t.data_ptr() for t in state])
+        if drop_seed is not None:
+            L.check(self.lib.xg_set_decode_dropout(self.handle, 1, drop_seed), "xg_set_decode_dropout", self.handle)
+        try:
+            L.check(self.lib.xg_scheduled_tokens(self.handle, V.data_ptr(), _ptr(Uv), pos.data_ptr(), stp, seq.data_ptr(),
+                                                 smask.data_ptr(), B, K, Lmax, Lp, float(ss_prob), ss_seed, out.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream()), "xg_scheduled_tokens", self.handle)
+        finally:
+            if drop_seed is not None:
+                L.check(self.lib.xg_set_decode_dropout(self.handle, 0, 0), "xg_set_decode_dropout", self.handle)
+        return out, Lp
+
     def sample_greedy(self, V, Uv, pos, state, T: int, sample_max: int, temperature: float, seed: int,
                       drop_seed: Optional[int] = None):
         """drop_seed: apply the TRAINING dropout of the word step with this Philox seed (self-critical sampling)."""
@@ -309,7 +333,7 @@ class Engine:
                 "xg_seq_steps", self.handle)
         return out.value
 
-    def train_fwd(self, rgb, opfl, fmask, pos, seq, smask, train: bool, seed: int, keep: bool):
+    def train_fwd(self, rgb, opfl, fmask, pos, seq, smask, train: bool, seed: int, keep: bool, steps: Optional[int] = None):
         self.bind()
         d = self.dims
         B, K = int(rgb.shape[0]), int(rgb.shape[1])
@@ -320,7 +344,7 @@ class Engine:
         pos = _req(pos, (B, d["H"]), torch.float32, "pos_feats")
         seq = _req(seq, (B, Lmax), torch.int64, "seq")
         smask = _req(smask, (B, Lmax), torch.float32, "seq_mask")
-        Lp = self.seq_steps(seq)
+        Lp = self.seq_steps(seq) if steps is None else int(steps)   # `steps`: loop length decided on another sequence
         dev = rgb.device
         logp = torch.empty(B, Lp, d["V"], device=dev)
         cat = torch.empty(B, Lp, d["C"], device=dev)

@@ -184,6 +184,17 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
                      int64_t* seq_out, float* logp_out, int* steps_out,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* Scheduled sampling, token pass (SAModel.py:89-99 inside SAModel.forward): walks the teacher-forced word loop
+ * WITHOUT gradients and returns the input token of every step in tokens_out (B,L) int64: column 0 and, with
+ * probability 1 - ss_prob per caption and step, column i are the ground truth seq[b,i]; otherwise the token is drawn
+ * from the previous step's word distribution (Philox stream ss_seed).  State masks are seq_mask[:, i]; the training
+ * dropout of the step is applied when xg_set_decode_dropout is on.  A teacher-forced xg_train_fwd on tokens_out with
+ * the same dropout seed then reproduces the activations and provides log-probs with gradients.  Workspace:
+ * XG_WS_GREEDY with T = L. */
+int xg_scheduled_tokens(xg_handle h, const float* V, const float* Uv, const float* pos, const float* const* state0,
+                        const int64_t* seq, const float* seq_mask, int B, int K, int L, int Lp, float ss_prob,
+                        uint64_t ss_seed, int64_t* tokens_out, void* ws, size_t ws_bytes, void* stream);
+
 /* SAModel.sample_beam + CaptionModel.beam_search (SAModel.py:129-161, CaptionModel.py:22-128),
  * all B videos x `beam` rows advanced together on the device.
  *   V (B,K,H) fused feats, feat_mask (B,K), pos (B,H)

@@ -69,3 +69,41 @@ def test_training_mode_sample_updates_batchnorm_once():
     m2(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
     for (k1, v1), (k2, v2) in zip(m1.named_buffers(), m2.named_buffers()):
         assert torch.equal(v1, v2), k1
+
+
+@pytest.mark.parametrize("name,ss", [("mid", 0.5), ("tiny", 1.0), ("mid", 0.25)])
+def test_scheduled_sampling_forward_matches_oracle_on_the_tokens_used(name, ss):
+    """ss_prob > 0 (SAModel.py:89-99): the token pass decides the inputs, the replayed forward must
+    equal the oracle's training forward on exactly those tokens (dropout masks replayed), gradients included."""
+    import controllable_xgating_b200 as X
+    cfg, P, b = make_case(name); d = dev(b)
+    dims, B, K = cfg["dims"], cfg["B"], cfg["K"]
+    p = 0.5
+    m = build_model(cfg, P, drop=p).train()
+    m.ss_prob = ss
+    torch.manual_seed(99)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    torch.manual_seed(99)
+    logp, cat = m(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
+    Lp = logp.shape[1]
+    used = m._last_ss_tokens.cpu()
+    gt = b["seq"]
+    assert torch.equal(used[:, 0], gt[:, 0])                       # step 0 is never sampled
+    changed = (used[:, 1:Lp] != gt[:, 1:Lp]).float().mean().item()
+    if ss == 1.0:
+        assert changed > 0.8                                       # every input drawn from the model (vocab >= 40)
+    else:
+        assert 0.0 < changed <= ss + 0.25                          # B*L Bernoulli draws around ss_prob
+    L = gt.shape[1]
+    masks = _masks(seed, p, B, K, dims["H"], L)
+    Pg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in P.items()}
+    logp_o, cat_o = O.forward(Pg, b["rgb"], b["opfl"], b["feat_mask"], b["pos"], used[:, :Lp], b["seq_mask"][:, :Lp], train=True,
+                              masks=masks)
+    assert rel_err(logp.detach().cpu().numpy(), logp_o.detach().numpy()[:, :Lp]) < RTOL
+    loss = X.LanguageModelCriterion()(logp, d["seq"][:, :Lp], d["seq_mask"][:, :Lp])     # targets stay the ground truth
+    loss.backward()
+    loss_o = O.language_model_criterion(logp_o[:, :Lp], gt[:, :Lp], b["seq_mask"][:, :Lp])
+    assert abs(float(loss) - float(loss_o)) < 1e-4 * abs(float(loss_o))
+    names = [k for k, v in Pg.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss_o, [Pg[k] for k in names], allow_unused=True)
+    _grad_check(m, {k: (gr.numpy() if gr is not None else np.zeros(tuple(Pg[k].shape), np.float32)) for k, gr in zip(names, grads)})
