@@ -102,6 +102,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, %1;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte swizzle atoms, 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -219,59 +225,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_small = tmem_base + 2 * BN;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
+  // warp-uniform role dispatch (the whole warp walks the loops, one elected lane issues): inside a divergent
+  // `lane == 0` region every UTCHMMA / UTMALDG compiles to an ELECT + R2UR.BROADCAST waterfall (~90 cycles each)
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+  if (uwarp == 0) {
+    // ===== TMA producer =====
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % Cfg::kStages;
+      const uint32_t ph = (kb / Cfg::kStages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* st = smem + s * Cfg::kStageBytes;
+      if (elect_one_sync()) {
         if (prm.dbg & 4) {
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes / 2);
           tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
           tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
-          continue;
+        } else {
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
+          tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * 32, p0);
+          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
+          tma_load_2d(st + 2 * 128 * 128 + BN * 128, &tmQl, &full_bar[s], kb * 32, q0);
         }
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
-        tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * 32, p0);
-        tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
-        tma_load_2d(st + 2 * 128 * 128 + BN * 128, &tmQl, &full_bar[s], kb * 32, q0);
       }
+      __syncwarp();
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
-      for (int c = 0; c < num_chunks; ++c) {
-        const int b = c & 1;
-        mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+  } else if (uwarp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tsmall = tb + 2 * BN;
+    const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+    for (int c = 0; c < num_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_main = tb + b * BN;
+      for (int kk = 0; kk < kchunk; ++kk) {
+        const int kb = c * kchunk + kk;
+        if (kb >= num_kb) break;
+        const int s = kb % Cfg::kStages;
+        mbar_wait(&full_bar[s], (kb / Cfg::kStages) & 1);
         tc_fence_after();
-        const uint32_t tmem_main = tmem_base + b * BN;
-        for (int kk = 0; kk < kchunk; ++kk) {
-          const int kb = c * kchunk + kk;
-          if (kb >= num_kb) break;
-          const int s = kb % Cfg::kStages;
-          mbar_wait(&full_bar[s], (kb / Cfg::kStages) & 1);
-          tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t dlo = (((smem0 + s * Cfg::kStageBytes) & 0x3FFFFu) >> 4);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {         // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-            const uint64_t ph_d = umma_desc_sw128(base + k4 * 32);
-            const uint64_t pl_d = umma_desc_sw128(base + 128 * 128 + k4 * 32);
-            const uint64_t qh_d = umma_desc_sw128(base + 2 * 128 * 128 + k4 * 32);
-            const uint64_t ql_d = umma_desc_sw128(base + 2 * 128 * 128 + BN * 128 + k4 * 32);
+            const uint64_t ph_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (1u << 16));
+            const uint64_t pl_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((128 * 128) >> 4) + (1u << 16));
+            const uint64_t qh_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128) >> 4) + (1u << 16));
+            const uint64_t ql_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128 + BN * 128) >> 4) + (1u << 16));
             if (prm.dbg & 1) continue;
             umma_tf32(tmem_main, ph_d, qh_d, idesc, (kk | k4) != 0);
-            umma_tf32(tmem_small, pl_d, qh_d, idesc, (kb | k4) != 0);
-            umma_tf32(tmem_small, ph_d, ql_d, idesc, 1);
+            umma_tf32(tsmall, pl_d, qh_d, idesc, (kb | k4) != 0);
+            umma_tf32(tsmall, ph_d, ql_d, idesc, 1);
           }
           umma_commit(&empty_bar[s]);               // stage reusable once these MMAs have read it
+          if (kk == kchunk - 1 || kb == num_kb - 1) umma_commit(&acc_full[b]);   // this chain is complete
+          if (kb == num_kb - 1) umma_commit(small_full);
         }
-        umma_commit(&acc_full[b]);                  // this chain is complete
+        __syncwarp();
       }
-      umma_commit(small_full);
     }
   } else {
     // ===== epilogue warps: drain short chains into fp32 registers, then fused epilogue =====

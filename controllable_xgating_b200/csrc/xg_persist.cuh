@@ -104,12 +104,6 @@ __device__ __forceinline__ void pk_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, %1;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
-  return pred != 0;
-}
-
 // grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency).
 // (A variant with one release flag per CTA written by the last arriver measured slower: 2.2 vs 1.8 us.)
 __device__ __noinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int G) {
