@@ -171,6 +171,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__
     if rank == 0:
