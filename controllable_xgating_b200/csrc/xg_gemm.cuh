@@ -278,70 +278,74 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmP p) {
   float* Bs = sk_smem + 64 * SK_PA;    // K-major: [64][SK_PA]   N-major: [SK_KC][SK_PB]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  const int kbeg = blockIdx.z * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
-  const int kc = kend - kbeg;                       // <= SK_KC, multiple of 4 except possibly at the very end of K
-  const int kc4 = (kc + 3) >> 2;
-  // ---- one-shot fetch ----
-  for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {          // A: 64 rows x 32 chunks of 4 floats
-    const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
-    const int gi = m0 + row, gk = kbeg + c4 * 4;
-    int nb = (gi < p.M && gk < kend) ? min(16, (kend - gk) * 4) : 0;
-    const float* src = nb ? p.A + (long)gi * p.sa_i + gk : p.A;
-    if (c4 < kc4) cp_async16(As + row * SK_PA + c4 * 4, src, nb);
-  }
-  if (B_KMAJOR) {
-    for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {
-      const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
-      const int gj = n0 + row, gk = kbeg + c4 * 4;
-      int nb = (gj < p.N && gk < kend) ? min(16, (kend - gk) * 4) : 0;
-      const float* src = nb ? p.B + (long)gj * p.sb_j + gk : p.B;
-      if (c4 < kc4) cp_async16(Bs + row * SK_PA + c4 * 4, src, nb);
-    }
-  } else {
-    for (int e = tid; e < SK_KC * 16; e += 256) {               // B: kc rows x 16 chunks of 4 columns
-      const int kr = e >> 4, c4 = e & 15;
-      const int gk = kbeg + kr, gj = n0 + c4 * 4;
-      int nb = (gk < kend && gj < p.N) ? min(16, (p.N - gj) * 4) : 0;
-      const float* src = nb ? p.B + (long)gk * p.sb_r + gj : p.B;
-      if (kr < kc4 * 4) cp_async16(Bs + kr * SK_PB + c4 * 4, src, nb);
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
+  const int kbeg0 = blockIdx.z * p.kchunk, kend = min(p.K, kbeg0 + p.kchunk);
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 2
-  for (int k4 = 0; k4 < kc4; ++k4) {
-    float4 av[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(As + (ty + 16 * a) * SK_PA + k4 * 4);
+  // the K range of this CTA in pieces of SK_KC (one piece when the product is split, K / SK_KC pieces otherwise)
+  for (int kbeg = kbeg0; kbeg < kend; kbeg += SK_KC) {
+    const int kc = min(SK_KC, kend - kbeg);           // multiple of 4 except possibly at the very end of K
+    const int kc4 = (kc + 3) >> 2;
+    const int kstop = kbeg + kc;
+    if (kbeg != kbeg0) __syncthreads();               // the previous piece has been consumed
+    // ---- one-shot fetch ----
+    for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {          // A: 64 rows x 32 chunks of 4 floats
+      const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
+      const int gi = m0 + row, gk = kbeg + c4 * 4;
+      int nb = (gi < p.M && gk < kstop) ? min(16, (kstop - gk) * 4) : 0;
+      const float* src = nb ? p.A + (long)gi * p.sa_i + gk : p.A;
+      if (c4 < kc4) cp_async16(As + row * SK_PA + c4 * 4, src, nb);
+    }
     if (B_KMAJOR) {
-      float4 bv[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(Bs + (tx + 16 * b) * SK_PA + k4 * 4);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]); acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
-          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]); acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
-        }
+      for (int e = tid; e < 64 * (SK_KC / 4); e += 256) {
+        const int row = e / (SK_KC / 4), c4 = e % (SK_KC / 4);
+        const int gj = n0 + row, gk = kbeg + c4 * 4;
+        int nb = (gj < p.N && gk < kstop) ? min(16, (kstop - gk) * 4) : 0;
+        const float* src = nb ? p.B + (long)gj * p.sb_j + gk : p.B;
+        if (c4 < kc4) cp_async16(Bs + row * SK_PA + c4 * 4, src, nb);
+      }
     } else {
-      float4 bk[4];
+      for (int e = tid; e < SK_KC * 16; e += 256) {               // B: kc rows x 16 chunks of 4 columns
+        const int kr = e >> 4, c4 = e & 15;
+        const int gk = kbeg + kr, gj = n0 + c4 * 4;
+        int nb = (gk < kstop && gj < p.N) ? min(16, (p.N - gj) * 4) : 0;
+        const float* src = nb ? p.B + (long)gk * p.sb_r + gj : p.B;
+        if (kr < kc4 * 4) cp_async16(Bs + kr * SK_PB + c4 * 4, src, nb);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll 2
+    for (int k4 = 0; k4 < kc4; ++k4) {
+      float4 av[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bk[q] = *reinterpret_cast<const float4*>(Bs + (k4 * 4 + q) * SK_PB + tx * 4);
+      for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(As + (ty + 16 * a) * SK_PA + k4 * 4);
+      if (B_KMAJOR) {
+        float4 bv[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float ak[4] = {av[a].x, av[a].y, av[a].z, av[a].w};
+        for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(Bs + (tx + 16 * b) * SK_PA + k4 * 4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          acc[a][0] = fmaf(ak[q], bk[q].x, acc[a][0]); acc[a][1] = fmaf(ak[q], bk[q].y, acc[a][1]);
-          acc[a][2] = fmaf(ak[q], bk[q].z, acc[a][2]); acc[a][3] = fmaf(ak[q], bk[q].w, acc[a][3]);
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]); acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+            acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]); acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+          }
+      } else {
+        float4 bk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bk[q] = *reinterpret_cast<const float4*>(Bs + (k4 * 4 + q) * SK_PB + tx * 4);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float ak[4] = {av[a].x, av[a].y, av[a].z, av[a].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[a][0] = fmaf(ak[q], bk[q].x, acc[a][0]); acc[a][1] = fmaf(ak[q], bk[q].y, acc[a][1]);
+            acc[a][2] = fmaf(ak[q], bk[q].z, acc[a][2]); acc[a][3] = fmaf(ak[q], bk[q].w, acc[a][3]);
+          }
         }
       }
     }
@@ -430,6 +434,12 @@ static int gemm_skinny_launch(ErrorSink& es, const GemmP& p, cudaStream_t st, bo
     max_ctas[kmaj] = per_sm * sms;
   }
   dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64), p.ksplit > 1 ? p.ksplit : 1);
+  if (p.ksplit <= 1) {            // unsplit: CTAs are independent, an ordinary launch (any grid size)
+    if (kmaj) gemm_skinny_kernel<true><<<grid, 256, SK_SMEM, st>>>(p);
+    else gemm_skinny_kernel<false><<<grid, 256, SK_SMEM, st>>>(p);
+    XG_LAUNCH_CHECK(es);
+    return XG_OK;
+  }
   if ((long)grid.x * grid.y * grid.z > max_ctas[kmaj]) { *too_large = true; return XG_OK; }
   GemmP pc = p;
   void* args[1] = {(void*)&pc};

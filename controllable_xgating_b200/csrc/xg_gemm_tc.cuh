@@ -511,7 +511,7 @@ static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMa
 // split-K word-step kernel takes them over.
 static bool tc_eligible(const GemmP& p) {
   const long tiles = (long)ceil_div(p.N, 128) * ceil_div(p.M, 64);
-  return p.K >= 64 && tiles >= 64 && (long)p.M * p.N * p.K >= (1L << 24);
+  return p.K >= 64 && tiles >= 56 && (long)p.M * p.N * p.K >= (1L << 24);
 }
 
 // C (M,N) = epi( A . B ) in the GemmP convention (A(i,r), B(r,j), arbitrary strides).

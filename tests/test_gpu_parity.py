@@ -66,7 +66,8 @@ def test_gemm_engine(layout, shape):
 
 @pytest.mark.parametrize("layout", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(64, 2048, 512), (64, 512, 2048), (64, 1024, 1536), (64, 1536, 1024), (2, 2048, 512),
-                                   (37, 130, 1000), (256, 512, 2048), (64, 468, 2048)])
+                                   (37, 130, 1000), (256, 512, 2048), (64, 468, 2048), (320, 2048, 512), (320, 1536, 468),
+                                   (300, 10000, 512)])
 def test_gemm_split_k(layout, shape):
     """skinny recurrent products: split-K SIMT path (engine 3) is deterministic and fp32-exact-grade."""
     from controllable_xgating_b200.engine import debug_gemm
