@@ -252,7 +252,14 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
                                                  w.st[cur ^ 1][0], w.st[cur ^ 1][1], w.st[cur ^ 1][2], w.st[cur ^ 1][3]));
       cur ^= 1;
     }
-    // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154)
+    // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154): one persistent cooperative launch
+    // when the shape allows it (xg_persist.cuh), else the per-product launches below
+    if (persist_eligible(ctx, n, K, 512)) {
+      PersistStepIO io;
+      io.tokens = w.tokens; io.state = w.st[cur]; io.logp = w.logits; io.feat_div = beam; io.first = (t == -1);
+      const int pst = persist_decode(ctx, V, w.Uv, pos, nullptr, n, K, 1, nullptr, nullptr, nullptr, nullptr, st, &io);
+      if (pst != PK_FALLBACK) { XG_TRY(pst); continue; }
+    }
     XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, n, 128, 0, st, P_(ctx, XG_P_EMBED_W), w.tokens, 1, 0, n, n, E, Vn, w.step.XT));
     StepState s{w.st[cur][0], H, w.st[cur][1], w.st[cur][2], H, w.st[cur][3],
                 w.st[cur][0], H, w.st[cur][1], w.st[cur][2], H, w.st[cur][3]};

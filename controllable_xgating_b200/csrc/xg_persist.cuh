@@ -20,6 +20,8 @@
 //
 // Warp roles (320 threads): 0 TMA producer, 1 MMA issuer, 2-5 epilogue (TMEM lane quads), 6-9 weight split.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -107,6 +109,12 @@ __device__ __forceinline__ void pk_commit(uint32_t bar) {
 // grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency).
 // (A variant with one release flag per CTA written by the last arriver measured slower: 2.2 vs 1.8 us.)
 __device__ __noinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int G) {
+#ifdef PK_CG_BARRIER
+  fence_proxy_async_global();
+  cooperative_groups::this_grid().sync();
+  fence_proxy_async_global();
+  return;
+#endif
   fence_proxy_async_global();          // generic-proxy global writes -> visible to later TMA reads
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -510,6 +518,11 @@ struct DecParams {
   int64_t* seq; float* seqlogp; int* flags;   // (B,T), (B,T), (T)
   unsigned int* sync_counter;
   long long* dbg_clock;         // diagnostics, or NULL
+  // single-step mode (beam search: B rows = videos x beam, every feat_div consecutive rows share V / Uv / pos):
+  int feat_div, build_euv;
+  const int64_t* tokens_in;     // (B) input token of every row
+  float* state_out[4];          // (B,H) h1,c1,h2,c2 after the step (may alias state0)
+  float* logp_out;              // (B,V) log-softmax of the step
   // mode 1: teacher-forced training forward (SAModel.forward, SAModel.py:88-111) — no logit / pick phases; the
   // input parts of lstm_1 are hoisted (G1s holds them + all three biases on entry); every activation the
   // hand-written backward needs is stored in the step-major layouts of TrainSaved
@@ -600,6 +613,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   if (threadIdx.x == 0) PK_FINE(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = P.K, A = P.A, H = P.H, Hh = H / 2;
+  const int fb = r / P.feat_div;                // feature row (beam rows of one video share V / Uv)
   float* red = sv.scratch;                      // [PK_WARPS][K] per-warp partial scores
   float* sc = sv.scratch + PK_WARPS * K;        // K floats
   const float* uv = reinterpret_cast<const float*>(sv.stages);
@@ -613,12 +627,12 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
       if (k0 >= k1) break;
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
       pk_expect_tx(sv.bulk_bar + 8 * c, nb);
-      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)r * K + k0) * A, nb, sv.bulk_bar + 8 * c);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)fb * K + k0) * A, nb, sv.bulk_bar + 8 * c);
     }
     if (v_behind) {
       pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
-      pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, r * K);
-      pk_tma_2d(sv.stages_u32 + v_off + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, r * K);
+      pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
+      pk_tma_2d(sv.stages_u32 + v_off + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
     }
   }
   float ahr[DEC_NA], wr[DEC_NA];
@@ -680,8 +694,8 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
       if (threadIdx.x == 0 && (c == 1 || (c == 0 && k1 == K))) {
         fence_proxy_async_smem();
         pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
-        pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, r * K);
-        pk_tma_2d(sv.stages_u32 + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, r * K);
+        pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
+        pk_tma_2d(sv.stages_u32 + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
       }
     }
   }
@@ -735,7 +749,7 @@ constexpr int DEC_TI = 2;          // columns per thread: embed (padded) and rnn
 __device__ __noinline__ void dec_token_inputs(const DecParams& P, int r, int tokv) {
   const float* src = P.embed + (long)tokv * P.E;
   const float* tg = P.tgate + (long)tokv * P.H;
-  const float* ps = P.pos + (long)r * P.H;
+  const float* ps = P.pos + (long)(r / P.feat_div) * P.H;
   float x[DEC_TI], g[DEC_TI], q[DEC_TI];
 #pragma unroll
   for (int i = 0; i < DEC_TI; ++i) {
@@ -829,6 +843,63 @@ __device__ __noinline__ int dec_pick(const DecParams& P, int r, int t, const Sme
     PK_FINE(7);
   }
   return bi;
+}
+
+// log-softmax of row r (single-step mode): logits = sum of the split-K slots + bias staged in shared memory
+__device__ __noinline__ void dec_logsoftmax_row(const DecParams& P, int r, const SmemView& sv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int V = P.V, R = P.R;
+  const GDesc& dl = P.d[DD_LOGIT];
+  const long sstr = (long)R * dl.n_rows;
+  float* lg = reinterpret_cast<float*>(sv.stages);            // V floats
+  float* redf = sv.scratch;                                   // [PK_WARPS]
+  const float* lp0 = dl.out + (long)r * dl.n_rows;
+  float best = -INFINITY;
+#pragma unroll 1
+  for (int n0 = threadIdx.x; n0 < V; n0 += PK_THREADS * DEC_PB) {
+    float v[DEC_PB];
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) v[i] = 0.f;
+    const float* lp = lp0;
+#pragma unroll 1
+    for (int k = 0; k < dl.ns; ++k, lp += sstr) {
+      float tl[DEC_PB];
+#pragma unroll
+      for (int i = 0; i < DEC_PB; ++i) tl[i] = __ldcg(lp + min(n0 + i * PK_THREADS, V - 1));
+#pragma unroll
+      for (int i = 0; i < DEC_PB; ++i) v[i] += tl[i];
+    }
+    float bl[DEC_PB];
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) bl[i] = __ldg(P.b_logit + min(n0 + i * PK_THREADS, V - 1));
+#pragma unroll
+    for (int i = 0; i < DEC_PB; ++i) {
+      const int n = n0 + i * PK_THREADS;
+      const float x = v[i] + bl[i];
+      if (n < V) { lg[n] = x; best = fmaxf(best, x); }
+    }
+  }
+  best = warp_max(best);
+  if (lane == 0) redf[warp] = best;
+  __syncthreads();
+  best = redf[0];
+#pragma unroll
+  for (int w = 1; w < PK_WARPS; ++w) best = fmaxf(best, redf[w]);
+  float s = 0.f;
+#pragma unroll 4
+  for (int n = threadIdx.x; n < V; n += PK_THREADS) s += expf(lg[n] - best);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) redf[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < PK_WARPS; ++w) tot += redf[w];
+  const float lse = best + logf(tot);
+  float* out = P.logp_out + (long)r * V;
+#pragma unroll 4
+  for (int n = threadIdx.x; n < V; n += PK_THREADS) out[n] = lg[n] - lse;
+  __syncthreads();
 }
 
 // diagnostics (XG_PERSIST_TRACE): SM-clock stamps of CTA 0 for every step + globaltimer stamps of EVERY CTA for step 3
@@ -1009,6 +1080,87 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
     }
   }
   gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
+  pipeline_teardown(tmem_base);
+}
+
+// ONE word step for arbitrary state rows (beam search, CaptionModel.py:121-125 -> SAModel.get_logprobs_state,
+// SAModel.py:117-127): states and tokens in, states and the log-softmax of every row out.  Launched once per step;
+// exp(2 Uv) and the POS-gate token table persist in the pool between launches.
+__global__ void __launch_bounds__(PK_THREADS, 1)
+decode_step_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
+  __shared__ DecParams Psm;
+  __shared__ PSched s_sched[3];
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(DecParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Psm)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
+  __syncthreads();
+  const DecParams& P = Psm;
+  for (int i = threadIdx.x; i < (int)(3 * sizeof(PSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(PSched) / 4), w = i % (int)(sizeof(PSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(P.sched + (long)ph * G + cta)[w];
+  }
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 17) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+  uint32_t bulk_phase = 0;
+
+  for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
+    const int r = e / H, j = e % H;
+    float h1 = 0.f, h2 = 0.f;
+    if (r < B) {
+      h1 = P.state0[0][e]; h2 = P.state0[2][e];
+      P.cx[e] = P.state0[1][e]; P.cx[(long)R * H + e] = P.state0[3][e];
+    }
+    P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
+    store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + j, h1);
+    store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + H + j, h2);
+  }
+  for (int r = cta; r < R; r += G) {
+    if (r < B) {
+      dec_token_inputs(P, r, (int)P.tokens_in[r]);
+    } else {
+      for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { P.xt_hi[(long)r * P.Ep + k] = 0.f; P.xt_lo[(long)r * P.Ep + k] = 0.f; }
+      for (int j = threadIdx.x; j < H; j += PK_THREADS) {
+        P.gp_hi[(long)r * H + j] = 0.f; P.gp_lo[(long)r * H + j] = 0.f;
+        P.af_hi[(long)r * H + j] = 0.f; P.af_lo[(long)r * H + j] = 0.f;
+      }
+    }
+  }
+  if (P.build_euv) {
+    const long n = (long)((B + P.feat_div - 1) / P.feat_div) * P.K * P.A;
+    for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
+      P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
+  }
+  gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+  gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);           // AH, Z1h, Z2h, Z1x, Z1g
+  grid_barrier(P.sync_counter, sync_target, G);
+#pragma unroll 1
+  for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[16], r, 0, sv, bulk_phase);
+  dec_cell_phase<0>(P, 0, 0, cta, G);
+  fence_proxy_async_smem();
+  gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+  gemm_phase(P.d, &s_sched[1], &s_sched[2], maps.m, R, sv, tmem_base, ps);           // Z2x, Z2a
+  grid_barrier(P.sync_counter, sync_target, G);
+  dec_cell_phase<0>(P, 1, 0, cta, G);
+  gemm_prefetch(P.d, &s_sched[2], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+  gemm_phase(P.d, &s_sched[2], nullptr, maps.m, R, sv, tmem_base, ps);               // logits
+  grid_barrier(P.sync_counter, sync_target, G);
+#pragma unroll 1
+  for (int r = cta; r < B; r += G) dec_logsoftmax_row(P, r, sv);
+  for (int e = cta * PK_THREADS + threadIdx.x; e < B * H; e += G * PK_THREADS) {
+    const int r = e / H, j = e % H;
+    P.state_out[0][e] = __ldcg(P.hx + (long)r * 2 * H + j);
+    P.state_out[2][e] = __ldcg(P.hx + (long)r * 2 * H + H + j);
+    P.state_out[1][e] = __ldcg(P.cx + e);
+    P.state_out[3][e] = __ldcg(P.cx + (long)R * H + e);
+  }
   pipeline_teardown(tmem_base);
 }
 
@@ -1506,12 +1658,12 @@ static void persist_release(xg_context* ctx) {
 
 static inline int env_flag(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
 
-static bool persist_eligible(const xg_context* ctx, int B, int K) {
+static bool persist_eligible(const xg_context* ctx, int B, int K, int max_rows = 256) {
   const xg_dims& d = ctx->d;
   const bool v_behind = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
   const bool v_over = (long)K * d.rnn <= (long)std::min(K, 2 * DEC_FPC) * d.att;
   return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
-         d.att % 32 == 0 && B <= 256 && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
+         d.att % 32 == 0 && B <= max_rows && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
          (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS &&
          (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && (v_behind || v_over) &&
          (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000;
@@ -1539,10 +1691,20 @@ struct PersistTrainIO {
   DropSpec drop1, drop2;
 };
 
-// mode 0 (tr == nullptr): greedy decoding, T = seq_length.  mode 1: teacher-forced forward over T = L' steps.
+// single word step on arbitrary state rows (beam search): B rows, every feat_div of them share V / Uv / pos
+struct PersistStepIO {
+  const int64_t* tokens;   // (B)
+  float* const* state;     // h1,c1,h2,c2 (B,H): read, then overwritten with the new state
+  float* logp;             // (B,V) out
+  int feat_div;
+  int first;               // first step of a call: (re)build exp(2 Uv)
+};
+
+// mode 0 (tr == step == nullptr): greedy decoding, T = seq_length.  mode 1 (tr): teacher-forced forward over T = L'
+// steps.  mode 2 (step): one word step, states and log-probs out (asynchronous).
 static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
                           int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, const PersistTrainIO* tr,
-                          cudaStream_t st) {
+                          cudaStream_t st, const PersistStepIO* step = nullptr) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
@@ -1568,16 +1730,21 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   mk(DD_Z2X, 5, 10, 0, 4 * H, kbH);
   mk(DD_Z2A, 6, 14, 0, 4 * H, kbH);
   mk(DD_LOGIT, 7, 10, kbH, V, kbH);
-  // both schedules are planned: the slot buffers (shared by the two modes) are sized by the larger slot count
+  // every mode's schedule is planned: the slot buffers are shared and sized by the largest slot count
   const std::vector<std::vector<int>> phases_dec = {{DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT, DD_AH, DD_Z1H, DD_Z2H}};
   const std::vector<std::vector<int>> phases_trn = {{DD_AH, DD_Z1H, DD_Z2H}, {DD_Z2X, DD_Z2A}, {}};
+  const std::vector<std::vector<int>> phases_stp = {{DD_AH, DD_Z1H, DD_Z2H, DD_Z1X, DD_Z1G}, {DD_Z2X, DD_Z2A}, {DD_LOGIT}};
+  const int mode = tr ? 1 : (step ? 2 : 0);
+  const std::vector<std::vector<int>>* plans[3] = {&phases_dec, &phases_trn, &phases_stp};
   std::vector<PSched> sched;
   int ns_cap[DD_COUNT];
-  for (int i = 0; i < DD_COUNT; ++i) hp.d[i].ns = 0;
-  if (!persist_plan(tr ? phases_dec : phases_trn, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
-  for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = hp.d[i].ns;
-  if (!persist_plan(tr ? phases_trn : phases_dec, hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;   // the one that runs
-  for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = std::max(ns_cap[i], hp.d[i].ns);
+  for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = 0;
+  for (int pm = 0; pm < 3; ++pm) {
+    const int m = (mode + 1 + pm) % 3;            // the mode that runs is planned last (its slot counts stay in hp.d)
+    for (int i = 0; i < DD_COUNT; ++i) hp.d[i].ns = 0;
+    if (!persist_plan(*plans[m], hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
+    for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = std::max(ns_cap[i], hp.d[i].ns);
+  }
 
   // ---- device pool ----
   if (S->R != R || S->K != K) {
@@ -1612,20 +1779,20 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   }
   // consumers add every slot up to the per-product maximum and rely on never-written slots being zero: that
   // holds per schedule, so the slot buffers are cleared when the schedule changes (decode <-> training)
-  if (S->sched_mode != (tr ? 1 : 0)) {
+  if (S->sched_mode != mode) {
     if (S->sched_mode != -1) {
       char* lo = reinterpret_cast<char*>(hp.d[0].out);
       char* hi = reinterpret_cast<char*>(hp.d[DD_COUNT - 1].out) + sizeof(float) * (size_t)ns_cap[DD_COUNT - 1] * R * hp.d[DD_COUNT - 1].n_rows;
       XG_CUDA_TRY(ctx->es, cudaMemsetAsync(lo, 0, (size_t)(hi - lo), st));
     }
-    S->sched_mode = tr ? 1 : 0;
+    S->sched_mode = mode;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(hp.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
   // ---- POS-gate table of every token: tgate = relu(embed . W_gate^T + b)  (sub_modules.py:29-32 applied to
   //      SAModel.py:198's embedding rows); rebuilt whenever the bound parameters change ----
-  if (!tr && S->tgate_epoch != ctx->param_epoch) {
+  if (mode != 1 && S->tgate_epoch != ctx->param_epoch) {
     GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], E, ctx->P[XG_P_DGATE_W], E, S->tgate, H, V, H, E);
     g.ep.bias0 = ctx->P[XG_P_DGATE_B];
     g.ep.act = XG_ACT_RELU;
@@ -1647,7 +1814,8 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_TRY(tc_make_map(ctx, ts, hp.gp_hi, R, H, PK_BN, &maps[12])); XG_TRY(tc_make_map(ctx, ts, hp.gp_lo, R, H, PK_BN, &maps[13]));
   XG_TRY(tc_make_map(ctx, ts, hp.af_hi, R, H, PK_BN, &maps[14])); XG_TRY(tc_make_map(ctx, ts, hp.af_lo, R, H, PK_BN, &maps[15]));
   {   // V as [B*K][H]: one box = (H/2 columns) x (K frames) of a caption, dense in shared memory
-    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)B * K};
+    const int fdiv = step ? step->feat_div : 1;
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)((B + fdiv - 1) / fdiv) * K};
     cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)(H / 2), (cuuint32_t)K};
     cuuint32_t estr[2] = {1u, 1u};
@@ -1667,6 +1835,12 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.Vf = Vf; hp.Uv = Uv; hp.pos = pos;
   for (int q = 0; q < 4; ++q) hp.state0[q] = state0 ? state0[q] : nullptr;
   hp.mode = tr ? 1 : 0;
+  hp.feat_div = step ? step->feat_div : 1;
+  hp.build_euv = step ? step->first : 1;
+  if (step) {
+    hp.tokens_in = step->tokens; hp.logp_out = step->logp;
+    for (int q = 0; q < 4; ++q) { hp.state0[q] = step->state[q]; hp.state_out[q] = step->state[q]; }
+  }
   if (tr) {
     hp.L = tr->L; hp.seq_mask = tr->seq_mask;
     hp.G1s = tr->G1; hp.G2s = tr->G2; hp.C1s = tr->C1; hp.C2s = tr->C2; hp.H12s = tr->H12;
@@ -1679,7 +1853,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
-  if (!tr) {
+  if (mode == 0) {
     XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
     XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
   }
@@ -1691,17 +1865,18 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     int nb = 0, nb1 = 0;
     XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_persistent_kernel<0>, PK_THREADS, PK_SMEM_BYTES));
     XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, decode_persistent_kernel<1>, PK_THREADS, PK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_step_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
     XG_REQUIRE(ctx->es, nb >= 1 && nb1 >= 1, XG_ERR_CUDA, "persistent decoder does not fit on an SM");
     S->attr_set = true;
   }
   {
-    ProfScope ps(ctx, tr ? "train_decode_persistent" : "decode_persistent", st);
+    ProfScope ps(ctx, mode == 1 ? "train_decode_persistent" : (mode == 2 ? "decode_step_persistent" : "decode_persistent"), st);
     const DecParams* dp = S->d_params;
     void* args[2] = {(void*)&dp, (void*)&mt};
-    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(tr ? (void*)decode_persistent_kernel<1> : (void*)decode_persistent_kernel<0>, dim3(G),
-                                                     dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    void* fn = mode == 1 ? (void*)decode_persistent_kernel<1> : (mode == 2 ? (void*)decode_step_persistent_kernel : (void*)decode_persistent_kernel<0>);
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   }
-  if (tr) return XG_OK;            // asynchronous: the batched heads follow on the same stream
+  if (mode != 0) return XG_OK;     // asynchronous: the caller's next kernels follow on the same stream
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
   int steps = 0;
