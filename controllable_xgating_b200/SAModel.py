@@ -190,8 +190,13 @@ class SAModel(CaptionModel):
         with torch.no_grad():
             seq, lps, dseq, dlps, dp, dn = self._engine.sample_beam(feats, feat_masks, pos_feats, self.seq_length, beam_size)
         seq, lps, dseq, dlps, dp, dn = (t.cpu() for t in (seq, lps, dseq, dlps, dp, dn))
-        self.done_beams = [[{"seq": dseq[k, j].clone(), "logps": dlps[k, j].clone(), "p": float(dp[k, j])}
-                            for j in range(int(dn[k]))] for k in range(seq.size(0))]
+        # rows of the (freshly copied) host tensors are handed out as views: building 2 x B x beam clones costs
+        # milliseconds of interpreter time per batch
+        sq = [r.unbind(0) for r in dseq.unbind(0)]
+        lp = [r.unbind(0) for r in dlps.unbind(0)]
+        dpl, dnl = dp.tolist(), dn.tolist()
+        self.done_beams = [[{"seq": sq[k][j], "logps": lp[k][j], "p": dpl[k][j]} for j in range(dnl[k])]
+                           for k in range(seq.size(0))]
         return seq, lps
 
     def sample(self, feats_rgb, feats_opfl, feat_mask, pos_feats, opt={}):

@@ -99,62 +99,67 @@ inline void carve_beam(Arena& a, const xg_dims& d, int B, int K, int T, int beam
   carve_step(a, d, (int)n, w.step);
 }
 
-// one thread per video: candidate merge + bookkeeping of beam_step and the done-beam harvest
+// one warp per video: candidate merge + bookkeeping of beam_step and the done-beam harvest.  The stable
+// descending sort is a rank count (rank = candidates that score higher, or equal with a lower index).
+constexpr int BEAM_MERGE_WARPS = 4;
 __global__ void beam_merge_kernel(const float* __restrict__ ys, const int* __restrict__ ix, int B, int beam, int T, int t,
                                   const int64_t* __restrict__ seq_in, const float* __restrict__ lps_in,
                                   int64_t* __restrict__ seq_out, float* __restrict__ lps_out, float* __restrict__ sum,
                                   int* __restrict__ parent, int64_t* __restrict__ tokens,
                                   int64_t* __restrict__ done_seq, float* __restrict__ done_lps,
                                   float* __restrict__ done_p, int* __restrict__ done_n) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_cp[BEAM_MERGE_WARPS][XG_MAX_BEAM * XG_MAX_BEAM];
+  __shared__ int s_sel[BEAM_MERGE_WARPS][XG_MAX_BEAM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * BEAM_MERGE_WARPS + warp;
   if (k >= B) return;
   const int rows = (t == 0) ? 1 : beam;
   const int ncand = rows * beam;
-  double cp[XG_MAX_BEAM * XG_MAX_BEAM];
-  int order[XG_MAX_BEAM * XG_MAX_BEAM];
+  double* cp = s_cp[warp];
+  int* sel = s_sel[warp];
   // enumerate column-major: c outer, q inner
-  int n = 0;
-  for (int c = 0; c < beam; ++c)
-    for (int q = 0; q < rows; ++q) {
-      cp[n] = (double)sum[(long)k * beam + q] + (double)ys[((long)k * beam + q) * beam + c];
-      order[n] = n;
-      ++n;
-    }
-  // stable insertion sort by descending score
-  for (int a = 1; a < ncand; ++a) {
-    const int oa = order[a];
-    const double pa = cp[oa];
-    int b = a - 1;
-    while (b >= 0 && cp[order[b]] < pa) { order[b + 1] = order[b]; --b; }
-    order[b + 1] = oa;
+  for (int n = lane; n < ncand; n += 32) {
+    const int c = n / rows, q = n % rows;
+    cp[n] = (double)sum[(long)k * beam + q] + (double)ys[((long)k * beam + q) * beam + c];
   }
-  float new_sum[XG_MAX_BEAM];
+  if (lane < beam) sel[lane] = lane < ncand ? lane : 0;
+  __syncwarp();
+  for (int n = lane; n < ncand; n += 32) {
+    const double pn = cp[n];
+    int rank = 0;
+    for (int m = 0; m < ncand; ++m) rank += (cp[m] > pn || (cp[m] == pn && m < n)) ? 1 : 0;
+    if (rank < beam) sel[rank] = n;
+  }
+  __syncwarp();
+  int dn = done_n[k];
+  __syncwarp();
   for (int vix = 0; vix < beam; ++vix) {
-    const int cand = order[vix];
+    const int cand = sel[vix];
     const int c = cand / rows, q = cand % rows;
     const long src = ((long)k * beam + q) * T, dst = ((long)k * beam + vix) * T;
-    for (int u = 0; u < t; ++u) { seq_out[dst + u] = seq_in[src + u]; lps_out[dst + u] = lps_in[src + u]; }
     const int word = ix[((long)k * beam + q) * beam + c];
-    seq_out[dst + t] = word;
-    lps_out[dst + t] = ys[((long)k * beam + q) * beam + c];
-    for (int u = t + 1; u < T; ++u) { seq_out[dst + u] = 0; lps_out[dst + u] = 0.f; }
-    new_sum[vix] = (float)cp[cand];
-    parent[(long)k * beam + vix] = k * beam + q;
-    tokens[(long)k * beam + vix] = word;
-  }
-  int dn = done_n[k];
-  for (int vix = 0; vix < beam; ++vix) {
-    const long dst = ((long)k * beam + vix) * T;
-    if (seq_out[dst + t] == 0 || t == T - 1) {
-      const long dd = ((long)k * T * beam + dn) * T;
-      for (int u = 0; u < T; ++u) { done_seq[dd + u] = seq_out[dst + u]; done_lps[dd + u] = lps_out[dst + u]; }
-      done_p[(long)k * T * beam + dn] = new_sum[vix];
-      ++dn;
-      new_sum[vix] = -1000.f;
+    const float wlp = ys[((long)k * beam + q) * beam + c];
+    float nsum = (float)cp[cand];
+    const bool done = word == 0 || t == T - 1;
+    const long dd = ((long)k * T * beam + dn) * T;
+    for (int u = lane; u < T; u += 32) {
+      const int64_t sv = u < t ? seq_in[src + u] : (u == t ? (int64_t)word : (int64_t)0);
+      const float lv = u < t ? lps_in[src + u] : (u == t ? wlp : 0.f);
+      seq_out[dst + u] = sv; lps_out[dst + u] = lv;
+      if (done) { done_seq[dd + u] = sv; done_lps[dd + u] = lv; }
     }
-    sum[(long)k * beam + vix] = new_sum[vix];
+    if (done) {
+      if (lane == 0) done_p[(long)k * T * beam + dn] = nsum;
+      ++dn;
+      nsum = -1000.f;
+    }
+    if (lane == 0) {
+      sum[(long)k * beam + vix] = nsum;
+      parent[(long)k * beam + vix] = k * beam + q;
+      tokens[(long)k * beam + vix] = word;
+    }
   }
-  done_n[k] = dn;
+  if (lane == 0) done_n[k] = dn;
 }
 
 // dst[row,:] = src[parent[row],:] for the four state tensors
@@ -240,25 +245,32 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(w.lps[0], 0, sizeof(float) * (size_t)n * T, st));
   int cur = 0;     // state buffer holding the current states
   int sb = 0;      // seq buffer holding the current beams
+  // the word step runs as one persistent cooperative launch when the shape allows it (xg_persist.cuh): it also
+  // gathers the parent states on the way in and leaves the per-row top-`beam` on the way out
+  bool fused = persist_eligible(ctx, n, K, 512) && beam <= XG_MAX_BEAM;
   for (int t = -1; t < T; ++t) {
     if (t >= 0) {
-      XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));
-      XG_TRY(launch(ctx, "beam_merge", beam_merge_kernel, ceil_div(B, 64), 64, 0, st, w.ys, w.ix, B, beam, T, t, w.seq[sb], w.lps[sb], w.seq[sb ^ 1],
-                                                       w.lps[sb ^ 1], w.sum, w.parent, w.tokens, w.done_seq, w.done_lps,
-                                                       w.done_p, w.done_n));
+      if (!fused) XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));
+      XG_TRY(launch(ctx, "beam_merge", beam_merge_kernel, ceil_div(B, BEAM_MERGE_WARPS), 32 * BEAM_MERGE_WARPS, 0, st, w.ys, w.ix, B, beam, T, t,
+                    w.seq[sb], w.lps[sb], w.seq[sb ^ 1], w.lps[sb ^ 1], w.sum, w.parent, w.tokens, w.done_seq, w.done_lps,
+                    w.done_p, w.done_n));
       sb ^= 1;
       if (t == T - 1) break;   // the reference's last get_logprobs_state result is never used
-      XG_TRY(launch(ctx, "beam_gather_state", beam_gather_state_kernel, n, 128, 0, st, w.parent, H, w.st[cur][0], w.st[cur][1], w.st[cur][2], w.st[cur][3],
-                                                 w.st[cur ^ 1][0], w.st[cur ^ 1][1], w.st[cur ^ 1][2], w.st[cur ^ 1][3]));
-      cur ^= 1;
+      if (!fused) {
+        XG_TRY(launch(ctx, "beam_gather_state", beam_gather_state_kernel, n, 128, 0, st, w.parent, H, w.st[cur][0], w.st[cur][1], w.st[cur][2], w.st[cur][3],
+                                                   w.st[cur ^ 1][0], w.st[cur ^ 1][1], w.st[cur ^ 1][2], w.st[cur ^ 1][3]));
+        cur ^= 1;
+      }
     }
-    // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154): one persistent cooperative launch
-    // when the shape allows it (xg_persist.cuh), else the per-product launches below
-    if (persist_eligible(ctx, n, K, 512)) {
+    // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154)
+    if (fused) {
       PersistStepIO io;
-      io.tokens = w.tokens; io.state = w.st[cur]; io.logp = w.logits; io.feat_div = beam; io.first = (t == -1);
+      io.tokens = w.tokens; io.state = w.st[cur]; io.logp = nullptr; io.feat_div = beam; io.first = (t == -1);
+      io.parent = t >= 0 ? w.parent : nullptr; io.ys = w.ys; io.ix = w.ix; io.topk = beam;
       const int pst = persist_decode(ctx, V, w.Uv, pos, nullptr, n, K, 1, nullptr, nullptr, nullptr, nullptr, st, &io);
       if (pst != PK_FALLBACK) { XG_TRY(pst); continue; }
+      XG_REQUIRE(ctx->es, t == -1, XG_ERR_CUDA, "persistent word step became unavailable inside a beam search");
+      fused = false;
     }
     XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, n, 128, 0, st, P_(ctx, XG_P_EMBED_W), w.tokens, 1, 0, n, n, E, Vn, w.step.XT));
     StepState s{w.st[cur][0], H, w.st[cur][1], w.st[cur][2], H, w.st[cur][3],

@@ -522,7 +522,10 @@ struct DecParams {
   int feat_div, build_euv;
   const int64_t* tokens_in;     // (B) input token of every row
   float* state_out[4];          // (B,H) h1,c1,h2,c2 after the step (may alias state0)
-  float* logp_out;              // (B,V) log-softmax of the step
+  float* logp_out;              // (B,V) log-softmax of the step, or NULL
+  const int* parent_in;         // (B) row of state0 each row continues from (beam reordering), or NULL = identity
+  float* ys_out; int* ix_out;   // (B,topk) per-row top-k of the log-probs with the UNK penalty (CaptionModel.py:94), or NULL
+  int topk;
   // mode 1: teacher-forced training forward (SAModel.forward, SAModel.py:88-111) — no logit / pick phases; the
   // input parts of lstm_1 are hoisted (G1s holds them + all three biases on entry); every activation the
   // hand-written backward needs is stored in the step-major layouts of TrainSaved
@@ -896,10 +899,56 @@ __device__ __noinline__ void dec_logsoftmax_row(const DecParams& P, int r, const
 #pragma unroll
   for (int w = 0; w < PK_WARPS; ++w) tot += redf[w];
   const float lse = best + logf(tot);
-  float* out = P.logp_out + (long)r * V;
+  float* out = P.logp_out ? P.logp_out + (long)r * V : nullptr;
 #pragma unroll 4
-  for (int n = threadIdx.x; n < V; n += PK_THREADS) out[n] = lg[n] - lse;
+  for (int n = threadIdx.x; n < V; n += PK_THREADS) {
+    const float y = lg[n] - lse;
+    if (out) out[n] = y;
+    lg[n] = n == 1 ? y - 1000.f : y;           // UNK penalty before the selection (CaptionModel.py:94)
+  }
   __syncthreads();
+  if (P.ys_out) {
+    // per-row top-k for the beam step: value descending, lowest index first on exact ties (the order a stable
+    // descending sort of the row gives, CaptionModel.py:40); a selected entry becomes NaN (never compares greater)
+    // Every thread keeps the best of the entries it owns (n = tid mod 320); after a selection only the owner of
+    // the selected entry rescans.
+    int* redi = reinterpret_cast<int*>(sv.scratch + 16);
+    auto scan_own = [&](float& bv, int& bi) {
+      bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll 4
+      for (int n = threadIdx.x; n < V; n += PK_THREADS) {
+        const float v = lg[n];
+        if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
+      }
+    };
+    float bv; int bi;
+    scan_own(bv, bi);
+#pragma unroll 1
+    for (int c = 0; c < P.topk; ++c) {
+      float wv = bv; int wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+      }
+      if (lane == 0) { redf[warp] = wv; redi[warp] = wi; }
+      __syncthreads();
+      wv = redf[0]; wi = redi[0];
+#pragma unroll
+      for (int w = 1; w < PK_WARPS; ++w)
+        if (redf[w] > wv || (redf[w] == wv && redi[w] < wi)) { wv = redf[w]; wi = redi[w]; }
+      if (threadIdx.x == 0) {
+        P.ys_out[(long)r * P.topk + c] = wv;
+        P.ix_out[(long)r * P.topk + c] = wi;
+      }
+      if (wi < V && wi % PK_THREADS == (int)threadIdx.x) {
+        lg[wi] = __int_as_float(0x7fc00000);
+        scan_own(bv, bi);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // diagnostics (XG_PERSIST_TRACE): SM-clock stamps of CTA 0 for every step + globaltimer stamps of EVERY CTA for step 3
@@ -1112,8 +1161,9 @@ decode_step_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_con
     const int r = e / H, j = e % H;
     float h1 = 0.f, h2 = 0.f;
     if (r < B) {
-      h1 = P.state0[0][e]; h2 = P.state0[2][e];
-      P.cx[e] = P.state0[1][e]; P.cx[(long)R * H + e] = P.state0[3][e];
+      const long src = P.parent_in ? (long)__ldg(P.parent_in + r) * H + j : (long)e;   // beam reordering (CaptionModel.py:62-64)
+      h1 = P.state0[0][src]; h2 = P.state0[2][src];
+      P.cx[e] = P.state0[1][src]; P.cx[(long)R * H + e] = P.state0[3][src];
     }
     P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
     store_split(P.hh_hi, P.hh_lo, (long)r * 2 * H + j, h1);
@@ -1611,8 +1661,14 @@ struct PersistState {
   long long* d_dbg = nullptr;
   float* tgate = nullptr;
   unsigned long long tgate_epoch = ~0ull;
-  int sched_mode = -1;           // schedule the slot buffers were last written under (0 decode, 1 training)
+  int sched_mode = -1;           // schedule the slot buffers were last written under (0 decode, 1 training, 2 single step)
   bool attr_set = false;
+  // single-step mode: everything but the per-step pointers is reused while the key below holds
+  bool step_valid = false;
+  int step_B = 0, step_fdiv = 0;
+  const float *step_V = nullptr, *step_Uv = nullptr, *step_pos = nullptr;
+  unsigned long long step_epoch = ~0ull;
+  MapTable step_mt;
   // decoder backward
   int dbB = 0, dbK = 0;
   char* dbpool = nullptr;
@@ -1695,9 +1751,12 @@ struct PersistTrainIO {
 struct PersistStepIO {
   const int64_t* tokens;   // (B)
   float* const* state;     // h1,c1,h2,c2 (B,H): read, then overwritten with the new state
-  float* logp;             // (B,V) out
+  float* logp;             // (B,V) out, or NULL
   int feat_div;
   int first;               // first step of a call: (re)build exp(2 Uv)
+  const int* parent;       // (B) or NULL: row r starts from state row parent[r] (read before any row is written)
+  float* ys; int* ix;      // (B,topk) top-k of every row with the UNK penalty, or NULL
+  int topk;
 };
 
 // mode 0 (tr == step == nullptr): greedy decoding, T = seq_length.  mode 1 (tr): teacher-forced forward over T = L'
@@ -1715,6 +1774,25 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   if (!S) S = new PersistState();
   DecParams& hp = S->hp;
   const int kbH = H / 32, kbE = Ep / 32;
+  auto step_io = [&]() {
+    hp.build_euv = step->first;
+    hp.tokens_in = step->tokens; hp.logp_out = step->logp;
+    hp.parent_in = step->parent; hp.ys_out = step->ys; hp.ix_out = step->ix; hp.topk = step->topk;
+    for (int q = 0; q < 4; ++q) { hp.state0[q] = step->state[q]; hp.state_out[q] = step->state[q]; }
+  };
+  if (step && S->step_valid && S->sched_mode == 2 && S->R == R && S->K == K && S->step_B == B && S->step_fdiv == step->feat_div &&
+      S->step_V == Vf && S->step_Uv == Uv && S->step_pos == pos && S->step_epoch == ctx->param_epoch && !step->first) {
+    // later steps of the same beam search: plans, tensor maps and the device schedule are those of the last launch
+    step_io();
+    XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
+    XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
+    ProfScope ps(ctx, "decode_step_persistent", st);
+    const DecParams* dp = S->d_params;
+    void* args[2] = {(void*)&dp, (void*)&S->step_mt};
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_step_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    return XG_OK;
+  }
+  S->step_valid = false;
 
   // ---- products ----
   auto mk = [&](int id, int wmap, int xmap, int xkb0, int n_rows, int nkb) {
@@ -1836,11 +1914,8 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int q = 0; q < 4; ++q) hp.state0[q] = state0 ? state0[q] : nullptr;
   hp.mode = tr ? 1 : 0;
   hp.feat_div = step ? step->feat_div : 1;
-  hp.build_euv = step ? step->first : 1;
-  if (step) {
-    hp.tokens_in = step->tokens; hp.logp_out = step->logp;
-    for (int q = 0; q < 4; ++q) { hp.state0[q] = step->state[q]; hp.state_out[q] = step->state[q]; }
-  }
+  hp.build_euv = 1;
+  if (step) step_io();
   if (tr) {
     hp.L = tr->L; hp.seq_mask = tr->seq_mask;
     hp.G1s = tr->G1; hp.G2s = tr->G2; hp.C1s = tr->C1; hp.C2s = tr->C2; hp.H12s = tr->H12;
@@ -1875,6 +1950,10 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     void* args[2] = {(void*)&dp, (void*)&mt};
     void* fn = mode == 1 ? (void*)decode_persistent_kernel<1> : (mode == 2 ? (void*)decode_step_persistent_kernel : (void*)decode_persistent_kernel<0>);
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  }
+  if (mode == 2) {
+    S->step_valid = true; S->step_B = B; S->step_fdiv = step->feat_div; S->step_V = Vf; S->step_Uv = Uv; S->step_pos = pos;
+    S->step_epoch = ctx->param_epoch; S->step_mt = mt;
   }
   if (mode != 0) return XG_OK;     // asynchronous: the caller's next kernels follow on the same stream
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
