@@ -243,7 +243,40 @@ def main():
         seq, lp = model.sample(rgb, opfl, fm, pos, gopt)
         return seq.cpu(), lp.cpu()
 
-    ms_e2e = timed(greedy_e2e, args.steps, args.warmup)
+    ms_e2e_serial = timed(greedy_e2e, args.steps, args.warmup)
+
+    # the same through the package's input pipeline (input_pipeline.DeviceStager): the host->device copy of batch
+    # i+1 runs on a copy stream while batch i decodes.  One timed region over all K steps; every step's H2D, L2
+    # flush, decode and id read-back are inside it.
+    from controllable_xgating_b200.input_pipeline import DeviceStager
+    stager = DeviceStager(dev)
+    host_in = {k: pinned[k] for k in ("rgb", "opfl", "feat_mask", "pos")}
+
+    def greedy_pipelined(steps):
+        out = []
+        nxt = stager.put(**host_in)
+        for i in range(steps):
+            cur = nxt
+            if i + 1 < steps:
+                nxt = stager.put(**host_in)
+            stager.wait(cur)
+            flush.fill_(1)
+            seq, lp = model.sample(cur["rgb"], cur["opfl"], cur["feat_mask"], cur["pos"], gopt)
+            out.append((seq.cpu(), lp.cpu()))
+        return out
+
+    greedy_pipelined(args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    greedy_pipelined(args.steps)
+    e1.record(); e1.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    barrier()
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt)
     clk = clocks.stop()
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
     h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("rgb", "opfl", "feat_mask", "pos"))
@@ -316,7 +349,11 @@ def main():
                        "parallelism": "dp%d (independent batches, no collective on the decode path)" % world},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "how": "DeviceStager double buffering: H2D of step i+1 on a copy stream under the decode of step i; "
+                           "one timed region over all steps with every step's H2D, L2 flush, decode and D2H inside",
+                    "unpipelined_value": world * BATCH * args.steps / (ms_e2e_serial * 1e-3),
+                    "unpipelined_ms_per_step": ms_e2e_serial / args.steps},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "roofline": roofline}
 

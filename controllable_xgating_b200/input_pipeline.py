@@ -75,22 +75,37 @@ class DeviceStager:
         buf.copy_(t)
         return buf
 
-    def put(self, **host: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def put(self, **host: torch.Tensor) -> "StagedBatch":
         slot = self._slot
         self._slot = (slot + 1) % self.depth
         if self._events[slot] is not None:
             self._events[slot].synchronize()           # the pinned buffers of this slot are free again
-        out = {}
+        out = StagedBatch()
         with torch.cuda.stream(self.stream):
             for name, t in host.items():
                 src = t if t.is_pinned() else self._pin(slot, name, t)
                 out[name] = src.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        out.ready = ev
         self._events[slot] = ev
         self._last = ev
         return out
 
-    def wait(self, stream: Optional[torch.cuda.Stream] = None):
-        if self._last is not None:
-            (stream or torch.cuda.current_stream(self.device)).wait_event(self._last)
+    def wait(self, batch: Optional["StagedBatch"] = None, stream: Optional[torch.cuda.Stream] = None):
+        """Make `stream` (default: the current stream) wait for the copies of `batch` (default: the last put()).
+        Passing the batch lets the NEXT batch be staged before the current one is consumed: put(next) ->
+        wait(current) -> compute(current), the copy of `next` overlapping the compute."""
+        ev = batch.ready if batch is not None else self._last
+        if ev is None:
+            return
+        stream = stream or torch.cuda.current_stream(self.device)
+        stream.wait_event(ev)
+        if batch is not None:
+            for t in batch.values():
+                t.record_stream(stream)                # allocated on the copy stream, consumed on this one
+
+
+class StagedBatch(dict):
+    """name -> device tensor of one put(); `.ready` is the event the copies complete at."""
+    ready: Optional[torch.cuda.Event] = None

@@ -44,3 +44,18 @@ def test_device_stager_round_trip():
         st.wait()
         torch.cuda.current_stream().synchronize()
         assert all(torch.equal(dev[n].cpu(), host[n]) for n in host)
+
+
+@pytest.mark.gpu
+def test_device_stager_prefetch_order():
+    """put(next) before wait(current): each batch carries its own event, the values stay those of its put()."""
+    mod = _collate()
+    st = mod.DeviceStager("cuda:0")
+    hosts = [{"a": torch.full((256, 1024), float(k)).pin_memory()} for k in range(5)]
+    nxt = st.put(**hosts[0])
+    for k in range(5):
+        cur = nxt
+        if k + 1 < 5:
+            nxt = st.put(**hosts[k + 1])
+        st.wait(cur)
+        assert float(cur["a"].sum()) == float(k) * 256 * 1024
