@@ -66,7 +66,15 @@ inline void carve_bwd(Arena& a, const xg_dims& d, int B, int K, int L, BwdBufs& 
 
 static int colsum_run(xg_context* ctx, const float* X, long ld, int R, int N, float beta, float* o0, float* o1,
                       float* o2, cudaStream_t st) {
-  XG_TRY(launch(ctx, "colsum", colsum_kernel, ceil_div(N, 32), dim3(32, 8), 0, st, X, ld, R, N, beta, o0, o1, o2));
+  // row slabs so that about two blocks per SM run (scratch and ticket counters of the handle; one stream at a time)
+  const int gx = ceil_div(N, 32);
+  int S = 1;
+  if (gx <= ctx->splitk.ctr_count && gx < 2 * ctx->sm_count) {
+    S = std::min(std::min(ceil_div(2 * ctx->sm_count, gx), ceil_div(R, 32)), 64);
+    if ((size_t)S * N > ctx->splitk.ws_floats) S = 1;
+  }
+  XG_TRY(launch(ctx, "colsum", colsum_kernel, dim3(gx, std::max(S, 1)), dim3(32, 8), 0, st, X, ld, R, N, beta, o0, o1, o2,
+                ctx->splitk.ws, ctx->splitk.ctr));
   return XG_OK;
 }
 

@@ -25,18 +25,48 @@ __global__ void logsoftmax_bwd_rows_kernel(const float* __restrict__ lp, const f
 }
 
 // out_x[j] = beta*out_x[j] + sum_r X[r*ld + j]   (up to three identical outputs: the three LSTM biases
-// of a cell share one column sum).  grid ceil(N/32), block (32,8); rows reduced in a fixed order.
+// of a cell share one column sum).  grid (ceil(N/32), S), block (32,8).  Narrow matrices would occupy a
+// handful of SMs with one block per 32 columns, so the rows are cut into S slabs: every block leaves its
+// partial sums in `part` [S][N] and the last block of a column group to finish (ticket counter, left at zero
+// again) adds the S partials in slab order -- the result does not depend on which block that is.
 __global__ void colsum_kernel(const float* __restrict__ X, long ld, int R, int N, float beta,
-                              float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2) {
+                              float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                              float* __restrict__ part, unsigned int* __restrict__ ctr) {
   __shared__ float sm[8][33];
+  __shared__ unsigned int ticket;
   const int j = blockIdx.x * 32 + threadIdx.x;
-  float a = 0.f;
-  if (j < N)
-    for (int r = threadIdx.y; r < R; r += 8) a += X[(long)r * ld + j];
+  const int S = gridDim.y, chunk = (R + S - 1) / S;
+  const int r0 = blockIdx.y * chunk, r1 = min(R, r0 + chunk);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (j < N) {
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      a0 += X[(long)r * ld + j]; a1 += X[(long)(r + 8) * ld + j];
+      a2 += X[(long)(r + 16) * ld + j]; a3 += X[(long)(r + 24) * ld + j];
+    }
+    for (; r < r1; r += 8) a0 += X[(long)r * ld + j];
+  }
+  float a = (a0 + a1) + (a2 + a3);
   sm[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
-  if (threadIdx.y == 0 && j < N) {
+  if (threadIdx.y == 0) {
     for (int y = 1; y < 8; ++y) a += sm[y][threadIdx.x];
+    if (S > 1 && j < N) __stcg(part + (long)blockIdx.y * N + j, a);
+  }
+  if (S > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) ticket = atomicAdd(ctr + blockIdx.x, 1u);
+    __syncthreads();
+    if (ticket != (unsigned int)(S - 1)) return;
+    __threadfence();
+    if (threadIdx.y == 0 && j < N) {
+      a = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) a += __ldcg(part + (long)s2 * N + j);
+    }
+    if (threadIdx.x == 0 && threadIdx.y == 0) ctr[blockIdx.x] = 0u;
+  }
+  if (threadIdx.y == 0 && j < N) {
     if (o0) o0[j] = (beta != 0.f ? beta * o0[j] : 0.f) + a;
     if (o1) o1[j] = (beta != 0.f ? beta * o1[j] : 0.f) + a;
     if (o2) o2[j] = (beta != 0.f ? beta * o2[j] : 0.f) + a;
