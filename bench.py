@@ -142,12 +142,21 @@ def run_reference(args):
             "train": {"value": BATCH / tr, "unit": "captions/s", "ms_per_step": tr * 1e3,
                       "workload": "config3: train fwd+bwd (XE loss), batch 64"},
             "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +166,12 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--skip-extra", action="store_true", help="skip the train / beam sub-objects")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (library
+    # banners such as "NCCL version ..." are written to fd 1 from native code) and the line goes to the saved fd
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -414,7 +429,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
