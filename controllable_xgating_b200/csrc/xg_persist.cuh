@@ -1584,8 +1584,14 @@ decode_bwd_persistent_kernel(const DecBwdParams* __restrict__ Pp, const __grid_c
     grid_barrier(P.sync_counter, sync_target, G);
     gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);     // Gb
     grid_barrier(P.sync_counter, sync_target, G);
-    if (cta < 2 * B) decb_attention(P, cta >> 1, cta & 1, i, sv);                // Pc
-    else decb_cell_phase(P, 0, i, cta - 2 * B, G - 2 * B);
+    if (G >= 2 * B + 8) {          // Pc, enough SMs: caption halves and cell elements on disjoint CTAs
+      if (cta < 2 * B) decb_attention(P, cta >> 1, cta & 1, i, sv);
+      else decb_cell_phase(P, 0, i, cta - 2 * B, G - 2 * B);
+    } else {                       // large batches: every CTA walks its caption halves, then its cell elements
+#pragma unroll 1
+      for (int u = cta; u < 2 * B; u += G) decb_attention(P, u >> 1, u & 1, i, sv);
+      decb_cell_phase(P, 0, i, cta, G);
+    }
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
     grid_barrier(P.sync_counter, sync_target, G);
     gemm_phase(P.d, &s_sched[1], &s_sched[0], maps.m, R, sv, tmem_base, ps);     // Gd
@@ -2150,10 +2156,10 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
                               cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, A = d.att, G = ctx->sm_count;
-  if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > 64 || G < 2 * B + 8 || G > 256 || T < 1 ||
+  if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > 256 || G < 16 || G > 256 || T < 1 ||
       2 * K + H + 8 > PK_SCRATCH_FLOATS)
     return PK_FALLBACK;
-  const int R = 64;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   PersistState*& S = persist_state(ctx);

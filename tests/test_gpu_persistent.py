@@ -62,7 +62,7 @@ def _train_grads(m, d, X):
     return logp.detach().cpu(), float(loss), {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("B", [64, 21, 150])
+@pytest.mark.parametrize("B", [64, 21, 150, 256])
 def test_persistent_training_forward_matches_unfused(B):
     """teacher-forced word loop in the persistent kernel (mode 1) vs the per-step launches: same log-probs,
     loss and gradients (the backward consumes the activations the kernel saved), with dropout 0.5."""
