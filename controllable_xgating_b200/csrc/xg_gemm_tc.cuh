@@ -157,6 +157,30 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, long sr, long sk,
   }
 }
 
+// K-contiguous sources with K == Kp (no padding column, 16-byte aligned rows of pitch sr): the split is elementwise,
+// so it runs as a float4 stream with 4 independent 16-byte loads per thread in flight (the tiled kernel above moves
+// 4 scalars per thread through shared memory: 10.6 -> 8.0 us per launch on the encoder activations).
+__global__ void __launch_bounds__(256)
+split_tf32_flat_kernel(const float4* __restrict__ X, long sr4, int k4, long n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+  const long stride = (long)gridDim.x * 256;
+  const bool dense = sr4 == (long)k4;
+  for (long i0 = (long)blockIdx.x * 256 + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const long i = i0 + q * stride; if (i < n4) v[q] = __ldg(X + (dense ? i : (i / k4) * sr4 + (i % k4))); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long i = i0 + q * stride;
+      if (i < n4) {
+        float4 h, l;
+        h.x = tf32_rna(v[q].x); h.y = tf32_rna(v[q].y); h.z = tf32_rna(v[q].z); h.w = tf32_rna(v[q].w);
+        l.x = tf32_rna(v[q].x - h.x); l.y = tf32_rna(v[q].y - h.y); l.z = tf32_rna(v[q].z - h.z); l.w = tf32_rna(v[q].w - h.w);
+        hi[i] = h; lo[i] = l;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // the GEMM kernel
 //
@@ -321,6 +345,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
 #pragma unroll
       for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
     }
+    const Epilogue& ep0 = prm.g.ep;
+    const bool direct = prm.swap_out && !ep0.drop.on() && ep0.aux == nullptr && ep0.tgt == nullptr && ep0.beta == 0.f &&
+                        (ep0.act == XG_ACT_NONE || ep0.act == XG_ACT_RELU);
+    if (direct) {
+      // Plain outputs (bias, optional ReLU, row permutation) — most products of the path — go straight from the
+      // register accumulators to global memory, fully unrolled (~8 instructions per column).  The rolled loop below
+      // re-read the staged tile through generic loads into ONE live register: ~195 cycles per column, and that tail
+      // was 47 % of a CTA's lifetime on 128 x 128 tiles (ncu source page, profiles/r1n_gemm_tc128_*).
+      if (p < prm.Pn) {
+        const float alpha = ep0.alpha, bias_p = epilogue_bias(ep0, p);
+        const bool relu = ep0.act == XG_ACT_RELU;
+        const int rb = prm.g.perm_rb, rs = prm.g.perm_rs;
+        const int qn = min(BN, prm.Qn - q0);
+        int qm = rb ? q0 % rb : 0, qd = rb ? q0 / rb : 0;
+        float* cbase = prm.g.C + p;
+        const long ldc = prm.g.ldc;
+#pragma unroll
+        for (int u = 0; u < BN; ++u) {
+          if (u < qn) {
+            float v = fmaf(alpha, acc[u], bias_p);
+            if (relu) v = fmaxf(v, 0.f);
+            const long orow = rb ? (long)qm * rs + qd : (long)(q0 + u);
+            cbase[orow * ldc] = v;
+            if (rb) { if (++qm == rb) { qm = 0; ++qd; } }
+          }
+        }
+      }
+    } else {
     // Stage the register accumulators through the pipeline buffers (idle now: every MMA has retired)
     // so that ONE rolled copy of the generic epilogue serves all BN columns.  Unrolling it BN times
     // produced an 84k-instruction kernel that was instruction-fetch bound (ncu, profiles/r1b).
@@ -360,6 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
           else epilogue_finish(prm.g, p, q, alpha * a + epilogue_bias(prm.g.ep, q));
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -438,8 +491,17 @@ static int tc_make_map(xg_context* ctx, TcState* ts, const float* base, int rows
 
 static int tc_split(xg_context* ctx, const float* X, long sr, long sk, int rows, int K, int Kp, float* hi, float* lo,
                     cudaStream_t st) {
-  dim3 grid(Kp / 32, ceil_div(rows, 32));
   ProfScope ps(ctx, "split_tf32", st);
+  if (sk == 1 && sr % 4 == 0 && sr >= (long)K && K == Kp && ((uintptr_t)X & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0) {
+    const long n4 = (long)rows * Kp / 4;
+    const long want = (n4 + 1023) / 1024;
+    const int blocks = (int)std::max<long>(1, std::min<long>(want, (long)ctx->sm_count * 8));
+    split_tf32_flat_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(X), sr / 4, Kp / 4, n4, reinterpret_cast<float4*>(hi),
+                                                   reinterpret_cast<float4*>(lo));
+    XG_LAUNCH_CHECK(ctx->es);
+    return XG_OK;
+  }
+  dim3 grid(Kp / 32, ceil_div(rows, 32));
   split_tf32_kernel<<<grid, dim3(32, 8), 0, st>>>(X, sr, sk, rows, K, Kp, hi, lo);
   XG_LAUNCH_CHECK(ctx->es);
   return XG_OK;
