@@ -221,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl, const TcParams prm) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the address space
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* acc_full = empty_bar + Cfg::kStages;   // [2]
@@ -385,31 +385,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
       const float alpha = ep.alpha;
       const float bias_p = prm.swap_out ? epilogue_bias(ep, p) : 0.f;   // j == p: per-lane constant
       const int qn = min(BN, prm.Qn - q0);
-      if (prm.swap_out && !ep.drop.on() && ep.aux == nullptr && ep.tgt == nullptr) {
-        // lean path (bias, activation, row permutation, accumulate): the generic per-element epilogue below costs
-        // ~35 dependent instructions per element on ONE warp per scheduler (27k cycles per 128x128 tile, measured)
-        const int rb = prm.g.perm_rb, rs = prm.g.perm_rs, act = ep.act;
+      if (prm.swap_out) {
+        // Everything else (dropout, auxiliary store, cross gate tgt.(1+v), accumulate, tanh / sigmoid): rounds of 8
+        // columns, every load of a round (staged accumulator, gate target, old output) issued before its first store.
+        // Written element by element the compiler may not move a load above the previous store (the pointers may
+        // alias), so each column paid a full global-load latency.
+        const GemmP& g = prm.g;
+        const int rb = g.perm_rb, rs = g.perm_rs;
         const float beta = ep.beta;
-        int qm = rb ? q0 % rb : 0, qd = rb ? q0 / rb : 0;
-        float* cbase = prm.g.C + p;
-        const long ldc = prm.g.ldc;
-#pragma unroll 4
-        for (int u = 0; u < qn; ++u) {
-          float v = alpha * stage_out[u * 128 + pl] + bias_p;
-          v = act == XG_ACT_NONE ? v : apply_act(v, act);
-          const long orow = rb ? (long)qm * rs + qd : (long)(q0 + u);
-          float* c = cbase + orow * ldc;
-          if (beta != 0.f) v += beta * (*c);
-          *c = v;
-          if (rb) { if (++qm == rb) { qm = 0; ++qd; } }
+        const bool has_drop = ep.drop.on();
+#pragma unroll 1
+        for (int u0 = 0; u0 < qn; u0 += 8) {
+          float a[8], tg[8], cold[8];
+          long coff[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int uu = min(u0 + k, qn - 1), q = q0 + uu;
+            a[k] = stage_out[uu * 128 + pl];
+            const long orow = rb ? (long)(q % rb) * rs + q / rb : (long)q;
+            coff[k] = orow * g.ldc + p;
+            tg[k] = 0.f; cold[k] = 0.f;
+            if (ep.tgt) {
+              const long trow = ep.tgt_div ? (q / ep.tgt_div) : (ep.tgt_mod ? (q % ep.tgt_mod) : q);
+              tg[k] = ep.tgt[trow * ep.ldt + p];
+            }
+            if (beta != 0.f) cold[k] = g.C[coff[k]];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (u0 + k < qn) {
+              const int q = q0 + u0 + k;
+              float v = apply_act(alpha * a[k] + bias_p, ep.act);
+              if (has_drop) v *= ep.drop.factor((uint64_t)q * (uint64_t)g.N + (uint64_t)p);
+              if (ep.aux) ep.aux[(long)q * ep.ldaux + p] = v;
+              if (ep.tgt) v = tg[k] * (1.f + v);
+              if (beta != 0.f) v += beta * cold[k];
+              g.C[coff[k]] = v;
+            }
+          }
         }
       } else {
 #pragma unroll 1
         for (int u = 0; u < qn; ++u) {
           const float a = stage_out[u * 128 + pl];
-          const int q = q0 + u;
-          if (prm.swap_out) epilogue_finish(prm.g, q, p, alpha * a + bias_p);
-          else epilogue_finish(prm.g, p, q, alpha * a + epilogue_bias(prm.g.ep, q));
+          epilogue_finish(prm.g, p, q0 + u, alpha * a + epilogue_bias(prm.g.ep, q0 + u));
         }
       }
     }
