@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 DIMS = dict(R=1536, F=1024, H=512, E=468, A=1536, V=10000, C=14)
 K_FRAMES, T_SEQ, BATCH = 28, 30, 64
-METRIC = "captions/sec (train fwd+bwd; greedy decode) MSRVTT-shape batch"
+METRIC = "captions/sec (train fwd+bwd; greedy decode) MSRVTT-shape batch @1/2/4/8 B200"   # BASELINE.json "metric", verbatim
 L2_FLUSH_BYTES = 256 << 20
 
 
