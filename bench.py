@@ -408,6 +408,18 @@ def main():
                                  "d2h_bytes_per_step": 4},
                          "allreduce_bytes_per_step": (dp.hook.bytes // max(dp.hook.calls, 1)) if dp else 0}
         if world == 1:
+            # the reference's whole iteration ("time/batch", starttrain.py:125-137): forward, backward, elementwise
+            # gradient clamp +-0.1 and Adam, all derived parameter tables rebuilt every step.  Timed LAST on this model:
+            # it moves the weights
+            from controllable_xgating_b200.optim import FusedAdam
+            fopt = FusedAdam(tmodel.parameters(), lr=4e-4, grad_clip=0.1)
+
+            def train_iter():
+                train_step(td)
+                fopt.step()
+            ms_it = timed(train_iter, nst, 2)
+            line["train"]["with_optimizer"] = {"workload": "config3 + clamp(+-0.1) + Adam step (xg_adam_step), parameter-derived tables rebuilt",
+                                               "value": tb * nst / (ms_it * 1e-3), "unit": "captions/s", "ms_per_step": ms_it / nst}
             bopt = {"beam_size": 5}
             ms_b = timed(lambda: model.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], bopt), 3, 1)
             line["beam"] = {"workload": "config5: sample_beam beam_size 5, batch 64", "value": BATCH * 3 / (ms_b * 1e-3),

@@ -188,8 +188,8 @@ int xg_bind_bn_buffers(xg_handle h, float* rm_rgb, float* rv_rgb, float* rm_opfl
 
 int xg_params_changed(xg_handle h) {
   CHECK_HANDLE(h);
-  XG_TRY(set_device(h));
-  XG_CUDA_TRY(h->es, cudaDeviceSynchronize());
+  // no device synchronisation: the derived copies keep their buffers and are refilled on the stream of the next call
+  // that uses them, i.e. after everything already queued on it (the update itself must be ordered on that stream too)
   tc_invalidate_weights(h);   // tf32 hi/lo splits of the bound parameters
   h->param_epoch++;           // POS-gate token table of the persistent decoder
   return XG_OK;

@@ -450,7 +450,7 @@ struct TcState {
   PFN_encodeTiled encode = nullptr;
   bool attr_set[3] = {false, false, false};
   // split copies of bound parameters: key = (param pointer, transposed?) -> {hi, lo, rows, Kp}
-  struct Split { float* hi; float* lo; int rows; int K; int Kp; };
+  struct Split { float* hi; float* lo; int rows; int K; int Kp; bool valid; };
   typedef std::tuple<const float*, long, long, int, int> SplitKey;   // (pointer, row stride, k stride, rows, K)
   std::map<SplitKey, Split> weight_cache;
   // scratch for on-the-fly operand splits (grown on demand)
@@ -485,11 +485,12 @@ static void tc_release(xg_context* ctx) {
   tc_state(ctx) = nullptr;
 }
 
+// the bound parameters changed (optimizer step, load_state_dict): the split copies are stale.  The buffers stay —
+// freeing them would synchronise the device once per training step — and are refilled on next use.
 static void tc_invalidate_weights(xg_context* ctx) {
   TcState* ts = tc_state(ctx);
   if (!ts) return;
-  for (auto& kv : ts->weight_cache) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
-  ts->weight_cache.clear();
+  for (auto& kv : ts->weight_cache) kv.second.valid = false;
 }
 
 // 2-D map over a K-major fp32 matrix [rows][Kp] (pitch Kp floats): box = 32 floats x box_rows, 128B swizzle
@@ -544,11 +545,14 @@ static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, lo
     const TcState::SplitKey key(X, sr, sk, rows, K);
     auto it = ts->weight_cache.find(key);
     if (it == ts->weight_cache.end()) {
-      TcState::Split sp{nullptr, nullptr, rows, K, Kp};
+      TcState::Split sp{nullptr, nullptr, rows, K, Kp, false};
       XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.hi, sizeof(float) * (size_t)rows * Kp));
       XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.lo, sizeof(float) * (size_t)rows * Kp));
-      XG_TRY(tc_split(ctx, X, sr, sk, rows, K, Kp, sp.hi, sp.lo, st));
       it = ts->weight_cache.emplace(key, sp).first;
+    }
+    if (!it->second.valid) {
+      XG_TRY(tc_split(ctx, X, sr, sk, rows, K, Kp, it->second.hi, it->second.lo, st));
+      it->second.valid = true;
     }
     *hi = it->second.hi;
     *lo = it->second.lo;

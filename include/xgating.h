@@ -123,7 +123,9 @@ int xg_bind_params(xg_handle h, const float* const* params, int count);
 /* BatchNorm1d running_mean / running_var of both streams (sub_modules.py:98,102); updated in place
  * by xg_train_fwd / xg_encode_fwd when train != 0. */
 int xg_bind_bn_buffers(xg_handle h, float* rm_rgb, float* rv_rgb, float* rm_opfl, float* rv_opfl);
-/* call after the optimizer (or load_state_dict) rewrites parameter storage: drops derived copies. */
+/* call after the optimizer (or load_state_dict) rewrites parameter storage: marks the derived copies (tf32 splits,
+ * POS-gate token table) stale.  Does not synchronise; the copies are rebuilt on the stream of the next call that needs
+ * them, so the parameter update has to be ordered before that call on the same stream (or by an event). */
 int xg_params_changed(xg_handle h);
 /* mode 0: everything on the SIMT fp32 engine; 1: dense contractions above a size gate run on the
  * tcgen05 3xTF32 engine (fp32-grade accuracy); 2 (default): 1 + greedy decoding in the fused persistent
