@@ -1100,12 +1100,21 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
       pk_stamp(P.dbg_clock, cta, t, 10);
       // ===== P4: greedy pick + next-step inputs (CTAs < B)  ||  attention of step t+1 (CTAs B..2B-1) =====
       if (split_roles) {
+#ifdef PK_FINE_TRACE   // -DPK_FINE_TRACE + XG_PERSIST_TRACE=1: SM-clock stamps inside the pick (CTA 0) and the attention (CTA B) of step 3
+        long long* gf = (P.dbg_clock && t == 3 && (cta == 0 || cta == B)) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + (cta == 0 ? 0 : 32) : nullptr;
+        if (gf && threadIdx.x == 0) gf[31] = clock64();
+#else
+        long long* gf = nullptr;
+#endif
         if (cta < B) {
-          const int tokv = dec_pick(P, cta, t, sv);
+          const int tokv = dec_pick(P, cta, t, sv, gf);
           dec_token_inputs(P, cta, tokv);
           __syncthreads();
+#ifdef PK_FINE_TRACE
+          if (gf && threadIdx.x == 0) gf[30] = clock64();
+#endif
         } else if (cta < 2 * B && t + 1 < T) {
-          dec_attention<TRAIN>(P, &maps.m[16], cta - B, t + 1, sv, bulk_phase);
+          dec_attention<TRAIN>(P, &maps.m[16], cta - B, t + 1, sv, bulk_phase, gf);
         }
       } else {
 #pragma unroll 1
@@ -1838,7 +1847,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_params = a.take<DecParams>(1);
       S->d_counter = a.take<unsigned int>(32 * 258 + 256);
       S->d_flags = a.take<int>(2048);
-      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS);
+      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
       hp.sched = a.take<PSched>(sched.size());
       for (int i = 0; i < DD_COUNT; ++i) hp.d[i].out = a.take<float>((size_t)ns_cap[i] * R * hp.d[i].n_rows);
       hp.xt_hi = a.take<float>((long)R * Ep); hp.xt_lo = a.take<float>((long)R * Ep);
@@ -1938,7 +1947,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
     XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
   }
-  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * (2048 + 256) * PK_STAMPS, st));
+  if (hp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
 
   if (!S->attr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_persistent_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
@@ -1985,6 +1994,17 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       fprintf(stderr, "[xg persist trace] %-26s own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
     }
     fprintf(stderr, "[xg persist trace] step %.0f cycles\n", tot);
+#ifdef PK_FINE_TRACE
+    {
+      long long f[64];
+      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS, sizeof(f), cudaMemcpyDeviceToHost);
+      for (int who = 0; who < 2; ++who) {
+        fprintf(stderr, "[xg persist trace] step 3 %s stamps (cycles after phase entry):", who == 0 ? "pick (cta 0)" : "attention (cta B)");
+        for (int i = 0; i < 31; ++i) if (f[who * 32 + i]) fprintf(stderr, " [%d] %lld", i, f[who * 32 + i] - f[who * 32 + 31]);
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
     if (steps > 3 && G <= 256) {   // step 3, all CTAs: when does each CTA finish its share of a phase (ns after the phase opened)?
       std::vector<long long> ga((size_t)G * PK_STAMPS);
       cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
