@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "xg_gemm_tc.cuh"
@@ -1141,11 +1142,12 @@ decode_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant
   pipeline_teardown(tmem_base);
 }
 
+constexpr unsigned int PK_STEP_BARRIERS = 6;   // grid barriers of one decode_step_persistent_kernel launch
 // ONE word step for arbitrary state rows (beam search, CaptionModel.py:121-125 -> SAModel.get_logprobs_state,
 // SAModel.py:117-127): states and tokens in, states and the log-softmax of every row out.  Launched once per step;
 // exp(2 Uv) and the POS-gate token table persist in the pool between launches.
 __global__ void __launch_bounds__(PK_THREADS, 1)
-decode_step_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant__ MapTable maps) {
+decode_step_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_constant__ MapTable maps, unsigned int sync_base) {
   __shared__ DecParams Psm;
   __shared__ PSched s_sched[3];
   const int cta = blockIdx.x, G = gridDim.x;
@@ -1163,7 +1165,7 @@ decode_step_persistent_kernel(const DecParams* __restrict__ Pp, const __grid_con
   const uint32_t tmem_base = pipeline_setup(sv);
   if (threadIdx.x < 17) tma_prefetch_desc(&maps.m[threadIdx.x]);
   PipeState ps{0, 0, 0, 0};
-  unsigned int sync_target = 0;
+  unsigned int sync_target = sync_base;   // the barrier counter runs on from launch to launch (PK_STEP_BARRIERS per launch)
   uint32_t bulk_phase = 0;
 
   for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
@@ -1680,6 +1682,8 @@ struct PersistState {
   bool attr_set = false;
   // single-step mode: everything but the per-step pointers is reused while the key below holds
   bool step_valid = false;
+  DecParams step_hp_dev;         // the parameter block as it lies on the device (later steps upload only when it differs)
+  unsigned int step_sync_base = 0;
   int step_B = 0, step_fdiv = 0;
   const float *step_V = nullptr, *step_Uv = nullptr, *step_pos = nullptr;
   unsigned long long step_epoch = ~0ull;
@@ -1798,13 +1802,19 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   if (step && S->step_valid && S->sched_mode == 2 && S->R == R && S->K == K && S->step_B == B && S->step_fdiv == step->feat_div &&
       S->step_V == Vf && S->step_Uv == Uv && S->step_pos == pos && S->step_epoch == ctx->param_epoch && !step->first) {
     // later steps of the same beam search: plans, tensor maps and the device schedule are those of the last launch
+    // From the third step of a search on nothing in the block changes (the fused step gathers states in place), and
+    // the barrier counter simply runs on: a step is then ONE stream operation instead of copy + memset + launch.
     step_io();
-    XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
-    XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (32 * 258 + 256), st));
+    if (memcmp(&hp, &S->step_hp_dev, sizeof(DecParams)) != 0) {
+      XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(DecParams), cudaMemcpyHostToDevice, st));
+      memcpy(&S->step_hp_dev, &hp, sizeof(DecParams));
+    }
     ProfScope ps(ctx, "decode_step_persistent", st);
     const DecParams* dp = S->d_params;
-    void* args[2] = {(void*)&dp, (void*)&S->step_mt};
+    unsigned int base = S->step_sync_base;
+    void* args[3] = {(void*)&dp, (void*)&S->step_mt, (void*)&base};
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_step_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    S->step_sync_base += PK_STEP_BARRIERS * (unsigned int)G;
     return XG_OK;
   }
   S->step_valid = false;
@@ -1962,11 +1972,14 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   {
     ProfScope ps(ctx, mode == 1 ? "train_decode_persistent" : (mode == 2 ? "decode_step_persistent" : "decode_persistent"), st);
     const DecParams* dp = S->d_params;
-    void* args[2] = {(void*)&dp, (void*)&mt};
+    unsigned int base = 0;          // the counter was cleared above
+    void* args[3] = {(void*)&dp, (void*)&mt, (void*)&base};      // the third argument exists in single-step mode only
     void* fn = mode == 1 ? (void*)decode_persistent_kernel<1> : (mode == 2 ? (void*)decode_step_persistent_kernel : (void*)decode_persistent_kernel<0>);
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   }
   if (mode == 2) {
+    memcpy(&S->step_hp_dev, &hp, sizeof(DecParams));
+    S->step_sync_base = PK_STEP_BARRIERS * (unsigned int)G;
     S->step_valid = true; S->step_B = B; S->step_fdiv = step->feat_div; S->step_V = Vf; S->step_Uv = Uv; S->step_pos = pos;
     S->step_epoch = ctx->param_epoch; S->step_mt = mt;
   }
