@@ -373,65 +373,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
         }
       }
     } else {
-    // Stage the register accumulators through the pipeline buffers (idle now: every MMA has retired)
-    // so that ONE rolled copy of the generic epilogue serves all BN columns.  Unrolling it BN times
-    // produced an 84k-instruction kernel that was instruction-fetch bound (ncu, profiles/r1b).
-    float* stage_out = reinterpret_cast<float*>(smem);
-    const int pl = quad * 32 + lane;
+      // Stage the register accumulators through the pipeline buffers (idle now: every MMA has retired)
+      // so that ONE rolled copy of the generic epilogue serves all BN columns.  Unrolling it BN times
+      // produced an 84k-instruction kernel that was instruction-fetch bound (ncu, profiles/r1b).
+      float* stage_out = reinterpret_cast<float*>(smem);
+      const int pl = quad * 32 + lane;
 #pragma unroll
-    for (int u = 0; u < BN; ++u) stage_out[u * 128 + pl] = acc[u];   // same thread reads it back: no barrier
-    if (p < prm.Pn) {
-      const Epilogue& ep = prm.g.ep;
-      const float alpha = ep.alpha;
-      const float bias_p = prm.swap_out ? epilogue_bias(ep, p) : 0.f;   // j == p: per-lane constant
-      const int qn = min(BN, prm.Qn - q0);
-      if (prm.swap_out) {
-        // Everything else (dropout, auxiliary store, cross gate tgt.(1+v), accumulate, tanh / sigmoid): rounds of 8
-        // columns, every load of a round (staged accumulator, gate target, old output) issued before its first store.
-        // Written element by element the compiler may not move a load above the previous store (the pointers may
-        // alias), so each column paid a full global-load latency.
-        const GemmP& g = prm.g;
-        const int rb = g.perm_rb, rs = g.perm_rs;
-        const float beta = ep.beta;
-        const bool has_drop = ep.drop.on();
+      for (int u = 0; u < BN; ++u) stage_out[u * 128 + pl] = acc[u];   // same thread reads it back: no barrier
+      if (p < prm.Pn) {
+        const Epilogue& ep = prm.g.ep;
+        const float alpha = ep.alpha;
+        const float bias_p = prm.swap_out ? epilogue_bias(ep, p) : 0.f;   // j == p: per-lane constant
+        const int qn = min(BN, prm.Qn - q0);
+        if (prm.swap_out) {
+          // Everything else (dropout, auxiliary store, cross gate tgt.(1+v), accumulate, tanh / sigmoid): rounds of 8
+          // columns, every load of a round (staged accumulator, gate target, old output) issued before its first store.
+          // Written element by element the compiler may not move a load above the previous store (the pointers may
+          // alias), so each column paid a full global-load latency.
+          const GemmP& g = prm.g;
+          const int rb = g.perm_rb, rs = g.perm_rs;
+          const float beta = ep.beta;
+          const bool has_drop = ep.drop.on();
 #pragma unroll 1
-        for (int u0 = 0; u0 < qn; u0 += 8) {
-          float a[8], tg[8], cold[8];
-          long coff[8];
+          for (int u0 = 0; u0 < qn; u0 += 8) {
+            float a[8], tg[8], cold[8];
+            long coff[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int uu = min(u0 + k, qn - 1), q = q0 + uu;
-            a[k] = stage_out[uu * 128 + pl];
-            const long orow = rb ? (long)(q % rb) * rs + q / rb : (long)q;
-            coff[k] = orow * g.ldc + p;
-            tg[k] = 0.f; cold[k] = 0.f;
-            if (ep.tgt) {
-              const long trow = ep.tgt_div ? (q / ep.tgt_div) : (ep.tgt_mod ? (q % ep.tgt_mod) : q);
-              tg[k] = ep.tgt[trow * ep.ldt + p];
+            for (int k = 0; k < 8; ++k) {
+              const int uu = min(u0 + k, qn - 1), q = q0 + uu;
+              a[k] = stage_out[uu * 128 + pl];
+              const long orow = rb ? (long)(q % rb) * rs + q / rb : (long)q;
+              coff[k] = orow * g.ldc + p;
+              tg[k] = 0.f; cold[k] = 0.f;
+              if (ep.tgt) {
+                const long trow = ep.tgt_div ? (q / ep.tgt_div) : (ep.tgt_mod ? (q % ep.tgt_mod) : q);
+                tg[k] = ep.tgt[trow * ep.ldt + p];
+              }
+              if (beta != 0.f) cold[k] = g.C[coff[k]];
             }
-            if (beta != 0.f) cold[k] = g.C[coff[k]];
-          }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (u0 + k < qn) {
-              const int q = q0 + u0 + k;
-              float v = apply_act(alpha * a[k] + bias_p, ep.act);
-              if (has_drop) v *= ep.drop.factor((uint64_t)q * (uint64_t)g.N + (uint64_t)p);
-              if (ep.aux) ep.aux[(long)q * ep.ldaux + p] = v;
-              if (ep.tgt) v = tg[k] * (1.f + v);
-              if (beta != 0.f) v += beta * cold[k];
-              g.C[coff[k]] = v;
+            for (int k = 0; k < 8; ++k) {
+              if (u0 + k < qn) {
+                const int q = q0 + u0 + k;
+                float v = apply_act(alpha * a[k] + bias_p, ep.act);
+                if (has_drop) v *= ep.drop.factor((uint64_t)q * (uint64_t)g.N + (uint64_t)p);
+                if (ep.aux) ep.aux[(long)q * ep.ldaux + p] = v;
+                if (ep.tgt) v = tg[k] * (1.f + v);
+                if (beta != 0.f) v += beta * cold[k];
+                g.C[coff[k]] = v;
+              }
             }
           }
-        }
-      } else {
+        } else {
 #pragma unroll 1
-        for (int u = 0; u < qn; ++u) {
-          const float a = stage_out[u * 128 + pl];
-          epilogue_finish(prm.g, p, q0 + u, alpha * a + epilogue_bias(prm.g.ep, q0 + u));
+          for (int u = 0; u < qn; ++u) {
+            const float a = stage_out[u * 128 + pl];
+            epilogue_finish(prm.g, p, q0 + u, alpha * a + epilogue_bias(prm.g.ep, q0 + u));
+          }
         }
       }
-    }
     }
   }
   tc_fence_before();
