@@ -45,7 +45,7 @@ constexpr int PK_SMEM_BYTES = PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4
 constexpr int PK_MAX_ITEMS = 6;
 constexpr int PK_MAX_SLOTS = 6;
 constexpr int PK_MAX_DESCS = 8;
-constexpr int PK_BULK_CHUNKS = 4;     // Uv chunks (+1 barrier for V)
+constexpr int PK_BULK_CHUNKS = 8;     // Uv chunks (+1 barrier for V)
 constexpr int PK_STAMPS = 16;
 
 struct PItem { short desc, slot, rt, cb, kb0, nkb; };
@@ -604,13 +604,13 @@ __device__ __noinline__ void dec_cell_phase(const DecParams& P, int layer, int t
   if (threadIdx.x == 0) PK_FINE(3);
 }
 
-// temporal attention of caption r on one CTA (sub_modules.py:677-680).  Uv[r] arrives in 8-frame chunks by bulk
+// temporal attention of caption r on one CTA (sub_modules.py:677-680).  Uv[r] arrives in 4-frame chunks by bulk
 // copies into the (idle) pipeline stages; every thread owns the attention units a = tid + 320 i (ah[a], w[a]
 // in registers) and runs the frames of a chunk with independent accumulators (their warp reductions
 // interleave); frame scores are reduced warp -> CTA in a fixed order; softmax over ALL K frames; V[r] is
 // fetched by TMA (two H/2-column panels) behind Uv when both fit, else over the first two consumed chunks.
 // (A CTA pair per caption was tried: the score exchange costs what halving the frames saves.)
-constexpr int DEC_FPC = 8;         // frames per Uv chunk (K <= 32)
+constexpr int DEC_FPC = 4;         // frames per Uv chunk (K <= 32): the first chunk (24 KB) lands before the query is ready
 template <int TRAIN>
 __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap* vmap, int r, int t, const SmemView& sv,
                                            uint32_t& bulk_phase, long long* g_fine = nullptr) {
@@ -624,6 +624,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   constexpr int fpc = DEC_FPC;
   const bool v_behind = (long)K * (A + H) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
   const uint32_t v_off = v_behind ? (uint32_t)K * A * 4u : 0u;
+  const int vc = max(0, (K * H + fpc * A - 1) / (fpc * A) - 1);   // chunk after which the consumed chunks cover V[r]
   if (threadIdx.x == 0) {
 #pragma unroll 1
     for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
@@ -693,9 +694,9 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
       for (int f = 0; f < DEC_FPC; ++f) if (k0 + f < k1) red[warp * K + k0 + f] = p[f];
     }
     if (threadIdx.x == 0) PK_FINE(3 + 2 * c);
-    if (!v_behind && (c == 1 || k1 == K)) {   // the first chunks are consumed by every warp: V[r] goes over them
+    if (!v_behind && (c == vc || k1 == K)) {  // the first chunks are consumed by every warp: V[r] goes over them
       __syncthreads();
-      if (threadIdx.x == 0 && (c == 1 || (c == 0 && k1 == K))) {
+      if (threadIdx.x == 0 && (c == vc || (c < vc && k1 == K))) {
         fence_proxy_async_smem();
         pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
         pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
@@ -704,7 +705,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) PK_FINE(10);
+  if (threadIdx.x == 0) PK_FINE(20);
   if (warp == 0) {
     const float ba = __ldg(P.b_a2w);
     float mx = -INFINITY;
@@ -732,7 +733,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   pk_wait(sv.bulk_bar + 8 * PK_BULK_CHUNKS, bulk_phase & 1);
   bulk_phase++;
   __syncthreads();
-  if (threadIdx.x == 0) PK_FINE(11);
+  if (threadIdx.x == 0) PK_FINE(21);
   const float* vs = reinterpret_cast<const float*>(sv.stages + v_off);            // two panels [K][Hh]
 #pragma unroll 1
   for (int j = threadIdx.x; j < H; j += PK_THREADS) {
@@ -743,7 +744,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
     if (TRAIN) P.AFs[((long)t * P.B + r) * H + j] = a;
     store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
-  if (threadIdx.x == 0) PK_FINE(12);
+  if (threadIdx.x == 0) PK_FINE(22);
   __syncthreads();
 }
 
@@ -1736,7 +1737,7 @@ static inline int env_flag(const char* name) { const char* e = getenv(name); ret
 static bool persist_eligible(const xg_context* ctx, int B, int K, int max_rows = 256) {
   const xg_dims& d = ctx->d;
   const bool v_behind = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
-  const bool v_over = (long)K * d.rnn <= (long)std::min(K, 2 * DEC_FPC) * d.att;
+  const bool v_over = d.rnn <= d.att;            // V[r] fits over the consumed exp(2Uv) chunks
   return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
          d.att % 32 == 0 && B <= max_rows && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
          (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS &&
