@@ -625,20 +625,19 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
   const bool v_behind = (long)K * (A + H) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
   const uint32_t v_off = v_behind ? (uint32_t)K * A * 4u : 0u;
   const int vc = max(0, (K * H + fpc * A - 1) / (fpc * A) - 1);   // chunk after which the consumed chunks cover V[r]
-  if (threadIdx.x == 0) {
-#pragma unroll 1
-    for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
-      const int k0 = c * fpc, k1 = min(K, k0 + fpc);
-      if (k0 >= k1) break;
+  if (warp == 0) {              // lane c requests chunk c: the chunk copies are issued in one pass of the warp
+    const int k0 = lane * fpc, k1 = min(K, k0 + fpc);
+    if (lane < PK_BULK_CHUNKS && k0 < k1) {
       const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
-      pk_expect_tx(sv.bulk_bar + 8 * c, nb);
-      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)fb * K + k0) * A, nb, sv.bulk_bar + 8 * c);
+      pk_expect_tx(sv.bulk_bar + 8 * lane, nb);
+      bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)fb * K + k0) * A, nb, sv.bulk_bar + 8 * lane);
     }
-    if (v_behind) {
+    if (lane == 0 && v_behind) {
       pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
       pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
       pk_tma_2d(sv.stages_u32 + v_off + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
     }
+    __syncwarp();
   }
   float ahr[DEC_NA], wr[DEC_NA];
   int aoff[DEC_NA];
