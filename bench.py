@@ -28,6 +28,8 @@ DIMS = dict(R=1536, F=1024, H=512, E=468, A=1536, V=10000, C=14)
 K_FRAMES, T_SEQ, BATCH = 28, 30, 64
 METRIC = "captions/sec (train fwd+bwd; greedy decode) MSRVTT-shape batch @1/2/4/8 B200"   # BASELINE.json "metric", verbatim
 L2_FLUSH_BYTES = 256 << 20
+WORKLOAD = "config2: greedy decode, batch 64 per GPU, 28 frames, 1536+1024 feats, hidden 512, vocab 10k, seq_len 30"   # both arms
+TRAIN_FLOP_PER_CAPTION = 3705.5e6      # algorithmic forward 1235.2 MFLOP (v2a once), train ~3x
 
 
 def peaks():
@@ -36,6 +38,14 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -88,57 +98,85 @@ def make_opt(drop):
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle port of the reference algorithm, all host threads)
 # ----------------------------------------------------------------------------------------------
-def cpu_greedy_seconds(P, batch, reps):
-    import torch
-    from oracle import xgating_oracle as O
-    best = None
-    with torch.no_grad():
-        O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)     # warm-up
+class CpuArm:
+    """The reference's algorithm on the host cores: the reference's OWN files (baseline/_ref, staged by build() from
+    /root/reference: kind "reference") when they travelled with the repo, else the oracle port (kind "port")."""
+
+    def __init__(self, P):
+        import torch
+        from baseline import reference_arm as RA
+        self.P = P
+        self.kind = "port"
+        self.RS = None
+        if RA.available():
+            try:
+                self.RA = RA
+                self.RS = RA.load()
+                self.kind = "reference"
+                self.model = RA.build_model(self.RS, DIMS, T_SEQ, 0.5, P)     # drop_prob_lm 0.5 as run_train.sh ships it
+            except Exception as e:      # a torch too new for the shims: say so and time the port instead
+                sys.stderr.write("[bench] staged reference not importable (%r): timing the oracle port\n" % (e,))
+                self.RS, self.kind = None, "port"
+        self.torch = torch
+
+    def greedy(self, batch):
+        if self.RS is not None:
+            return self.RA.greedy(self.model, batch)
+        from oracle import xgating_oracle as O
+        with self.torch.no_grad():
+            return O.sample_greedy(self.P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
+
+    def train(self, batch):
+        if self.RS is not None:
+            return self.RA.train_step(self.model, self.RS, batch)
+        from oracle import xgating_oracle as O
+        return O.train_step_grads(self.P, batch, train=True)
+
+    def beam(self, batch, rows):
+        if self.RS is not None:
+            return self.RA.beam(self.model, batch, 5, rows)
+        from oracle import xgating_oracle as O
+        sl = slice(0, rows)
+        with self.torch.no_grad():
+            V = O.encoder_fwd(self.P, batch["rgb"][sl], batch["opfl"][sl], batch["feat_mask"][sl])
+            return O.sample_beam(self.P, V, batch["feat_mask"][sl], batch["pos"][sl], 5, T_SEQ)
+
+    def seconds(self, fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
         t0 = time.perf_counter()
         for _ in range(reps):
-            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
-        best = (time.perf_counter() - t0) / reps
-    return best
-
-
-def cpu_train_seconds(P, batch, reps):
-    from oracle import xgating_oracle as O
-    O.train_step_grads(P, batch, train=True)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        O.train_step_grads(P, batch, train=True)
-    return (time.perf_counter() - t0) / reps
+            fn()
+        return (time.perf_counter() - t0) / reps
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm (oracle port: same op sequence incl. the per-step
-    v2a(V) recomputation, torch CPU fp32) on the host cores, same metric/config."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (all threads), same
+    metric / config / warm-up policy as the GPU arm; each step = one batch of 64 captions."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from oracle import xgating_oracle as O
+    from oracle import xgating_oracle as O          # input / weight generators (and the port when baseline/_ref is absent)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P = O.synth_params(DIMS, 1024)
     P["logit.bias"][0] = -1e4
     batch = O.synth_inputs(DIMS, BATCH, K_FRAMES, T_SEQ, 0)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.sample_greedy(P, batch["rgb"], batch["opfl"], batch["feat_mask"], batch["pos"], T_SEQ)
-        dt = (time.perf_counter() - t0) / args.steps
+    arm = CpuArm(P)
+    dt = arm.seconds(lambda: arm.greedy(batch), args.steps, warm=args.warmup)
     val = BATCH / dt
-    tr = cpu_train_seconds(P, batch, max(1, min(args.steps, 3)))
+    tbatch = O.synth_inputs(DIMS, BATCH, K_FRAMES, T_SEQ, seed=100, full_length=False)
+    tr = arm.seconds(lambda: arm.train(tbatch), max(1, min(args.steps, 3)), warm=1)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "captions/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: greedy decode, batch 64, 28 frames, 1536+1024 feats, hidden 512, vocab 10k, seq_len 30",
-                       "sample": "each step = one full batch of 64 captions on the host CPU"},
-            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": "port",
-                             "sample": "%d greedy batches of 64 captions" % args.steps},
+            "config": {"workload": WORKLOAD,
+                       "sample": "each step = one full batch of 64 captions on the host CPU, rank 0 only"},
+            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": arm.kind,
+                             "sample": "%d greedy batches of 64 captions (%s)" % (
+                                 args.steps, "the reference's own caption_src files from baseline/_ref, torch CPU fp32"
+                                 if arm.kind == "reference" else "oracle port of the reference, torch CPU fp32")},
             "train": {"value": BATCH / tr, "unit": "captions/s", "ms_per_step": tr * 1e3,
                       "workload": "config3: train fwd+bwd (XE loss), batch 64"},
             "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -172,9 +210,9 @@ def main():
     sys.stdout.flush()
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    args.warmup = max(args.warmup, 3)           # same warm-up policy in both arms
     if args.impl == "reference":
         return run_reference(args)
-    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -207,6 +245,7 @@ def main():
     model = X.SAModel(make_opt(0.5))
     model.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
     model.cuda().eval()
+    model._engine.set_strict(True)                  # no silent per-step fallback on the measured path
     d = {k: v.to(dev) for k, v in batch.items() if isinstance(v, torch.Tensor)}
     pinned = {k: batch[k].pin_memory() for k in ("rgb", "opfl", "feat_mask", "pos", "seq", "seq_mask")}
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -369,7 +408,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: greedy decode, batch 64 per GPU, 28 frames, 1536+1024 feats, hidden 512, vocab 10k, seq_len 30",
+            "config": {"workload": WORKLOAD,
                        "word_steps_executed": int(min(steps_seen)) if steps_seen else None,
                        "l2": "flushed (256 MiB write) before every timed step", "weights": "random init (reference init distributions)",
                        "parallelism": "dp%d (independent batches, no collective on the decode path)" % world},
@@ -392,6 +431,7 @@ def main():
         tmodel = X.SAModel(make_opt(0.5))
         tmodel.load_state_dict({k: v.clone() for k, v in P.items()}, strict=True)
         tmodel.cuda().train()
+        tmodel._engine.set_strict(True)
         crit = X.LanguageModelCriterion()
         dp = DataParallelSAModel(tmodel) if world > 1 else None
         fwd = dp if dp is not None else tmodel
@@ -418,6 +458,16 @@ def main():
                                  "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in tp.values()),
                                  "d2h_bytes_per_step": 4},
                          "allreduce_bytes_per_step": (dp.hook.bytes // max(dp.hook.calls, 1)) if dp else 0}
+        # the train step is dense-contraction work: its roofline is the tensor pipe.  fp32-grade results come from three
+        # tf32 MMAs per product (3xTF32), so the reachable ceiling of THIS arithmetic is peak / 6 (tf32 = bf16 / 2, x 1/3).
+        tpk, tpk_src = tensor_peak()
+        tfl = TRAIN_FLOP_PER_CAPTION * tb * world
+        ach = tfl / (ms_t / nst * 1e-3) / 1e12
+        line["train"]["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tpk * world, "unit": "TFLOP/s", "frac": ach / (tpk * world),
+                                     "peak_source": tpk_src, "algorithmic_flops_per_step": tfl,
+                                     "cap_3xtf32": "fp32-grade accuracy costs 3 tf32 MMAs per product: ceiling = peak/6 = %.0f TFLOP/s"
+                                                   % (tpk * world / 6.0),
+                                     "frac_of_3xtf32_cap": ach / (tpk * world / 6.0)}
         if world == 1:
             # the reference's whole iteration ("time/batch", starttrain.py:125-137): forward, backward, elementwise
             # gradient clamp +-0.1 and Adam, all derived parameter tables rebuilt every step.  Timed LAST on this model:
@@ -440,15 +490,20 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        arm = CpuArm(P)
         reps = 10
-        cb = {k: v for k, v in batch.items()}
-        sec = cpu_greedy_seconds(P, cb, reps)
-        line["cpu_baseline"] = {"value": BATCH / sec, "unit": "captions/s", "cores": cores, "kind": "port",
-                                "sample": "%d greedy batches of 64 captions (config 2) with the oracle port, torch CPU fp32, %d threads"
-                                          % (reps, cores)}
+        sec = arm.seconds(lambda: arm.greedy(batch), reps)
+        src = "the reference's own caption_src files (baseline/_ref)" if arm.kind == "reference" else "the oracle port of the reference"
+        line["cpu_baseline"] = {"value": BATCH / sec, "unit": "captions/s", "cores": cores, "kind": arm.kind,
+                                "sample": "%d greedy batches of 64 captions (config 2) with %s, torch CPU fp32, %d threads"
+                                          % (reps, src, cores)}
         if not args.skip_extra:
-            sect = cpu_train_seconds(P, tbatch, 3)
+            sect = arm.seconds(lambda: arm.train(tbatch), 3)
             line["cpu_baseline"]["train_value"] = BATCH / sect
+            rows = 4
+            secb = arm.seconds(lambda: arm.beam(batch, rows), 1, warm=0)
+            line["cpu_baseline"]["beam_value"] = rows / secb
+            line["cpu_baseline"]["beam_sample"] = "beam-5 on the first %d videos of the batch (config 5), one pass" % rows
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -97,6 +97,34 @@ class SAModel(CaptionModel):
         self.embed.weight.data.uniform_(-initrange, initrange)
         self.logit.bias.data.fill_(0)
         self.logit.weight.data.uniform_(-initrange, initrange)
+        self.params_changed()
+
+    def params_changed(self):
+        """Tell the engine that parameter storage was rewritten through `.data` (p.data.copy_/uniform_/add_, an
+        old-style optimizer, dist.broadcast(p.data)): such writes do not bump Tensor._version, so the tables the
+        library derives from the parameters (tf32 weight splits, POS-gate token table) would otherwise go stale.
+        In-place updates through the parameter itself (torch.optim, load_state_dict, FusedAdam) are detected."""
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.params_changed()
+
+    def __deepcopy__(self, memo):
+        """a copy gets its own Engine (and native handle): two Python objects never share / double-free one xg_handle"""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in ("_engine", "_grad_hook"):
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        object.__setattr__(new, "_engine", Engine(new, dict(self._engine.dims)))
+        new._engine._engine_mode = self._engine._engine_mode
+        new._engine._strict = self._engine._strict
+        object.__setattr__(new, "_grad_hook", None)
+        ref = weakref.ref(new)
+        object.__setattr__(new.two_spatial_encoder, "_owner", ref)
+        object.__setattr__(new.lstmcore, "_owner", ref)
+        return new
 
     # nn.Module plumbing: parameter storage can move (.cuda(), .to()); re-bind lazily
     def _apply(self, fn, *a, **k):
@@ -206,7 +234,12 @@ class SAModel(CaptionModel):
         temperature = opt.get("temperature", 1.0)
         if self.training:
             if beam_size > 1:
-                raise NotImplementedError("sample_beam() under model.train() is not supported; call model.eval() first")
+                # SAModel.py:169-175 under model.train(): the encoder runs in training mode (batch-statistics BatchNorm,
+                # dropout, running statistics updated); the beam search then walks the word steps.  The word steps here
+                # are the deterministic ones (the reference also drops units inside every step with torch's RNG, which
+                # no other implementation can reproduce mask for mask).
+                feats, _, _ = self._encode(feats_rgb, feats_opfl, feat_mask, want_state=False)
+                return self.sample_beam(feats, feat_mask, pos_feats, opt)
             return self._sample_training(feats_rgb, feats_opfl, feat_mask, pos_feats, sample_max, temperature)
         feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
         if beam_size > 1:
@@ -263,6 +296,9 @@ class SAModel(CaptionModel):
             raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
         seq = seq[:, :steps]
         B = seq.size(0)
+        if not torch.is_grad_enabled():
+            # the greedy baseline of get_self_critical_reward (myutils.py:45) runs under no_grad: nothing to replay
+            return seq, lps[:, :steps]
         # inputs of the steps: <bos>, then the tokens just sampled; the state mask of step t >= 1 is `unfinished`
         seq_in = torch.cat([seq.new_zeros(B, 1), seq[:, :steps - 1]], 1)
         mask = torch.cat([torch.ones(B, 1, device=seq.device), (seq[:, :steps - 1] > 0).float()], 1)

@@ -126,6 +126,7 @@ int xg_create(const xg_dims* dims, int device, xg_handle* out) {
     return fail(nullptr, XG_ERR_UNSUPPORTED, "xg_create: this library is built for sm_100a (B200) only");
   }
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->strict_persist = env_flag("XG_STRICT_PERSIST") ? 1 : 0;
   if (cudaMallocHost(&ctx->h_pinned, sizeof(int) * xg_context::kPinnedInts) != cudaSuccess ||
       cudaMalloc(&ctx->d_small, sizeof(int) * xg_context::kSmallInts) != cudaSuccess) {
     delete ctx;
@@ -199,6 +200,19 @@ int xg_set_decode_dropout(xg_handle h, int on, uint64_t seed) {
   CHECK_HANDLE(h);
   h->dec_drop_on = on ? 1 : 0;
   h->dec_drop_seed = seed;
+  return XG_OK;
+}
+
+int xg_set_strict(xg_handle h, int on) {
+  CHECK_HANDLE(h);
+  h->strict_persist = on ? 1 : 0;
+  return XG_OK;
+}
+
+int xg_path_counters(xg_handle h, uint64_t* fused, uint64_t* unfused) {
+  CHECK_HANDLE(h);
+  if (fused) *fused = h->n_fused;
+  if (unfused) *unfused = h->n_unfused;
   return XG_OK;
 }
 
@@ -322,8 +336,11 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     Uv = g.Uv;
   }
   const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;     // training-mode sampling (self-critical path)
-  if (sample_max && !step_drop && persist_eligible(h, B, K)) {   // fused persistent word loop (xg_persist.cuh)
+  if (sample_max && !step_drop) {   // fused persistent word loop (xg_persist.cuh)
     const int ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
+    if (ps != PK_FALLBACK) return ps;
+  } else {
+    const int ps = persist_refuse(h, "the sampling word loop", "multinomial draws and training-mode dropout run on per-step launches");
     if (ps != PK_FALLBACK) return ps;
   }
   for (int q = 0; q < 4; ++q)
@@ -381,6 +398,10 @@ int xg_scheduled_tokens(xg_handle h, const float* V, const float* Uv, const floa
     Uv = g.Uv;
   }
   const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;
+  {
+    const int ps = persist_refuse(h, "the scheduled-sampling token pass", "it runs on per-step launches");
+    if (ps != PK_FALLBACK) return ps;
+  }
   for (int q = 0; q < 4; ++q)
     XG_CUDA_TRY(h->es, cudaMemcpyAsync(g.st[q], state0[q], sizeof(float) * (size_t)B * H, cudaMemcpyDeviceToDevice, st));
   XG_CUDA_TRY(h->es, cudaMemcpyAsync(tokens_out, seq, sizeof(int64_t) * (size_t)B * L, cudaMemcpyDeviceToDevice, st));

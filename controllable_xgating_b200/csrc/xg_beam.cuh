@@ -247,7 +247,7 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
   int sb = 0;      // seq buffer holding the current beams
   // the word step runs as one persistent cooperative launch when the shape allows it (xg_persist.cuh): it also
   // gathers the parent states on the way in and leaves the per-row top-`beam` on the way out
-  bool fused = persist_eligible(ctx, n, K, 512) && beam <= XG_MAX_BEAM;
+  bool fused = beam <= XG_MAX_BEAM;      // persist_decode checks the shape (and refuses loudly on a strict handle)
   for (int t = -1; t < T; ++t) {
     if (t >= 0) {
       if (!fused) XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));

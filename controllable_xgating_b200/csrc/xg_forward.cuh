@@ -254,7 +254,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   }
   // the word loop: one persistent cooperative kernel for all L' steps when the shape allows it (xg_persist.cuh)
   int pst = PK_FALLBACK;
-  if (persist_eligible(ctx, B, K) && Lp >= 1) {
+  if (Lp >= 1) {
     PersistTrainIO io;
     io.seq_mask = seq_mask; io.L = L;
     io.G1 = S.G1; io.G2 = S.G2; io.C1 = S.C1; io.C2 = S.C2; io.H12 = S.H12; io.AH = S.AH; io.ALPHA = S.ALPHA; io.AF = S.AF;

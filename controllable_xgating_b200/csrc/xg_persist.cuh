@@ -42,7 +42,7 @@ constexpr int PK_THREADS = 320;
 constexpr int PK_WARPS = PK_THREADS / 32;
 constexpr int PK_SCRATCH_FLOATS = 2304;
 constexpr int PK_SMEM_BYTES = PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4 + 1024 + 512;
-constexpr int PK_MAX_ITEMS = 6;
+constexpr int PK_MAX_ITEMS = 20;
 constexpr int PK_MAX_SLOTS = 6;
 constexpr int PK_MAX_DESCS = 8;
 constexpr int PK_BULK_CHUNKS = 8;     // Uv chunks (+1 barrier for V)
@@ -1641,9 +1641,15 @@ static PhaseSchedule build_phase(const std::vector<int>& desc_ids, const GDesc* 
     for (int rt = 0; rt < rts; ++rt)
       for (int cb = 0; cb < ncb; ++cb) { strips.push_back({id, rt, cb, descs[id].nkb, 0}); U += descs[id].nkb; }
   }
+  // A strip of nkb k-blocks cut into runs of at least q k-blocks collects at most ceil(nkb / q) + 1 slots.  When a
+  // phase holds less work than CTAs x q (small vocabularies, tiny batches: SURVEY config 1) the runs are kept at q
+  // and the trailing CTAs idle, instead of one k-block per CTA and more partial tiles per strip than consumers add.
+  int max_nkb = 1;
+  for (const Strip& s : strips) max_nkb = std::max(max_nkb, s.nkb);
+  const long q_min = max_slots > 1 ? (max_nkb + max_slots - 2) / (max_slots - 1) : max_nkb;
   size_t si = 0; int off = 0;
   for (int c = 0; c < G; ++c) {
-    long need = (long)(c + 1) * U / G - (long)c * U / G;
+    long need = std::max<long>((long)(c + 1) * U / G - (long)c * U / G, q_min);
     PSched& sc = ph.per_cta[c];
     while (need > 0 && si < strips.size()) {
       Strip& s = strips[si];
@@ -1733,12 +1739,28 @@ static void persist_release(xg_context* ctx) {
 
 static inline int env_flag(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
 
-static bool persist_eligible(const xg_context* ctx, int B, int K, int max_rows = 256) {
+constexpr int PK_MAX_ROWS = 1024;    // caption rows (batch, or videos x beam) of one persistent launch: 16 column blocks
+
+// A serial loop stays off its persistent kernel (shape outside the kernel's limits, or a mode it does not cover): the
+// caller runs the per-step launches.  On a strict handle (xg_set_strict / XG_STRICT_PERSIST=1) that is an error instead
+// of a silent slow path; with the persistent engine switched off by xg_set_engine it is what the caller asked for.
+static int persist_refuse(xg_context* ctx, const char* loop, const char* why) {
+  ctx->n_unfused++;
+  if (ctx->strict_persist && ctx->persist_mode) {
+    ctx->es.msg = std::string("strict mode: ") + loop + " cannot run on its persistent kernel (" + why + ")";
+    return XG_ERR_UNSUPPORTED;
+  }
+  return PK_FALLBACK;
+}
+
+static bool persist_eligible(const xg_context* ctx, int B, int K, int max_rows = PK_MAX_ROWS) {
   const xg_dims& d = ctx->d;
   const bool v_behind = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
   const bool v_over = d.rnn <= d.att;            // V[r] fits over the consumed exp(2Uv) chunks
+  // bulk copies of exp(2Uv) need 16-byte rows; the V panels behind / over them must start on 128-byte boundaries
+  const bool aligned = d.att % 4 == 0 && ((long)K * d.att * 4) % 128 == 0 && ((long)K * d.rnn * 2) % 128 == 0;
   return ctx->persist_mode && d.rnn % 32 == 0 && d.rnn <= 512 && d.embed <= DEC_TI * PK_THREADS && d.embed % 4 == 0 &&
-         d.att % 32 == 0 && B <= max_rows && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
+         aligned && B <= max_rows && K >= 1 && K <= PK_BULK_CHUNKS * DEC_FPC && ctx->sm_count >= 16 && ctx->sm_count <= 256 &&
          (PK_WARPS + 1) * K + 8 <= PK_SCRATCH_FLOATS && d.att <= DEC_NA * PK_THREADS &&
          (long)K * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && (v_behind || v_over) &&
          (long)d.vocab * 4 <= (long)PK_STAGES * PK_STAGE_BYTES && d.vocab >= 2 && d.vocab < 32000 && d.att < 32000;
@@ -1786,7 +1808,9 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
-  if (T > 2048) return PK_FALLBACK;
+  const char* loop_name = tr ? "the teacher-forced word loop" : (step ? "the beam-search word step" : "the greedy word loop");
+  if (!persist_eligible(ctx, B, K)) return persist_refuse(ctx, loop_name, "dimensions outside the persistent decoder's limits, see xgating.h");
+  if (T > 2048) return persist_refuse(ctx, loop_name, "more than 2048 word steps");
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   PersistState*& S = persist_state(ctx);
@@ -1814,6 +1838,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     unsigned int base = S->step_sync_base;
     void* args[3] = {(void*)&dp, (void*)&S->step_mt, (void*)&base};
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_step_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    ctx->n_fused++;
     S->step_sync_base += PK_STEP_BARRIERS * (unsigned int)G;
     return XG_OK;
   }
@@ -1845,7 +1870,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int pm = 0; pm < 3; ++pm) {
     const int m = (mode + 1 + pm) % 3;            // the mode that runs is planned last (its slot counts stay in hp.d)
     for (int i = 0; i < DD_COUNT; ++i) hp.d[i].ns = 0;
-    if (!persist_plan(*plans[m], hp.d, R / PK_BN, G, sched)) return PK_FALLBACK;
+    if (!persist_plan(*plans[m], hp.d, R / PK_BN, G, sched)) return persist_refuse(ctx, loop_name, "no work schedule for this shape");
     for (int i = 0; i < DD_COUNT; ++i) ns_cap[i] = std::max(ns_cap[i], hp.d[i].ns);
   }
 
@@ -1976,6 +2001,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     void* args[3] = {(void*)&dp, (void*)&mt, (void*)&base};      // the third argument exists in single-step mode only
     void* fn = mode == 1 ? (void*)decode_persistent_kernel<1> : (mode == 2 ? (void*)decode_step_persistent_kernel : (void*)decode_persistent_kernel<0>);
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    ctx->n_fused++;
   }
   if (mode == 2) {
     memcpy(&S->step_hp_dev, &hp, sizeof(DecParams));
@@ -2043,9 +2069,11 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
 static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, EncBufs& eb, cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, G = ctx->sm_count;
-  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || K < 2 || G > 256) return PK_FALLBACK;
+  if (K < 2) return PK_FALLBACK;          // a single frame has no recurrence to fuse
+  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || G > 256)
+    return persist_refuse(ctx, "the encoder frame recurrence", "rnn_size must be a multiple of 32, at most 4096");
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
-  if (R / PK_BN > 32) return PK_FALLBACK;
+  if (R > PK_MAX_ROWS) return persist_refuse(ctx, "the encoder frame recurrence", "more than 1024 captions per launch");
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   PersistState*& S = persist_state(ctx);
@@ -2057,7 +2085,7 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
     g.w_map = s; g.x_hi = 2; g.x_lo = 3; g.xkb0 = s * kbH; g.n_rows = 4 * H; g.nkb = kbH;
   }
   std::vector<PSched> sched;
-  if (!persist_plan({{0, 1}}, ep.d, R / PK_BN, G, sched)) return PK_FALLBACK;
+  if (!persist_plan({{0, 1}}, ep.d, R / PK_BN, G, sched)) return persist_refuse(ctx, "the encoder frame recurrence", "no work schedule for this shape");
   if (S->eB != B) {
     if (S->epool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->epool); S->epool = nullptr; }
     for (int pass = 0; pass < 2; ++pass) {
@@ -2100,6 +2128,7 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
   const EncParams* dp = S->d_eparams;
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  ctx->n_fused++;
   return XG_OK;
 }
 
@@ -2108,9 +2137,11 @@ static int persist_encode(xg_context* ctx, const float* fmask, int B, int K, Enc
 static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K, const EncBufs& eb, float* const* dH, cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, G = ctx->sm_count;
-  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || K < 2 || G > 256) return PK_FALLBACK;
+  if (K < 2) return PK_FALLBACK;
+  if (!ctx->persist_mode || H % 32 != 0 || B < 1 || H > 4096 || G > 256)
+    return persist_refuse(ctx, "the encoder backward recurrence", "rnn_size must be a multiple of 32, at most 4096");
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
-  if (R / PK_BN > 32) return PK_FALLBACK;
+  if (R > PK_MAX_ROWS) return persist_refuse(ctx, "the encoder backward recurrence", "more than 1024 captions per launch");
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   PersistState*& S = persist_state(ctx);
@@ -2122,7 +2153,8 @@ static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K,
     g.w_map = s; g.x_hi = 2; g.x_lo = 3; g.xkb0 = s * kb4H; g.n_rows = H; g.nkb = kb4H;
   }
   std::vector<PSched> sched;
-  if (!persist_plan({{0, 1}}, bp.d, R / PK_BN, G, sched, ENCB_MAX_SLOTS)) return PK_FALLBACK;
+  if (!persist_plan({{0, 1}}, bp.d, R / PK_BN, G, sched, ENCB_MAX_SLOTS))
+    return persist_refuse(ctx, "the encoder backward recurrence", "no work schedule for this shape");
   if (S->bB != B) {
     if (S->bpool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->bpool); S->bpool = nullptr; }
     for (int pass = 0; pass < 2; ++pass) {
@@ -2173,6 +2205,7 @@ static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K,
   const EncBwdParams* dp = S->d_bparams;
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  ctx->n_fused++;
   return XG_OK;
 }
 
@@ -2189,9 +2222,9 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
                               cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, A = d.att, G = ctx->sm_count;
-  if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > 256 || G < 16 || G > 256 || T < 1 ||
+  if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > PK_MAX_ROWS || G < 16 || G > 256 || T < 1 ||
       2 * K + H + 8 > PK_SCRATCH_FLOATS)
-    return PK_FALLBACK;
+    return persist_refuse(ctx, "the backward word loop", "rnn_size and att_size must be multiples of 32, at most 1024 captions");
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
@@ -2210,7 +2243,8 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
   mk(DB_GG, 3, 7, H, kb4H);
   mk(DB_GH, 4, 9, 2 * H, kbA);
   std::vector<PSched> sched;
-  if (!persist_plan({{DB_GB, DB_GC, DB_GD}, {DB_GG, DB_GH}}, bp.d, R / PK_BN, G, sched, DECB_MAX_SLOTS)) return PK_FALLBACK;
+  if (!persist_plan({{DB_GB, DB_GC, DB_GD}, {DB_GG, DB_GH}}, bp.d, R / PK_BN, G, sched, DECB_MAX_SLOTS))
+    return persist_refuse(ctx, "the backward word loop", "no work schedule for this shape");
   if (S->dbB != R || S->dbK != K) {
     if (S->dbpool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->dbpool); S->dbpool = nullptr; }
     for (int pass = 0; pass < 2; ++pass) {
@@ -2271,6 +2305,7 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
   const DecBwdParams* dp = S->d_dbparams;
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  ctx->n_fused++;
   return XG_OK;
 }
 

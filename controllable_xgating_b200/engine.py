@@ -83,6 +83,7 @@ class Engine:
         self._device = None
         self._param_version = None
         self._engine_mode = 2
+        self._strict = None          # None: the library default (XG_STRICT_PERSIST in the environment)
         self._force_changed = False
         if Engine._live is None:
             import weakref
@@ -95,6 +96,32 @@ class Engine:
         self._engine_mode = (2 if persistent else 1) if tensor_cores else 0
         if self.handle:
             L.check(self.lib.xg_set_engine(self.handle, self._engine_mode), "xg_set_engine", self.handle)
+
+    def set_strict(self, strict: bool = True):
+        """strict: a serial loop that cannot run on its persistent kernel raises instead of quietly taking the
+        per-step launches (xg_set_strict)."""
+        self._strict = bool(strict)
+        if self.handle:
+            L.check(self.lib.xg_set_strict(self.handle, int(self._strict)), "xg_set_strict", self.handle)
+
+    def path_counters(self) -> Tuple[int, int]:
+        """(serial loops run by a persistent kernel, serial loops run as per-step launches) so far."""
+        if not self.handle:
+            return 0, 0
+        a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        L.check(self.lib.xg_path_counters(self.handle, ctypes.byref(a), ctypes.byref(b)), "xg_path_counters", self.handle)
+        return int(a.value), int(b.value)
+
+    def profile(self, on: bool):
+        self.bind()
+        L.check(self.lib.xg_profile_enable(self.handle, int(on)), "xg_profile_enable", self.handle)
+
+    def profile_report(self) -> List[dict]:
+        """per-kernel CUDA-event timings since profile(True): [{"name", "launches", "ms"}, ...]"""
+        import json
+        buf = ctypes.create_string_buffer(1 << 20)
+        L.check(self.lib.xg_profile_report(self.handle, buf, len(buf)), "xg_profile_report", self.handle)
+        return json.loads(buf.value.decode())
 
     # ---- handle lifecycle -------------------------------------------------------------
     def _ensure_handle(self, device: torch.device):
@@ -112,6 +139,8 @@ class Engine:
         idx = device.index if device.index is not None else torch.cuda.current_device()
         L.check(self.lib.xg_create(ctypes.byref(xd), idx, ctypes.byref(self.handle)), "xg_create")
         L.check(self.lib.xg_set_engine(self.handle, self._engine_mode), "xg_set_engine", self.handle)
+        if self._strict is not None:
+            L.check(self.lib.xg_set_strict(self.handle, int(self._strict)), "xg_set_strict", self.handle)
         self._device = device
         self._bound_key = None
         self._ws.clear()
@@ -131,6 +160,10 @@ class Engine:
             self._blist = [bufs[n] for n in BN_BUFFER_NAMES]
         return self._plist
 
+    def params_changed(self):
+        """parameter storage was rewritten behind autograd's back (p.data writes): rebuild derived tables on next use"""
+        self._force_changed = True
+
     def invalidate_param_cache(self):
         self._plist = None
         self._bound_key = None
@@ -140,8 +173,10 @@ class Engine:
         dev = plist[0].device
         self._ensure_handle(dev)
         key = tuple(p.data_ptr() for p in plist) + tuple(b.data_ptr() for b in self._blist)
-        # in-place parameter updates (optimizer.step, load_state_dict, .data.copy_) bump Tensor._version:
-        # derived copies inside the library (tf32 hi/lo splits) must be dropped
+        # In-place updates THROUGH THE PARAMETER (optimizer.step, load_state_dict, p.copy_ under no_grad) bump
+        # Tensor._version: the derived copies inside the library (tf32 hi/lo splits, POS-gate token table) are then
+        # dropped.  Writes through `p.data` (p.data.copy_/uniform_/add_) do NOT bump it and cannot be seen from here:
+        # whoever does that calls SAModel.params_changed() (init_weights, DataParallelSAModel and FusedAdam do).
         ver = sum(p._version for p in plist)
         if key == self._bound_key:
             if ver != self._param_version or self._force_changed:

@@ -89,21 +89,21 @@ class DeviceStager:
             ev.record(self.stream)
         out.ready = ev
         self._events[slot] = ev
-        self._last = ev
+        self._last = out
         return out
 
     def wait(self, batch: Optional["StagedBatch"] = None, stream: Optional[torch.cuda.Stream] = None):
         """Make `stream` (default: the current stream) wait for the copies of `batch` (default: the last put()).
         Passing the batch lets the NEXT batch be staged before the current one is consumed: put(next) ->
         wait(current) -> compute(current), the copy of `next` overlapping the compute."""
-        ev = batch.ready if batch is not None else self._last
-        if ev is None:
+        batch = batch if batch is not None else self._last
+        if batch is None:
             return
         stream = stream or torch.cuda.current_stream(self.device)
-        stream.wait_event(ev)
-        if batch is not None:
-            for t in batch.values():
-                t.record_stream(stream)                # allocated on the copy stream, consumed on this one
+        stream.wait_event(batch.ready)
+        for t in batch.values():
+            t.record_stream(stream)                    # allocated on the copy stream, consumed on this one: the caching
+                                                       # allocator must not hand the block to a later put() too early
 
 
 class StagedBatch(dict):

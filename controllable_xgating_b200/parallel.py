@@ -10,6 +10,9 @@ Loss normalisation: `LanguageModelCriterion` divides by the LOCAL sum(mask) (SAM
 the result equals the single-device gradient of the loss over the concatenated batch (up to BatchNorm,
 whose train-mode statistics stay per replica).  With `exact=False` gradients are averaged (DDP style).
 Elementwise clamping (`myutils.clip_gradient`) happens after the reduction, as in the reference.
+The `exact` rescale knows two normalisers: sum(seq_mask) of forward() (XE loss) and the sampled-sequence mask of
+sample() (RewardCriterion).  A loss that mixes in ClassiferCriterion with weight_class > 0 has a second normaliser,
+sum(mask * class_mask), for its own term; pass `exact=False` (plain averaging) or call `hook.set_mask()` yourself then.
 """
 from __future__ import annotations
 
@@ -74,8 +77,10 @@ class DataParallelSAModel(torch.nn.Module):
         self.hook = GradAllReduce(group, exact)
         object.__setattr__(model, "_grad_hook", self.hook)
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
-            for p in model.parameters():
-                dist.broadcast(p.data, src=0, group=group)
+            with torch.no_grad():
+                for p in model.parameters():
+                    dist.broadcast(p, src=0, group=group)      # through the parameter: bumps Tensor._version
+            model.params_changed()                             # ... and tell the engine explicitly as well
             self.sync_buffers()
 
     def sync_buffers(self):
@@ -87,5 +92,12 @@ class DataParallelSAModel(torch.nn.Module):
         self.hook.set_mask(seq_mask)
         return self.module(feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask)
 
-    def sample(self, *a, **k):
-        return self.module.sample(*a, **k)
+    def sample(self, feats_rgb, feats_opfl, feat_mask, pos_feats, opt={}):
+        """Under model.train() this is the self-critical path (starttrain.py:131): the log-probs carry gradients and
+        RewardCriterion normalises by the mask of the SAMPLED sequence, sum(cat[1, (seq > 0)[:, :-1]]) (SAModel.py:262-266);
+        the `exact` rescale of the gradient all-reduce has to use that normaliser, not the last XE batch's."""
+        seq, lps = self.module.sample(feats_rgb, feats_opfl, feat_mask, pos_feats, opt)
+        if self.module.training and torch.is_grad_enabled() and lps.requires_grad:
+            m = torch.cat([torch.ones_like(seq[:, :1]), (seq[:, :-1] > 0).to(seq.dtype)], 1)
+            self.hook.set_mask(m)
+        return seq, lps

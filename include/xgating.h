@@ -131,6 +131,17 @@ int xg_params_changed(xg_handle h);
  * tcgen05 3xTF32 engine (fp32-grade accuracy); 2 (default): 1 + greedy decoding in the fused persistent
  * word-step kernel.  Results agree to ~1e-6 relative. */
 int xg_set_engine(xg_handle h, int mode);
+/* Fused-path policy.  Every serial loop of the path (encoder frame recurrence and its backward, greedy word loop,
+ * teacher-forced word loop and its backward, beam-search word step) runs as ONE persistent kernel when the shape is
+ * inside that kernel's limits: rnn_size a multiple of 32 and <= 512 (encoder: <= 4096), att_size a multiple of 4
+ * (backward: of 32) and <= 1600, input_encoding_size a multiple of 4 and <= 640, frames <= 32, vocab < 32000,
+ * at most 1024 caption rows (batch, or videos x beam) per call.  Outside the limits, and for multinomial sampling /
+ * sampling with training dropout / the scheduled-sampling token pass, the same arithmetic runs as per-step launches.
+ * strict = 1 (or XG_STRICT_PERSIST=1 in the environment at xg_create) turns every such downgrade into
+ * XG_ERR_UNSUPPORTED, unless mode < 2 was asked for with xg_set_engine. */
+int xg_set_strict(xg_handle h, int strict);
+/* how many serial loops this handle has run on a persistent kernel / on per-step launches so far */
+int xg_path_counters(xg_handle h, uint64_t* fused, uint64_t* unfused);
 
 size_t xg_workspace_bytes(xg_handle h, int kind, int B, int K, int L_or_T, int beam);
 

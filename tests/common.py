@@ -1,4 +1,5 @@
 """Shared helpers for the test-suite: golden loading, config table, tolerances."""
+import contextlib
 import os
 
 import numpy as np
@@ -44,3 +45,32 @@ def rel_err(a, b):
 def fro_err(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# kernels that only the per-step (unfused) launches use: none of them may appear when a persistent kernel ran the loop
+UNFUSED_KERNELS = {"greedy_pick", "att_fwd", "dec_cell", "enc_cell", "att_bwd", "dec_cell_bwd", "enc_cell_bwd",
+                   "beam_topk", "beam_gather_state"}
+
+
+@contextlib.contextmanager
+def fused_path(model, expect):
+    """Run the body on a STRICT handle (a loop that cannot run on its persistent kernel raises, xg_set_strict) with
+    per-launch profiling on; afterwards assert that every kernel named in `expect` launched and that no per-step
+    kernel did.  `expect` uses the profile names: decode_persistent, train_decode_persistent, decode_step_persistent,
+    decode_bwd_persistent, encode_persistent, encode_bwd_persistent."""
+    eng = model._engine
+    eng.set_strict(True)
+    eng.profile(True)
+    fused0, unfused0 = eng.path_counters()
+    try:
+        yield
+    finally:
+        rep = eng.profile_report()
+        eng.profile(False)
+        eng.set_strict(False)
+    names = {r["name"] for r in rep}
+    for e in expect:
+        assert e in names, "fused kernel %s did not launch; launched: %s" % (e, sorted(names))
+    assert not (names & UNFUSED_KERNELS), "per-step kernels launched: %s" % sorted(names & UNFUSED_KERNELS)
+    fused1, unfused1 = eng.path_counters()
+    assert unfused1 == unfused0 and fused1 >= fused0 + len(expect), (fused0, fused1, unfused0, unfused1)

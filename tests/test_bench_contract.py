@@ -1,5 +1,5 @@
 """bench.py contract checks that need no GPU: the metric string is BASELINE.json's, and the reference arm
-(`--impl reference`: the oracle port on the host cores) prints ONE JSON line with the agreed keys."""
+(`--impl reference`: the reference's own files from baseline/_ref, or the oracle port, on the host cores) prints ONE JSON line with the agreed keys."""
 import json
 import os
 import subprocess
@@ -24,7 +24,13 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "captions/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the reference's own files staged under baseline/_ref by build(); "port" where they are absent
+    staged = all(os.path.exists(os.path.join(ROOT, "baseline", "_ref", "caption_src", f)) for f in ("SAModel.py", "sub_modules.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD and d["warmup"] >= 3      # same strings / warm-up policy as the GPU arm
     assert d["e2e"] == {"value": d["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -392,10 +392,15 @@ def test_full_size_train_config3():
     assert float(m.classifer[0].weight.grad.abs().max()) == 0.0
 
 
-def test_full_size_beam_config5_subset():
-    cfg, P, b = _full_case(8, seed=2); d = dev(b)
+@pytest.mark.parametrize("NB,min_exact", [(8, 8), (64, 63)])
+def test_full_size_beam_config5(NB, min_exact):
+    """config 5 (beam 5, V=10k, T=30) against the oracle: 8 videos must all be bit-exact (they are, deterministically);
+    the whole batch of 64 may hold at most one PROVEN fp32 near-tie (policy below)."""
+    from tests.common import fused_path
+    cfg, P, b = _full_case(NB, seed=2); d = dev(b)
     m = build_model(cfg, P).eval()
-    seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": 5})
+    with fused_path(m, ["encode_persistent", "decode_step_persistent"]):
+        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": 5})
     with torch.no_grad():
         V = O.encoder_fwd(P, b["rgb"], b["opfl"], b["feat_mask"])
         seq_o, lps_o, done_o = O.sample_beam(P, V, b["feat_mask"], b["pos"], 5, 30)
@@ -406,7 +411,7 @@ def test_full_size_beam_config5_subset():
     # score equals the oracle's within 1e-4 relative and (b) the oracle, teacher-forced on the device's
     # sequence, reproduces the device's per-step log-probs (the result is a true near-tie, not an error).
     exact = 0
-    for k in range(8):
+    for k in range(NB):
         same = np.array_equal(seq[k].numpy(), seq_o[k].numpy())
         p_dev, p_or = m.done_beams[k][0]["p"], done_o[k][0]["p"]
         if same:
@@ -427,8 +432,10 @@ def test_full_size_beam_config5_subset():
                 tot += float(lp_t[0, it[0]])
                 assert abs(float(lp_t[0, it[0]]) - float(lps[k, t])) < 1e-3 * max(1.0, abs(float(lps[k, t])))
         assert abs(tot - p_dev) <= 1e-4 * abs(p_dev)
-    print("beam-5 full size: %d/8 videos bit-exact" % exact)
-    assert exact >= 6
+    print("beam-5 full size: %d/%d videos bit-exact" % (exact, NB))
+    assert exact >= min_exact
+    if NB != 8:
+        return
     # a beam-1 search through the beam kernels reproduces greedy decoding (UNK aside)
     s1, _ = m.sample_beam(m.two_spatial_encoder(d["rgb"], d["opfl"], d["feat_mask"]), d["feat_mask"], d["pos"], {"beam_size": 1})
     sg, _ = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})

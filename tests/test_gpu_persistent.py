@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import xgating_oracle as O
-from tests.common import RTOL, load_golden, make_case, rel_err
+from tests.common import RTOL, fused_path, load_golden, make_case, rel_err
 from tests.test_gpu_parity import _full_case, build_model, dev
 
 pytestmark = pytest.mark.gpu
@@ -12,17 +12,74 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name", ["mid", "c1"])
 def test_persistent_matches_unfused_and_golden(name):
+    """goldens cut from the real reference, decoded by encode_persistent + decode_persistent_kernel<0> (asserted: the
+    handle is strict and the launch list is checked), and by the per-step launches."""
     g = load_golden(name); cfg, P, b = make_case(name); d = dev(b)
     res = []
     for persistent in (True, False):
         m = build_model(cfg, P).eval()
         m._engine.set_engine(True, persistent)
-        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+        if persistent:
+            with fused_path(m, ["encode_persistent", "decode_persistent"]):
+                seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+        else:
+            seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+            assert m._engine.path_counters()[0] == 0          # nothing fused when the persistent engine is off
         res.append((seq.cpu(), lps.cpu()))
     assert np.array_equal(res[0][0].numpy(), g["greedy_seq"])
     assert torch.equal(res[0][0], res[1][0])
     assert rel_err(res[0][1].numpy(), g["greedy_logp"]) < RTOL
     assert rel_err(res[0][1].numpy(), res[1][1].numpy()) < 1e-4
+
+
+def test_golden_train_step_on_persistent_kernels():
+    """config 1 goldens (real reference): forward log-probs, loss and gradients with the teacher-forced word loop, its
+    backward and both encoder recurrences on their persistent kernels (asserted)."""
+    import controllable_xgating_b200 as X
+    g = load_golden("c1"); cfg, P, b = make_case("c1"); d = dev(b)
+    m = build_model(cfg, P, drop=0.0).train()
+    with fused_path(m, ["encode_persistent", "train_decode_persistent", "decode_bwd_persistent", "encode_bwd_persistent"]):
+        logp, cat = m(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
+        loss = X.LanguageModelCriterion()(logp, d["seq"], d["seq_mask"])
+        loss.backward()
+    assert rel_err(logp.detach().cpu().numpy(), g["fwd_train_logp"]) < RTOL
+    assert abs(float(loss) - float(g["loss_lang"])) < 1e-4 * abs(float(g["loss_lang"]))
+    for n, p in m.named_parameters():
+        ref_norm = float(g["grad_w0_norm/" + n])
+        if ref_norm < 1e-7:
+            continue
+        idx = g["grad_w0_idx/" + n]; val = g["grad_w0_val/" + n]
+        gv = p.grad.reshape(-1)[torch.from_numpy(idx).cuda()].cpu().numpy()
+        scale = max(np.max(np.abs(val)), ref_norm / np.sqrt(p.numel()))
+        assert np.max(np.abs(gv - val)) <= RTOL * scale, n
+
+
+@pytest.mark.parametrize("name,beam", [("c1", 3), ("c1", 5), ("mid", 3)])
+def test_golden_beam_on_persistent_step(name, beam):
+    """beam goldens (real reference) through decode_step_persistent (asserted)."""
+    g = load_golden(name); cfg, P, b = make_case(name); d = dev(b)
+    m = build_model(cfg, P).eval()
+    with fused_path(m, ["encode_persistent", "decode_step_persistent"]):
+        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": beam})
+    assert np.array_equal(seq.numpy(), g["beam%d_seq" % beam])
+    assert rel_err(lps.numpy(), g["beam%d_logp" % beam]) < RTOL
+
+
+def test_strict_handle_refuses_unfusable_shapes():
+    """`tiny` (rnn_size 16) is outside the persistent kernels' limits: the default handle runs the per-step launches
+    (counted), a strict handle raises instead."""
+    from controllable_xgating_b200._lib import XGatingError
+    cfg, P, b = make_case("tiny"); d = dev(b)
+    m = build_model(cfg, P).eval()
+    seq, _ = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+    fused, unfused = m._engine.path_counters()
+    assert fused == 0 and unfused >= 2           # encoder recurrence + word loop
+    m._engine.set_strict(True)
+    with pytest.raises(XGatingError, match="strict mode"):
+        m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+    m._engine.set_strict(False)
+    seq2, _ = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+    assert torch.equal(seq, seq2)
 
 
 def test_persistent_full_size_with_eos():
@@ -31,7 +88,8 @@ def test_persistent_full_size_with_eos():
     P = {k: v.clone() for k, v in P.items()}
     P["logit.bias"][0] = 0.12              # EOS becomes likely: exercises unfinished / mask-carry bookkeeping
     m = build_model(cfg, P).eval()
-    seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+    with fused_path(m, ["encode_persistent", "decode_persistent"]):
+        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
     with torch.no_grad():
         seq_o, lps_o = O.sample_greedy(P, b["rgb"], b["opfl"], b["feat_mask"], b["pos"], 30)
     assert tuple(seq.shape) == tuple(seq_o.shape)
@@ -40,13 +98,14 @@ def test_persistent_full_size_with_eos():
     assert rel_err(lps.cpu().numpy(), lps_o.numpy()) < RTOL
 
 
-@pytest.mark.parametrize("B", [1, 7, 33, 100, 200])
+@pytest.mark.parametrize("B", [1, 7, 33, 100, 200, 300])
 def test_persistent_partial_batches(B):
     cfg, P, b = _full_case(B, seed=B); d = dev(b)
     P = {k: v.clone() for k, v in P.items()}
     P["logit.bias"][0] = -1e4
     m = build_model(cfg, P).eval()
-    seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+    with fused_path(m, ["encode_persistent", "decode_persistent"]):
+        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
     m._engine.set_engine(True, False)
     seq2, lps2 = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
     assert torch.equal(seq, seq2)
@@ -62,7 +121,7 @@ def _train_grads(m, d, X):
     return logp.detach().cpu(), float(loss), {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("B", [64, 21, 150, 256])
+@pytest.mark.parametrize("B", [64, 21, 150, 256, 300])
 def test_persistent_training_forward_matches_unfused(B):
     """teacher-forced word loop in the persistent kernel (mode 1) vs the per-step launches: same log-probs,
     loss and gradients (the backward consumes the activations the kernel saved), with dropout 0.5."""
@@ -73,7 +132,11 @@ def test_persistent_training_forward_matches_unfused(B):
         m = build_model(cfg, P, drop=0.5).train()
         m._engine.set_engine(True, persistent)
         torch.manual_seed(5)                      # same dropout seed for both runs
-        outs.append(_train_grads(m, d, X))
+        if persistent:
+            with fused_path(m, ["encode_persistent", "train_decode_persistent", "decode_bwd_persistent", "encode_bwd_persistent"]):
+                outs.append(_train_grads(m, d, X))
+        else:
+            outs.append(_train_grads(m, d, X))
     (lp0, l0, g0), (lp1, l1, g1) = outs
     assert rel_err(lp0.numpy(), lp1.numpy()) < 1e-4
     assert abs(l0 - l1) < 1e-5 * abs(l1)
@@ -117,7 +180,11 @@ def test_persistent_beam_step_matches_unfused(B, beam):
     for persistent in (True, False):
         m = build_model(cfg, P).eval()
         m._engine.set_engine(True, persistent)
-        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": beam})
+        if persistent:
+            with fused_path(m, ["encode_persistent", "decode_step_persistent"]):
+                seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": beam})
+        else:
+            seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"beam_size": beam})
         out.append((seq.cpu(), lps.cpu(), [[(e["seq"].clone(), float(e["p"])) for e in v] for v in m.done_beams.values()]
                     if isinstance(m.done_beams, dict) else [[(e["seq"].clone(), float(e["p"])) for e in v] for v in m.done_beams]))
     (s0, l0, d0), (s1, l1, d1) = out
