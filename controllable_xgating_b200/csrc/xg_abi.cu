@@ -7,6 +7,7 @@
 #include "xg_forward.cuh"
 #include "xg_optim.cuh"
 #include "xg_persist.cuh"
+#include "xg_grouped.cuh"
 
 using namespace xg;
 
@@ -149,6 +150,7 @@ int xg_destroy(xg_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   persist_release(h);
+  grouped_release(h);
   tc_release(h);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
@@ -337,7 +339,9 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
   }
   const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;     // training-mode sampling (self-critical path)
   if (sample_max && !step_drop) {   // fused persistent word loop (xg_persist.cuh)
-    const int ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
+    // grouped-cell kernel (xg_grouped.cuh) when the shape fits it, else the six-phase kernel (xg_persist.cuh)
+    int ps = grouped_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
+    if (ps == PK_FALLBACK) ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
     if (ps != PK_FALLBACK) return ps;
   } else {
     const int ps = persist_refuse(h, "the sampling word loop", "multinomial draws and training-mode dropout run on per-step launches");

@@ -1,0 +1,781 @@
+// Greedy word loop, second generation: the LSTM cells run in the epilogue of their own products.
+//
+// decode_persistent_kernel<0> (xg_persist.cuh) spends six grid barriers per word step: every LSTM layer is a GEMM
+// phase (split-K partial tiles to L2), a grid barrier, a pointwise phase that reads the partial tiles back, and
+// another grid barrier.  Here a layer is ONE phase:
+//
+//   * the 4H weight rows are tiled as (32 hidden units) x (4 gates): a 128-row operand tile is four 32-row TMA boxes
+//     taken at rows g*H + 32*tile of the nn.Parameter storage (no permuted weight copy), so a tile holds everything
+//     the cell of its 32 units needs;
+//   * the K extent of ALL products of the layer (lstm_1: xt, gp, h1; lstm_2: h1', af, h2: 47 / 48 k-blocks of 32) is
+//     laid end to end and cut over the `members` CTAs of the tile's GROUP (148 SMs / 16 tiles = 9): each member runs
+//     one accumulation chain of 5-6 k-blocks through the same TMA -> split -> tcgen05 pipeline as before;
+//   * members publish their 128 x 64 partial tile to L2 and arrive on the GROUP's counter (9 arrivals instead of a
+//     148-CTA grid barrier), then each member adds the 9 partial tiles of its share of the captions (one warp per
+//     caption, lane = hidden unit: every load is a 128-byte line) and runs the cell;
+//   * [h1|h2] is double buffered (a cell overwrites h while other groups still stream the old one through TMA).
+//
+// Word step: F1 {lstm_1} | F3 {lstm_2} | G4 {logits + attention query of step t+1} | P4 {pick || attention}: four grid
+// barriers instead of six, and the recurrent products Z1h / Z2h leave the logits phase.
+// Hardware thread-block clusters + distributed shared memory were measured for the same job
+// (scripts/microbench/cluster_probe.cu, profiles/r2_cluster_probe.txt): a B200 co-schedules only 15 clusters of 8 CTAs
+// with this kernel's shared-memory footprint (120 CTAs, 16 are needed), and clusters of 4 need 64-row tiles whose
+// longer K runs cost what the DSMEM reduction saves; the L2 version keeps all 148 SMs in every phase.
+#pragma once
+#include "xg_persist.cuh"
+
+namespace xg {
+
+constexpr int GK_MAX_ITEMS = 8;
+constexpr int GK_MAX_MEMBERS = 9;
+enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4 };
+
+struct GItem {            // one run of k-blocks (24 bytes)
+  short w_map;            // tensor map of the weight matrix (standalone: 128-row boxes; fused: 32-row boxes)
+  short x_map;            // hi map of the activation operand (lo = +1)
+  short xsel;             // 0: x_map as is; 1: [h1|h2] entering the step (buffer t & 1); 2: the one being written
+  short flags;            // GI_CONT_PREV: accumulate onto the previous item; GI_CONT_NEXT: the next item continues; GI_FUSED
+  short wrow;             // standalone: first weight row of the tile; fused: first hidden unit (boxes at g*H + wrow)
+  short wk0, xk0, nkb;    // first k-block in the weight / activation matrix, run length
+  short desc, slot;       // standalone: product (DecParams.d[desc]) and split-K slot; fused: group, member
+  short cb, pad;          // caption column block
+};
+struct GSched { short n, tot_kb, tot_chunks, n_chains; GItem it[GK_MAX_ITEMS]; };   // 200 bytes
+
+struct MapTable2 { CUtensorMap m[26]; };
+// 0-7 raw weights, 128-row boxes (h2a, l1_h2h, l2_h2h, l1_i2h, l1_a2h, l2_i2h, l2_a2h, logit); 8,9 xt; 10,11 / 12,13 the two
+// [h1|h2] buffers; 14,15 gp; 16,17 af; 18 V; 19-24 32-row boxes of l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
+constexpr int GM_XT = 8, GM_HH = 10, GM_GP = 14, GM_AF = 16, GM_V = 18, GM_W32 = 19;
+
+struct GroupParams {
+  DecParams dp;                  // the pick / attention / token-input phases of xg_persist.cuh read this part
+  const GSched* gsched;          // [3][G]: F1, F3, G4
+  float* fslots;                 // [groups][members][64 captions][128 rows] partial tiles of a fused cell phase
+  unsigned int* group_ctr;       // [2][groups] arrival counters (monotonic over the steps of a launch)
+  int members, groups, ncb;      // CTAs per group; groups = (H/32) x caption column blocks
+  float* hh_hi[2]; float* hh_lo[2];   // [R][2H] x 2: [h1|h2] entering the step / being written
+};
+
+// all work items of this CTA for one GEMM phase.  Same pipeline and accumulation discipline as gemm_phase
+// (xg_persist.cuh); items may chain (several k-block runs, possibly of different products, into one accumulator
+// set) and a fused chain leaves its partial tile in the group's slot buffer.
+__device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
+                                    int par, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
+  const int R = C.dp.R, H = C.dp.H;
+  if (warp == 0) {            // ===== TMA producer =====
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
+    int npre = (int)__shfl_sync(0xffffffffu, ps.npre, 0);
+    const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
+    const uint32_t full_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii) {
+      const GItem it = sc->it[ii];
+      const int xm = it.x_map + (it.xsel ? 2 * ((par + it.xsel - 1) & 1) : 0);
+      const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
+      const CUtensorMap* mxh = maps + __shfl_sync(0xffffffffu, xm, 0);
+      const CUtensorMap* mxl = mxh + 1;
+      int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0), xk = __shfl_sync(0xffffffffu, it.xk0 * 32, 0);
+      const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0), col = __shfl_sync(0xffffffffu, it.cb * PK_BN, 0);
+      const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+      const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += 32, xk += 32) {
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        const uint32_t st = stages_u32 + s * PK_STAGE_BYTES, fb = full_bar + 8 * s;
+        if (npre > 0) {         // weights already on their way (gprefetch): only the activation tiles remain
+          --npre;
+          if (elect_one_sync()) {
+            pk_expect_tx(fb, 2 * PK_X_BYTES);
+            pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
+            pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
+          }
+        } else {
+          pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            pk_expect_tx(fb, PK_TX_BYTES);
+            if (fused) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row);
+            } else {
+              pk_tma_2d(st, mw, fb, wk, row);
+            }
+            pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
+            pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (sc_next != nullptr) {       // the weight tiles of the NEXT GEMM phase go to L2 now
+      const int nn = __shfl_sync(0xffffffffu, (int)sc_next->n, 0);
+#pragma unroll 1
+      for (int ii = 0; ii < nn; ++ii) {
+        const GItem it = sc_next->it[ii];
+        const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
+        int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0);
+        const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0);
+        const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+        const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb, wk += 32) {
+          if (elect_one_sync()) {
+            if (fused) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2(mw, wk, g * H + row);
+            } else {
+              pk_tma_prefetch_l2(mw, wk, row);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {     // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_tf32(128, PK_BN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tmem_small = tb + 2 * PK_BN;
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0),
+             ic = __shfl_sync(0xffffffffu, ps.item_count, 0);
+    const uint32_t split_bar = __shfl_sync(0xffffffffu, sv.split_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+    const uint32_t acc_full = __shfl_sync(0xffffffffu, sv.acc_full, 0), acc_empty = __shfl_sync(0xffffffffu, sv.acc_empty, 0);
+    const uint32_t small_full = __shfl_sync(0xffffffffu, sv.small_full, 0), small_empty = __shfl_sync(0xffffffffu, sv.small_empty, 0);
+    const uint32_t desc_lo0 = __shfl_sync(0xffffffffu, (uint32_t)umma_desc_sw128(sv.stages_u32), 0);
+    const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii) {
+      const int nkb = __shfl_sync(0xffffffffu, (int)sc->it[ii].nkb, 0);
+      const int fl = __shfl_sync(0xffffffffu, (int)sc->it[ii].flags, 0);
+      const bool first = !(fl & GI_CONT_PREV), last = !(fl & GI_CONT_NEXT);
+      if (first) {
+        pk_wait(small_empty, (ic & 1) ^ 1);      // previous chain's cross-term accumulator read out
+        tc_fence_after();
+      }
+      uint32_t tmem_main = tb, b = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+        if ((kb & 1) == 0) {
+          b = cc & 1;
+          pk_wait(acc_empty + 8 * b, ((cc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          tmem_main = tb + b * PK_BN;
+        }
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        pk_wait(split_bar + 8 * s, (cnt / PK_STAGES) & 1);     // TMA landed AND lo tile written
+        tc_fence_after();
+        const uint32_t dlo = desc_lo0 + ((s * PK_STAGE_BYTES) >> 4);
+        const uint32_t small_acc0 = (first && kb == 0) ? 0u : 1u;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t wh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2);
+            const uint64_t wl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (PK_W_BYTES >> 4));
+            const uint64_t xh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES) >> 4));
+            const uint64_t xl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES + PK_X_BYTES) >> 4));
+            umma_tf32(tmem_main, wh, xh, idesc, ((kb & 1) | k4) != 0);
+            umma_tf32(tmem_small, wl, xh, idesc, (small_acc0 | (uint32_t)k4) != 0);
+            umma_tf32(tmem_small, wh, xl, idesc, 1);
+          }
+          pk_commit(empty_bar + 8 * s);
+          if ((kb & 1) || kb == nkb - 1) pk_commit(acc_full + 8 * b);
+          if (kb == nkb - 1 && last) pk_commit(small_full);
+        }
+        __syncwarp();
+        if ((kb & 1) || kb == nkb - 1) ++cc;
+      }
+      if (last) ++ic;
+    }
+  } else if (warp < 6) {      // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
+    const int quad = warp & 3;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t cc = ps.chunk_count, ic = ps.item_count;
+    float acc[PK_BN];
+#pragma unroll 1
+    for (int ii = 0; ii < n_items; ++ii) {
+      const GItem it = sc->it[ii];
+      const bool first = !(it.flags & GI_CONT_PREV), last = !(it.flags & GI_CONT_NEXT);
+      const int n_chunks = (it.nkb + PK_CHUNK - 1) / PK_CHUNK;
+      if (first) {
+#pragma unroll
+        for (int u = 0; u < PK_BN; ++u) acc[u] = 0.f;
+      }
+      const int rounds = n_chunks + (last ? 1 : 0);      // a chain's last round: the cross-term accumulator
+#pragma unroll 1
+      for (int c = 0; c < rounds; ++c) {
+        uint32_t col;
+        if (c < n_chunks) {
+          const uint32_t b = cc & 1;
+          pk_wait(sv.acc_full + 8 * b, (cc >> 1) & 1);
+          col = b * PK_BN;
+        } else {
+          pk_wait(sv.small_full, ic & 1);
+          col = 2 * PK_BN;
+        }
+        tc_fence_after();
+        {
+          uint32_t r[32];
+          tmem_ld32(taddr + col, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc[u] += __uint_as_float(r[u]);
+          tmem_ld32(taddr + col + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc[32 + u] += __uint_as_float(r[u]);
+        }
+        tc_fence_before();
+        if (c < n_chunks) { pk_arrive(sv.acc_empty + 8 * (cc & 1)); ++cc; }
+        else { pk_arrive(sv.small_empty); ++ic; }
+      }
+      if (last) {
+        if (it.flags & GI_FUSED) {      // [group][member][caption][row]: lanes -> consecutive rows
+          float* o = C.fslots + ((long)(it.desc * C.members + it.slot) * PK_BN) * 128 + quad * 32 + lane;
+#pragma unroll
+          for (int u = 0; u < PK_BN; ++u) { __stcg(o, acc[u]); o += 128; }
+        } else {
+          const GDesc& d = C.dp.d[it.desc];
+          const int n = it.wrow + quad * 32 + lane;          // weight row held by this thread
+          if (n < d.n_rows) {
+            float* o = d.out + ((long)it.slot * R + it.cb * PK_BN) * d.n_rows + n;
+            const long str = d.n_rows;
+#pragma unroll
+            for (int u = 0; u < PK_BN; ++u) { __stcg(o, acc[u]); o += str; }
+          }
+        }
+      }
+    }
+  } else {                    // ===== weight split: lo = rna_tf32(w - trunc_tf32(w)) =====
+    const int t = threadIdx.x - 6 * 32;
+    uint32_t cnt = ps.kb_count;
+    const int tot = sc->tot_kb;
+#pragma unroll 1
+    for (int q0 = 0; q0 < tot; ++q0, ++cnt) {
+      const uint32_t s = cnt & (PK_STAGES - 1);
+      pk_wait(sv.full_bar + 8 * s, (cnt / PK_STAGES) & 1);
+      const float4* src = reinterpret_cast<const float4*>(sv.stages + s * PK_STAGE_BYTES) + t;
+      float4* dst = reinterpret_cast<float4*>(sv.stages + s * PK_STAGE_BYTES + PK_W_BYTES) + t;
+#pragma unroll 4
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[128 * q];
+        float4 l;
+        l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
+        dst[128 * q] = l;
+      }
+      fence_proxy_async_smem();
+      pk_arrive(sv.split_bar + 8 * s);
+    }
+  }
+  ps.kb_count += sc->tot_kb;
+  ps.chunk_count += sc->tot_chunks;
+  ps.item_count += sc->n_chains;
+  ps.npre = 0;
+}
+
+// weight tiles of the first k-blocks of the next GEMM phase, issued before the grid barrier that precedes it
+__device__ __noinline__ void gprefetch(const GroupParams& C, const GSched* sc, const CUtensorMap* maps, const SmemView& sv, PipeState& ps) {
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
+  const int H = C.dp.H;
+  if (warp == 0) {
+    int npre = 0;
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
+    const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
+    const uint32_t full_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+#pragma unroll 1
+    for (int ii = 0; ii < n_items && npre < PK_STAGES; ++ii) {
+      const GItem it = sc->it[ii];
+      const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
+      int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0);
+      const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0);
+      const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
+      const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+#pragma unroll 1
+      for (int kb = 0; kb < nkb && npre < PK_STAGES; ++kb, ++cnt, wk += 32, ++npre) {
+        const uint32_t s = cnt & (PK_STAGES - 1);
+        pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+        if (elect_one_sync()) {
+          pk_expect_tx_noarrive(full_bar + 8 * s, PK_W_BYTES);
+          const uint32_t st = stages_u32 + s * PK_STAGE_BYTES;
+          if (fused) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row);
+          } else {
+            pk_tma_2d(st, mw, full_bar + 8 * s, wk, row);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  const int tot = sc->tot_kb;
+  ps.npre = (uint32_t)(tot < PK_STAGES ? tot : PK_STAGES);
+}
+
+// One LSTM layer of the word step (two_inputs_lstmcell, sub_modules.py:750-770): the products of the layer as one chain
+// per group member, the group's partial tiles summed and the cell applied by the members themselves.
+__device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
+                                              int layer, int t, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
+  const int par = t & 1;
+  gphase(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  const int cta = blockIdx.x, m = C.members;
+  if (cta >= C.groups * m) return;
+  const int grp = cta / m, mem = cta % m;
+  __syncthreads();                       // this member's partial tile is written (all four epilogue warps)
+  if (threadIdx.x == 0) {
+    unsigned int* ctr = C.group_ctr + layer * C.groups + grp;
+    const unsigned int target = (unsigned int)m * (unsigned int)(t + 1);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    const long long t0 = clock64();
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 8000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, R = P.R, B = P.B;
+  const int tile = grp / C.ncb, cb = grp % C.ncb;
+  const int c0 = mem * PK_BN / m, c1 = (mem + 1) * PK_BN / m;
+  const int j = tile * 32 + lane;                              // hidden unit of this lane
+  const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
+  float* cst = P.cx + (long)layer * R * H;
+  float* hi_new = C.hh_hi[par ^ 1]; float* lo_new = C.hh_lo[par ^ 1];
+#pragma unroll 1
+  for (int c = c0 + warp; c < c1; c += PK_WARPS) {
+    const int r = cb * PK_BN + c;                              // caption row
+    float v[4][GK_MAX_MEMBERS], bias[4];
+    const float* base = C.fslots + ((long)(grp * m) * PK_BN + c) * 128 + lane;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                              // every load of the element is in flight before the first add
+#pragma unroll
+      for (int k = 0; k < GK_MAX_MEMBERS; ++k) v[g][k] = k < m ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
+      const int n = g * H + j;
+      bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n);
+    }
+    if (r >= B) continue;                                      // padding rows of the 64-wide operand tiles stay zero
+    const long e = (long)r * H + j;
+    float* hxp = P.hx + (long)r * 2 * H + layer * H + j;
+    const float mk = t > 0 ? __ldcg(P.unfinished + r) : 1.f;
+    const float cp = __ldcg(cst + e);
+    const float hp = __ldcg(hxp);
+    float z[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < GK_MAX_MEMBERS; ++k) s += v[g][k];
+      z[g] = s + bias[g];
+    }
+    const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
+    float cn = fg * cp + ig * gg;
+    cn = cn * mk + cp * (1.f - mk);
+    float h = og * tanh_fast(cn);
+    h = h * mk + hp * (1.f - mk);
+    cst[e] = cn;
+    *hxp = h;
+    store_split(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
+  }
+}
+
+// the greedy word loop of SAModel.sample (SAModel.py:182-219), grouped-cell form
+__global__ void __launch_bounds__(PK_THREADS, 1)
+decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps) {
+  __shared__ GroupParams Csm;
+  __shared__ GSched s_sched[3];
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(GroupParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Csm)[i] = reinterpret_cast<const uint32_t*>(Cp)[i];
+  __syncthreads();
+  const GroupParams& C = Csm;
+  const DecParams& P = C.dp;
+  for (int i = threadIdx.x; i < (int)(3 * sizeof(GSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(GSched) / 4), w = i % (int)(sizeof(GSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(C.gsched + (long)ph * G + cta)[w];
+  }
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B, T = P.T;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 26) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+  uint32_t bulk_phase = 0;
+
+  // ---- prologue: states into buffer 0, <bos> inputs, bookkeeping ----
+  for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
+    const int r = e / H, j = e % H;
+    float h1 = 0.f, h2 = 0.f;
+    if (r < B) {
+      h1 = P.state0[0][e]; h2 = P.state0[2][e];
+      P.cx[e] = P.state0[1][e]; P.cx[(long)R * H + e] = P.state0[3][e];
+    }
+    P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
+    store_split(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
+    store_split(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2);
+    if (r >= B) {                                                   // padding rows of the second buffer
+      C.hh_hi[1][(long)r * 2 * H + j] = 0.f; C.hh_lo[1][(long)r * 2 * H + j] = 0.f;
+      C.hh_hi[1][(long)r * 2 * H + H + j] = 0.f; C.hh_lo[1][(long)r * 2 * H + H + j] = 0.f;
+    }
+  }
+  for (int r = cta; r < R; r += G) {
+    if (r < B) {
+      dec_token_inputs(P, r, 0);                      // token 0 = <bos> (SAModel.py:184)
+    } else {
+      for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { P.xt_hi[(long)r * P.Ep + k] = 0.f; P.xt_lo[(long)r * P.Ep + k] = 0.f; }
+      for (int j = threadIdx.x; j < H; j += PK_THREADS) {
+        P.gp_hi[(long)r * H + j] = 0.f; P.gp_lo[(long)r * H + j] = 0.f;
+        P.af_hi[(long)r * H + j] = 0.f; P.af_lo[(long)r * H + j] = 0.f;
+      }
+    }
+    if (threadIdx.x == 0) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
+  }
+  {   // EUv = exp(2 Uv), clamped like the per-step factor
+    const long n = (long)B * P.K * P.A;
+    for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
+      P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
+  }
+  // attention query of step 0: the G4 schedule once on the initial state (its logits are ignored); the state sits in
+  // buffer 0, which is "the buffer being written" of an odd step
+  gprefetch(C, &s_sched[2], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+  gphase(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+#pragma unroll 1
+  for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, 0, sv, bulk_phase);
+  fence_proxy_async_smem();
+  gprefetch(C, &s_sched[0], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+  const bool split_roles = G >= 2 * B;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    pk_stamp(P.dbg_clock, cta, t, 0);
+    // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1) =====
+    fused_cell_phase(C, &s_sched[0], &s_sched[1], maps.m, 0, t, sv, tmem_base, ps);
+    gprefetch(C, &s_sched[1], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 1);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 2);
+    // ===== F3: lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) =====
+    fused_cell_phase(C, &s_sched[1], &s_sched[2], maps.m, 1, t, sv, tmem_base, ps);
+    gprefetch(C, &s_sched[2], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 3);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 4);
+    // ===== G4: logits of step t  +  attention query of step t+1 (both read the buffer just written) =====
+    gphase(C, &s_sched[2], &s_sched[0], maps.m, t & 1, sv, tmem_base, ps);
+    pk_stamp(P.dbg_clock, cta, t, 5);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 6);
+    // ===== P4: greedy pick + next-step inputs (CTAs < B)  ||  attention of step t+1 (CTAs B..2B-1) =====
+    if (split_roles) {
+      if (cta < B) {
+        const int tokv = dec_pick(P, cta, t, sv);
+        dec_token_inputs(P, cta, tokv);
+        __syncthreads();
+      } else if (cta < 2 * B && t + 1 < T) {
+        dec_attention<0>(P, &maps.m[GM_V], cta - B, t + 1, sv, bulk_phase);
+      }
+    } else {
+#pragma unroll 1
+      for (int r = cta; r < B; r += G) {
+        const int tokv = dec_pick(P, r, t, sv);
+        dec_token_inputs(P, r, tokv);
+        __syncthreads();
+      }
+      if (t + 1 < T) {
+        fence_proxy_async_smem();
+#pragma unroll 1
+        for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, t + 1, sv, bulk_phase);
+      }
+    }
+    fence_proxy_async_smem();
+    if (t + 1 < T) gprefetch(C, &s_sched[0], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 7);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 8);
+    if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
+  }
+  gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
+  pipeline_teardown(tmem_base);
+}
+
+}  // namespace xg
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+namespace xg {
+
+struct GroupedState {
+  int R = 0, K = 0;
+  char* pool = nullptr;
+  size_t pool_bytes = 0;
+  GroupParams hp;
+  GroupParams* d_params = nullptr;
+  unsigned int* d_counter = nullptr;
+  int* d_flags = nullptr;
+  long long* d_dbg = nullptr;
+  float* tgate = nullptr;
+  unsigned long long tgate_epoch = ~0ull;
+  bool attr_set = false;
+};
+inline GroupedState*& grouped_state(xg_context* ctx) {
+  static std::unordered_map<xg_context*, GroupedState*> m;
+  return m[ctx];
+}
+static void grouped_release(xg_context* ctx) {
+  GroupedState* s = grouped_state(ctx);
+  if (!s) return;
+  if (s->pool) cudaFree(s->pool);
+  delete s;
+  grouped_state(ctx) = nullptr;
+}
+
+static int tc_make_map_rows(xg_context* ctx, TcState* ts, const float* base, int rows, int Kp, int box_rows, CUtensorMap* out) {
+  return tc_make_map(ctx, ts, base, rows, Kp, box_rows, out);
+}
+
+// Greedy decoding on decode_grouped_kernel.  PK_FALLBACK: the shape is outside this kernel (the caller runs
+// decode_persistent_kernel<0>, which covers every shape persist_eligible() accepts).
+static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
+                          int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
+  if (env_flag("XG_NO_GROUPED") || !persist_eligible(ctx, B, K) || T > 2048) return PK_FALLBACK;
+  const int kbH = H / 32, kbE = Ep / 32;
+  const int ntiles = H / 32, ncb = R / PK_BN, groups = ntiles * ncb;
+  if (groups > G || 4 * H > 32000) return PK_FALLBACK;
+  const int members = std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), kbE + 2 * kbH));
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  GroupedState*& S = grouped_state(ctx);
+  if (!S) S = new GroupedState();
+  GroupParams& hp = S->hp;
+  DecParams& dp = hp.dp;
+
+  // ---- standalone products of the G4 phase: logits of step t + attention query of step t+1 ----
+  auto mk = [&](int id, int wmap, int xkb0, int n_rows, int nkb) {
+    GDesc& g = dp.d[id];
+    g.w_map = wmap; g.x_hi = GM_HH; g.x_lo = GM_HH + 1; g.xkb0 = xkb0; g.n_rows = n_rows; g.nkb = nkb; g.ns = 0;
+  };
+  for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
+  mk(DD_AH, 0, 0, A, 2 * kbH);
+  mk(DD_LOGIT, 7, kbH, V, kbH);
+  std::vector<PSched> g4;
+  if (!persist_plan({{DD_LOGIT, DD_AH}}, dp.d, ncb, G, g4)) return PK_FALLBACK;
+
+  std::vector<GSched> sched((size_t)3 * G);
+  memset(sched.data(), 0, sizeof(GSched) * sched.size());
+  // ---- fused cell phases: one chain per member over the layer's K extent ----
+  struct Prod { int w_map, x_map, xsel, xkb0, nkb; };
+  const Prod layers[2][3] = {
+      {{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 1, GM_GP, 0, 0, kbH}, {GM_W32 + 2, GM_HH, 1, 0, kbH}},
+      {{GM_W32 + 3, GM_HH, 2, 0, kbH}, {GM_W32 + 4, GM_AF, 0, 0, kbH}, {GM_W32 + 5, GM_HH, 1, kbH, kbH}}};
+  for (int layer = 0; layer < 2; ++layer) {
+    int Ktot = 0;
+    for (int p = 0; p < 3; ++p) Ktot += layers[layer][p].nkb;
+    for (int grp = 0; grp < groups; ++grp) {
+      const int tile = grp / ncb, cb = grp % ncb;
+      for (int mem = 0; mem < members; ++mem) {
+        GSched& sc = sched[(size_t)layer * G + grp * members + mem];
+        int k0 = (int)((long)mem * Ktot / members), k1 = (int)((long)(mem + 1) * Ktot / members);
+        int base = 0;
+        for (int p = 0; p < 3 && k0 < k1; ++p) {
+          const Prod& pr = layers[layer][p];
+          const int lo = std::max(k0, base), hi = std::min(k1, base + pr.nkb);
+          if (lo < hi) {
+            GItem it{};
+            it.w_map = (short)pr.w_map; it.x_map = (short)pr.x_map; it.xsel = (short)pr.xsel;
+            it.flags = (short)(GI_FUSED | (sc.n > 0 ? GI_CONT_PREV : 0));
+            it.wrow = (short)(tile * 32); it.wk0 = (short)(lo - base); it.xk0 = (short)(pr.xkb0 + lo - base); it.nkb = (short)(hi - lo);
+            it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb;
+            if (sc.n > 0) sc.it[sc.n - 1].flags |= GI_CONT_NEXT;
+            sc.it[sc.n++] = it;
+            sc.tot_kb += (short)(hi - lo);
+            sc.tot_chunks += (short)((hi - lo + PK_CHUNK - 1) / PK_CHUNK);
+          }
+          base += pr.nkb;
+        }
+        sc.n_chains = sc.n > 0 ? 1 : 0;
+      }
+    }
+  }
+  for (int c = 0; c < G; ++c) {
+    const PSched& ps = g4[c];
+    GSched& sc = sched[(size_t)2 * G + c];
+    if (ps.n > GK_MAX_ITEMS) return PK_FALLBACK;
+    for (int i = 0; i < ps.n; ++i) {
+      const PItem& pi = ps.it[i];
+      const GDesc& gd = dp.d[pi.desc];
+      GItem it{};
+      it.w_map = (short)gd.w_map; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = 0;
+      it.wrow = (short)(pi.rt * 128); it.wk0 = pi.kb0; it.xk0 = (short)(gd.xkb0 + pi.kb0); it.nkb = pi.nkb;
+      it.desc = pi.desc; it.slot = pi.slot; it.cb = pi.cb;
+      sc.it[sc.n++] = it;
+    }
+    sc.tot_kb = ps.tot_kb; sc.tot_chunks = ps.tot_chunks; sc.n_chains = ps.n;
+  }
+
+  // ---- device pool ----
+  if (S->R != R || S->K != K) {
+    if (S->pool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->pool); S->pool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
+      S->d_params = a.take<GroupParams>(1);
+      S->d_counter = a.take<unsigned int>(64 + 2 * groups);
+      S->d_flags = a.take<int>(2048);
+      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
+      hp.gsched = a.take<GSched>(sched.size());
+      dp.d[DD_LOGIT].out = a.take<float>((size_t)PK_MAX_SLOTS * R * V);
+      dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);
+      hp.fslots = a.take<float>((size_t)groups * members * PK_BN * 128);
+      dp.xt_hi = a.take<float>((long)R * Ep); dp.xt_lo = a.take<float>((long)R * Ep);
+      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<float>((long)R * 2 * H); hp.hh_lo[q] = a.take<float>((long)R * 2 * H); }
+      dp.gp_hi = a.take<float>((long)R * H); dp.gp_lo = a.take<float>((long)R * H);
+      dp.af_hi = a.take<float>((long)R * H); dp.af_lo = a.take<float>((long)R * H);
+      dp.hx = a.take<float>((long)R * 2 * H);
+      dp.cx = a.take<float>((long)2 * R * H);
+      dp.unfinished = a.take<float>(R);
+      dp.tok = a.take<int64_t>(R);
+      S->tgate = a.take<float>((long)V * H);
+      dp.EUv = a.take<float>((long)R * K * A);
+      if (pass == 0) {
+        S->pool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->pool, S->pool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->pool, 0, S->pool_bytes, st));
+      }
+    }
+    S->R = R; S->K = K;
+    S->tgate_epoch = ~0ull;
+  }
+  dp.hh_hi = hp.hh_hi[0]; dp.hh_lo = hp.hh_lo[0];
+  hp.group_ctr = S->d_counter + 64;
+  hp.members = members; hp.groups = groups; hp.ncb = ncb;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
+                                       cudaMemcpyHostToDevice, st));
+
+  // ---- POS-gate table of every token (as in persist_decode) ----
+  if (S->tgate_epoch != ctx->param_epoch) {
+    GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], E, ctx->P[XG_P_DGATE_W], E, S->tgate, H, V, H, E);
+    g.ep.bias0 = ctx->P[XG_P_DGATE_B];
+    g.ep.act = XG_ACT_RELU;
+    XG_TRY(gemm_run(ctx, g, st));
+    S->tgate_epoch = ctx->param_epoch;
+  }
+
+  // ---- tensor maps ----
+  MapTable2 mt;
+  CUtensorMap* maps = mt.m;
+  const int wpid[8] = {XG_P_H2A_W, XG_P_L1_H2H_W, XG_P_L2_H2H_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_LOGIT_W};
+  for (int i = 0; i < 8; ++i) {
+    int rows, cols;
+    param_shape(d, wpid[i], &rows, &cols);
+    XG_TRY(tc_make_map(ctx, ts, ctx->P[wpid[i]], rows, cols, 128, &maps[i]));
+  }
+  XG_TRY(tc_make_map(ctx, ts, dp.xt_hi, R, Ep, PK_BN, &maps[GM_XT])); XG_TRY(tc_make_map(ctx, ts, dp.xt_lo, R, Ep, PK_BN, &maps[GM_XT + 1]));
+  for (int q = 0; q < 2; ++q) {
+    XG_TRY(tc_make_map(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q]));
+    XG_TRY(tc_make_map(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q + 1]));
+  }
+  XG_TRY(tc_make_map(ctx, ts, dp.gp_hi, R, H, PK_BN, &maps[GM_GP])); XG_TRY(tc_make_map(ctx, ts, dp.gp_lo, R, H, PK_BN, &maps[GM_GP + 1]));
+  XG_TRY(tc_make_map(ctx, ts, dp.af_hi, R, H, PK_BN, &maps[GM_AF])); XG_TRY(tc_make_map(ctx, ts, dp.af_lo, R, H, PK_BN, &maps[GM_AF + 1]));
+  {   // V as [B*K][H]: one box = (H/2 columns) x (K frames) of a caption, dense in shared memory
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)B * K};
+    cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)(H / 2), (cuuint32_t)K};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = ts->encode(&maps[GM_V], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vf), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (V) failed", nullptr); return XG_ERR_CUDA; }
+  }
+  const int w32[6] = {XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
+  for (int i = 0; i < 6; ++i) {
+    int rows, cols;
+    param_shape(d, w32[i], &rows, &cols);
+    XG_TRY(tc_make_map(ctx, ts, ctx->P[w32[i]], rows, cols, 32, &maps[GM_W32 + i]));
+  }
+  maps[25] = maps[0];
+
+  dp.sched = nullptr;
+  dp.B = B; dp.R = R; dp.K = K; dp.H = H; dp.E = E; dp.Ep = Ep; dp.A = A; dp.V = V; dp.T = T;
+  dp.b_h2a = ctx->P[XG_P_H2A_B]; dp.w_a2w = ctx->P[XG_P_A2W_W]; dp.b_a2w = ctx->P[XG_P_A2W_B];
+  dp.bias[0][0] = ctx->P[XG_P_L1_I2H_B]; dp.bias[0][1] = ctx->P[XG_P_L1_A2H_B]; dp.bias[0][2] = ctx->P[XG_P_L1_H2H_B];
+  dp.bias[1][0] = ctx->P[XG_P_L2_I2H_B]; dp.bias[1][1] = ctx->P[XG_P_L2_A2H_B]; dp.bias[1][2] = ctx->P[XG_P_L2_H2H_B];
+  dp.b_logit = ctx->P[XG_P_LOGIT_B]; dp.embed = ctx->P[XG_P_EMBED_W];
+  dp.tgate = S->tgate;
+  dp.Vf = Vf; dp.Uv = Uv; dp.pos = pos;
+  for (int q = 0; q < 4; ++q) dp.state0[q] = state0[q];
+  dp.mode = 0; dp.feat_div = 1; dp.build_euv = 1;
+  dp.seq = seq_out; dp.seqlogp = logp_out; dp.flags = S->d_flags;
+  dp.sync_counter = S->d_counter;
+  dp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (64 + 2 * groups), st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
+  if (dp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
+  if (!S->attr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_grouped_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped decoder does not fit on an SM");
+    S->attr_set = true;
+  }
+  {
+    ProfScope ps(ctx, "decode_persistent", st);
+    const GroupParams* gp = S->d_params;
+    void* args[2] = {(void*)&gp, (void*)&mt};
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_grouped_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    ctx->n_fused++;
+  }
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
+  XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+  int steps = 0;
+  while (steps < T && ctx->h_pinned[steps] != 0) ++steps;
+  *steps_out = steps;
+  if (dp.dbg_clock) {   // XG_PERSIST_TRACE=1: average SM cycles per phase (CTA 0) + step 3 across all CTAs
+    std::vector<long long> h((size_t)T * PK_STAMPS);
+    cudaMemcpy(h.data(), S->d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    const char* names[4] = {"F1 (lstm_1 fused)", "F3 (lstm_2 fused)", "G4 (logits, ah)", "P4 (pick || attention t+1)"};
+    double tot = 0;
+    const int n = steps > 1 ? steps - 1 : 1;
+    for (int i = 0; i < 4; ++i) {
+      double w = 0, b = 0;
+      for (int t = 1; t < std::max(steps, 2); ++t) {
+        w += (double)(h[t * PK_STAMPS + 2 * i + 1] - h[t * PK_STAMPS + 2 * i]);
+        b += (double)(h[t * PK_STAMPS + 2 * i + 2] - h[t * PK_STAMPS + 2 * i + 1]);
+      }
+      w /= n; b /= n;
+      tot += w + b;
+      fprintf(stderr, "[xg grouped trace] %-28s own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
+    }
+    fprintf(stderr, "[xg grouped trace] step %.0f cycles\n", tot);
+    if (steps > 3 && G <= 256) {
+      std::vector<long long> ga((size_t)G * PK_STAMPS);
+      cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < 4; ++i) {
+        long long open = 0, close = 0;
+        for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);
+        std::vector<long long> fin(G);
+        for (int c = 0; c < G; ++c) fin[c] = ga[(size_t)c * PK_STAMPS + 2 * i + 1] - open;
+        std::vector<long long> srt = fin;
+        std::sort(srt.begin(), srt.end());
+        for (int c = 0; c < G; ++c) close = std::max(close, ga[(size_t)c * PK_STAMPS + 2 * i + 2]);
+        const int worst = (int)(std::max_element(fin.begin(), fin.end()) - fin.begin());
+        fprintf(stderr, "[xg grouped trace] step 3 %-28s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
+                names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, close - open);
+      }
+    }
+  }
+  return XG_OK;
+}
+
+}  // namespace xg
