@@ -28,7 +28,8 @@ namespace xg {
 
 constexpr int GK_MAX_ITEMS = 8;
 constexpr int GK_MAX_MEMBERS = 9;
-enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4 };
+enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4, GI_LOGITS = 8 };
+constexpr int GK_LT_STRIDE = 130;     // row stride of the transposed logits tile in shared memory (conflict-free both ways)
 
 struct GItem {            // one run of k-blocks (24 bytes)
   short w_map;            // tensor map of the weight matrix (standalone: 128-row boxes; fused: 32-row boxes)
@@ -52,8 +53,12 @@ struct GroupParams {
   const GSched* gsched;          // [3][G]: F1, F3, G4
   float* fslots;                 // [groups][members][64 captions][128 rows] partial tiles of a fused cell phase
   unsigned int* group_ctr;       // [2][groups] arrival counters (monotonic over the steps of a launch)
-  int members, groups, ncb;      // CTAs per group; groups = (H/32) x caption column blocks
+  int members[2], groups, ncb;   // CTAs per group in F1 / F3; groups = (H/32) x caption column blocks
+  int n_att;                     // the last n_att CTAs run the attention of step t+1 THROUGH the pick phase and F1
+  unsigned int* pick_ctr;        // barrier counter of the pick phase (the attention CTAs are not part of it)
   float* hh_hi[2]; float* hh_lo[2];   // [R][2H] x 2: [h1|h2] entering the step / being written
+  float4* lpart;                 // [R][ntv] per (caption, 128-row vocabulary tile): max logit, sum exp(x - max), arg-max
+  int ntv;                       // vocabulary tiles
 };
 
 // all work items of this CTA for one GEMM phase.  Same pipeline and accumulation discipline as gemm_phase
@@ -229,9 +234,41 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         if (c < n_chunks) { pk_arrive(sv.acc_empty + 8 * (cc & 1)); ++cc; }
         else { pk_arrive(sv.small_empty); ++ic; }
       }
-      if (last) {
+      if (last && (it.flags & GI_LOGITS)) {
+        // The logits of this 128-row vocabulary tile never leave the SM: + bias, transposed through shared memory (the
+        // pipeline stages are idle: a logits item is the only item of its CTA), then per caption the tile's max /
+        // lowest arg-max / sum exp(x - max).  The pick phase combines the ntv partial results of a caption.
+        const int V = C.dp.V;
+        const int nl = quad * 32 + lane, n = it.wrow + nl;
+        const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
+        float* T = reinterpret_cast<float*>(sv.stages);
+#pragma unroll
+        for (int u = 0; u < PK_BN; ++u) T[u * GK_LT_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = (warp - 2) * 32 + lane, c = e >> 1, hh = e & 1;
+        const float* row = T + c * GK_LT_STRIDE + hh;
+        float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+          const float x = row[2 * i];
+          if (x > best) { best = x; bi = 2 * i + hh; }          // ascending rows: the first maximum is kept
+        }
+        {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        float sum = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) sum += __expf(row[2 * i] - best);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        if (hh == 0)
+          C.lpart[(long)(it.cb * PK_BN + c) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(it.wrow + bi), 0.f);
+        fence_proxy_async_smem();        // the stages go back to the TMA / bulk-copy engines
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (last) {
         if (it.flags & GI_FUSED) {      // [group][member][caption][row]: lanes -> consecutive rows
-          float* o = C.fslots + ((long)(it.desc * C.members + it.slot) * PK_BN) * 128 + quad * 32 + lane;
+          float* o = C.fslots + ((long)(it.desc * it.pad + it.slot) * PK_BN) * 128 + quad * 32 + lane;   // pad = members
 #pragma unroll
           for (int u = 0; u < PK_BN; ++u) { __stcg(o, acc[u]); o += 128; }
         } else {
@@ -319,7 +356,7 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
                                               int layer, int t, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   const int par = t & 1;
   gphase(C, sc, sc_next, maps, par, sv, tmem_base, ps);
-  const int cta = blockIdx.x, m = C.members;
+  const int cta = blockIdx.x, m = C.members[layer];
   if (cta >= C.groups * m) return;
   const int grp = cta / m, mem = cta % m;
   __syncthreads();                       // this member's partial tile is written (all four epilogue warps)
@@ -382,6 +419,68 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
   }
 }
 
+// greedy pick of caption r at step t (SAModel.py:185-210) from the per-tile partial results of the logits phase:
+// global max, lowest arg-max, log-sum-exp; one warp.  Returns the raw arg-max token to every thread.
+__device__ __noinline__ int dec_pick_tiles(const GroupParams& C, int r, int t, const SmemView& sv) {
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* redi = reinterpret_cast<int*>(sv.scratch + 16);
+  if (warp == 0) {
+    const float4* lp = C.lpart + (long)r * C.ntv;
+    float4 q[8];
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int tile = lane + 32 * i;
+      q[i] = tile < C.ntv ? __ldcg(lp + tile) : make_float4(-INFINITY, 0.f, __int_as_float(0x7fffffff), 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = __float_as_int(q[i].z);
+      if (q[i].x > best || (q[i].x == best && idx < bi)) { best = q[i].x; bi = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += q[i].y * __expf(q[i].x - best);       // empty tiles: 0 * exp(-inf) = 0
+    tot = warp_sum(tot);
+    if (lane == 0) {
+      float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
+      unf = (unf != 0.f && bi > 0) ? 1.f : 0.f;
+      P.unfinished[r] = unf;
+      P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)bi : 0;
+      P.seqlogp[(long)r * P.T + t] = -logf(tot);
+      P.tok[r] = bi;
+      if (unf != 0.f) P.flags[t] = 1;
+      redi[0] = bi;
+    }
+  }
+  __syncthreads();
+  const int tok = redi[0];
+  __syncthreads();
+  return tok;
+}
+
+// wait (without arriving) until a counter barrier has completed: CTAs that are not part of a phase
+__device__ __noinline__ void grid_barrier_observe(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 8000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+
 // the greedy word loop of SAModel.sample (SAModel.py:182-219), grouped-cell form
 __global__ void __launch_bounds__(PK_THREADS, 1)
 decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps) {
@@ -441,20 +540,21 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   }
   // attention query of step 0: the G4 schedule once on the initial state (its logits are ignored); the state sits in
   // buffer 0, which is "the buffer being written" of an odd step
+  const int n_att = C.n_att;
+  const bool is_att = cta >= G - n_att;             // attention CTA: caption cta - (G - n_att)
+  unsigned int pick_target = 0;
   gprefetch(C, &s_sched[2], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
   gphase(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
   grid_barrier(P.sync_counter, sync_target, G);
-#pragma unroll 1
-  for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, 0, sv, bulk_phase);
+  if (is_att) dec_attention<0>(P, &maps.m[GM_V], cta - (G - n_att), 0, sv, bulk_phase);
   fence_proxy_async_smem();
   gprefetch(C, &s_sched[0], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
-  const bool split_roles = G >= 2 * B;
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     pk_stamp(P.dbg_clock, cta, t, 0);
-    // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1) =====
+    // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1)   [attention CTAs: still busy with step t's attention] =====
     fused_cell_phase(C, &s_sched[0], &s_sched[1], maps.m, 0, t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
@@ -471,32 +571,27 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
     pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 6);
-    // ===== P4: greedy pick + next-step inputs (CTAs < B)  ||  attention of step t+1 (CTAs B..2B-1) =====
-    if (split_roles) {
-      if (cta < B) {
-        const int tokv = dec_pick(P, cta, t, sv);
-        dec_token_inputs(P, cta, tokv);
-        __syncthreads();
-      } else if (cta < 2 * B && t + 1 < T) {
-        dec_attention<0>(P, &maps.m[GM_V], cta - B, t + 1, sv, bulk_phase);
-      }
+    // ===== P4: greedy pick + next-step inputs on the first B CTAs.  The attention of step t+1 starts here on the last
+    // n_att CTAs and runs on through F1 of step t+1 (it needs the query, not the token; its result feeds F3): those
+    // CTAs are not part of the pick barrier, they only observe it (for the early-exit flag) when they are done. =====
+    pick_target += (unsigned int)(G - n_att);
+    if (is_att) {
+      if (t + 1 < T) dec_attention<0>(P, &maps.m[GM_V], cta - (G - n_att), t + 1, sv, bulk_phase);
+      fence_proxy_async_smem();
+      pk_stamp(P.dbg_clock, cta, t, 7);
+      grid_barrier_observe(C.pick_ctr, pick_target);
     } else {
 #pragma unroll 1
-      for (int r = cta; r < B; r += G) {
-        const int tokv = dec_pick(P, r, t, sv);
+      for (int r = cta; r < B; r += G - n_att) {
+        const int tokv = dec_pick_tiles(C, r, t, sv);
         dec_token_inputs(P, r, tokv);
         __syncthreads();
       }
-      if (t + 1 < T) {
-        fence_proxy_async_smem();
-#pragma unroll 1
-        for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, t + 1, sv, bulk_phase);
-      }
+      if (t + 1 < T) gprefetch(C, &s_sched[0], maps.m, sv, ps);
+      pk_stamp(P.dbg_clock, cta, t, 7);
+      unsigned int tgt = pick_target - (unsigned int)(G - n_att);
+      grid_barrier(C.pick_ctr, tgt, G - n_att);
     }
-    fence_proxy_async_smem();
-    if (t + 1 < T) gprefetch(C, &s_sched[0], maps.m, sv, ps);
-    pk_stamp(P.dbg_clock, cta, t, 7);
-    grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 8);
     if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
@@ -551,7 +646,12 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   const int kbH = H / 32, kbE = Ep / 32;
   const int ntiles = H / 32, ncb = R / PK_BN, groups = ntiles * ncb;
   if (groups > G || 4 * H > 32000) return PK_FALLBACK;
-  const int members = std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), kbE + 2 * kbH));
+  // the attention of step t+1 keeps the last n_att CTAs through the pick phase and F1: F1's groups live on the others
+  const int n_att = B;
+  if (ncb != 1 || G - n_att < groups || G - n_att < B) return PK_FALLBACK;
+  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - n_att) / groups), kbE + 2 * kbH)),
+                            std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 3 * kbH))};
+  const int members_max = std::max(members_l[0], members_l[1]);
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   GroupedState*& S = grouped_state(ctx);
@@ -566,9 +666,13 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   };
   for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
   mk(DD_AH, 0, 0, A, 2 * kbH);
-  mk(DD_LOGIT, 7, kbH, V, kbH);
+  mk(DD_LOGIT, 7, kbH, V, kbH);      // (full-K tiles reduced in the epilogue: no slots)
+  // logits: one CTA per (128-row vocabulary tile, column block), full K, reduced in the epilogue; the attention query
+  // is split-K over the remaining CTAs
+  const int ntv = (V + 127) / 128, nlog = ntv * ncb;
+  if (nlog > G - 8 || ntv > 256) return PK_FALLBACK;
   std::vector<PSched> g4;
-  if (!persist_plan({{DD_LOGIT, DD_AH}}, dp.d, ncb, G, g4)) return PK_FALLBACK;
+  if (!persist_plan({{DD_AH}}, dp.d, ncb, G - nlog, g4)) return PK_FALLBACK;
 
   std::vector<GSched> sched((size_t)3 * G);
   memset(sched.data(), 0, sizeof(GSched) * sched.size());
@@ -580,6 +684,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int layer = 0; layer < 2; ++layer) {
     int Ktot = 0;
     for (int p = 0; p < 3; ++p) Ktot += layers[layer][p].nkb;
+    const int members = members_l[layer];
     for (int grp = 0; grp < groups; ++grp) {
       const int tile = grp / ncb, cb = grp % ncb;
       for (int mem = 0; mem < members; ++mem) {
@@ -594,7 +699,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
             it.w_map = (short)pr.w_map; it.x_map = (short)pr.x_map; it.xsel = (short)pr.xsel;
             it.flags = (short)(GI_FUSED | (sc.n > 0 ? GI_CONT_PREV : 0));
             it.wrow = (short)(tile * 32); it.wk0 = (short)(lo - base); it.xk0 = (short)(pr.xkb0 + lo - base); it.nkb = (short)(hi - lo);
-            it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb;
+            it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb; it.pad = (short)members;
             if (sc.n > 0) sc.it[sc.n - 1].flags |= GI_CONT_NEXT;
             sc.it[sc.n++] = it;
             sc.tot_kb += (short)(hi - lo);
@@ -606,8 +711,17 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       }
     }
   }
-  for (int c = 0; c < G; ++c) {
-    const PSched& ps = g4[c];
+  for (int c = 0; c < nlog; ++c) {
+    GSched& sc = sched[(size_t)2 * G + c];
+    GItem it{};
+    it.w_map = 7; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = GI_LOGITS;
+    it.wrow = (short)((c / ncb) * 128); it.wk0 = 0; it.xk0 = (short)kbH; it.nkb = (short)kbH;
+    it.desc = DD_LOGIT; it.slot = 0; it.cb = (short)(c % ncb);
+    sc.it[sc.n++] = it;
+    sc.tot_kb = (short)kbH; sc.tot_chunks = (short)((kbH + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains = 1;
+  }
+  for (int c = nlog; c < G; ++c) {
+    const PSched& ps = g4[c - nlog];
     GSched& sc = sched[(size_t)2 * G + c];
     if (ps.n > GK_MAX_ITEMS) return PK_FALLBACK;
     for (int i = 0; i < ps.n; ++i) {
@@ -628,13 +742,13 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     for (int pass = 0; pass < 2; ++pass) {
       Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
       S->d_params = a.take<GroupParams>(1);
-      S->d_counter = a.take<unsigned int>(64 + 2 * groups);
+      S->d_counter = a.take<unsigned int>(128 + 2 * groups);
       S->d_flags = a.take<int>(2048);
       S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
       hp.gsched = a.take<GSched>(sched.size());
-      dp.d[DD_LOGIT].out = a.take<float>((size_t)PK_MAX_SLOTS * R * V);
+      hp.lpart = a.take<float4>((size_t)R * ntv);
       dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);
-      hp.fslots = a.take<float>((size_t)groups * members * PK_BN * 128);
+      hp.fslots = a.take<float>((size_t)groups * members_max * PK_BN * 128);
       dp.xt_hi = a.take<float>((long)R * Ep); dp.xt_lo = a.take<float>((long)R * Ep);
       for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<float>((long)R * 2 * H); hp.hh_lo[q] = a.take<float>((long)R * 2 * H); }
       dp.gp_hi = a.take<float>((long)R * H); dp.gp_lo = a.take<float>((long)R * H);
@@ -655,8 +769,9 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     S->tgate_epoch = ~0ull;
   }
   dp.hh_hi = hp.hh_hi[0]; dp.hh_lo = hp.hh_lo[0];
-  hp.group_ctr = S->d_counter + 64;
-  hp.members = members; hp.groups = groups; hp.ncb = ncb;
+  hp.pick_ctr = S->d_counter + 64;
+  hp.group_ctr = S->d_counter + 128;
+  hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = n_att;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
@@ -717,7 +832,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   dp.sync_counter = S->d_counter;
   dp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (64 + 2 * groups), st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (128 + 2 * groups), st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
