@@ -27,8 +27,9 @@
 namespace xg {
 
 constexpr int GK_MAX_ITEMS = 8;
-constexpr int GK_MAX_MEMBERS = 9;
-enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4, GI_LOGITS = 8 };
+constexpr int GK_MAX_MEMBERS = 9;      // CTAs of a group
+constexpr int GK_MAX_SLOTS = 12;       // partial tiles a cell adds: the group's members + the "early" ones (below)
+enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4, GI_LOGITS = 8, GI_LAYER1 = 16 };
 constexpr int GK_LT_STRIDE = 130;     // row stride of the transposed logits tile in shared memory (conflict-free both ways)
 
 struct GItem {            // one run of k-blocks (24 bytes)
@@ -51,15 +52,36 @@ constexpr int GM_XT = 8, GM_HH = 10, GM_GP = 14, GM_AF = 16, GM_V = 18, GM_W32 =
 struct GroupParams {
   DecParams dp;                  // the pick / attention / token-input phases of xg_persist.cuh read this part
   const GSched* gsched;          // [3][G]: F1, F3, G4
-  float* fslots;                 // [groups][members][64 captions][128 rows] partial tiles of a fused cell phase
+  float* fslots[2];              // per layer [groups][nslots][64 captions][128 rows] partial tiles of a fused cell phase
   unsigned int* group_ctr;       // [2][groups] arrival counters (monotonic over the steps of a launch)
   int members[2], groups, ncb;   // CTAs per group in F1 / F3; groups = (H/32) x caption column blocks
+  int nslots[2];                 // members + early slots: the recurrent products W_h2h1.h1 / W_h2h2.h2 of step t+1 are
+                                 //   computed next to the logits of step t (G4) into slots members..nslots-1
   int n_att;                     // the last n_att CTAs run the attention of step t+1 THROUGH the pick phase and F1
   unsigned int* pick_ctr;        // barrier counter of the pick phase (the attention CTAs are not part of it)
   float* hh_hi[2]; float* hh_lo[2];   // [R][2H] x 2: [h1|h2] entering the step / being written
   float4* lpart;                 // [R][ntv] per (caption, 128-row vocabulary tile): max logit, sum exp(x - max), arg-max
   int ntv;                       // vocabulary tiles
+  int l2_hints;                  // 1: L2 eviction hints on the weight loads (XG_L2_HINT=0 switches them off)
 };
+
+// L2 residency: the recurrent weights + the attention operands (47 MB) are re-read every word step and fit one L2
+// partition; the 20.5 MB logit matrix streamed behind them every step does not, and under the default policy it cycles
+// everything out (ncu r1: 42 of the 52.6 MB of weights came from DRAM every step).  Weight tiles of the recurrent
+// products are loaded evict_last, the logit stream evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void pk_tma_2d_hint(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void pk_tma_prefetch_l2_hint(const CUtensorMap* tm, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;" ::"l"(tm), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
 
 // all work items of this CTA for one GEMM phase.  Same pipeline and accumulation discipline as gemm_phase
 // (xg_persist.cuh); items may chain (several k-block runs, possibly of different products, into one accumulator
@@ -71,6 +93,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
   const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
   const int R = C.dp.R, H = C.dp.H;
   if (warp == 0) {            // ===== TMA producer =====
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
     int npre = (int)__shfl_sync(0xffffffffu, ps.npre, 0);
     const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
@@ -86,6 +109,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0), col = __shfl_sync(0xffffffffu, it.cb * PK_BN, 0);
       const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
       const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+      const uint64_t pol = (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) && C.l2_hints) ? pol_stream : pol_keep;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += 32, xk += 32) {
         const uint32_t s = cnt & (PK_STAGES - 1);
@@ -101,11 +125,18 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
             pk_expect_tx(fb, PK_TX_BYTES);
-            if (fused) {
+            if (!C.l2_hints) {
+              if (fused) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row);
+                for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row);
+              } else {
+                pk_tma_2d(st, mw, fb, wk, row);
+              }
+            } else if (fused) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row, pol);
             } else {
-              pk_tma_2d(st, mw, fb, wk, row);
+              pk_tma_2d_hint(st, mw, fb, wk, row, pol);
             }
             pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
             pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
@@ -124,14 +155,22 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0);
         const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
         const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+        const uint64_t pol = (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) && C.l2_hints) ? pol_stream : pol_keep;
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb, wk += 32) {
           if (elect_one_sync()) {
-            if (fused) {
+            if (!C.l2_hints) {
+              if (fused) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2(mw, wk, g * H + row);
+                for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2(mw, wk, g * H + row);
+              } else {
+                pk_tma_prefetch_l2(mw, wk, row);
+              }
+            } else if (fused) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2_hint(mw, wk, g * H + row, pol);
             } else {
-              pk_tma_prefetch_l2(mw, wk, row);
+              pk_tma_prefetch_l2_hint(mw, wk, row, pol);
             }
           }
           __syncwarp();
@@ -268,7 +307,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         asm volatile("bar.sync 1, 128;" ::: "memory");
       } else if (last) {
         if (it.flags & GI_FUSED) {      // [group][member][caption][row]: lanes -> consecutive rows
-          float* o = C.fslots + ((long)(it.desc * it.pad + it.slot) * PK_BN) * 128 + quad * 32 + lane;   // pad = members
+          float* o = C.fslots[(it.flags & GI_LAYER1) ? 1 : 0] + ((long)(it.desc * it.pad + it.slot) * PK_BN) * 128 + quad * 32 + lane;   // pad = nslots
 #pragma unroll
           for (int u = 0; u < PK_BN; ++u) { __stcg(o, acc[u]); o += 128; }
         } else {
@@ -335,11 +374,21 @@ __device__ __noinline__ void gprefetch(const GroupParams& C, const GSched* sc, c
         if (elect_one_sync()) {
           pk_expect_tx_noarrive(full_bar + 8 * s, PK_W_BYTES);
           const uint32_t st = stages_u32 + s * PK_STAGE_BYTES;
-          if (fused) {
+          if (!C.l2_hints) {
+            if (fused) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row);
+              for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row);
+            } else {
+              pk_tma_2d(st, mw, full_bar + 8 * s, wk, row);
+            }
           } else {
-            pk_tma_2d(st, mw, full_bar + 8 * s, wk, row);
+            const uint64_t pol = (it.flags & GI_LOGITS) ? l2_policy_evict_first() : l2_policy_evict_last();
+            if (fused) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row, pol);
+            } else {
+              pk_tma_2d_hint(st, mw, full_bar + 8 * s, wk, row, pol);
+            }
           }
         }
         __syncwarp();
@@ -350,16 +399,86 @@ __device__ __noinline__ void gprefetch(const GroupParams& C, const GSched* sc, c
   ps.npre = (uint32_t)(tot < PK_STAGES ? tot : PK_STAGES);
 }
 
+// cell of the captions [c0, c1) of a group: one warp per caption, lane = hidden unit; NCAP captions per pass with every
+// partial-tile load of all of them in flight before the first add (MAXS bounds the slots a cell adds)
+template <int MAXS, int NCAP>
+__device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int t, int grp, int c0, int c1) {
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, R = P.R, B = P.B;
+  const int tile = grp / C.ncb, cb = grp % C.ncb;
+  const int ns = C.nslots[layer], par = t & 1;
+  const int j = tile * 32 + lane;                              // hidden unit of this lane
+  const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
+  float* cst = P.cx + (long)layer * R * H;
+  float* hi_new = C.hh_hi[par ^ 1]; float* lo_new = C.hh_lo[par ^ 1];
+  const float* fs = C.fslots[layer] + ((long)(grp * ns) * PK_BN) * 128 + lane;
+  float bias[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { const int n = g * H + j; bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n); }
+#pragma unroll 1
+  for (int cA = c0 + warp; cA < c1; cA += NCAP * PK_WARPS) {
+    float v[NCAP][4][MAXS], mk[NCAP], cp[NCAP], hp[NCAP];
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int c = cA + q * PK_WARPS;
+      const bool on = c < c1;
+      const float* base = fs + (long)(on ? c : cA) * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) v[q][g][k] = (on && k < ns) ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
+      const int r = cb * PK_BN + c;
+      const bool live = on && r < B;
+      mk[q] = (live && t > 0) ? __ldcg(P.unfinished + r) : 1.f;
+      cp[q] = live ? __ldcg(cst + (long)r * H + j) : 0.f;
+      hp[q] = live ? __ldcg(P.hx + (long)r * 2 * H + layer * H + j) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int c = cA + q * PK_WARPS, r = cb * PK_BN + c;
+      if (c >= c1 || r >= B) continue;                         // padding rows of the 64-wide operand tiles stay zero
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) sum += v[q][g][k];
+        z[g] = sum + bias[g];
+      }
+      const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
+      float cn = fg * cp[q] + ig * gg;
+      cn = cn * mk[q] + cp[q] * (1.f - mk[q]);
+      float h = og * tanh_fast(cn);
+      h = h * mk[q] + hp[q] * (1.f - mk[q]);
+      cst[(long)r * H + j] = cn;
+      P.hx[(long)r * 2 * H + layer * H + j] = h;
+      store_split(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
+    }
+  }
+}
+
 // One LSTM layer of the word step (two_inputs_lstmcell, sub_modules.py:750-770): the products of the layer as one chain
 // per group member, the group's partial tiles summed and the cell applied by the members themselves.
 __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
                                               int layer, int t, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   const int par = t & 1;
+#ifdef GK_FINE
+  long long* gf = (C.dp.dbg_clock && t == 3 && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + layer * 16 : nullptr;
+  if (gf && threadIdx.x == 0) gf[0] = clock64();
+#define GKF(i) do { if (gf && threadIdx.x == 0) gf[i] = clock64(); } while (0)
+#define GKF_T(tid, i) do { if (gf && threadIdx.x == (tid)) gf[i] = clock64(); } while (0)
+#else
+#define GKF(i) do { } while (0)
+#define GKF_T(tid, i) do { } while (0)
+#endif
   gphase(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  GKF(1); GKF_T(64, 2);                  // producer done / first epilogue warp done
   const int cta = blockIdx.x, m = C.members[layer];
   if (cta >= C.groups * m) return;
   const int grp = cta / m, mem = cta % m;
   __syncthreads();                       // this member's partial tile is written (all four epilogue warps)
+  GKF(3);
   if (threadIdx.x == 0) {
     unsigned int* ctr = C.group_ctr + layer * C.groups + grp;
     const unsigned int target = (unsigned int)m * (unsigned int)(t + 1);
@@ -372,51 +491,14 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
       if (clock64() - t0 > 8000000000LL) __trap();
     }
   }
+  GKF(4);
   __syncthreads();
-  const DecParams& P = C.dp;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = P.H, R = P.R, B = P.B;
-  const int tile = grp / C.ncb, cb = grp % C.ncb;
+  GKF(5);
   const int c0 = mem * PK_BN / m, c1 = (mem + 1) * PK_BN / m;
-  const int j = tile * 32 + lane;                              // hidden unit of this lane
-  const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
-  float* cst = P.cx + (long)layer * R * H;
-  float* hi_new = C.hh_hi[par ^ 1]; float* lo_new = C.hh_lo[par ^ 1];
-#pragma unroll 1
-  for (int c = c0 + warp; c < c1; c += PK_WARPS) {
-    const int r = cb * PK_BN + c;                              // caption row
-    float v[4][GK_MAX_MEMBERS], bias[4];
-    const float* base = C.fslots + ((long)(grp * m) * PK_BN + c) * 128 + lane;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {                              // every load of the element is in flight before the first add
-#pragma unroll
-      for (int k = 0; k < GK_MAX_MEMBERS; ++k) v[g][k] = k < m ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
-      const int n = g * H + j;
-      bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n);
-    }
-    if (r >= B) continue;                                      // padding rows of the 64-wide operand tiles stay zero
-    const long e = (long)r * H + j;
-    float* hxp = P.hx + (long)r * 2 * H + layer * H + j;
-    const float mk = t > 0 ? __ldcg(P.unfinished + r) : 1.f;
-    const float cp = __ldcg(cst + e);
-    const float hp = __ldcg(hxp);
-    float z[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < GK_MAX_MEMBERS; ++k) s += v[g][k];
-      z[g] = s + bias[g];
-    }
-    const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
-    float cn = fg * cp + ig * gg;
-    cn = cn * mk + cp * (1.f - mk);
-    float h = og * tanh_fast(cn);
-    h = h * mk + hp * (1.f - mk);
-    cst[e] = cn;
-    *hxp = h;
-    store_split(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
-  }
+  if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2>(C, layer, t, grp, c0, c1);
+  else if (C.nslots[layer] <= 8) group_cell<8, 1>(C, layer, t, grp, c0, c1);
+  else group_cell<GK_MAX_SLOTS, 1>(C, layer, t, grp, c0, c1);
+  GKF(6);
 }
 
 // greedy pick of caption r at step t (SAModel.py:185-210) from the per-tile partial results of the logits phase:
@@ -649,9 +731,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   // the attention of step t+1 keeps the last n_att CTAs through the pick phase and F1: F1's groups live on the others
   const int n_att = B;
   if (ncb != 1 || G - n_att < groups || G - n_att < B) return PK_FALLBACK;
-  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - n_att) / groups), kbE + 2 * kbH)),
-                            std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 3 * kbH))};
-  const int members_max = std::max(members_l[0], members_l[1]);
+  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - n_att) / groups), kbE + kbH)),
+                            std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH))};
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   GroupedState*& S = grouped_state(ctx);
@@ -659,7 +740,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   GroupParams& hp = S->hp;
   DecParams& dp = hp.dp;
 
-  // ---- standalone products of the G4 phase: logits of step t + attention query of step t+1 ----
+  // ---- products ----
   auto mk = [&](int id, int wmap, int xkb0, int n_rows, int nkb) {
     GDesc& g = dp.d[id];
     g.w_map = wmap; g.x_hi = GM_HH; g.x_lo = GM_HH + 1; g.xkb0 = xkb0; g.n_rows = n_rows; g.nkb = nkb; g.ns = 0;
@@ -667,39 +748,46 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
   mk(DD_AH, 0, 0, A, 2 * kbH);
   mk(DD_LOGIT, 7, kbH, V, kbH);      // (full-K tiles reduced in the epilogue: no slots)
-  // logits: one CTA per (128-row vocabulary tile, column block), full K, reduced in the epilogue; the attention query
-  // is split-K over the remaining CTAs
+  // logits: one CTA per (128-row vocabulary tile, column block), full K, reduced in the epilogue
   const int ntv = (V + 127) / 128, nlog = ntv * ncb;
   if (nlog > G - 8 || ntv > 256) return PK_FALLBACK;
-  std::vector<PSched> g4;
-  if (!persist_plan({{DD_AH}}, dp.d, ncb, G - nlog, g4)) return PK_FALLBACK;
+  const int nside = G - nlog;
 
   std::vector<GSched> sched((size_t)3 * G);
   memset(sched.data(), 0, sizeof(GSched) * sched.size());
-  // ---- fused cell phases: one chain per member over the layer's K extent ----
+  // ---- fused cell phases: one chain per member over the layer's token / attention dependent K extent; the recurrent
+  //      product of the layer (it needs only the state) is computed one phase-set earlier, next to the logits, by the
+  //      CTAs that have no logits tile, into nv "early" slots of the same group ----
   struct Prod { int w_map, x_map, xsel, xkb0, nkb; };
-  const Prod layers[2][3] = {
-      {{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 1, GM_GP, 0, 0, kbH}, {GM_W32 + 2, GM_HH, 1, 0, kbH}},
-      {{GM_W32 + 3, GM_HH, 2, 0, kbH}, {GM_W32 + 4, GM_AF, 0, 0, kbH}, {GM_W32 + 5, GM_HH, 1, kbH, kbH}}};
+  // in-phase products of a layer; the third one (recurrent: reads the [h1|h2] buffer entering the step) only when the layer
+  // has no early slots
+  const Prod layers[2][3] = {{{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 1, GM_GP, 0, 0, kbH}, {GM_W32 + 2, GM_HH, 1, 0, kbH}},
+                             {{GM_W32 + 3, GM_HH, 2, 0, kbH}, {GM_W32 + 4, GM_AF, 0, 0, kbH}, {GM_W32 + 5, GM_HH, 1, kbH, kbH}}};
+  const Prod early[2] = {{GM_W32 + 2, GM_HH, 2, 0, kbH}, {GM_W32 + 5, GM_HH, 2, kbH, kbH}};   // W_h2h1.h1', W_h2h2.h2' (the buffer just written)
+  const int early_mask = getenv("XG_EARLY") ? atoi(getenv("XG_EARLY")) : 3;     // bit l: layer l's recurrent product runs early
+  const int nv_l[2] = {(early_mask & 1) ? (kbH >= 2 ? 2 : 1) : 0, (early_mask & 2) ? (kbH >= 2 ? 2 : 1) : 0};
+  const int nslots_l[2] = {members_l[0] + nv_l[0], members_l[1] + nv_l[1]};
+  if (nslots_l[0] > GK_MAX_SLOTS || nslots_l[1] > GK_MAX_SLOTS) return PK_FALLBACK;
   for (int layer = 0; layer < 2; ++layer) {
+    const int members = members_l[layer], ns = nslots_l[layer];
+    const int nprod = nv_l[layer] ? 2 : 3;
     int Ktot = 0;
-    for (int p = 0; p < 3; ++p) Ktot += layers[layer][p].nkb;
-    const int members = members_l[layer];
+    for (int p = 0; p < nprod; ++p) Ktot += layers[layer][p].nkb;
     for (int grp = 0; grp < groups; ++grp) {
       const int tile = grp / ncb, cb = grp % ncb;
       for (int mem = 0; mem < members; ++mem) {
         GSched& sc = sched[(size_t)layer * G + grp * members + mem];
         int k0 = (int)((long)mem * Ktot / members), k1 = (int)((long)(mem + 1) * Ktot / members);
         int base = 0;
-        for (int p = 0; p < 3 && k0 < k1; ++p) {
+        for (int p = 0; p < nprod && k0 < k1; ++p) {
           const Prod& pr = layers[layer][p];
           const int lo = std::max(k0, base), hi = std::min(k1, base + pr.nkb);
           if (lo < hi) {
             GItem it{};
             it.w_map = (short)pr.w_map; it.x_map = (short)pr.x_map; it.xsel = (short)pr.xsel;
-            it.flags = (short)(GI_FUSED | (sc.n > 0 ? GI_CONT_PREV : 0));
+            it.flags = (short)(GI_FUSED | (layer ? GI_LAYER1 : 0) | (sc.n > 0 ? GI_CONT_PREV : 0));
             it.wrow = (short)(tile * 32); it.wk0 = (short)(lo - base); it.xk0 = (short)(pr.xkb0 + lo - base); it.nkb = (short)(hi - lo);
-            it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb; it.pad = (short)members;
+            it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb; it.pad = (short)ns;
             if (sc.n > 0) sc.it[sc.n - 1].flags |= GI_CONT_NEXT;
             sc.it[sc.n++] = it;
             sc.tot_kb += (short)(hi - lo);
@@ -711,6 +799,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       }
     }
   }
+  // ---- G4: logits tiles on the first nlog CTAs; the others share runs of: the attention query (split-K slots, consumed by
+  //      the attention phase) and the early slots of both layers ----
   for (int c = 0; c < nlog; ++c) {
     GSched& sc = sched[(size_t)2 * G + c];
     GItem it{};
@@ -720,20 +810,42 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     sc.it[sc.n++] = it;
     sc.tot_kb = (short)kbH; sc.tot_chunks = (short)((kbH + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains = 1;
   }
-  for (int c = nlog; c < G; ++c) {
-    const PSched& ps = g4[c - nlog];
-    GSched& sc = sched[(size_t)2 * G + c];
-    if (ps.n > GK_MAX_ITEMS) return PK_FALLBACK;
-    for (int i = 0; i < ps.n; ++i) {
-      const PItem& pi = ps.it[i];
-      const GDesc& gd = dp.d[pi.desc];
-      GItem it{};
-      it.w_map = (short)gd.w_map; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = 0;
-      it.wrow = (short)(pi.rt * 128); it.wk0 = pi.kb0; it.xk0 = (short)(gd.xkb0 + pi.kb0); it.nkb = pi.nkb;
-      it.desc = pi.desc; it.slot = pi.slot; it.cb = pi.cb;
+  {
+    std::vector<GItem> runs;
+    const int ah_slots = std::min(4, 2 * kbH), ah_run = (2 * kbH + ah_slots - 1) / ah_slots;
+    dp.d[DD_AH].ns = (2 * kbH + ah_run - 1) / ah_run;
+    for (int rt = 0; rt < (A + 127) / 128; ++rt)
+      for (int cb = 0; cb < ncb; ++cb)
+        for (int k0 = 0, sl = 0; k0 < 2 * kbH; k0 += ah_run, ++sl) {
+          GItem it{};
+          it.w_map = 0; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = 0;
+          it.wrow = (short)(rt * 128); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)std::min(ah_run, 2 * kbH - k0);
+          it.desc = DD_AH; it.slot = (short)sl; it.cb = (short)cb;
+          runs.push_back(it);
+        }
+    for (int layer = 0; layer < 2; ++layer)
+      for (int grp = 0; grp < groups; ++grp)
+        for (int v = 0; v < nv_l[layer]; ++v) {
+          const Prod& pr = early[layer];
+          const int nv = nv_l[layer];
+          const int k0 = v * pr.nkb / nv, k1 = (v + 1) * pr.nkb / nv;
+          GItem it{};
+          it.w_map = (short)pr.w_map; it.x_map = (short)pr.x_map; it.xsel = (short)pr.xsel;
+          it.flags = (short)(GI_FUSED | (layer ? GI_LAYER1 : 0));
+          it.wrow = (short)((grp / ncb) * 32); it.wk0 = (short)k0; it.xk0 = (short)(pr.xkb0 + k0); it.nkb = (short)(k1 - k0);
+          it.desc = (short)grp; it.slot = (short)(members_l[layer] + v); it.cb = (short)(grp % ncb); it.pad = (short)nslots_l[layer];
+          runs.push_back(it);
+        }
+    std::stable_sort(runs.begin(), runs.end(), [](const GItem& a, const GItem& b) { return a.nkb > b.nkb; });
+    std::vector<int> load(nside, 0);
+    for (const GItem& it : runs) {
+      const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      GSched& sc = sched[(size_t)2 * G + nlog + c];
+      if (sc.n >= GK_MAX_ITEMS) return PK_FALLBACK;
       sc.it[sc.n++] = it;
+      sc.tot_kb += it.nkb; sc.tot_chunks += (short)((it.nkb + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains++;
+      load[c] += it.nkb;
     }
-    sc.tot_kb = ps.tot_kb; sc.tot_chunks = ps.tot_chunks; sc.n_chains = ps.n;
   }
 
   // ---- device pool ----
@@ -747,8 +859,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
       hp.gsched = a.take<GSched>(sched.size());
       hp.lpart = a.take<float4>((size_t)R * ntv);
-      dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);
-      hp.fslots = a.take<float>((size_t)groups * members_max * PK_BN * 128);
+      dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);   // [slot][caption][row]
+      for (int q = 0; q < 2; ++q) hp.fslots[q] = a.take<float>((size_t)groups * nslots_l[q] * PK_BN * 128);
       dp.xt_hi = a.take<float>((long)R * Ep); dp.xt_lo = a.take<float>((long)R * Ep);
       for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<float>((long)R * 2 * H); hp.hh_lo[q] = a.take<float>((long)R * 2 * H); }
       dp.gp_hi = a.take<float>((long)R * H); dp.gp_lo = a.take<float>((long)R * H);
@@ -772,6 +884,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.pick_ctr = S->d_counter + 64;
   hp.group_ctr = S->d_counter + 128;
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = n_att;
+  hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
+  hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
@@ -873,6 +987,16 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       fprintf(stderr, "[xg grouped trace] %-28s own work %7.0f cycles   barrier wait %7.0f cycles\n", names[i], w, b);
     }
     fprintf(stderr, "[xg grouped trace] step %.0f cycles\n", tot);
+#ifdef GK_FINE
+    {
+      long long f[32];
+      cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS, sizeof(f), cudaMemcpyDeviceToHost);
+      for (int l = 0; l < 2; ++l)
+        fprintf(stderr, "[xg grouped trace] step 3 cta 0 fused layer %d (cycles after phase entry): producer done %lld, epilogue warp done %lld, "
+                "cta synced %lld, group counter seen %lld, cta synced %lld, cell done %lld\n", l, f[l * 16 + 1] - f[l * 16], f[l * 16 + 2] - f[l * 16],
+                f[l * 16 + 3] - f[l * 16], f[l * 16 + 4] - f[l * 16], f[l * 16 + 5] - f[l * 16], f[l * 16 + 6] - f[l * 16]);
+    }
+#endif
     if (steps > 3 && G <= 256) {
       std::vector<long long> ga((size_t)G * PK_STAMPS);
       cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);

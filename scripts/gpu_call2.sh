@@ -5,3 +5,4 @@ tail -15 gpurun_out/pytest_grouped.log
 XG_PERSIST_TRACE=1 timeout 300 python scripts/greedy_once.py 4 2>&1 | grep "trace" | tail -12
 timeout 600 python bench.py --steps 10 --warmup 3 --skip-extra --skip-cpu > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; python -c "
 import json; d=json.load(open('gpurun_out/bench_b.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['avg_launch_us'], d['roofline']['frac'])"
+bash scripts/gpu_fine.sh 2>&1 | grep "fused layer"
