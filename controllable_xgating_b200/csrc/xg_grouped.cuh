@@ -44,10 +44,29 @@ struct GItem {            // one run of k-blocks (24 bytes)
 };
 struct GSched { short n, tot_kb, tot_chunks, n_chains; GItem it[GK_MAX_ITEMS]; };   // 200 bytes
 
-struct MapTable2 { CUtensorMap m[26]; };
-// 0-7 raw weights, 128-row boxes (h2a, l1_h2h, l2_h2h, l1_i2h, l1_a2h, l2_i2h, l2_a2h, logit); 8,9 xt; 10,11 / 12,13 the two
-// [h1|h2] buffers; 14,15 gp; 16,17 af; 18 V; 19-24 32-row boxes of l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
-constexpr int GM_XT = 8, GM_HH = 10, GM_GP = 14, GM_AF = 16, GM_V = 18, GM_W32 = 19;
+// Operands are fp16 hi / lo PAIRS (3xFP16: hi.hi + (lo.hi + hi.lo) / 2^11, the same 11 + 11 mantissa bits as the 3xTF32
+// products of xg_persist.cuh): the weights as derived tables rebuilt when the bound parameters change (like the
+// POS-gate table), the activations written that way by the pointwise phases.  A k-block is 64 wide (128-byte rows), a
+// stage holds [W hi 16K | W lo 16K | X hi 8K | X lo 8K], all of it delivered by TMA: no in-kernel split pass, and
+// 60 KB of shared-memory traffic per 32 K-elements instead of 136 KB (the GEMM phases were shared-memory bound).
+constexpr int GK_KB = 64;             // K elements of a k-block
+struct MapTable2 { CUtensorMap m[28]; };
+// hi map (lo = +1) of: 0 h2a, 2 logit (128-row boxes); 4,6,8,10,12,14 l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h (32-row
+// boxes); 16 xt; 18 / 20 the two [h1|h2] buffers; 22 gp; 24 af; 26: V as [B*K][H] fp32 (box H/2 x K, no swizzle)
+constexpr int GM_H2A = 0, GM_LOGIT = 2, GM_W32 = 4, GM_XT = 16, GM_HH = 18, GM_GP = 22, GM_AF = 24, GM_V = 26;
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: D fp32, A/B fp16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 struct GroupParams {
   DecParams dp;                  // the pick / attention / token-input phases of xg_persist.cuh read this part
@@ -59,7 +78,7 @@ struct GroupParams {
                                  //   computed next to the logits of step t (G4) into slots members..nslots-1
   int n_att;                     // the last n_att CTAs run the attention of step t+1 THROUGH the pick phase and F1
   unsigned int* pick_ctr;        // barrier counter of the pick phase (the attention CTAs are not part of it)
-  float* hh_hi[2]; float* hh_lo[2];   // [R][2H] x 2: [h1|h2] entering the step / being written
+  __half* hh_hi[2]; __half* hh_lo[2]; // [R][2H] x 2: [h1|h2] entering the step / being written (fp16 hi / lo pairs)
   float4* lpart;                 // [R][ntv] per (caption, 128-row vocabulary tile): max logit, sum exp(x - max), arg-max
   int ntv;                       // vocabulary tiles
   int l2_hints;                  // 1: L2 eviction hints on the weight loads (XG_L2_HINT=0 switches them off)
@@ -71,6 +90,9 @@ struct GroupParams {
 // products are loaded evict_last, the logit stream evict_first.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_normal() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
@@ -93,7 +115,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
   const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
   const int R = C.dp.R, H = C.dp.H;
   if (warp == 0) {            // ===== TMA producer =====
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first(), pol_norm = l2_policy_normal();
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
     int npre = (int)__shfl_sync(0xffffffffu, ps.npre, 0);
     const uint32_t stages_u32 = __shfl_sync(0xffffffffu, sv.stages_u32, 0);
@@ -103,15 +125,16 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       const GItem it = sc->it[ii];
       const int xm = it.x_map + (it.xsel ? 2 * ((par + it.xsel - 1) & 1) : 0);
       const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
+      const CUtensorMap* mwl = mw + 1;
       const CUtensorMap* mxh = maps + __shfl_sync(0xffffffffu, xm, 0);
       const CUtensorMap* mxl = mxh + 1;
-      int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0), xk = __shfl_sync(0xffffffffu, it.xk0 * 32, 0);
+      int wk = __shfl_sync(0xffffffffu, it.wk0 * GK_KB, 0), xk = __shfl_sync(0xffffffffu, it.xk0 * GK_KB, 0);
       const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0), col = __shfl_sync(0xffffffffu, it.cb * PK_BN, 0);
       const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
       const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
-      const uint64_t pol = (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) && C.l2_hints) ? pol_stream : pol_keep;
+      const uint64_t pol = !C.l2_hints ? pol_norm : (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) ? pol_stream : pol_keep);
 #pragma unroll 1
-      for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += 32, xk += 32) {
+      for (int kb = 0; kb < nkb; ++kb, ++cnt, wk += GK_KB, xk += GK_KB) {
         const uint32_t s = cnt & (PK_STAGES - 1);
         const uint32_t st = stages_u32 + s * PK_STAGE_BYTES, fb = full_bar + 8 * s;
         if (npre > 0) {         // weights already on their way (gprefetch): only the activation tiles remain
@@ -124,19 +147,16 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         } else {
           pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
-            pk_expect_tx(fb, PK_TX_BYTES);
-            if (!C.l2_hints) {
-              if (fused) {
+            pk_expect_tx(fb, PK_STAGE_BYTES);
+            if (fused) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row);
-              } else {
-                pk_tma_2d(st, mw, fb, wk, row);
+              for (int g = 0; g < 4; ++g) {
+                pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row, pol);
+                pk_tma_2d_hint(st + PK_W_BYTES + g * (PK_W_BYTES / 4), mwl, fb, wk, g * H + row, pol);
               }
-            } else if (fused) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row, pol);
             } else {
               pk_tma_2d_hint(st, mw, fb, wk, row, pol);
+              pk_tma_2d_hint(st + PK_W_BYTES, mwl, fb, wk, row, pol);
             }
             pk_tma_2d(st + 2 * PK_W_BYTES, mxh, fb, xk, col);
             pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
@@ -151,26 +171,19 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       for (int ii = 0; ii < nn; ++ii) {
         const GItem it = sc_next->it[ii];
         const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
-        int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0);
+        int wk = __shfl_sync(0xffffffffu, it.wk0 * GK_KB, 0);
         const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0);
         const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
         const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
-        const uint64_t pol = (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) && C.l2_hints) ? pol_stream : pol_keep;
+        const uint64_t pol = !C.l2_hints ? pol_norm : (__shfl_sync(0xffffffffu, (int)(it.flags & GI_LOGITS), 0) ? pol_stream : pol_keep);
 #pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb, wk += 32) {
+        for (int kb = 0; kb < nkb; ++kb, wk += GK_KB) {
           if (elect_one_sync()) {
-            if (!C.l2_hints) {
-              if (fused) {
+            if (fused) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2(mw, wk, g * H + row);
-              } else {
-                pk_tma_prefetch_l2(mw, wk, row);
-              }
-            } else if (fused) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_prefetch_l2_hint(mw, wk, g * H + row, pol);
+              for (int g = 0; g < 4; ++g) { pk_tma_prefetch_l2_hint(mw, wk, g * H + row, pol); pk_tma_prefetch_l2_hint(mw + 1, wk, g * H + row, pol); }
             } else {
-              pk_tma_prefetch_l2_hint(mw, wk, row, pol);
+              pk_tma_prefetch_l2_hint(mw, wk, row, pol); pk_tma_prefetch_l2_hint(mw + 1, wk, row, pol);
             }
           }
           __syncwarp();
@@ -178,12 +191,12 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       }
     }
   } else if (warp == 1) {     // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_tf32(128, PK_BN);
+    constexpr uint32_t idesc = umma_idesc_f16(128, PK_BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tmem_small = tb + 2 * PK_BN;
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0),
              ic = __shfl_sync(0xffffffffu, ps.item_count, 0);
-    const uint32_t split_bar = __shfl_sync(0xffffffffu, sv.split_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
+    const uint32_t ready_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
     const uint32_t acc_full = __shfl_sync(0xffffffffu, sv.acc_full, 0), acc_empty = __shfl_sync(0xffffffffu, sv.acc_empty, 0);
     const uint32_t small_full = __shfl_sync(0xffffffffu, sv.small_full, 0), small_empty = __shfl_sync(0xffffffffu, sv.small_empty, 0);
     const uint32_t desc_lo0 = __shfl_sync(0xffffffffu, (uint32_t)umma_desc_sw128(sv.stages_u32), 0);
@@ -207,7 +220,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           tmem_main = tb + b * PK_BN;
         }
         const uint32_t s = cnt & (PK_STAGES - 1);
-        pk_wait(split_bar + 8 * s, (cnt / PK_STAGES) & 1);     // TMA landed AND lo tile written
+        pk_wait(ready_bar + 8 * s, (cnt / PK_STAGES) & 1);     // all four tiles of the stage landed
         tc_fence_after();
         const uint32_t dlo = desc_lo0 + ((s * PK_STAGE_BYTES) >> 4);
         const uint32_t small_acc0 = (first && kb == 0) ? 0u : 1u;
@@ -218,9 +231,9 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
             const uint64_t wl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (PK_W_BYTES >> 4));
             const uint64_t xh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES) >> 4));
             const uint64_t xl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES + PK_X_BYTES) >> 4));
-            umma_tf32(tmem_main, wh, xh, idesc, ((kb & 1) | k4) != 0);
-            umma_tf32(tmem_small, wl, xh, idesc, (small_acc0 | (uint32_t)k4) != 0);
-            umma_tf32(tmem_small, wh, xl, idesc, 1);
+            umma_f16(tmem_main, wh, xh, idesc, ((kb & 1) | k4) != 0);
+            umma_f16(tmem_small, wl, xh, idesc, (small_acc0 | (uint32_t)k4) != 0);
+            umma_f16(tmem_small, wh, xl, idesc, 1);
           }
           pk_commit(empty_bar + 8 * s);
           if ((kb & 1) || kb == nkb - 1) pk_commit(acc_full + 8 * b);
@@ -259,15 +272,16 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         }
         tc_fence_after();
         {
+          const float sc_r = c < n_chunks ? 1.f : 1.f / X16_SCALE;     // the cross terms carry the 2^11 of the lo parts
           uint32_t r[32];
           tmem_ld32(taddr + col, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 32; ++u) acc[u] += __uint_as_float(r[u]);
+          for (int u = 0; u < 32; ++u) acc[u] = fmaf(__uint_as_float(r[u]), sc_r, acc[u]);
           tmem_ld32(taddr + col + 32, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 32; ++u) acc[32 + u] += __uint_as_float(r[u]);
+          for (int u = 0; u < 32; ++u) acc[32 + u] = fmaf(__uint_as_float(r[u]), sc_r, acc[32 + u]);
         }
         tc_fence_before();
         if (c < n_chunks) { pk_arrive(sv.acc_empty + 8 * (cc & 1)); ++cc; }
@@ -322,27 +336,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         }
       }
     }
-  } else {                    // ===== weight split: lo = rna_tf32(w - trunc_tf32(w)) =====
-    const int t = threadIdx.x - 6 * 32;
-    uint32_t cnt = ps.kb_count;
-    const int tot = sc->tot_kb;
-#pragma unroll 1
-    for (int q0 = 0; q0 < tot; ++q0, ++cnt) {
-      const uint32_t s = cnt & (PK_STAGES - 1);
-      pk_wait(sv.full_bar + 8 * s, (cnt / PK_STAGES) & 1);
-      const float4* src = reinterpret_cast<const float4*>(sv.stages + s * PK_STAGE_BYTES) + t;
-      float4* dst = reinterpret_cast<float4*>(sv.stages + s * PK_STAGE_BYTES + PK_W_BYTES) + t;
-#pragma unroll 4
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = src[128 * q];
-        float4 l;
-        l.x = tf32_lo(v.x); l.y = tf32_lo(v.y); l.z = tf32_lo(v.z); l.w = tf32_lo(v.w);
-        dst[128 * q] = l;
-      }
-      fence_proxy_async_smem();
-      pk_arrive(sv.split_bar + 8 * s);
-    }
-  }
+  }                           // (warps 6-9 have no role in the GEMM phases: the operands arrive split)
   ps.kb_count += sc->tot_kb;
   ps.chunk_count += sc->tot_chunks;
   ps.item_count += sc->n_chains;
@@ -363,32 +357,27 @@ __device__ __noinline__ void gprefetch(const GroupParams& C, const GSched* sc, c
     for (int ii = 0; ii < n_items && npre < PK_STAGES; ++ii) {
       const GItem it = sc->it[ii];
       const CUtensorMap* mw = maps + __shfl_sync(0xffffffffu, (int)it.w_map, 0);
-      int wk = __shfl_sync(0xffffffffu, it.wk0 * 32, 0);
+      int wk = __shfl_sync(0xffffffffu, it.wk0 * GK_KB, 0);
       const int row = __shfl_sync(0xffffffffu, (int)it.wrow, 0);
       const int nkb = __shfl_sync(0xffffffffu, (int)it.nkb, 0);
       const int fused = __shfl_sync(0xffffffffu, (int)(it.flags & GI_FUSED), 0);
+      const uint64_t pol = !C.l2_hints ? l2_policy_normal() : ((it.flags & GI_LOGITS) ? l2_policy_evict_first() : l2_policy_evict_last());
 #pragma unroll 1
-      for (int kb = 0; kb < nkb && npre < PK_STAGES; ++kb, ++cnt, wk += 32, ++npre) {
+      for (int kb = 0; kb < nkb && npre < PK_STAGES; ++kb, ++cnt, wk += GK_KB, ++npre) {
         const uint32_t s = cnt & (PK_STAGES - 1);
         pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
         if (elect_one_sync()) {
-          pk_expect_tx_noarrive(full_bar + 8 * s, PK_W_BYTES);
-          const uint32_t st = stages_u32 + s * PK_STAGE_BYTES;
-          if (!C.l2_hints) {
-            if (fused) {
+          pk_expect_tx_noarrive(full_bar + 8 * s, 2 * PK_W_BYTES);
+          const uint32_t st = stages_u32 + s * PK_STAGE_BYTES, fb = full_bar + 8 * s;
+          if (fused) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_2d(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row);
-            } else {
-              pk_tma_2d(st, mw, full_bar + 8 * s, wk, row);
+            for (int g = 0; g < 4; ++g) {
+              pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, fb, wk, g * H + row, pol);
+              pk_tma_2d_hint(st + PK_W_BYTES + g * (PK_W_BYTES / 4), mw + 1, fb, wk, g * H + row, pol);
             }
           } else {
-            const uint64_t pol = (it.flags & GI_LOGITS) ? l2_policy_evict_first() : l2_policy_evict_last();
-            if (fused) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) pk_tma_2d_hint(st + g * (PK_W_BYTES / 4), mw, full_bar + 8 * s, wk, g * H + row, pol);
-            } else {
-              pk_tma_2d_hint(st, mw, full_bar + 8 * s, wk, row, pol);
-            }
+            pk_tma_2d_hint(st, mw, fb, wk, row, pol);
+            pk_tma_2d_hint(st + PK_W_BYTES, mw + 1, fb, wk, row, pol);
           }
         }
         __syncwarp();
@@ -411,7 +400,7 @@ __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int 
   const int j = tile * 32 + lane;                              // hidden unit of this lane
   const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
   float* cst = P.cx + (long)layer * R * H;
-  float* hi_new = C.hh_hi[par ^ 1]; float* lo_new = C.hh_lo[par ^ 1];
+  __half* hi_new = C.hh_hi[par ^ 1]; __half* lo_new = C.hh_lo[par ^ 1];
   const float* fs = C.fslots[layer] + ((long)(grp * ns) * PK_BN) * 128 + lane;
   float bias[4];
 #pragma unroll
@@ -453,7 +442,7 @@ __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int 
       h = h * mk[q] + hp[q] * (1.f - mk[q]);
       cst[(long)r * H + j] = cn;
       P.hx[(long)r * 2 * H + layer * H + j] = h;
-      store_split(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
+      store_split16(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
     }
   }
 }
@@ -582,7 +571,7 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   const SmemView sv = carve_smem(smem_raw);
   const int H = P.H, R = P.R, B = P.B, T = P.T;
   const uint32_t tmem_base = pipeline_setup(sv);
-  if (threadIdx.x < 26) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  if (threadIdx.x < 27) tma_prefetch_desc(&maps.m[threadIdx.x]);
   PipeState ps{0, 0, 0, 0};
   unsigned int sync_target = 0;
   uint32_t bulk_phase = 0;
@@ -596,21 +585,26 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
       P.cx[e] = P.state0[1][e]; P.cx[(long)R * H + e] = P.state0[3][e];
     }
     P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
-    store_split(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
-    store_split(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2);
+    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
+    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2);
     if (r >= B) {                                                   // padding rows of the second buffer
-      C.hh_hi[1][(long)r * 2 * H + j] = 0.f; C.hh_lo[1][(long)r * 2 * H + j] = 0.f;
-      C.hh_hi[1][(long)r * 2 * H + H + j] = 0.f; C.hh_lo[1][(long)r * 2 * H + H + j] = 0.f;
+      const __half z = __float2half_rn(0.f);
+      C.hh_hi[1][(long)r * 2 * H + j] = z; C.hh_lo[1][(long)r * 2 * H + j] = z;
+      C.hh_hi[1][(long)r * 2 * H + H + j] = z; C.hh_lo[1][(long)r * 2 * H + H + j] = z;
     }
   }
   for (int r = cta; r < R; r += G) {
     if (r < B) {
       dec_token_inputs(P, r, 0);                      // token 0 = <bos> (SAModel.py:184)
     } else {
-      for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { P.xt_hi[(long)r * P.Ep + k] = 0.f; P.xt_lo[(long)r * P.Ep + k] = 0.f; }
+      const __half z = __float2half_rn(0.f);
+      __half* xh = reinterpret_cast<__half*>(P.xt_hi); __half* xl = reinterpret_cast<__half*>(P.xt_lo);
+      __half* gh = reinterpret_cast<__half*>(P.gp_hi); __half* gl = reinterpret_cast<__half*>(P.gp_lo);
+      __half* ah = reinterpret_cast<__half*>(P.af_hi); __half* al = reinterpret_cast<__half*>(P.af_lo);
+      for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { xh[(long)r * P.Ep + k] = z; xl[(long)r * P.Ep + k] = z; }
       for (int j = threadIdx.x; j < H; j += PK_THREADS) {
-        P.gp_hi[(long)r * H + j] = 0.f; P.gp_lo[(long)r * H + j] = 0.f;
-        P.af_hi[(long)r * H + j] = 0.f; P.af_lo[(long)r * H + j] = 0.f;
+        gh[(long)r * H + j] = z; gl[(long)r * H + j] = z;
+        ah[(long)r * H + j] = z; al[(long)r * H + j] = z;
       }
     }
     if (threadIdx.x == 0) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
@@ -688,6 +682,34 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
 // ------------------------------------------------------------------------------------
 namespace xg {
 
+// derived weight tables: W (rows x K fp32, row-major) -> fp16 hi / lo pairs (rows x Kp, Kp = K rounded up to 64, zero padded)
+__global__ void split_weights_f16_kernel(const float* __restrict__ W, int rows, int K, int Kp, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long n = (long)rows * Kp;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Kp), k = (int)(e % Kp);
+    const float w = k < K ? __ldg(W + (long)r * K + k) : 0.f;
+    const __half h = __float2half_rn(w);
+    hi[e] = h;
+    lo[e] = __float2half_rn((w - __half2float(h)) * X16_SCALE);
+  }
+}
+
+// K-major fp16 operand map: boxes of 64 halves (128 bytes, SWIZZLE_128B) x box_rows rows
+static int make_map16(xg_context* ctx, TcState* ts, const __half* base, int rows, int Kp, int box_rows, CUtensorMap* out) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)GK_KB, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ts->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (fp16 operand) failed", nullptr);
+    return XG_ERR_CUDA;
+  }
+  return XG_OK;
+}
+
 struct GroupedState {
   int R = 0, K = 0;
   char* pool = nullptr;
@@ -699,6 +721,7 @@ struct GroupedState {
   long long* d_dbg = nullptr;
   float* tgate = nullptr;
   unsigned long long tgate_epoch = ~0ull;
+  __half* w16[8][2] = {};        // hi / lo tables of h2a, logit, l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
   bool attr_set = false;
 };
 inline GroupedState*& grouped_state(xg_context* ctx) {
@@ -713,25 +736,23 @@ static void grouped_release(xg_context* ctx) {
   grouped_state(ctx) = nullptr;
 }
 
-static int tc_make_map_rows(xg_context* ctx, TcState* ts, const float* base, int rows, int Kp, int box_rows, CUtensorMap* out) {
-  return tc_make_map(ctx, ts, base, rows, Kp, box_rows, out);
-}
-
 // Greedy decoding on decode_grouped_kernel.  PK_FALLBACK: the shape is outside this kernel (the caller runs
 // decode_persistent_kernel<0>, which covers every shape persist_eligible() accepts).
 static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
                           int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
-  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + 31) / 32 * 32, G = ctx->sm_count;
-  if (env_flag("XG_NO_GROUPED") || !persist_eligible(ctx, B, K) || T > 2048) return PK_FALLBACK;
-  const int kbH = H / 32, kbE = Ep / 32;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + GK_KB - 1) / GK_KB * GK_KB, G = ctx->sm_count;
+  if (env_flag("XG_NO_GROUPED") || !persist_eligible(ctx, B, K) || T > 2048 || H % GK_KB != 0 || Ep > DEC_TI * PK_THREADS) return PK_FALLBACK;
+  const int kbH = H / GK_KB, kbE = Ep / GK_KB;
   const int ntiles = H / 32, ncb = R / PK_BN, groups = ntiles * ncb;
   if (groups > G || 4 * H > 32000) return PK_FALLBACK;
   // the attention of step t+1 keeps the last n_att CTAs through the pick phase and F1: F1's groups live on the others
   const int n_att = B;
-  if (ncb != 1 || G - n_att < groups || G - n_att < B) return PK_FALLBACK;
-  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - n_att) / groups), kbE + kbH)),
+  if (ncb != 1 || G - R < groups || G - R < B) return PK_FALLBACK;
+  // (the schedule depends on the padded row count only, never on B: a caption's arithmetic - K split, summation order -
+  //  is the same whatever batch it is decoded in)
+  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - R) / groups), kbE + kbH)),
                             std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH))};
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
@@ -746,8 +767,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     g.w_map = wmap; g.x_hi = GM_HH; g.x_lo = GM_HH + 1; g.xkb0 = xkb0; g.n_rows = n_rows; g.nkb = nkb; g.ns = 0;
   };
   for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
-  mk(DD_AH, 0, 0, A, 2 * kbH);
-  mk(DD_LOGIT, 7, kbH, V, kbH);      // (full-K tiles reduced in the epilogue: no slots)
+  mk(DD_AH, GM_H2A, 0, A, 2 * kbH);
+  mk(DD_LOGIT, GM_LOGIT, kbH, V, kbH);      // (full-K tiles reduced in the epilogue: no slots)
   // logits: one CTA per (128-row vocabulary tile, column block), full K, reduced in the epilogue
   const int ntv = (V + 127) / 128, nlog = ntv * ncb;
   if (nlog > G - 8 || ntv > 256) return PK_FALLBACK;
@@ -761,9 +782,9 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   struct Prod { int w_map, x_map, xsel, xkb0, nkb; };
   // in-phase products of a layer; the third one (recurrent: reads the [h1|h2] buffer entering the step) only when the layer
   // has no early slots
-  const Prod layers[2][3] = {{{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 1, GM_GP, 0, 0, kbH}, {GM_W32 + 2, GM_HH, 1, 0, kbH}},
-                             {{GM_W32 + 3, GM_HH, 2, 0, kbH}, {GM_W32 + 4, GM_AF, 0, 0, kbH}, {GM_W32 + 5, GM_HH, 1, kbH, kbH}}};
-  const Prod early[2] = {{GM_W32 + 2, GM_HH, 2, 0, kbH}, {GM_W32 + 5, GM_HH, 2, kbH, kbH}};   // W_h2h1.h1', W_h2h2.h2' (the buffer just written)
+  const Prod layers[2][3] = {{{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 2, GM_GP, 0, 0, kbH}, {GM_W32 + 4, GM_HH, 1, 0, kbH}},
+                             {{GM_W32 + 6, GM_HH, 2, 0, kbH}, {GM_W32 + 8, GM_AF, 0, 0, kbH}, {GM_W32 + 10, GM_HH, 1, kbH, kbH}}};
+  const Prod early[2] = {{GM_W32 + 4, GM_HH, 2, 0, kbH}, {GM_W32 + 10, GM_HH, 2, kbH, kbH}};   // W_h2h1.h1', W_h2h2.h2' (the buffer just written)
   const int early_mask = getenv("XG_EARLY") ? atoi(getenv("XG_EARLY")) : 3;     // bit l: layer l's recurrent product runs early
   const int nv_l[2] = {(early_mask & 1) ? (kbH >= 2 ? 2 : 1) : 0, (early_mask & 2) ? (kbH >= 2 ? 2 : 1) : 0};
   const int nslots_l[2] = {members_l[0] + nv_l[0], members_l[1] + nv_l[1]};
@@ -804,7 +825,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   for (int c = 0; c < nlog; ++c) {
     GSched& sc = sched[(size_t)2 * G + c];
     GItem it{};
-    it.w_map = 7; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = GI_LOGITS;
+    it.w_map = (short)GM_LOGIT; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = GI_LOGITS;
     it.wrow = (short)((c / ncb) * 128); it.wk0 = 0; it.xk0 = (short)kbH; it.nkb = (short)kbH;
     it.desc = DD_LOGIT; it.slot = 0; it.cb = (short)(c % ncb);
     sc.it[sc.n++] = it;
@@ -818,7 +839,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       for (int cb = 0; cb < ncb; ++cb)
         for (int k0 = 0, sl = 0; k0 < 2 * kbH; k0 += ah_run, ++sl) {
           GItem it{};
-          it.w_map = 0; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = 0;
+          it.w_map = (short)GM_H2A; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = 0;
           it.wrow = (short)(rt * 128); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)std::min(ah_run, 2 * kbH - k0);
           it.desc = DD_AH; it.slot = (short)sl; it.cb = (short)cb;
           runs.push_back(it);
@@ -861,10 +882,20 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       hp.lpart = a.take<float4>((size_t)R * ntv);
       dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);   // [slot][caption][row]
       for (int q = 0; q < 2; ++q) hp.fslots[q] = a.take<float>((size_t)groups * nslots_l[q] * PK_BN * 128);
-      dp.xt_hi = a.take<float>((long)R * Ep); dp.xt_lo = a.take<float>((long)R * Ep);
-      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<float>((long)R * 2 * H); hp.hh_lo[q] = a.take<float>((long)R * 2 * H); }
-      dp.gp_hi = a.take<float>((long)R * H); dp.gp_lo = a.take<float>((long)R * H);
-      dp.af_hi = a.take<float>((long)R * H); dp.af_lo = a.take<float>((long)R * H);
+      // fp16 hi / lo pairs (the DecParams fields are float*: the pointwise phases cast them back when x16 is set)
+      dp.xt_hi = reinterpret_cast<float*>(a.take<__half>((long)R * Ep)); dp.xt_lo = reinterpret_cast<float*>(a.take<__half>((long)R * Ep));
+      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<__half>((long)R * 2 * H); hp.hh_lo[q] = a.take<__half>((long)R * 2 * H); }
+      dp.gp_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.gp_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
+      dp.af_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.af_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
+      {
+        const int wp[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
+        for (int i = 0; i < 8; ++i) {
+          int rows, cols;
+          param_shape(d, wp[i], &rows, &cols);
+          const long n = (long)rows * ((cols + GK_KB - 1) / GK_KB * GK_KB);
+          S->w16[i][0] = a.take<__half>(n); S->w16[i][1] = a.take<__half>(n);
+        }
+      }
       dp.hx = a.take<float>((long)R * 2 * H);
       dp.cx = a.take<float>((long)2 * R * H);
       dp.unfinished = a.take<float>(R);
@@ -880,7 +911,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     S->R = R; S->K = K;
     S->tgate_epoch = ~0ull;
   }
-  dp.hh_hi = hp.hh_hi[0]; dp.hh_lo = hp.hh_lo[0];
+  dp.hh_hi = nullptr; dp.hh_lo = nullptr;
   hp.pick_ctr = S->d_counter + 64;
   hp.group_ctr = S->d_counter + 128;
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = n_att;
@@ -889,31 +920,46 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
-  // ---- POS-gate table of every token (as in persist_decode) ----
+  // ---- tables derived from the bound parameters (rebuilt when they change): POS-gate factor of every token,
+  //      fp16 hi / lo pairs of the eight weight matrices of the word step ----
+  const int wp[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
   if (S->tgate_epoch != ctx->param_epoch) {
     GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], E, ctx->P[XG_P_DGATE_W], E, S->tgate, H, V, H, E);
     g.ep.bias0 = ctx->P[XG_P_DGATE_B];
     g.ep.act = XG_ACT_RELU;
     XG_TRY(gemm_run(ctx, g, st));
+    for (int i = 0; i < 8; ++i) {
+      int rows, cols;
+      param_shape(d, wp[i], &rows, &cols);
+      const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
+      ProfScope ps(ctx, "split_weights_f16", st);
+      split_weights_f16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->P[wp[i]], rows, cols, Kp, S->w16[i][0], S->w16[i][1]);
+      XG_LAUNCH_CHECK(ctx->es);
+    }
     S->tgate_epoch = ctx->param_epoch;
   }
 
   // ---- tensor maps ----
   MapTable2 mt;
   CUtensorMap* maps = mt.m;
-  const int wpid[8] = {XG_P_H2A_W, XG_P_L1_H2H_W, XG_P_L2_H2H_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_LOGIT_W};
   for (int i = 0; i < 8; ++i) {
     int rows, cols;
-    param_shape(d, wpid[i], &rows, &cols);
-    XG_TRY(tc_make_map(ctx, ts, ctx->P[wpid[i]], rows, cols, 128, &maps[i]));
+    param_shape(d, wp[i], &rows, &cols);
+    const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
+    const int base = i < 2 ? 2 * i : GM_W32 + 2 * (i - 2);
+    XG_TRY(make_map16(ctx, ts, S->w16[i][0], rows, Kp, i < 2 ? 128 : 32, &maps[base]));
+    XG_TRY(make_map16(ctx, ts, S->w16[i][1], rows, Kp, i < 2 ? 128 : 32, &maps[base + 1]));
   }
-  XG_TRY(tc_make_map(ctx, ts, dp.xt_hi, R, Ep, PK_BN, &maps[GM_XT])); XG_TRY(tc_make_map(ctx, ts, dp.xt_lo, R, Ep, PK_BN, &maps[GM_XT + 1]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_hi), R, Ep, PK_BN, &maps[GM_XT]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_lo), R, Ep, PK_BN, &maps[GM_XT + 1]));
   for (int q = 0; q < 2; ++q) {
-    XG_TRY(tc_make_map(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q]));
-    XG_TRY(tc_make_map(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q + 1]));
+    XG_TRY(make_map16(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q]));
+    XG_TRY(make_map16(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q + 1]));
   }
-  XG_TRY(tc_make_map(ctx, ts, dp.gp_hi, R, H, PK_BN, &maps[GM_GP])); XG_TRY(tc_make_map(ctx, ts, dp.gp_lo, R, H, PK_BN, &maps[GM_GP + 1]));
-  XG_TRY(tc_make_map(ctx, ts, dp.af_hi, R, H, PK_BN, &maps[GM_AF])); XG_TRY(tc_make_map(ctx, ts, dp.af_lo, R, H, PK_BN, &maps[GM_AF + 1]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.gp_hi), R, H, PK_BN, &maps[GM_GP]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.gp_lo), R, H, PK_BN, &maps[GM_GP + 1]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_hi), R, H, PK_BN, &maps[GM_AF]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_lo), R, H, PK_BN, &maps[GM_AF + 1]));
   {   // V as [B*K][H]: one box = (H/2 columns) x (K frames) of a caption, dense in shared memory
     cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)B * K};
     cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
@@ -924,13 +970,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (V) failed", nullptr); return XG_ERR_CUDA; }
   }
-  const int w32[6] = {XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
-  for (int i = 0; i < 6; ++i) {
-    int rows, cols;
-    param_shape(d, w32[i], &rows, &cols);
-    XG_TRY(tc_make_map(ctx, ts, ctx->P[w32[i]], rows, cols, 32, &maps[GM_W32 + i]));
-  }
-  maps[25] = maps[0];
+  maps[27] = maps[0];
 
   dp.sched = nullptr;
   dp.B = B; dp.R = R; dp.K = K; dp.H = H; dp.E = E; dp.Ep = Ep; dp.A = A; dp.V = V; dp.T = T;
@@ -941,7 +981,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   dp.tgate = S->tgate;
   dp.Vf = Vf; dp.Uv = Uv; dp.pos = pos;
   for (int q = 0; q < 4; ++q) dp.state0[q] = state0[q];
-  dp.mode = 0; dp.feat_div = 1; dp.build_euv = 1;
+  dp.mode = 0; dp.feat_div = 1; dp.build_euv = 1; dp.x16 = 1;
   dp.seq = seq_out; dp.seqlogp = logp_out; dp.flags = S->d_flags;
   dp.sync_counter = S->d_counter;
   dp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;

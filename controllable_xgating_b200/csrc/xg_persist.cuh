@@ -21,6 +21,7 @@
 // Warp roles (320 threads): 0 TMA producer, 1 MMA issuer, 2-5 epilogue (TMEM lane quads), 6-9 weight split.
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstring>
@@ -462,6 +463,15 @@ __device__ __forceinline__ void store_split(float* hi, float* lo, long idx, floa
   lo[idx] = tf32_rna(v - h);
 }
 
+// fp16 operand pair of the 3xFP16 products (xg_grouped.cuh): hi = fp16(v), lo = fp16((v - hi) * 2^11); the 11 + 11
+// mantissa bits equal what a tf32 hi / lo pair carries, the scale keeps lo out of the fp16 subnormals
+constexpr float X16_SCALE = 2048.f;
+__device__ __forceinline__ void store_split16(__half* hi, __half* lo, long idx, float v) {
+  const __half h = __float2half_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2half_rn((v - __half2float(h)) * X16_SCALE);
+}
+
 // split-K partial slots of element (r, n): zload issues every load (one L2 round trip for the whole
 // batch a caller builds), zadd adds them in slot order.
 template <int MAXS>
@@ -537,6 +547,7 @@ struct DecParams {
   float *H12s;                  // (T+1, B, 2H) [h1 | h2] entering each step (after dropout)
   float *AHs, *ALPHAs, *AFs;    // (T,B,A), (T,B,K), (T,B,H)
   DropSpec drop1, drop2;        // dropout on the carried h of lstm_1 / lstm_2 (index = t*B*H + b*H + j)
+  int x16;                      // 1: xt / gp / af are fp16 hi / lo pairs (the grouped greedy kernel, xg_grouped.cuh)
 };
 
 constexpr int DEC_NA = 5;          // attention units per thread: att <= 5 * 320
@@ -741,7 +752,8 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
 #pragma unroll 4
     for (int k = 0; k < K; ++k) a += sc[k] * vp[k * Hh];
     if (TRAIN) P.AFs[((long)t * P.B + r) * H + j] = a;
-    store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
+    if (P.x16) store_split16(reinterpret_cast<__half*>(P.af_hi), reinterpret_cast<__half*>(P.af_lo), (long)r * H + j, a);
+    else store_split(P.af_hi, P.af_lo, (long)r * H + j, a);
   }
   if (threadIdx.x == 0) PK_FINE(22);
   __syncthreads();
@@ -765,8 +777,13 @@ __device__ __noinline__ void dec_token_inputs(const DecParams& P, int r, int tok
 #pragma unroll
   for (int i = 0; i < DEC_TI; ++i) {
     const int k = threadIdx.x + i * PK_THREADS;
-    if (k < P.Ep) store_split(P.xt_hi, P.xt_lo, (long)r * P.Ep + k, x[i]);
-    if (k < P.H) store_split(P.gp_hi, P.gp_lo, (long)r * P.H + k, q[i] * (1.f + g[i]));
+    if (P.x16) {
+      if (k < P.Ep) store_split16(reinterpret_cast<__half*>(P.xt_hi), reinterpret_cast<__half*>(P.xt_lo), (long)r * P.Ep + k, x[i]);
+      if (k < P.H) store_split16(reinterpret_cast<__half*>(P.gp_hi), reinterpret_cast<__half*>(P.gp_lo), (long)r * P.H + k, q[i] * (1.f + g[i]));
+    } else {
+      if (k < P.Ep) store_split(P.xt_hi, P.xt_lo, (long)r * P.Ep + k, x[i]);
+      if (k < P.H) store_split(P.gp_hi, P.gp_lo, (long)r * P.H + k, q[i] * (1.f + g[i]));
+    }
   }
 }
 
