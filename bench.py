@@ -433,7 +433,7 @@ def main():
         tmodel.cuda().train()
         tmodel._engine.set_strict(True)
         crit = X.LanguageModelCriterion()
-        dp = DataParallelSAModel(tmodel) if world > 1 else None
+        dp = DataParallelSAModel(tmodel, overlap=os.environ.get("XG_DP_OVERLAP", "1") != "0") if world > 1 else None
         fwd = dp if dp is not None else tmodel
 
         def train_step(src):

@@ -30,6 +30,7 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, rgb, opfl, fmask, pos, seq, smask, seed, *params):
         eng = model._engine
+        eng.split_event_wanted = bool(getattr(model._grad_hook, "overlap", False))
         logp, cat, c = eng.train_fwd(rgb, opfl, fmask, pos, seq, smask, model._train_flags(), seed, keep=True,
                                      steps=getattr(model, "_forced_steps", None))
         ctx.model = model
@@ -49,7 +50,7 @@ class _TrainForward(torch.autograd.Function):
         ctx.c = None
         hook = model._grad_hook
         if hook is not None:
-            hook(model._engine.last_flat_grad)
+            hook(model._engine.last_flat_grad, model._engine.last_split)
         plist = model._engine.params()
         out = [g if p.requires_grad else None for g, p in zip(grads, plist)]
         return (None,) * 8 + tuple(out)

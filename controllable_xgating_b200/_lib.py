@@ -48,6 +48,7 @@ SIGNATURES = {
     "xg_bind_bn_buffers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xg_params_changed": (c_int, [c_void_p]),
     "xg_set_engine": (c_int, [c_void_p, c_int]),
+    "xg_set_bwd_split_event": (c_int, [c_void_p, c_void_p]),
     "xg_set_strict": (c_int, [c_void_p, c_int]),
     "xg_path_counters": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64)]),
     "xg_set_decode_dropout": (c_int, [c_void_p, c_int, c_uint64]),

@@ -218,6 +218,12 @@ int xg_path_counters(xg_handle h, uint64_t* fused, uint64_t* unfused) {
   return XG_OK;
 }
 
+int xg_set_bwd_split_event(xg_handle h, void* cuda_event) {
+  CHECK_HANDLE(h);
+  h->bwd_split_event = (cudaEvent_t)cuda_event;
+  return XG_OK;
+}
+
 int xg_set_engine(xg_handle h, int tensor_cores) {
   CHECK_HANDLE(h);
   h->tc_mode = tensor_cores >= 1 ? 1 : 0;

@@ -234,6 +234,10 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     XG_TRY(gemm_run(ctx, gv, st));
   }
 
+  // Every gradient of the decoder side (init-state linears, POS gate, both LSTM cells, attention, embedding, logit and
+  // classifier heads: parameters XG_P_INIT_H1_W .. XG_P_CLS3_B, the tail of the flat gradient buffer) is final here; what
+  // follows only writes the encoder's.  Data-parallel callers start the all-reduce of that tail on another stream now.
+  if (ctx->bwd_split_event) XG_CUDA_TRY(ctx->es, cudaEventRecord(ctx->bwd_split_event, st));
   // ---------------- encoder backward (rows (k,b)) ----------------
   const EncBufs& eb = S.enc;
   XG_TRY(launch(ctx, "fusion_bwd", fusion_bwd_kernel, ew_grid((long)KB * H), 256, 0, st, W.dV, S.V, B, K, H, d.fusion_act,

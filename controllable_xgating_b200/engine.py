@@ -41,6 +41,7 @@ def _build_param_names() -> List[str]:
 
 
 PARAM_NAMES = _build_param_names()
+DECODER_FIRST = PARAM_NAMES.index("img_embed_h_1.weight")     # XG_P_INIT_H1_W: first parameter of the decoder side
 BN_BUFFER_NAMES = ["two_spatial_encoder.visual_emb_rgb.1.running_mean", "two_spatial_encoder.visual_emb_rgb.1.running_var",
                    "two_spatial_encoder.visual_emb_opfl.1.running_mean", "two_spatial_encoder.visual_emb_opfl.1.running_var"]
 
@@ -410,11 +411,22 @@ class Engine:
         if dcat is not None:
             dcat = _req(dcat, tuple(cat.shape), torch.float32, "grad of cat")
         saved = ctx["saved"]
+        # data-parallel overlap: an event recorded inside xg_train_bwd when the decoder-side gradients (the tail of `flat`
+        # from PARAM_NAMES[DECODER_FIRST] on) are final; the gradient hook all-reduces that tail under the encoder backward
+        ev = None
+        if getattr(self, "split_event_wanted", False):
+            ev = torch.cuda.Event()
+            ev.record()                                   # materialises the cudaEvent_t; re-recorded by the library
+            L.check(self.lib.xg_set_bwd_split_event(self.handle, c_void_p(ev.cuda_event)), "xg_set_bwd_split_event", self.handle)
+        self.last_split = None
         L.check(self.lib.xg_train_bwd(self.handle, ctx["rgb"].data_ptr(), ctx["opfl"].data_ptr(), ctx["fmask"].data_ptr(),
                                       ctx["pos"].data_ptr(), ctx["seq"].data_ptr(), ctx["smask"].data_ptr(), B, K, Lmax, Lp,
                                       ctx["train"], ctx["seed"], logp.data_ptr(), cat.data_ptr(), _ptr(dlogp), _ptr(dcat),
                                       saved.data_ptr(), saved.numel(), table, 0, ws.data_ptr(), ws.numel(), _stream()),
                 "xg_train_bwd", self.handle)
+        if ev is not None:
+            L.check(self.lib.xg_set_bwd_split_event(self.handle, None), "xg_set_bwd_split_event", self.handle)
+            self.last_split = (ev, sum(sizes[:DECODER_FIRST]))
         self.last_flat_grad = flat
         return views
 

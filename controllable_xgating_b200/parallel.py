@@ -38,29 +38,77 @@ def shard_batch(batch: dict, world: int, rank: int) -> dict:
 class GradAllReduce:
     """Callable installed as `model._grad_hook`: reduces the flat gradient buffer in place."""
 
-    def __init__(self, group=None, exact: bool = True):
+    def __init__(self, group=None, exact: bool = True, overlap: bool = True):
         self.group = group
         self.exact = exact
+        self.overlap = overlap          # all-reduce the decoder-side tail of the buffer under the encoder backward
+        self._side = None
         self.local_mask_sum: Optional[torch.Tensor] = None
         self.calls = 0
         self.bytes = 0
 
     def set_mask(self, seq_mask: torch.Tensor):
         self.local_mask_sum = seq_mask.sum().reshape(1).to(torch.float32)
+        self._mask_event = None
+        if self.local_mask_sum.is_cuda:
+            self._mask_event = torch.cuda.Event()
+            self._mask_event.record()                     # the side stream waits for this sum, not for the backward pass
 
-    def __call__(self, flat: torch.Tensor):
+    def __call__(self, flat: torch.Tensor, split=None):
+        """`split` = (event, n_head) from the engine: the event fires inside the backward pass once flat[n_head:] (the
+        decoder-side gradients, 3/4 of the buffer) is final; that tail is then scaled and all-reduced on a side stream
+        while the encoder backward still runs, and only the head waits for the end of the pass.  Still ONE logical
+        all-reduce of the flat buffer per step (two NCCL calls on disjoint halves)."""
         world = dist.get_world_size(self.group)
         if world == 1:
             return
         if self.exact:
             if self.local_mask_sum is None:
                 raise RuntimeError("GradAllReduce(exact=True): call set_mask(seq_mask) before backward")
-            tot = self.local_mask_sum.to(flat.device).clone()
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
-            flat.mul_(self.local_mask_sum.to(flat.device) / tot)
+            loc = self.local_mask_sum.to(flat.device)
+            tot = loc.clone()
+            # the scalar all-reduce must not queue behind the backward kernels: it runs on the side stream too
         else:
-            flat.div_(world)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            loc = tot = None
+        main = torch.cuda.current_stream(flat.device) if flat.is_cuda else None
+        if split is not None and self.overlap and flat.is_cuda:
+            ev, n_head = split
+            if self._side is None:
+                self._side = torch.cuda.Stream(flat.device)
+            side = self._side
+            head, tail = flat[:n_head], flat[n_head:]
+            with torch.cuda.stream(side):
+                scale, scale_ready = None, None
+                if self.exact:
+                    if getattr(self, "_mask_event", None) is not None:
+                        side.wait_event(self._mask_event)
+                    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+                    scale = loc / tot
+                    scale_ready = torch.cuda.Event()
+                    scale_ready.record(side)
+                side.wait_event(ev)                       # decoder-side gradients are final
+                if self.exact:
+                    tail.mul_(scale)
+                else:
+                    tail.div_(world)
+                w_tail = dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if self.exact:
+                main.wait_event(scale_ready)              # `scale` was produced on the side stream
+                head.mul_(scale)
+            else:
+                head.div_(world)
+            w_head = dist.all_reduce(head, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w_tail.wait(); w_head.wait()
+            main.wait_stream(side)
+            for t in (flat, tot, loc) if self.exact else (flat,):
+                t.record_stream(side)
+        else:
+            if self.exact:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.group)
+                flat.mul_(loc / tot)
+            else:
+                flat.div_(world)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         self.calls += 1
         self.bytes += flat.numel() * 4
 
@@ -70,11 +118,11 @@ class DataParallelSAModel(torch.nn.Module):
     backward hook all-reduces gradients.  Parameters are broadcast from rank 0 at construction, and
     BatchNorm running statistics can be re-synchronised with sync_buffers()."""
 
-    def __init__(self, model, group=None, exact: bool = True, broadcast: bool = True):
+    def __init__(self, model, group=None, exact: bool = True, broadcast: bool = True, overlap: bool = True):
         super().__init__()
         self.module = model
         self.group = group
-        self.hook = GradAllReduce(group, exact)
+        self.hook = GradAllReduce(group, exact, overlap)
         object.__setattr__(model, "_grad_hook", self.hook)
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
             with torch.no_grad():

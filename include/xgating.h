@@ -247,6 +247,13 @@ int xg_train_bwd(xg_handle h, const float* rgb, const float* opfl, const float* 
                  const void* saved, size_t saved_bytes, float* const* grads, int accumulate,
                  void* ws, size_t ws_bytes, void* stream);
 
+/* Data-parallel overlap hook ("overlapped with backward in 2-3 buckets").  When a cudaEvent_t is set,
+ * xg_train_bwd records it on its stream at the point where every decoder-side gradient (parameters XG_P_INIT_H1_W and
+ * after: the contiguous tail of a flat gradient buffer laid out in xg_param order) is final and only the encoder's are
+ * still being written, so that a caller can all-reduce the tail on another stream under the encoder backward.
+ * NULL (default) disables it. */
+int xg_set_bwd_split_event(xg_handle h, void* cuda_event);
+
 /* LanguageModelCriterion (SAModel.py:225-234; rotate != 0: target rotated left by one) and
  * ClassiferCriterion (SAModel.py:241-253; rotate == 0, optional class_mask):
  *     loss = -sum_r logp[r, tgt(r)] * w(r) / sum_r w(r),   w = mask (* class_mask),  r = (b,i), i < Lp
