@@ -5,6 +5,7 @@
 #include "xg_fwd_kernels.cuh"
 #include "xg_gemm_tc.cuh"
 #include "xg_persist.cuh"
+#include "xg_grouped.cuh"
 
 namespace xg {
 
@@ -72,7 +73,8 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
   }
   // recurrence over frames (:132-147); the two streams are independent: one persistent cooperative
   // kernel for all frames of both streams when the shape allows it (xg_persist.cuh)
-  const int pst = persist_encode(ctx, fmask, B, K, eb, st);
+  int pst = grouped_encode(ctx, fmask, B, K, eb, st);      // stationary-weight grouped kernel (xg_grouped.cuh) when the shape fits
+  if (pst == PK_FALLBACK) pst = persist_encode(ctx, fmask, B, K, eb, st);
   if (pst != PK_FALLBACK) XG_TRY(pst);
   for (int t = 0; t < K && pst == PK_FALLBACK; ++t) {
     for (int s = 0; s < 2; ++s) {

@@ -677,6 +677,153 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
 
 }  // namespace xg
 
+namespace xg {
+
+// ====================================================================================
+// encoder frame recurrence (both streams, sub_modules.py:132-147), grouped form with STATIONARY weights:
+//   tiles = (stream) x (32 hidden units x 4 gates of nn.LSTMCell: i,f,g,o); a tile's K = H extent is cut over the members
+//   of its group (148 / 32 = 4: two 64-wide k-blocks each), whose fp16 hi / lo weight tiles are loaded into the pipeline
+//   stages ONCE per launch; a frame step only streams the new [h_rgb | h_opfl] operand tiles (16 KB per k-block), adds
+//   the group's partial tiles and runs the cell.  One grid barrier per frame.
+// ====================================================================================
+// cell of nn.LSTMCell (gate order i,f,g,o) + frame mask for the captions [c0, c1) of group (stream s, unit tile)
+template <int MAXS>
+__device__ __forceinline__ void enc_group_cell(const GroupParams& C, const EncParams& E, int t, int grp, int ns, int c0, int c1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = E.H, B = E.B, K = E.K;
+  const int ntile = H / 32;
+  const int s = (grp / C.ncb) / ntile, tile = (grp / C.ncb) % ntile, cb = grp % C.ncb;
+  const int j = tile * 32 + lane;
+  const float* fs = C.fslots[0] + ((long)(grp * ns) * PK_BN) * 128 + lane;
+  __half* hi_new = C.hh_hi[(t & 1) ^ 1]; __half* lo_new = C.hh_lo[(t & 1) ^ 1];
+#pragma unroll 1
+  for (int cA = c0 + warp; cA < c1; cA += 2 * PK_WARPS) {
+    float v[2][4][MAXS], zz[2][4], mk[2], cp[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = cA + q * PK_WARPS, b = cb * PK_BN + c;
+      const bool live = c < c1 && b < B;
+      const float* base = fs + (long)(c < c1 ? c : cA) * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) v[q][g][k] = (live && t > 0 && k < ns) ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
+        zz[q][g] = live ? E.Gt[s][((long)t * B + b) * 4 * H + g * H + j] : 0.f;
+      }
+      mk[q] = live ? __ldg(E.fmask + (long)b * K + t) : 0.f;
+      cp[q] = (live && t > 0) ? E.Cs[s][((long)(t - 1) * B + b) * H + j] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = cA + q * PK_WARPS, b = cb * PK_BN + c;
+      if (c >= c1 || b >= B) continue;
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) sum += v[q][g][k];
+        z[g] = zz[q][g] + sum;
+      }
+      const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), gg = tanh_fast(z[2]), og = sigmoid_fast(z[3]);
+      const float c2 = fg * cp[q] + ig * gg;
+      const float h = og * tanh_fast(c2) * mk[q];      // h' *= mask (sub_modules.py:139,146)
+      const float cn = c2 * mk[q];                     // c' *= mask (:140,147)
+      float* zo = E.Gt[s] + ((long)t * B + b) * 4 * H + j;
+      zo[0] = ig; zo[H] = fg; zo[2 * H] = gg; zo[3 * H] = og;
+      const long o = ((long)t * B + b) * H + j;
+      E.Cs[s][o] = cn;
+      E.Hs[s][o] = h;
+      if (t + 1 < K) store_split16(hi_new, lo_new, (long)b * 2 * H + s * H + j, h);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+encode_grouped_kernel(const GroupParams* __restrict__ Cp, const EncParams* __restrict__ Ep, const __grid_constant__ MapTable2 maps) {
+  __shared__ GroupParams Csm;
+  __shared__ EncParams Esm;
+  __shared__ GSched s_sched;
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(GroupParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Csm)[i] = reinterpret_cast<const uint32_t*>(Cp)[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(EncParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Esm)[i] = reinterpret_cast<const uint32_t*>(Ep)[i];
+  __syncthreads();
+  const GroupParams& C = Csm;
+  const EncParams& E = Esm;
+  for (int i = threadIdx.x; i < (int)(sizeof(GSched) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&s_sched)[i] = reinterpret_cast<const uint32_t*>(C.gsched + cta)[i];
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = E.H, R = E.R, B = E.B, K = E.K;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 8) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+  const int m = C.members[0], ns = C.nslots[0];
+  const bool member = cta < C.groups * m;
+  const int grp = cta / m, mem = cta % m;
+  const int tot_kb = s_sched.tot_kb;
+
+  // padding rows of both operand buffers
+  for (int e = cta * PK_THREADS + threadIdx.x; e < (R - B) * 2 * H; e += G * PK_THREADS) {
+    const __half z = __float2half_rn(0.f);
+    for (int q = 0; q < 2; ++q) { C.hh_hi[q][(long)B * 2 * H + e] = z; C.hh_lo[q][(long)B * 2 * H + e] = z; }
+  }
+  // stationary weights: stage st holds the hi / lo tiles of k-block (st mod tot_kb) of this member's chain for the whole
+  // launch (a step walks the stage ring tot_kb stages at a time; tot_kb divides the ring)
+  if (member && tot_kb > 0 && threadIdx.x == 0) {
+    const uint64_t pol = l2_policy_evict_first();
+    pk_expect_tx(sv.bulk_bar, (uint32_t)PK_STAGES * 2 * PK_W_BYTES);
+    for (int st = 0; st < PK_STAGES; ++st) {
+      int kk = st % tot_kb, ii = 0;
+      while (kk >= s_sched.it[ii].nkb) { kk -= s_sched.it[ii].nkb; ++ii; }
+      const GItem it = s_sched.it[ii];
+      const uint32_t dst = sv.stages_u32 + st * PK_STAGE_BYTES;
+      const int wk = (it.wk0 + kk) * GK_KB;
+      for (int g = 0; g < 4; ++g) {
+        pk_tma_2d_hint(dst + g * (PK_W_BYTES / 4), &maps.m[it.w_map], sv.bulk_bar, wk, g * H + it.wrow, pol);
+        pk_tma_2d_hint(dst + PK_W_BYTES + g * (PK_W_BYTES / 4), &maps.m[it.w_map + 1], sv.bulk_bar, wk, g * H + it.wrow, pol);
+      }
+    }
+    pk_wait(sv.bulk_bar, 0);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int t = 0; t < K; ++t) {
+    if (t > 0) {
+      ps.npre = (uint32_t)tot_kb;        // "weights already in the stage": the producer only streams the operand tiles
+      gphase(C, &s_sched, nullptr, maps.m, t & 1, sv, tmem_base, ps);      // h of frame t-1 sits in buffer t & 1
+    }
+    if (member) {
+      if (t > 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned int* ctr = C.group_ctr + grp;
+          const unsigned int target = (unsigned int)m * (unsigned int)t;
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+          const long long t0 = clock64();
+          while (true) {
+            unsigned v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if ((int)(v - target) >= 0) break;
+            if (clock64() - t0 > 8000000000LL) __trap();
+          }
+        }
+        __syncthreads();
+      }
+      const int c0 = mem * PK_BN / m, c1 = (mem + 1) * PK_BN / m;
+      if (ns <= 4) enc_group_cell<4>(C, E, t, grp, ns, c0, c1);
+      else enc_group_cell<GK_MAX_MEMBERS>(C, E, t, grp, ns, c0, c1);
+    }
+    if (t + 1 < K) grid_barrier(E.sync_counter, sync_target, G);
+  }
+  pipeline_teardown(tmem_base);
+}
+
+}  // namespace xg
+
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
@@ -1054,6 +1201,133 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       }
     }
   }
+  return XG_OK;
+}
+
+// ---- encoder frame recurrence on encode_grouped_kernel; PK_FALLBACK: shape outside it (caller: encode_persistent_kernel) ----
+struct GroupedEncState {
+  int R = 0;
+  char* pool = nullptr;
+  size_t pool_bytes = 0;
+  GroupParams hp;
+  EncParams ep;
+  GroupParams* d_gparams = nullptr;
+  EncParams* d_eparams = nullptr;
+  unsigned int* d_counter = nullptr;
+  __half* w16[2][2] = {};
+  unsigned long long w_epoch = ~0ull;
+  bool attr_set = false;
+};
+inline GroupedEncState*& grouped_enc_state(xg_context* ctx) {
+  static std::unordered_map<xg_context*, GroupedEncState*> m;
+  return m[ctx];
+}
+static void grouped_enc_release(xg_context* ctx) {
+  GroupedEncState* s = grouped_enc_state(ctx);
+  if (!s) return;
+  if (s->pool) cudaFree(s->pool);
+  delete s;
+  grouped_enc_state(ctx) = nullptr;
+}
+
+static int grouped_encode(xg_context* ctx, const float* fmask, int B, int K, EncBufs& eb, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, G = ctx->sm_count;
+  if (env_flag("XG_NO_GROUPED") || !ctx->persist_mode || H % GK_KB != 0 || B < 1 || K < 2 || G > 256 || 4 * H > 32000) return PK_FALLBACK;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
+  const int kbH = H / GK_KB, ntile = H / 32, ncb = R / PK_BN, groups = 2 * ntile * ncb;
+  if (groups > G) return PK_FALLBACK;
+  int members = 0;
+  for (int m = std::min(std::min(GK_MAX_MEMBERS, G / groups), kbH); m >= 1; --m) {
+    const int q = kbH / m;
+    if (kbH % m == 0 && (q == 1 || q == 2 || q == 4)) { members = m; break; }
+  }
+  if (members == 0) return PK_FALLBACK;      // the member's weight tiles must fit (and tile) the 4 pipeline stages
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  GroupedEncState*& S = grouped_enc_state(ctx);
+  if (!S) S = new GroupedEncState();
+  GroupParams& hp = S->hp;
+  EncParams& ep = S->ep;
+  std::vector<GSched> sched(G);
+  memset(sched.data(), 0, sizeof(GSched) * sched.size());
+  for (int grp = 0; grp < groups; ++grp) {
+    const int s = (grp / ncb) / ntile, tile = (grp / ncb) % ntile, cb = grp % ncb;
+    for (int mem = 0; mem < members; ++mem) {
+      GSched& sc = sched[(size_t)grp * members + mem];
+      const int k0 = mem * kbH / members, k1 = (mem + 1) * kbH / members;
+      GItem it{};
+      it.w_map = (short)(2 * s); it.x_map = 4; it.xsel = 1; it.flags = GI_FUSED;
+      it.wrow = (short)(tile * 32); it.wk0 = (short)k0; it.xk0 = (short)(s * kbH + k0); it.nkb = (short)(k1 - k0);
+      it.desc = (short)grp; it.slot = (short)mem; it.cb = (short)cb; it.pad = (short)members;
+      sc.it[sc.n++] = it;
+      sc.tot_kb = (short)(k1 - k0); sc.tot_chunks = (short)((k1 - k0 + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains = 1;
+    }
+  }
+  if (S->R != R) {
+    if (S->pool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->pool); S->pool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
+      S->d_gparams = a.take<GroupParams>(1);
+      S->d_eparams = a.take<EncParams>(1);
+      S->d_counter = a.take<unsigned int>(64 + groups);
+      hp.gsched = a.take<GSched>(sched.size());
+      hp.fslots[0] = a.take<float>((size_t)groups * members * PK_BN * 128);
+      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<__half>((long)R * 2 * H); hp.hh_lo[q] = a.take<__half>((long)R * 2 * H); }
+      for (int s = 0; s < 2; ++s) for (int q = 0; q < 2; ++q) S->w16[s][q] = a.take<__half>((long)4 * H * H);
+      if (pass == 0) {
+        S->pool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->pool, S->pool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->pool, 0, S->pool_bytes, st));
+      }
+    }
+    S->R = R;
+    S->w_epoch = ~0ull;
+  }
+  hp.fslots[1] = hp.fslots[0];
+  hp.group_ctr = S->d_counter + 64;
+  hp.members[0] = hp.members[1] = members; hp.nslots[0] = hp.nslots[1] = members;
+  hp.groups = groups; hp.ncb = ncb; hp.ntv = 0; hp.n_att = 0; hp.l2_hints = 1; hp.lpart = nullptr; hp.pick_ctr = nullptr;
+  hp.dp.R = R; hp.dp.H = H; hp.dp.B = B; hp.dp.V = 0;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(), cudaMemcpyHostToDevice, st));
+  const int whh[2] = {XG_P_LSTM_RGB_WHH, XG_P_LSTM_OPFL_WHH};
+  if (S->w_epoch != ctx->param_epoch) {
+    for (int s = 0; s < 2; ++s) {
+      ProfScope ps(ctx, "split_weights_f16", st);
+      split_weights_f16_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(ctx->P[whh[s]], 4 * H, H, H, S->w16[s][0], S->w16[s][1]);
+      XG_LAUNCH_CHECK(ctx->es);
+    }
+    S->w_epoch = ctx->param_epoch;
+  }
+  MapTable2 mt;
+  for (int s = 0; s < 2; ++s)
+    for (int q = 0; q < 2; ++q) XG_TRY(make_map16(ctx, ts, S->w16[s][q], 4 * H, H, 32, &mt.m[2 * s + q]));
+  for (int q = 0; q < 2; ++q) {
+    XG_TRY(make_map16(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &mt.m[4 + 2 * q]));
+    XG_TRY(make_map16(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &mt.m[4 + 2 * q + 1]));
+  }
+  for (int i = 8; i < 28; ++i) mt.m[i] = mt.m[0];
+  ep.B = B; ep.R = R; ep.K = K; ep.H = H;
+  for (int s = 0; s < 2; ++s) { ep.Gt[s] = eb.G[s]; ep.Hs[s] = eb.Hs[s]; ep.Cs[s] = eb.Cs[s]; }
+  ep.fmask = fmask;
+  ep.sync_counter = S->d_counter;
+  ep.sched = nullptr; ep.hh_hi = nullptr; ep.hh_lo = nullptr;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_gparams, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_eparams, &ep, sizeof(EncParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (64 + groups), st));
+  if (!S->attr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(encode_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_grouped_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped encoder does not fit on an SM");
+    S->attr_set = true;
+  }
+  ProfScope ps(ctx, "encode_persistent", st);
+  const GroupParams* gp = S->d_gparams;
+  const EncParams* epp = S->d_eparams;
+  void* args[3] = {(void*)&gp, (void*)&epp, (void*)&mt};
+  XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)encode_grouped_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+  ctx->n_fused++;
   return XG_OK;
 }
 
