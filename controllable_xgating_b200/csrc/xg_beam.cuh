@@ -267,7 +267,8 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
       PersistStepIO io;
       io.tokens = w.tokens; io.state = w.st[cur]; io.logp = nullptr; io.feat_div = beam; io.first = (t == -1);
       io.parent = t >= 0 ? w.parent : nullptr; io.ys = w.ys; io.ix = w.ix; io.topk = beam;
-      const int pst = persist_decode(ctx, V, w.Uv, pos, nullptr, n, K, 1, nullptr, nullptr, nullptr, nullptr, st, &io);
+      int pst = grouped_step(ctx, V, w.Uv, pos, n, K, io, st);      // grouped-cell form (xg_grouped.cuh) when the shape fits
+      if (pst == PK_FALLBACK) pst = persist_decode(ctx, V, w.Uv, pos, nullptr, n, K, 1, nullptr, nullptr, nullptr, nullptr, st, &io);
       if (pst != PK_FALLBACK) { XG_TRY(pst); continue; }
       XG_REQUIRE(ctx->es, t == -1, XG_ERR_CUDA, "persistent word step became unavailable inside a beam search");
       fused = false;

@@ -26,11 +26,15 @@
 
 namespace xg {
 
-constexpr int GK_MAX_ITEMS = 8;
+constexpr int GK_MAX_ITEMS = 12;
 constexpr int GK_MAX_MEMBERS = 9;      // CTAs of a group
 constexpr int GK_MAX_SLOTS = 12;       // partial tiles a cell adds: the group's members + the "early" ones (below)
 enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4, GI_LOGITS = 8, GI_LAYER1 = 16 };
 constexpr int GK_LT_STRIDE = 130;     // row stride of the transposed logits tile in shared memory (conflict-free both ways)
+constexpr int GK_LH_STRIDE = 132;     // ... of the half tile of the single-step mode (four threads per caption)
+constexpr int GK_LT_BYTES = 32 * GK_LH_STRIDE * 4;          // 32 captions x 128 vocabulary rows (+ padding)
+constexpr int GK_SMEM_BYTES = PK_SMEM_BYTES + GK_LT_BYTES;  // the half tile lives behind the pipeline's shared memory
+constexpr int GK_TOPK = 8;            // per-row candidates the logits epilogue can keep (beam search: beam_size <= 8)
 
 struct GItem {            // one run of k-blocks (24 bytes)
   short w_map;            // tensor map of the weight matrix (standalone: 128-row boxes; fused: 32-row boxes)
@@ -42,7 +46,7 @@ struct GItem {            // one run of k-blocks (24 bytes)
   short desc, slot;       // standalone: product (DecParams.d[desc]) and split-K slot; fused: group, member
   short cb, pad;          // caption column block
 };
-struct GSched { short n, tot_kb, tot_chunks, n_chains; GItem it[GK_MAX_ITEMS]; };   // 200 bytes
+struct GSched { short n, tot_kb, tot_chunks, n_chains; GItem it[GK_MAX_ITEMS]; };   // 296 bytes
 
 // Operands are fp16 hi / lo PAIRS (3xFP16: hi.hi + (lo.hi + hi.lo) / 2^11, the same 11 + 11 mantissa bits as the 3xTF32
 // products of xg_persist.cuh): the weights as derived tables rebuilt when the bound parameters change (like the
@@ -82,6 +86,10 @@ struct GroupParams {
   float4* lpart;                 // [R][ntv] per (caption, 128-row vocabulary tile): max logit, sum exp(x - max), arg-max
   int ntv;                       // vocabulary tiles
   int l2_hints;                  // 1: L2 eviction hints on the weight loads (XG_L2_HINT=0 switches them off)
+  // single-step mode (beam search): the logits (+ bias) of every row are also stored, [R][ntv * 128] (-inf beyond V): the
+  // row merge rescans the few vocabulary tiles that can hold a row's topk
+  int topk;
+  float* lraw;
 };
 
 // L2 residency: the recurrent weights + the attention operands (47 MB) are re-read every word step and fit one L2
@@ -108,6 +116,7 @@ __device__ __forceinline__ void pk_tma_prefetch_l2_hint(const CUtensorMap* tm, i
 // all work items of this CTA for one GEMM phase.  Same pipeline and accumulation discipline as gemm_phase
 // (xg_persist.cuh); items may chain (several k-block runs, possibly of different products, into one accumulator
 // set) and a fused chain leaves its partial tile in the group's slot buffer.
+template <bool STEP>
 __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
                                     int par, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -288,37 +297,87 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         else { pk_arrive(sv.small_empty); ++ic; }
       }
       if (last && (it.flags & GI_LOGITS)) {
-        // The logits of this 128-row vocabulary tile never leave the SM: + bias, transposed through shared memory (the
-        // pipeline stages are idle: a logits item is the only item of its CTA), then per caption the tile's max /
-        // lowest arg-max / sum exp(x - max).  The pick phase combines the ntv partial results of a caption.
-        const int V = C.dp.V;
-        const int nl = quad * 32 + lane, n = it.wrow + nl;
-        const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
-        float* T = reinterpret_cast<float*>(sv.stages);
+        if (!STEP) {                     // greedy decoding
+          // The logits of this 128-row vocabulary tile never leave the SM: + bias, transposed through shared memory (the
+          // pipeline stages are idle: a logits item is the only item of its CTA), then per caption the tile's max /
+          // lowest arg-max / sum exp(x - max).  The pick phase combines the ntv partial results of a caption.
+          const int V = C.dp.V;
+          const int nl = quad * 32 + lane, n = it.wrow + nl;
+          const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
+          float* T = reinterpret_cast<float*>(sv.stages);
 #pragma unroll
-        for (int u = 0; u < PK_BN; ++u) T[u * GK_LT_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = (warp - 2) * 32 + lane, c = e >> 1, hh = e & 1;
-        const float* row = T + c * GK_LT_STRIDE + hh;
-        float best = -INFINITY; int bi = 0x7fffffff;
+          for (int u = 0; u < PK_BN; ++u) T[u * GK_LT_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int e = (warp - 2) * 32 + lane, c = e >> 1, hh = e & 1;
+          const float* row = T + c * GK_LT_STRIDE + hh;
+          float best = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 8
-        for (int i = 0; i < 64; ++i) {
-          const float x = row[2 * i];
-          if (x > best) { best = x; bi = 2 * i + hh; }          // ascending rows: the first maximum is kept
-        }
-        {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
-          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        float sum = 0.f;
+          for (int i = 0; i < 64; ++i) {
+            const float x = row[2 * i];
+            if (x > best) { best = x; bi = 2 * i + hh; }          // ascending rows: the first maximum is kept
+          }
+          {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          }
+          float sum = 0.f;
 #pragma unroll 8
-        for (int i = 0; i < 64; ++i) sum += __expf(row[2 * i] - best);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        if (hh == 0)
-          C.lpart[(long)(it.cb * PK_BN + c) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(it.wrow + bi), 0.f);
-        fence_proxy_async_smem();        // the stages go back to the TMA / bulk-copy engines
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = 0; i < 64; ++i) sum += __expf(row[2 * i] - best);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          if (hh == 0)
+            C.lpart[(long)(it.cb * PK_BN + c) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(it.wrow + bi), 0.f);
+          fence_proxy_async_smem();        // the stages go back to the TMA / bulk-copy engines
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        } else {                         // beam search: several items per CTA, logits stored for the row merge
+          // The logits of this 128-row vocabulary tile: + bias, transposed through shared memory in two halves of 32
+          // captions (a buffer of its own: the pipeline stages may already hold the next item), then per caption the tile's
+          // max / lowest arg-max / sum exp(x - max): four threads per caption.  Greedy decoding needs nothing else (the
+          // logits never leave the SM); beam search also stores them for the row merge.
+          const int V = C.dp.V;
+          const int nl = quad * 32 + lane, n = it.wrow + nl;
+          const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
+          if (C.topk > 0) {
+            float* o = C.lraw + (long)(it.cb * PK_BN) * (C.ntv * 128) + n;
+            const long str = (long)C.ntv * 128;
+#pragma unroll
+            for (int u = 0; u < PK_BN; ++u) { __stcg(o, n < V ? acc[u] + bl : -INFINITY); o += str; }
+          }
+          float* T = reinterpret_cast<float*>(sv.stages + PK_SMEM_BYTES - 1024);      // behind scratch + barriers (carve_smem keeps 1 KB of slack in front)
+          const int e = (warp - 2) * 32 + lane, cl = e >> 2, part = e & 3;
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            if (hf == 0) {
+#pragma unroll
+              for (int u = 0; u < 32; ++u) T[u * GK_LH_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 32; ++u) T[u * GK_LH_STRIDE + nl] = n < V ? acc[32 + u] + bl : -INFINITY;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float* row = T + cl * GK_LH_STRIDE + part;
+            float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+              const float x = row[4 * i];
+              if (x > best) { best = x; bi = it.wrow + 4 * i + part; }      // ascending ids: the first maximum is kept
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            float sum = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) sum += __expf(row[4 * i] - best);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (part == 0)
+              C.lpart[(long)(it.cb * PK_BN + hf * 32 + cl) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(bi), 0.f);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+        }
       } else if (last) {
         if (it.flags & GI_FUSED) {      // [group][member][caption][row]: lanes -> consecutive rows
           float* o = C.fslots[(it.flags & GI_LAYER1) ? 1 : 0] + ((long)(it.desc * it.pad + it.slot) * PK_BN) * 128 + quad * 32 + lane;   // pad = nslots
@@ -447,13 +506,79 @@ __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int 
   }
 }
 
+// cells of the captions [c0, c1) of every column block of a tile (group = tile * ncb + cb): one warp per (column block,
+// caption) pair, lane = hidden unit; NCAP pairs per pass with every partial-tile load of all of them in flight before
+// the first add (MAXS bounds the slots a cell adds)
+template <int MAXS, int NCAP>
+__device__ __noinline__ void group_cell_tile(const GroupParams& C, int layer, int t, int tile, int c0, int c1) {
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, R = P.R, B = P.B;
+  const int ncb = C.ncb, nc = c1 - c0, npairs = ncb * nc;
+  const int ns = C.nslots[layer], par = t & 1;
+  const int j = tile * 32 + lane;                              // hidden unit of this lane
+  const float* bi = P.bias[layer][0]; const float* ba = P.bias[layer][1]; const float* bh = P.bias[layer][2];
+  float* cst = P.cx + (long)layer * R * H;
+  __half* hi_new = C.hh_hi[par ^ 1]; __half* lo_new = C.hh_lo[par ^ 1];
+  const float* fs = C.fslots[layer] + ((long)(tile * ncb * ns) * PK_BN) * 128 + lane;
+  float bias[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) { const int n = g * H + j; bias[g] = __ldg(bi + n) + __ldg(ba + n) + __ldg(bh + n); }
+#pragma unroll 1
+  for (int pA = warp; pA < npairs; pA += NCAP * PK_WARPS) {
+    float v[NCAP][4][MAXS], mk[NCAP], cp[NCAP], hp[NCAP];
+    int rr[NCAP];
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int pr = pA + q * PK_WARPS;
+      const bool on = pr < npairs;
+      const int pe = on ? pr : pA;
+      const int cb = pe / nc, c = c0 + pe % nc;
+      const float* base = fs + ((long)(cb * ns) * PK_BN + c) * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) v[q][g][k] = (on && k < ns) ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
+      const int r = cb * PK_BN + c;
+      const bool live = on && r < B;
+      rr[q] = live ? r : -1;
+      mk[q] = (live && t > 0) ? __ldcg(P.unfinished + r) : 1.f;
+      cp[q] = live ? __ldcg(cst + (long)r * H + j) : 0.f;
+      hp[q] = live ? __ldcg(P.hx + (long)r * 2 * H + layer * H + j) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int r = rr[q];
+      if (r < 0) continue;                                     // padding rows of the 64-wide operand tiles stay zero
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) sum += v[q][g][k];
+        z[g] = sum + bias[g];
+      }
+      const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
+      float cn = fg * cp[q] + ig * gg;
+      cn = cn * mk[q] + cp[q] * (1.f - mk[q]);
+      float h = og * tanh_fast(cn);
+      h = h * mk[q] + hp[q] * (1.f - mk[q]);
+      cst[(long)r * H + j] = cn;
+      P.hx[(long)r * 2 * H + layer * H + j] = h;
+      store_split16(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
+    }
+  }
+}
+
 // One LSTM layer of the word step (two_inputs_lstmcell, sub_modules.py:750-770): the products of the layer as one chain
 // per group member, the group's partial tiles summed and the cell applied by the members themselves.
+template <bool STEP>
 __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
-                                              int layer, int t, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
+                                              int layer, int t, unsigned int sync_epoch, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
+  // t: word step (buffer parity, state mask); sync_epoch: how many times this group counter has been used before
   const int par = t & 1;
 #ifdef GK_FINE
-  long long* gf = (C.dp.dbg_clock && t == 3 && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + layer * 16 : nullptr;
+  long long* gf = (C.dp.dbg_clock && (t == 3 || C.topk > 0) && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + layer * 16 : nullptr;
   if (gf && threadIdx.x == 0) gf[0] = clock64();
 #define GKF(i) do { if (gf && threadIdx.x == 0) gf[i] = clock64(); } while (0)
 #define GKF_T(tid, i) do { if (gf && threadIdx.x == (tid)) gf[i] = clock64(); } while (0)
@@ -461,16 +586,20 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
 #define GKF(i) do { } while (0)
 #define GKF_T(tid, i) do { } while (0)
 #endif
-  gphase(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  gphase<STEP>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
   GKF(1); GKF_T(64, 2);                  // producer done / first epilogue warp done
-  const int cta = blockIdx.x, m = C.members[layer];
-  if (cta >= C.groups * m) return;
-  const int grp = cta / m, mem = cta % m;
-  __syncthreads();                       // this member's partial tile is written (all four epilogue warps)
+  // a CTA is member `mem` of the groups (tile, cb) of EVERY caption column block cb of its tile (one chain per column
+  // block above); the members of those groups are the same CTAs, so one counter per tile covers them all
+  const int cta = blockIdx.x, m = C.members[layer], ncb = C.ncb;
+  if (cta >= (C.groups / ncb) * m) return;
+  const int tile = cta / m, mem = cta % m;
+  __syncthreads();                       // this member's partial tiles are written (all four epilogue warps)
   GKF(3);
-  if (threadIdx.x == 0) {
-    unsigned int* ctr = C.group_ctr + layer * C.groups + grp;
-    const unsigned int target = (unsigned int)m * (unsigned int)(t + 1);
+  if (m == 1) {
+    __threadfence();                     // a group of one: its own partial tile, read back through L2 below
+  } else if (threadIdx.x == 0) {
+    unsigned int* ctr = C.group_ctr + layer * C.groups + tile;
+    const unsigned int target = (unsigned int)m * (sync_epoch + 1u);
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     const long long t0 = clock64();
     while (true) {
@@ -484,9 +613,14 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
   __syncthreads();
   GKF(5);
   const int c0 = mem * PK_BN / m, c1 = (mem + 1) * PK_BN / m;
-  if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2>(C, layer, t, grp, c0, c1);
-  else if (C.nslots[layer] <= 8) group_cell<8, 1>(C, layer, t, grp, c0, c1);
-  else group_cell<GK_MAX_SLOTS, 1>(C, layer, t, grp, c0, c1);
+  if (!STEP || ncb == 1) {
+    if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2>(C, layer, t, tile, c0, c1);
+    else if (C.nslots[layer] <= 8) group_cell<8, 1>(C, layer, t, tile, c0, c1);
+    else group_cell<GK_MAX_SLOTS, 1>(C, layer, t, tile, c0, c1);
+  } else {                                // single-step mode with several column blocks: (column block, caption) pairs
+    if (C.nslots[layer] <= 8) group_cell_tile<8, 2>(C, layer, t, tile, c0, c1);
+    else group_cell_tile<GK_MAX_SLOTS, 2>(C, layer, t, tile, c0, c1);
+  }
   GKF(6);
 }
 
@@ -621,7 +755,7 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   unsigned int pick_target = 0;
   gprefetch(C, &s_sched[2], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
-  gphase(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
+  gphase<false>(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
   grid_barrier(P.sync_counter, sync_target, G);
   if (is_att) dec_attention<0>(P, &maps.m[GM_V], cta - (G - n_att), 0, sv, bulk_phase);
   fence_proxy_async_smem();
@@ -631,19 +765,19 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   for (int t = 0; t < T; ++t) {
     pk_stamp(P.dbg_clock, cta, t, 0);
     // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1)   [attention CTAs: still busy with step t's attention] =====
-    fused_cell_phase(C, &s_sched[0], &s_sched[1], maps.m, 0, t, sv, tmem_base, ps);
+    fused_cell_phase<false>(C, &s_sched[0], &s_sched[1], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== F3: lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) =====
-    fused_cell_phase(C, &s_sched[1], &s_sched[2], maps.m, 1, t, sv, tmem_base, ps);
+    fused_cell_phase<false>(C, &s_sched[1], &s_sched[2], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[2], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 4);
     // ===== G4: logits of step t  +  attention query of step t+1 (both read the buffer just written) =====
-    gphase(C, &s_sched[2], &s_sched[0], maps.m, t & 1, sv, tmem_base, ps);
+    gphase<false>(C, &s_sched[2], &s_sched[0], maps.m, t & 1, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 6);
@@ -672,6 +806,207 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
     if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
   gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
+  pipeline_teardown(tmem_base);
+}
+
+}  // namespace xg
+
+namespace xg {
+
+// ====================================================================================
+// ONE word step for arbitrary state rows (beam search: CaptionModel.py:121-125 -> SAModel.get_logprobs_state,
+// SAModel.py:117-127), grouped form.  Rows = videos x beam; every feat_div consecutive rows share V / exp(2Uv) / pos.
+//   prologue {gather parent states, token inputs} | A {lstm_1 fused + attention query} | B {attention} | C {lstm_2 fused}
+//   | D {logits tiles: max / sum-exp / topk per (row, tile) in the epilogue} | E {per row: log-sum-exp, topk merge, states out}
+// The log-probs never exist as a (rows, V) matrix: a row's candidates are the topk of each of its vocabulary tiles.
+// ====================================================================================
+constexpr unsigned int GK_STEP_BARRIERS = 5;
+
+// row r (one warp): log-sum-exp from the per-tile results, then the topk (log-prob, id) of the row with the UNK penalty of
+// CaptionModel.py:94, value descending, lowest id first (the order of a stable descending sort, CaptionModel.py:39-40).
+// An entry of the topk can only sit in one of the topk best vocabulary tiles (ordered by their max, lowest arg-max first)
+// - or in tile 0, whose max does not know about the penalty on id 1 and which is therefore always scanned.
+__device__ __forceinline__ void step_row_merge(const GroupParams& C, int r) {
+  const DecParams& P = C.dp;
+  const int lane = threadIdx.x & 31;
+  const int ntv = C.ntv, topk = C.topk;
+  const float4* lp = C.lpart + (long)r * ntv;
+  float4 q[8];
+  float best = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int tile = lane + 32 * i;
+    q[i] = tile < ntv ? __ldcg(lp + tile) : make_float4(-INFINITY, 0.f, __int_as_float(0x7fffffff), 0.f);
+    best = fmaxf(best, q[i].x);
+  }
+  best = warp_max(best);
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += q[i].y * __expf(q[i].x - best);
+  tot = warp_sum(tot);
+  const float lse = best + logf(tot);
+  // ---- the tiles to scan: tile 0 + the topk best of the others ----
+  const float* lr = C.lraw + (long)r * ntv * 128;
+  float4 cand[GK_TOPK + 1];
+  int ctile[GK_TOPK + 1];
+  cand[0] = __ldcg(reinterpret_cast<const float4*>(lr) + lane);
+  ctile[0] = 0;
+  if (lane == 0) cand[0].y -= 1000.f;                // id 1 = UNK
+  unsigned used = lane == 0 ? 1u : 0u;               // bit i: tile lane + 32 i is taken (tile 0 from the start)
+#pragma unroll
+  for (int c = 1; c <= GK_TOPK; ++c) {
+    cand[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    ctile[c] = 0;
+    if (c <= topk) {                                 // warp-uniform
+      float bv = -INFINITY; int bid = 0x7fffffff, bsl = -1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = __float_as_int(q[i].z);
+        if (!((used >> i) & 1u) && lane + 32 * i < ntv && (q[i].x > bv || (q[i].x == bv && id < bid))) { bv = q[i].x; bid = id; bsl = i; }
+      }
+      float wv = bv; int wid = bid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wid, o);
+        if (ov > wv || (ov == wv && oi < wid)) { wv = ov; wid = oi; }
+      }
+      if (wid != 0x7fffffff) {                       // (ids are unique: exactly one lane owns the winner)
+        if (bsl >= 0 && wid == bid) used |= 1u << bsl;
+        ctile[c] = wid >> 7;
+        cand[c] = __ldcg(reinterpret_cast<const float4*>(lr + (long)ctile[c] * 128) + lane);
+      }
+    }
+  }
+  // ---- topk of the scanned entries ----
+  unsigned long long taken = 0ull;
+#pragma unroll 1
+  for (int c = 0; c < topk; ++c) {
+    float bv = -INFINITY; int bid = 0x7fffffff, bpos = -1;
+#pragma unroll
+    for (int u = 0; u <= GK_TOPK; ++u) {
+      const float xs[4] = {cand[u].x, cand[u].y, cand[u].z, cand[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int id = ctile[u] * 128 + lane * 4 + e;
+        if (!((taken >> (u * 4 + e)) & 1ull) && (xs[e] > bv || (xs[e] == bv && id < bid))) { bv = xs[e]; bid = id; bpos = u * 4 + e; }
+      }
+    }
+    float wv = bv; int wid = bid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wid, o);
+      if (ov > wv || (ov == wv && oi < wid)) { wv = ov; wid = oi; }
+    }
+    if (bpos >= 0 && wid == bid && wv == bv) taken |= 1ull << bpos;
+    if (lane == 0) {
+      // the selection value carries the UNK penalty; the log-prob is value - lse (CaptionModel.py:94 subtracts 1000 from the log-prob)
+      P.ys_out[(long)r * topk + c] = wv - lse;
+      P.ix_out[(long)r * topk + c] = wid;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps, unsigned int sync_base,
+                           unsigned int epoch) {
+  __shared__ GroupParams Csm;
+  __shared__ GSched s_sched[3];
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(GroupParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Csm)[i] = reinterpret_cast<const uint32_t*>(Cp)[i];
+  __syncthreads();
+  const GroupParams& C = Csm;
+  const DecParams& P = C.dp;
+  for (int i = threadIdx.x; i < (int)(3 * sizeof(GSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(GSched) / 4), w = i % (int)(sizeof(GSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(C.gsched + (long)ph * G + cta)[w];
+  }
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 27) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = sync_base;
+  uint32_t bulk_phase = 0;
+
+  pk_stamp(P.dbg_clock, cta, 3, 0);
+  // ---- prologue: parent states (beam reordering, CaptionModel.py:62-64) into the working buffers, token inputs ----
+  for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
+    const int r = e / H, j = e % H;
+    float h1 = 0.f, h2 = 0.f;
+    if (r < B) {
+      const long src = P.parent_in ? (long)__ldg(P.parent_in + r) * H + j : (long)e;
+      h1 = P.state0[0][src]; h2 = P.state0[2][src];
+      P.cx[e] = P.state0[1][src]; P.cx[(long)R * H + e] = P.state0[3][src];
+    }
+    P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
+    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
+    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2);
+    if (r >= B) {
+      const __half z = __float2half_rn(0.f);
+      C.hh_hi[1][(long)r * 2 * H + j] = z; C.hh_lo[1][(long)r * 2 * H + j] = z;
+      C.hh_hi[1][(long)r * 2 * H + H + j] = z; C.hh_lo[1][(long)r * 2 * H + H + j] = z;
+    }
+  }
+  for (int r = cta; r < R; r += G) {
+    if (r < B) {
+      dec_token_inputs(P, r, (int)P.tokens_in[r]);
+    } else {
+      const __half z = __float2half_rn(0.f);
+      __half* xh = reinterpret_cast<__half*>(P.xt_hi); __half* xl = reinterpret_cast<__half*>(P.xt_lo);
+      __half* gh = reinterpret_cast<__half*>(P.gp_hi); __half* gl = reinterpret_cast<__half*>(P.gp_lo);
+      __half* ah = reinterpret_cast<__half*>(P.af_hi); __half* al = reinterpret_cast<__half*>(P.af_lo);
+      for (int k = threadIdx.x; k < P.Ep; k += PK_THREADS) { xh[(long)r * P.Ep + k] = z; xl[(long)r * P.Ep + k] = z; }
+      for (int j = threadIdx.x; j < H; j += PK_THREADS) {
+        gh[(long)r * H + j] = z; gl[(long)r * H + j] = z;
+        ah[(long)r * H + j] = z; al[(long)r * H + j] = z;
+      }
+    }
+  }
+  if (P.build_euv) {
+    const long n = (long)((B + P.feat_div - 1) / P.feat_div) * P.K * P.A;
+    for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
+      P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
+  }
+  pk_stamp(P.dbg_clock, cta, 3, 1);
+  grid_barrier(P.sync_counter, sync_target, G);
+  pk_stamp(P.dbg_clock, cta, 3, 2);
+  // ===== A: lstm_1 (x, gp, h1 chains, fused cell)  +  attention query W_h2a.[h1|h2] (split-K slots) =====
+  fused_cell_phase<true>(C, &s_sched[0], &s_sched[1], maps.m, 0, 0, epoch, sv, tmem_base, ps);
+  pk_stamp(P.dbg_clock, cta, 3, 3);
+  grid_barrier(P.sync_counter, sync_target, G);
+  pk_stamp(P.dbg_clock, cta, 3, 4);
+  // ===== B: temporal attention of every row =====
+#pragma unroll 1
+  for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, 0, sv, bulk_phase);
+  fence_proxy_async_smem();
+  pk_stamp(P.dbg_clock, cta, 3, 5);
+  grid_barrier(P.sync_counter, sync_target, G);
+  pk_stamp(P.dbg_clock, cta, 3, 6);
+  // ===== C: lstm_2 (h1', af, h2 chains, fused cell) =====
+  fused_cell_phase<true>(C, &s_sched[1], &s_sched[2], maps.m, 1, 0, epoch, sv, tmem_base, ps);
+  pk_stamp(P.dbg_clock, cta, 3, 7);
+  grid_barrier(P.sync_counter, sync_target, G);
+  pk_stamp(P.dbg_clock, cta, 3, 8);
+  // ===== D: logits tiles (reduced in the epilogue) =====
+  gphase<true>(C, &s_sched[2], nullptr, maps.m, 0, sv, tmem_base, ps);
+  pk_stamp(P.dbg_clock, cta, 3, 9);
+  grid_barrier(P.sync_counter, sync_target, G);
+  pk_stamp(P.dbg_clock, cta, 3, 10);
+  // ===== E: per row log-sum-exp + topk merge; new states out (every read of the old states happened in the prologue) =====
+#pragma unroll 1
+  for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r);      // one warp per row
+  for (int e = cta * PK_THREADS + threadIdx.x; e < B * H; e += G * PK_THREADS) {
+    const int r = e / H, j = e % H;
+    P.state_out[0][e] = __ldcg(P.hx + (long)r * 2 * H + j);
+    P.state_out[2][e] = __ldcg(P.hx + (long)r * 2 * H + H + j);
+    P.state_out[1][e] = __ldcg(P.cx + e);
+    P.state_out[3][e] = __ldcg(P.cx + (long)R * H + e);
+  }
+    pk_stamp(P.dbg_clock, cta, 3, 11);
   pipeline_teardown(tmem_base);
 }
 
@@ -794,7 +1129,7 @@ encode_grouped_kernel(const GroupParams* __restrict__ Cp, const EncParams* __res
   for (int t = 0; t < K; ++t) {
     if (t > 0) {
       ps.npre = (uint32_t)tot_kb;        // "weights already in the stage": the producer only streams the operand tiles
-      gphase(C, &s_sched, nullptr, maps.m, t & 1, sv, tmem_base, ps);      // h of frame t-1 sits in buffer t & 1
+      gphase<false>(C, &s_sched, nullptr, maps.m, t & 1, sv, tmem_base, ps);      // h of frame t-1 sits in buffer t & 1
     }
     if (member) {
       if (t > 0) {
@@ -857,6 +1192,71 @@ static int make_map16(xg_context* ctx, TcState* ts, const __half* base, int rows
   return XG_OK;
 }
 
+// tables derived from the bound parameters, shared by the grouped word-loop kernels of a handle: the POS-gate factor of
+// every token (tgate = relu(embed . W_gate^T + b), V x H) and the fp16 hi / lo pairs of the eight weight matrices of the
+// word step.  Rebuilt (on the caller's stream) whenever the parameter epoch moved.
+struct WordTables {
+  float* tgate = nullptr;
+  __half* w16[8][2] = {};        // h2a, logit, l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
+  unsigned long long epoch = ~0ull;
+};
+inline WordTables*& word_tables_slot(xg_context* ctx) {
+  static std::unordered_map<xg_context*, WordTables*> m;
+  return m[ctx];
+}
+static void word_tables_release(xg_context* ctx) {
+  WordTables* t = word_tables_slot(ctx);
+  if (!t) return;
+  if (t->tgate) cudaFree(t->tgate);
+  for (int i = 0; i < 8; ++i) for (int q = 0; q < 2; ++q) if (t->w16[i][q]) cudaFree(t->w16[i][q]);
+  delete t;
+  word_tables_slot(ctx) = nullptr;
+}
+static const int kWordParams[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
+static int word_tables(xg_context* ctx, cudaStream_t st, WordTables** out) {
+  const xg_dims& d = ctx->d;
+  WordTables*& T = word_tables_slot(ctx);
+  if (!T) {
+    T = new WordTables();
+    XG_CUDA_TRY(ctx->es, cudaMalloc(&T->tgate, sizeof(float) * (size_t)d.vocab * d.rnn));
+    for (int i = 0; i < 8; ++i) {
+      int rows, cols;
+      param_shape(d, kWordParams[i], &rows, &cols);
+      const size_t n = (size_t)rows * ((cols + GK_KB - 1) / GK_KB * GK_KB);
+      for (int q = 0; q < 2; ++q) XG_CUDA_TRY(ctx->es, cudaMalloc(&T->w16[i][q], sizeof(__half) * n));
+    }
+  }
+  if (T->epoch != ctx->param_epoch) {
+    GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], d.embed, ctx->P[XG_P_DGATE_W], d.embed, T->tgate, d.rnn, d.vocab, d.rnn, d.embed);
+    g.ep.bias0 = ctx->P[XG_P_DGATE_B];
+    g.ep.act = XG_ACT_RELU;
+    XG_TRY(gemm_run(ctx, g, st));
+    for (int i = 0; i < 8; ++i) {
+      int rows, cols;
+      param_shape(d, kWordParams[i], &rows, &cols);
+      const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
+      ProfScope ps(ctx, "split_weights_f16", st);
+      split_weights_f16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->P[kWordParams[i]], rows, cols, Kp, T->w16[i][0], T->w16[i][1]);
+      XG_LAUNCH_CHECK(ctx->es);
+    }
+    T->epoch = ctx->param_epoch;
+  }
+  *out = T;
+  return XG_OK;
+}
+// weight maps of the word step: 0 h2a, 2 logit (128-row boxes), GM_W32.. the six LSTM matrices (32-row boxes)
+static int word_weight_maps(xg_context* ctx, TcState* ts, const WordTables* T, CUtensorMap* maps) {
+  for (int i = 0; i < 8; ++i) {
+    int rows, cols;
+    param_shape(ctx->d, kWordParams[i], &rows, &cols);
+    const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
+    const int base = i < 2 ? 2 * i : GM_W32 + 2 * (i - 2);
+    XG_TRY(make_map16(ctx, ts, T->w16[i][0], rows, Kp, i < 2 ? 128 : 32, &maps[base]));
+    XG_TRY(make_map16(ctx, ts, T->w16[i][1], rows, Kp, i < 2 ? 128 : 32, &maps[base + 1]));
+  }
+  return XG_OK;
+}
+
 struct GroupedState {
   int R = 0, K = 0;
   char* pool = nullptr;
@@ -866,9 +1266,6 @@ struct GroupedState {
   unsigned int* d_counter = nullptr;
   int* d_flags = nullptr;
   long long* d_dbg = nullptr;
-  float* tgate = nullptr;
-  unsigned long long tgate_epoch = ~0ull;
-  __half* w16[8][2] = {};        // hi / lo tables of h2a, logit, l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
   bool attr_set = false;
 };
 inline GroupedState*& grouped_state(xg_context* ctx) {
@@ -1034,20 +1431,11 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<__half>((long)R * 2 * H); hp.hh_lo[q] = a.take<__half>((long)R * 2 * H); }
       dp.gp_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.gp_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
       dp.af_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.af_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
-      {
-        const int wp[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
-        for (int i = 0; i < 8; ++i) {
-          int rows, cols;
-          param_shape(d, wp[i], &rows, &cols);
-          const long n = (long)rows * ((cols + GK_KB - 1) / GK_KB * GK_KB);
-          S->w16[i][0] = a.take<__half>(n); S->w16[i][1] = a.take<__half>(n);
-        }
-      }
+
       dp.hx = a.take<float>((long)R * 2 * H);
       dp.cx = a.take<float>((long)2 * R * H);
       dp.unfinished = a.take<float>(R);
       dp.tok = a.take<int64_t>(R);
-      S->tgate = a.take<float>((long)V * H);
       dp.EUv = a.take<float>((long)R * K * A);
       if (pass == 0) {
         S->pool_bytes = a.off + 1024;
@@ -1056,7 +1444,6 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       }
     }
     S->R = R; S->K = K;
-    S->tgate_epoch = ~0ull;
   }
   dp.hh_hi = nullptr; dp.hh_lo = nullptr;
   hp.pick_ctr = S->d_counter + 64;
@@ -1064,39 +1451,16 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = n_att;
   hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
+  hp.topk = 0; hp.lraw = nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
-  // ---- tables derived from the bound parameters (rebuilt when they change): POS-gate factor of every token,
-  //      fp16 hi / lo pairs of the eight weight matrices of the word step ----
-  const int wp[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
-  if (S->tgate_epoch != ctx->param_epoch) {
-    GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], E, ctx->P[XG_P_DGATE_W], E, S->tgate, H, V, H, E);
-    g.ep.bias0 = ctx->P[XG_P_DGATE_B];
-    g.ep.act = XG_ACT_RELU;
-    XG_TRY(gemm_run(ctx, g, st));
-    for (int i = 0; i < 8; ++i) {
-      int rows, cols;
-      param_shape(d, wp[i], &rows, &cols);
-      const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
-      ProfScope ps(ctx, "split_weights_f16", st);
-      split_weights_f16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->P[wp[i]], rows, cols, Kp, S->w16[i][0], S->w16[i][1]);
-      XG_LAUNCH_CHECK(ctx->es);
-    }
-    S->tgate_epoch = ctx->param_epoch;
-  }
-
-  // ---- tensor maps ----
+  // ---- tables derived from the bound parameters + tensor maps ----
+  WordTables* WT = nullptr;
+  XG_TRY(word_tables(ctx, st, &WT));
   MapTable2 mt;
   CUtensorMap* maps = mt.m;
-  for (int i = 0; i < 8; ++i) {
-    int rows, cols;
-    param_shape(d, wp[i], &rows, &cols);
-    const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
-    const int base = i < 2 ? 2 * i : GM_W32 + 2 * (i - 2);
-    XG_TRY(make_map16(ctx, ts, S->w16[i][0], rows, Kp, i < 2 ? 128 : 32, &maps[base]));
-    XG_TRY(make_map16(ctx, ts, S->w16[i][1], rows, Kp, i < 2 ? 128 : 32, &maps[base + 1]));
-  }
+  XG_TRY(word_weight_maps(ctx, ts, WT, maps));
   XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_hi), R, Ep, PK_BN, &maps[GM_XT]));
   XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_lo), R, Ep, PK_BN, &maps[GM_XT + 1]));
   for (int q = 0; q < 2; ++q) {
@@ -1125,7 +1489,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   dp.bias[0][0] = ctx->P[XG_P_L1_I2H_B]; dp.bias[0][1] = ctx->P[XG_P_L1_A2H_B]; dp.bias[0][2] = ctx->P[XG_P_L1_H2H_B];
   dp.bias[1][0] = ctx->P[XG_P_L2_I2H_B]; dp.bias[1][1] = ctx->P[XG_P_L2_A2H_B]; dp.bias[1][2] = ctx->P[XG_P_L2_H2H_B];
   dp.b_logit = ctx->P[XG_P_LOGIT_B]; dp.embed = ctx->P[XG_P_EMBED_W];
-  dp.tgate = S->tgate;
+  dp.tgate = WT->tgate;
   dp.Vf = Vf; dp.Uv = Uv; dp.pos = pos;
   for (int q = 0; q < 4; ++q) dp.state0[q] = state0[q];
   dp.mode = 0; dp.feat_div = 1; dp.build_euv = 1; dp.x16 = 1;
@@ -1139,9 +1503,9 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
   if (dp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
   if (!S->attr_set) {
-    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
     int nb = 0;
-    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_grouped_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_grouped_kernel, PK_THREADS, GK_SMEM_BYTES));
     XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped decoder does not fit on an SM");
     S->attr_set = true;
   }
@@ -1149,7 +1513,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     ProfScope ps(ctx, "decode_persistent", st);
     const GroupParams* gp = S->d_params;
     void* args[2] = {(void*)&gp, (void*)&mt};
-    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_grouped_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_grouped_kernel, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
     ctx->n_fused++;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
@@ -1201,6 +1565,300 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       }
     }
   }
+  return XG_OK;
+}
+
+// ---- one word step on decode_step_grouped_kernel (beam search); PK_FALLBACK: shape / outputs outside it (caller:
+//      decode_step_persistent_kernel through persist_decode) ----
+struct GroupedStepState {
+  int R = 0, K = 0;
+  char* pool = nullptr;
+  size_t pool_bytes = 0;
+  GroupParams hp, hp_dev;
+  GroupParams* d_params = nullptr;
+  unsigned int* d_counter = nullptr;
+  MapTable2 mt;
+  bool valid = false, attr_set = false;
+  int B = 0, fdiv = 0, topk = 0;
+  const float *Vf = nullptr, *Uv = nullptr, *pos = nullptr;
+  unsigned long long epoch = ~0ull;
+  unsigned int sync_base = 0, launches = 0;
+  long long* d_dbg = nullptr;
+};
+inline GroupedStepState*& grouped_step_state(xg_context* ctx) {
+  static std::unordered_map<xg_context*, GroupedStepState*> m;
+  return m[ctx];
+}
+static void grouped_step_release(xg_context* ctx) {
+  GroupedStepState* s = grouped_step_state(ctx);
+  if (!s) return;
+  if (s->pool) cudaFree(s->pool);
+  delete s;
+  grouped_step_state(ctx) = nullptr;
+}
+
+static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, int B, int K, const PersistStepIO& io,
+                        cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + GK_KB - 1) / GK_KB * GK_KB, G = ctx->sm_count;
+  if (env_flag("XG_NO_GROUPED") || env_flag("XG_NO_GROUPED_STEP") || !persist_eligible(ctx, B, K) || H % GK_KB != 0 ||
+      Ep > DEC_TI * PK_THREADS || 4 * H > 32000)
+    return PK_FALLBACK;
+  if (io.logp != nullptr || io.ys == nullptr || io.ix == nullptr || io.topk < 1 || io.topk > GK_TOPK) return PK_FALLBACK;
+  GroupedStepState*& S = grouped_step_state(ctx);
+  if (!S) S = new GroupedStepState();
+  GroupParams& hp = S->hp;
+  DecParams& dp = hp.dp;
+  auto step_io = [&]() {
+    dp.build_euv = io.first;
+    dp.tokens_in = io.tokens; dp.logp_out = nullptr;
+    dp.parent_in = io.parent; dp.ys_out = io.ys; dp.ix_out = io.ix; dp.topk = io.topk;
+    hp.topk = io.topk;
+    for (int q = 0; q < 4; ++q) { dp.state0[q] = io.state[q]; dp.state_out[q] = io.state[q]; }
+  };
+  auto launch_step = [&]() -> int {
+    ProfScope ps(ctx, "decode_step_persistent", st);
+    const GroupParams* gp = S->d_params;
+    unsigned int base = S->sync_base, ep = S->launches;
+    void* args[4] = {(void*)&gp, (void*)&S->mt, (void*)&base, (void*)&ep};
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_step_grouped_kernel, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
+    ctx->n_fused++;
+    S->sync_base += GK_STEP_BARRIERS * (unsigned int)G;
+    S->launches++;
+    if (S->hp.dp.dbg_clock && S->launches == 6 && G <= 256) {   // XG_PERSIST_TRACE=1: phase timeline of the sixth step, all CTAs
+      XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+      std::vector<long long> ga((size_t)G * PK_STAMPS);
+      cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
+      const char* names[6] = {"prologue", "A (lstm_1 fused, ah)", "B (attention)", "C (lstm_2 fused)", "D (logits tiles)", "E (row merge, states)"};
+      for (int i = 0; i < 6; ++i) {
+        long long open = 0, close = 0;
+        for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);
+        std::vector<long long> fin(G);
+        for (int c = 0; c < G; ++c) fin[c] = ga[(size_t)c * PK_STAMPS + 2 * i + 1] - open;
+        std::vector<long long> srt = fin;
+        std::sort(srt.begin(), srt.end());
+        if (i < 5) for (int c = 0; c < G; ++c) close = std::max(close, ga[(size_t)c * PK_STAMPS + 2 * i + 2]);
+        const int worst = (int)(std::max_element(fin.begin(), fin.end()) - fin.begin());
+        fprintf(stderr, "[xg grouped step trace] %-26s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
+                names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, i < 5 ? close - open : 0LL);
+      }
+#ifdef GK_FINE
+      {
+        long long f[32];
+        cudaMemcpy(f, S->d_dbg + (2048 + 256) * PK_STAMPS, sizeof(f), cudaMemcpyDeviceToHost);
+        for (int l = 0; l < 2; ++l)
+          fprintf(stderr, "[xg grouped step trace] cta 0 fused layer %d (cycles after phase entry): producer done %lld, epilogue warp done %lld, "
+                  "cta synced %lld, group counter seen %lld, cta synced %lld, cell done %lld\n", l, f[l * 16 + 1] - f[l * 16], f[l * 16 + 2] - f[l * 16],
+                  f[l * 16 + 3] - f[l * 16], f[l * 16 + 4] - f[l * 16], f[l * 16 + 5] - f[l * 16], f[l * 16 + 6] - f[l * 16]);
+      }
+#endif
+    }
+    return XG_OK;
+  };
+  if (S->valid && S->R == R && S->K == K && S->B == B && S->fdiv == io.feat_div && S->Vf == Vf && S->Uv == Uv && S->pos == pos &&
+      S->epoch == ctx->param_epoch && !io.first) {
+    // later steps of the same search: schedule, tensor maps and counters of the last launch (the barrier and group
+    // counters run on from launch to launch)
+    step_io();
+    if (memcmp(&hp, &S->hp_dev, sizeof(GroupParams)) != 0) {
+      XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
+      memcpy(&S->hp_dev, &hp, sizeof(GroupParams));
+    }
+    return launch_step();
+  }
+  S->valid = false;
+
+  const int kbH = H / GK_KB, kbE = Ep / GK_KB;
+  const int ntiles = H / 32, ncb = R / PK_BN, groups = ntiles * ncb;
+  const int ntv = (V + 127) / 128, nlog = ntv * ncb, nat = (A + 127) / 128;
+  if (ntiles >= G || ntv > 256 || (nlog + G - 1) / G > GK_MAX_ITEMS) return PK_FALLBACK;
+  // A CTA of a fused phase is member `mem` of a 32-unit tile and runs that member's K slice once per caption column
+  // block (fused_cell_phase).  Phase A shares the grid between the lstm_1 tiles and the attention query (split-K
+  // slots on the remaining "side" CTAs): the member count that balances the two is taken.
+  const int Ktot0 = kbE + 2 * kbH, Ktot1 = 3 * kbH;
+  int members0 = 0, ah_slots = 1, best_load = 1 << 30;
+  const int max_members = ncb > 1 ? 8 : GK_MAX_MEMBERS;      // (several column blocks: the cells take two (block, caption) pairs per pass, 8 slots)
+  for (int m = 1; m <= max_members && ntiles * m < G; ++m) {
+    const int nside = G - ntiles * m;
+    for (int sl = 1; sl <= std::min(4, 2 * kbH); sl *= 2) {
+      const int per = (nat * ncb * sl + nside - 1) / nside;
+      if (per > GK_MAX_ITEMS || 2 * ncb > GK_MAX_ITEMS) continue;
+      const int load = std::max(ncb * ((Ktot0 + m - 1) / m), per * ((2 * kbH + sl - 1) / sl));
+      if (load < best_load) { best_load = load; members0 = m; ah_slots = sl; }
+    }
+  }
+  if (members0 == 0 || ah_slots > PK_MAX_SLOTS) return PK_FALLBACK;
+  const int nside = G - ntiles * members0;
+  const int members_l[2] = {members0, std::max(1, std::min(std::min(max_members, G / ntiles), Ktot1))};
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+
+  for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
+  {
+    GDesc& g = dp.d[DD_AH];
+    g.w_map = GM_H2A; g.x_hi = GM_HH; g.x_lo = GM_HH + 1; g.xkb0 = 0; g.n_rows = A; g.nkb = 2 * kbH;
+    GDesc& l = dp.d[DD_LOGIT];
+    l.w_map = GM_LOGIT; l.x_hi = GM_HH; l.x_lo = GM_HH + 1; l.xkb0 = kbH; l.n_rows = V; l.nkb = kbH;
+  }
+  std::vector<GSched> sched((size_t)3 * G);
+  memset(sched.data(), 0, sizeof(GSched) * sched.size());
+  struct Prod { int w_map, x_map, xsel, xkb0, nkb; };
+  // the state entering the step sits in buffer 0 (xsel 1 at parity 0), the cells write buffer 1 (xsel 2)
+  const Prod layers[2][3] = {{{GM_W32 + 0, GM_XT, 0, 0, kbE}, {GM_W32 + 2, GM_GP, 0, 0, kbH}, {GM_W32 + 4, GM_HH, 1, 0, kbH}},
+                             {{GM_W32 + 6, GM_HH, 2, 0, kbH}, {GM_W32 + 8, GM_AF, 0, 0, kbH}, {GM_W32 + 10, GM_HH, 1, kbH, kbH}}};
+  for (int layer = 0; layer < 2; ++layer) {
+    const int members = members_l[layer];
+    int Ktot = 0;
+    for (int p = 0; p < 3; ++p) Ktot += layers[layer][p].nkb;
+    for (int tile = 0; tile < ntiles; ++tile)
+      for (int mem = 0; mem < members; ++mem) {
+        GSched& sc = sched[(size_t)layer * G + tile * members + mem];
+        const int k0 = (int)((long)mem * Ktot / members), k1 = (int)((long)(mem + 1) * Ktot / members);
+        for (int cb = 0; cb < ncb && k0 < k1; ++cb) {      // one chain per column block
+          int base = 0, first = 1;
+          for (int p = 0; p < 3; ++p) {
+            const Prod& pr = layers[layer][p];
+            const int lo = std::max(k0, base), hi = std::min(k1, base + pr.nkb);
+            if (lo < hi) {
+              if (sc.n >= GK_MAX_ITEMS) return PK_FALLBACK;
+              GItem it{};
+              it.w_map = (short)pr.w_map; it.x_map = (short)pr.x_map; it.xsel = (short)pr.xsel;
+              it.flags = (short)(GI_FUSED | (layer ? GI_LAYER1 : 0) | (first ? 0 : GI_CONT_PREV));
+              it.wrow = (short)(tile * 32); it.wk0 = (short)(lo - base); it.xk0 = (short)(pr.xkb0 + lo - base); it.nkb = (short)(hi - lo);
+              it.desc = (short)(tile * ncb + cb); it.slot = (short)mem; it.cb = (short)cb; it.pad = (short)members;
+              if (!first) sc.it[sc.n - 1].flags |= GI_CONT_NEXT;
+              sc.it[sc.n++] = it;
+              sc.tot_kb += (short)(hi - lo);
+              sc.tot_chunks += (short)((hi - lo + PK_CHUNK - 1) / PK_CHUNK);
+              first = 0;
+            }
+            base += pr.nkb;
+          }
+          sc.n_chains++;
+        }
+      }
+  }
+  {   // attention query W_h2a.[h1|h2] (state entering the step): split-K slots on the side CTAs of phase A
+    const int ah_run = (2 * kbH + ah_slots - 1) / ah_slots;
+    dp.d[DD_AH].ns = (2 * kbH + ah_run - 1) / ah_run;
+    int c = 0;
+    for (int rt = 0; rt < nat; ++rt)
+      for (int cb = 0; cb < ncb; ++cb)
+        for (int k0 = 0, sl = 0; k0 < 2 * kbH; k0 += ah_run, ++sl) {
+          GItem it{};
+          it.w_map = (short)GM_H2A; it.x_map = (short)GM_HH; it.xsel = 1; it.flags = 0;
+          it.wrow = (short)(rt * 128); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)std::min(ah_run, 2 * kbH - k0);
+          it.desc = DD_AH; it.slot = (short)sl; it.cb = (short)cb;
+          GSched& sc = sched[(size_t)ntiles * members0 + (c++ % nside)];
+          if (sc.n >= GK_MAX_ITEMS) return PK_FALLBACK;
+          sc.it[sc.n++] = it;
+          sc.tot_kb += it.nkb; sc.tot_chunks += (short)((it.nkb + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains++;
+        }
+  }
+  for (int i = 0; i < nlog; ++i) {   // logits: (vocabulary tile, column block) items, a tile's column blocks side by side
+    const int c = (int)((long)i * G / nlog);
+    GSched& sc = sched[(size_t)2 * G + c];
+    if (sc.n >= GK_MAX_ITEMS) return PK_FALLBACK;
+    GItem it{};
+    it.w_map = (short)GM_LOGIT; it.x_map = (short)GM_HH; it.xsel = 2; it.flags = GI_LOGITS;
+    it.wrow = (short)((i / ncb) * 128); it.wk0 = 0; it.xk0 = (short)kbH; it.nkb = (short)kbH;
+    it.desc = DD_LOGIT; it.slot = 0; it.cb = (short)(i % ncb);
+    sc.it[sc.n++] = it;
+    sc.tot_kb += (short)kbH; sc.tot_chunks += (short)((kbH + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains++;
+  }
+
+  if (S->R != R || S->K != K) {
+    if (S->pool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->pool); S->pool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
+      S->d_params = a.take<GroupParams>(1);
+      S->d_counter = a.take<unsigned int>(128 + 2 * groups);
+      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
+      hp.gsched = a.take<GSched>(sched.size());
+      hp.lpart = a.take<float4>((size_t)R * ntv);
+      hp.lraw = a.take<float>((size_t)R * ntv * 128);
+      dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);
+      for (int q = 0; q < 2; ++q) hp.fslots[q] = a.take<float>((size_t)groups * members_l[q] * PK_BN * 128);   // (members depend on R only)
+      dp.xt_hi = reinterpret_cast<float*>(a.take<__half>((long)R * Ep)); dp.xt_lo = reinterpret_cast<float*>(a.take<__half>((long)R * Ep));
+      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<__half>((long)R * 2 * H); hp.hh_lo[q] = a.take<__half>((long)R * 2 * H); }
+      dp.gp_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.gp_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
+      dp.af_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.af_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
+      dp.hx = a.take<float>((long)R * 2 * H);
+      dp.cx = a.take<float>((long)2 * R * H);
+      dp.unfinished = a.take<float>(R);
+      dp.tok = a.take<int64_t>(R);
+      dp.EUv = a.take<float>((long)R * K * A);
+      if (pass == 0) {
+        S->pool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->pool, S->pool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->pool, 0, S->pool_bytes, st));
+      }
+    }
+    S->R = R; S->K = K;
+  }
+  dp.hh_hi = nullptr; dp.hh_lo = nullptr;
+  hp.pick_ctr = S->d_counter + 64;
+  hp.group_ctr = S->d_counter + 128;
+  hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = 0;
+  hp.nslots[0] = members_l[0]; hp.nslots[1] = members_l[1];
+  hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
+                                       cudaMemcpyHostToDevice, st));
+  WordTables* WT = nullptr;
+  XG_TRY(word_tables(ctx, st, &WT));
+  CUtensorMap* maps = S->mt.m;
+  XG_TRY(word_weight_maps(ctx, ts, WT, maps));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_hi), R, Ep, PK_BN, &maps[GM_XT]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.xt_lo), R, Ep, PK_BN, &maps[GM_XT + 1]));
+  for (int q = 0; q < 2; ++q) {
+    XG_TRY(make_map16(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q]));
+    XG_TRY(make_map16(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q + 1]));
+  }
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.gp_hi), R, H, PK_BN, &maps[GM_GP]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.gp_lo), R, H, PK_BN, &maps[GM_GP + 1]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_hi), R, H, PK_BN, &maps[GM_AF]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_lo), R, H, PK_BN, &maps[GM_AF + 1]));
+  {
+    const int nvid = (B + io.feat_div - 1) / io.feat_div;
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)nvid * K};
+    cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)(H / 2), (cuuint32_t)K};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = ts->encode(&maps[GM_V], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vf), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (V) failed", nullptr); return XG_ERR_CUDA; }
+  }
+  maps[27] = maps[0];
+
+  dp.sched = nullptr;
+  dp.B = B; dp.R = R; dp.K = K; dp.H = H; dp.E = E; dp.Ep = Ep; dp.A = A; dp.V = V; dp.T = 1;
+  dp.b_h2a = ctx->P[XG_P_H2A_B]; dp.w_a2w = ctx->P[XG_P_A2W_W]; dp.b_a2w = ctx->P[XG_P_A2W_B];
+  dp.bias[0][0] = ctx->P[XG_P_L1_I2H_B]; dp.bias[0][1] = ctx->P[XG_P_L1_A2H_B]; dp.bias[0][2] = ctx->P[XG_P_L1_H2H_B];
+  dp.bias[1][0] = ctx->P[XG_P_L2_I2H_B]; dp.bias[1][1] = ctx->P[XG_P_L2_A2H_B]; dp.bias[1][2] = ctx->P[XG_P_L2_H2H_B];
+  dp.b_logit = ctx->P[XG_P_LOGIT_B]; dp.embed = ctx->P[XG_P_EMBED_W];
+  dp.tgate = WT->tgate;
+  dp.Vf = Vf; dp.Uv = Uv; dp.pos = pos;
+  dp.mode = 0; dp.feat_div = io.feat_div; dp.x16 = 1;
+  dp.seq = nullptr; dp.seqlogp = nullptr; dp.flags = nullptr;
+  dp.sync_counter = S->d_counter;
+  dp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
+  step_io();
+  dp.build_euv = 1;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
+  memcpy(&S->hp_dev, &hp, sizeof(GroupParams));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (128 + 2 * groups), st));
+  S->sync_base = 0; S->launches = 0;
+  if (!S->attr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_step_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_step_grouped_kernel, PK_THREADS, GK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped word step does not fit on an SM");
+    S->attr_set = true;
+  }
+  XG_TRY(launch_step());
+  S->valid = true; S->B = B; S->fdiv = io.feat_div; S->Vf = Vf; S->Uv = Uv; S->pos = pos; S->epoch = ctx->param_epoch;
   return XG_OK;
 }
 
