@@ -262,7 +262,8 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     io.G1 = S.G1; io.G2 = S.G2; io.C1 = S.C1; io.C2 = S.C2; io.H12 = S.H12; io.AH = S.AH; io.ALPHA = S.ALPHA; io.AF = S.AF;
     io.drop1 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H1);
     io.drop2 = make_drop(train, d.drop_prob, seed, XG_DROP_DEC_H2);
-    pst = persist_decode(ctx, S.V, S.Uv, pos, nullptr, B, K, Lp, nullptr, nullptr, nullptr, &io, st);
+    pst = grouped_train(ctx, S.V, S.Uv, B, K, Lp, io, st);      // grouped-cell form (xg_grouped.cuh) when the shape fits
+    if (pst == PK_FALLBACK) pst = persist_decode(ctx, S.V, S.Uv, pos, nullptr, B, K, Lp, nullptr, nullptr, nullptr, &io, st);
     if (pst != PK_FALLBACK) XG_TRY(pst);
   }
   for (int i = 0; i < Lp && pst == PK_FALLBACK; ++i) {

@@ -570,9 +570,78 @@ __device__ __noinline__ void group_cell_tile(const GroupParams& C, int layer, in
   }
 }
 
+// cell of the captions [c0, c1) of a group in the teacher-forced training loop (SAModel.py:88-111): the mask is the
+// caption's seq_mask at step t, the carried state and every activation the hand-written backward reads live in the
+// step-major buffers of TrainSaved (gates i,f,o,g activated in place, c / [h1|h2] of step t+1, h after dropout);
+// lstm_1's token-dependent parts and all three biases were hoisted into G1s by batched GEMMs.
+template <int MAXS, int NCAP>
+__device__ __forceinline__ void group_cell_train(const GroupParams& C, int layer, int t, int grp, int c0, int c1) {
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, B = P.B;
+  const int ns = C.nslots[layer], par = t & 1;
+  const int j = grp * 32 + lane;                               // hidden unit of this lane (one column block: group = tile)
+  __half* hi_new = C.hh_hi[par ^ 1]; __half* lo_new = C.hh_lo[par ^ 1];
+  const float* fs = C.fslots[layer] + ((long)(grp * ns) * PK_BN) * 128 + lane;
+  float* Gs = layer == 0 ? P.G1s : P.G2s;
+  float* Cs = layer == 0 ? P.C1s : P.C2s;
+  const DropSpec& drop = layer == 0 ? P.drop1 : P.drop2;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (layer == 1) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { const int n = g * H + j; bias[g] = __ldg(P.bias[1][0] + n) + __ldg(P.bias[1][1] + n) + __ldg(P.bias[1][2] + n); }
+  }
+#pragma unroll 1
+  for (int cA = c0 + warp; cA < c1; cA += NCAP * PK_WARPS) {
+    float v[NCAP][4][MAXS], zb[NCAP][4], mk[NCAP], cp[NCAP], hp[NCAP];
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int c = cA + q * PK_WARPS;
+      const bool on = c < c1;
+      const float* base = fs + (long)(on ? c : cA) * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) v[q][g][k] = (on && k < ns) ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
+      const bool live = on && c < B;
+      const long tb = (long)t * B + c;
+      mk[q] = live ? __ldg(P.seq_mask + (long)c * P.L + t) : 0.f;
+      cp[q] = live ? __ldcg(Cs + tb * H + j) : 0.f;
+      hp[q] = live ? __ldcg(P.H12s + tb * 2 * H + layer * H + j) : 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) zb[q][g] = (layer == 0 && live) ? __ldcg(Gs + tb * 4 * H + g * H + j) : bias[g];
+    }
+#pragma unroll
+    for (int q = 0; q < NCAP; ++q) {
+      const int c = cA + q * PK_WARPS;
+      if (c >= c1 || c >= B) continue;                         // padding rows of the 64-wide operand tiles stay zero
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) sum += v[q][g][k];
+        z[g] = sum + zb[q][g];
+      }
+      const float ig = sigmoid_fast(z[0]), fg = sigmoid_fast(z[1]), og = sigmoid_fast(z[2]), gg = tanh_fast(z[3]);
+      float cn = fg * cp[q] + ig * gg;
+      cn = cn * mk[q] + cp[q] * (1.f - mk[q]);
+      float h = og * tanh_fast(cn);
+      h = h * mk[q] + hp[q] * (1.f - mk[q]);
+      h *= drop.factor((uint64_t)t * B * H + (uint64_t)c * H + j);
+      const long tb = (long)t * B + c;
+      float* gsave = Gs + tb * 4 * H + j;
+      gsave[0] = ig; gsave[H] = fg; gsave[2 * H] = og; gsave[3 * H] = gg;
+      Cs[(tb + B) * H + j] = cn;
+      P.H12s[(tb + B) * 2 * H + layer * H + j] = h;
+      store_split16(hi_new, lo_new, (long)c * 2 * H + layer * H + j, h);
+    }
+  }
+}
+
 // One LSTM layer of the word step (two_inputs_lstmcell, sub_modules.py:750-770): the products of the layer as one chain
 // per group member, the group's partial tiles summed and the cell applied by the members themselves.
-template <bool STEP>
+template <int MODE>      // 0: greedy loop, 1: single step (beam search), 2: teacher-forced training loop
 __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
                                               int layer, int t, unsigned int sync_epoch, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   // t: word step (buffer parity, state mask); sync_epoch: how many times this group counter has been used before
@@ -586,7 +655,7 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
 #define GKF(i) do { } while (0)
 #define GKF_T(tid, i) do { } while (0)
 #endif
-  gphase<STEP>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  gphase<MODE == 1>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
   GKF(1); GKF_T(64, 2);                  // producer done / first epilogue warp done
   // a CTA is member `mem` of the groups (tile, cb) of EVERY caption column block cb of its tile (one chain per column
   // block above); the members of those groups are the same CTAs, so one counter per tile covers them all
@@ -613,7 +682,11 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
   __syncthreads();
   GKF(5);
   const int c0 = mem * PK_BN / m, c1 = (mem + 1) * PK_BN / m;
-  if (!STEP || ncb == 1) {
+  if (MODE == 2) {
+    if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell_train<8, 2>(C, layer, t, tile, c0, c1);
+    else if (C.nslots[layer] <= 8) group_cell_train<8, 1>(C, layer, t, tile, c0, c1);
+    else group_cell_train<GK_MAX_SLOTS, 1>(C, layer, t, tile, c0, c1);
+  } else if (MODE == 0 || ncb == 1) {
     if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2>(C, layer, t, tile, c0, c1);
     else if (C.nslots[layer] <= 8) group_cell<8, 1>(C, layer, t, tile, c0, c1);
     else group_cell<GK_MAX_SLOTS, 1>(C, layer, t, tile, c0, c1);
@@ -765,13 +838,13 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   for (int t = 0; t < T; ++t) {
     pk_stamp(P.dbg_clock, cta, t, 0);
     // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1)   [attention CTAs: still busy with step t's attention] =====
-    fused_cell_phase<false>(C, &s_sched[0], &s_sched[1], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
+    fused_cell_phase<0>(C, &s_sched[0], &s_sched[1], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== F3: lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) =====
-    fused_cell_phase<false>(C, &s_sched[1], &s_sched[2], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
+    fused_cell_phase<0>(C, &s_sched[1], &s_sched[2], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[2], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
@@ -806,6 +879,94 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
     if (__ldcg(P.flags + t) == 0) break;     // every caption finished (SAModel.py:206)
   }
   gemm_prefetch_drain(sv, ps);               // early exit with weight tiles in flight
+  pipeline_teardown(tmem_base);
+}
+
+}  // namespace xg
+
+namespace xg {
+
+// ====================================================================================
+// the teacher-forced word loop of SAModel.forward (SAModel.py:88-111), grouped-cell form.  The ground-truth tokens
+// are known, so the token-dependent parts of lstm_1 are hoisted (batched GEMMs into G1s) and a step is THREE grid
+// synchronised phases:
+//   A {attention query W_h2a.[h1|h2]: split-K slots}
+//   B {temporal attention on the last B CTAs  ||  lstm_1 = cell(G1s[t] + W_h2h1.h1) as a fused group phase, and the
+//      recurrent product W_h2h2.h2 of lstm_2 into its early slots, on the others}
+//   C {lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) as a fused group phase on all CTAs}
+// (decode_persistent_kernel<1>, xg_persist.cuh: four phases, cells as separate pointwise phases, tf32 operand pairs
+// split in the kernel.)  The logit / classifier heads run batched over all steps after the loop.
+// ====================================================================================
+__global__ void __launch_bounds__(PK_THREADS, 1)
+train_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps) {
+  __shared__ GroupParams Csm;
+  __shared__ GSched s_sched[3];
+  const int cta = blockIdx.x, G = gridDim.x;
+  for (int i = threadIdx.x; i < (int)(sizeof(GroupParams) / 4); i += PK_THREADS)
+    reinterpret_cast<uint32_t*>(&Csm)[i] = reinterpret_cast<const uint32_t*>(Cp)[i];
+  __syncthreads();
+  const GroupParams& C = Csm;
+  const DecParams& P = C.dp;
+  for (int i = threadIdx.x; i < (int)(3 * sizeof(GSched) / 4); i += PK_THREADS) {
+    const int ph = i / (int)(sizeof(GSched) / 4), w = i % (int)(sizeof(GSched) / 4);
+    reinterpret_cast<uint32_t*>(&s_sched[ph])[w] = reinterpret_cast<const uint32_t*>(C.gsched + (long)ph * G + cta)[w];
+  }
+  extern __shared__ uint8_t smem_raw[];
+  const SmemView sv = carve_smem(smem_raw);
+  const int H = P.H, R = P.R, B = P.B, T = P.T;
+  const uint32_t tmem_base = pipeline_setup(sv);
+  if (threadIdx.x < 27) tma_prefetch_desc(&maps.m[threadIdx.x]);
+  PipeState ps{0, 0, 0, 0};
+  unsigned int sync_target = 0;
+  uint32_t bulk_phase = 0;
+  const int n_att = C.n_att;
+  const bool is_att = cta >= G - n_att;             // attention CTA: caption cta - (G - n_att)
+
+  // ---- prologue: [h1|h2] of step 0 (init_hidden wrote H12s[0]) as fp16 pairs, zero padding rows, exp(2 Uv) ----
+  for (int e = cta * PK_THREADS + threadIdx.x; e < R * 2 * H; e += G * PK_THREADS) {
+    const int r = e / (2 * H);
+    const float h = r < B ? P.H12s[e] : 0.f;
+    store_split16(C.hh_hi[0], C.hh_lo[0], e, h);
+    if (r >= B) { const __half z = __float2half_rn(0.f); C.hh_hi[1][e] = z; C.hh_lo[1][e] = z; }
+  }
+  for (int e = cta * PK_THREADS + threadIdx.x; e < (R - B) * H; e += G * PK_THREADS) {
+    const __half z = __float2half_rn(0.f);
+    reinterpret_cast<__half*>(P.af_hi)[(long)B * H + e] = z; reinterpret_cast<__half*>(P.af_lo)[(long)B * H + e] = z;
+  }
+  {
+    const long n = (long)B * P.K * P.A;
+    for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
+      P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
+  }
+  gprefetch(C, &s_sched[0], maps.m, sv, ps);
+  grid_barrier(P.sync_counter, sync_target, G);
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    pk_stamp(P.dbg_clock, cta, t, 0);
+    // ===== A: attention query of step t =====
+    gphase<false>(C, &s_sched[0], &s_sched[1], maps.m, t & 1, sv, tmem_base, ps);
+    if (!is_att) gprefetch(C, &s_sched[1], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 1);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 2);
+    // ===== B: attention || lstm_1 (+ the recurrent product of lstm_2) =====
+    if (is_att) {
+      dec_attention<1>(P, &maps.m[GM_V], cta - (G - n_att), t, sv, bulk_phase);
+      fence_proxy_async_smem();
+    } else {
+      fused_cell_phase<2>(C, &s_sched[1], &s_sched[2], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
+    }
+    gprefetch(C, &s_sched[2], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 3);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 4);
+    // ===== C: lstm_2 =====
+    fused_cell_phase<2>(C, &s_sched[2], &s_sched[0], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
+    if (t + 1 < T) gprefetch(C, &s_sched[0], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, t, 5);
+    grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, t, 6);
+  }
   pipeline_teardown(tmem_base);
 }
 
@@ -975,7 +1136,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 2);
   // ===== A: lstm_1 (x, gp, h1 chains, fused cell)  +  attention query W_h2a.[h1|h2] (split-K slots) =====
-  fused_cell_phase<true>(C, &s_sched[0], &s_sched[1], maps.m, 0, 0, epoch, sv, tmem_base, ps);
+  fused_cell_phase<1>(C, &s_sched[0], &s_sched[1], maps.m, 0, 0, epoch, sv, tmem_base, ps);
   pk_stamp(P.dbg_clock, cta, 3, 3);
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 4);
@@ -987,7 +1148,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 6);
   // ===== C: lstm_2 (h1', af, h2 chains, fused cell) =====
-  fused_cell_phase<true>(C, &s_sched[1], &s_sched[2], maps.m, 1, 0, epoch, sv, tmem_base, ps);
+  fused_cell_phase<1>(C, &s_sched[1], &s_sched[2], maps.m, 1, 0, epoch, sv, tmem_base, ps);
   pk_stamp(P.dbg_clock, cta, 3, 7);
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 8);
@@ -1198,7 +1359,7 @@ static int make_map16(xg_context* ctx, TcState* ts, const __half* base, int rows
 struct WordTables {
   float* tgate = nullptr;
   __half* w16[8][2] = {};        // h2a, logit, l1_i2h, l1_a2h, l1_h2h, l2_i2h, l2_a2h, l2_h2h
-  unsigned long long epoch = ~0ull;
+  unsigned long long tgate_epoch = ~0ull, w_epoch[8] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
 };
 inline WordTables*& word_tables_slot(xg_context* ctx) {
   static std::unordered_map<xg_context*, WordTables*> m;
@@ -1213,7 +1374,24 @@ static void word_tables_release(xg_context* ctx) {
   word_tables_slot(ctx) = nullptr;
 }
 static const int kWordParams[8] = {XG_P_H2A_W, XG_P_LOGIT_W, XG_P_L1_I2H_W, XG_P_L1_A2H_W, XG_P_L1_H2H_W, XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W};
-static int word_tables(xg_context* ctx, cudaStream_t st, WordTables** out) {
+constexpr unsigned WT_ALL = 0xffu, WT_TRAIN = 0x01u | 0x10u | 0x20u | 0x40u | 0x80u;    // the training loop streams h2a, l1_h2h and lstm_2
+struct SplitJobs { const float* W[8]; __half* hi[8]; __half* lo[8]; int rows[8], K[8], Kp[8]; int n; };
+// every stale table of a call in ONE launch: blockIdx.y = job
+__global__ void split_weights_f16_multi_kernel(const SplitJobs J) {
+  const int q = blockIdx.y;
+  const float* W = J.W[q];
+  __half* hi = J.hi[q]; __half* lo = J.lo[q];
+  const int K = J.K[q], Kp = J.Kp[q];
+  const long n = (long)J.rows[q] * Kp;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Kp), k = (int)(e % Kp);
+    const float w = k < K ? __ldg(W + (long)r * K + k) : 0.f;
+    const __half h = __float2half_rn(w);
+    hi[e] = h;
+    lo[e] = __float2half_rn((w - __half2float(h)) * X16_SCALE);
+  }
+}
+static int word_tables(xg_context* ctx, cudaStream_t st, WordTables** out, bool need_tgate = true, unsigned need = WT_ALL) {
   const xg_dims& d = ctx->d;
   WordTables*& T = word_tables_slot(ctx);
   if (!T) {
@@ -1226,20 +1404,28 @@ static int word_tables(xg_context* ctx, cudaStream_t st, WordTables** out) {
       for (int q = 0; q < 2; ++q) XG_CUDA_TRY(ctx->es, cudaMalloc(&T->w16[i][q], sizeof(__half) * n));
     }
   }
-  if (T->epoch != ctx->param_epoch) {
+  if (need_tgate && T->tgate_epoch != ctx->param_epoch) {
     GemmP g = gemm_nt(ctx->P[XG_P_EMBED_W], d.embed, ctx->P[XG_P_DGATE_W], d.embed, T->tgate, d.rnn, d.vocab, d.rnn, d.embed);
     g.ep.bias0 = ctx->P[XG_P_DGATE_B];
     g.ep.act = XG_ACT_RELU;
     XG_TRY(gemm_run(ctx, g, st));
-    for (int i = 0; i < 8; ++i) {
-      int rows, cols;
-      param_shape(d, kWordParams[i], &rows, &cols);
-      const int Kp = (cols + GK_KB - 1) / GK_KB * GK_KB;
-      ProfScope ps(ctx, "split_weights_f16", st);
-      split_weights_f16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->P[kWordParams[i]], rows, cols, Kp, T->w16[i][0], T->w16[i][1]);
-      XG_LAUNCH_CHECK(ctx->es);
-    }
-    T->epoch = ctx->param_epoch;
+    T->tgate_epoch = ctx->param_epoch;
+  }
+  SplitJobs J;
+  J.n = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (!((need >> i) & 1u) || T->w_epoch[i] == ctx->param_epoch) continue;
+    int rows, cols;
+    param_shape(d, kWordParams[i], &rows, &cols);
+    J.W[J.n] = ctx->P[kWordParams[i]]; J.hi[J.n] = T->w16[i][0]; J.lo[J.n] = T->w16[i][1];
+    J.rows[J.n] = rows; J.K[J.n] = cols; J.Kp[J.n] = (cols + GK_KB - 1) / GK_KB * GK_KB;
+    ++J.n;
+    T->w_epoch[i] = ctx->param_epoch;
+  }
+  if (J.n > 0) {
+    ProfScope ps(ctx, "split_weights_f16", st);
+    split_weights_f16_multi_kernel<<<dim3(ctx->sm_count, J.n), 256, 0, st>>>(J);
+    XG_LAUNCH_CHECK(ctx->es);
   }
   *out = T;
   return XG_OK;
@@ -1563,6 +1749,229 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
         fprintf(stderr, "[xg grouped trace] step 3 %-28s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
                 names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, close - open);
       }
+    }
+  }
+  return XG_OK;
+}
+
+// ---- teacher-forced word loop on train_grouped_kernel; PK_FALLBACK: shape outside it (caller: decode_persistent_kernel<1>) ----
+struct GroupedTrainState {
+  int R = 0, K = 0;
+  char* pool = nullptr;
+  size_t pool_bytes = 0;
+  GroupParams hp;
+  GroupParams* d_params = nullptr;
+  unsigned int* d_counter = nullptr;
+  long long* d_dbg = nullptr;
+  bool attr_set = false;
+};
+inline GroupedTrainState*& grouped_train_state(xg_context* ctx) {
+  static std::unordered_map<xg_context*, GroupedTrainState*> m;
+  return m[ctx];
+}
+static void grouped_train_release(xg_context* ctx) {
+  GroupedTrainState* s = grouped_train_state(ctx);
+  if (!s) return;
+  if (s->pool) cudaFree(s->pool);
+  delete s;
+  grouped_train_state(ctx) = nullptr;
+}
+
+static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int B, int K, int T, const PersistTrainIO& tr, cudaStream_t st) {
+  const xg_dims& d = ctx->d;
+  const int H = d.rnn, A = d.att;
+  const int R = (B + PK_BN - 1) / PK_BN * PK_BN, G = ctx->sm_count;
+  if (env_flag("XG_NO_GROUPED") || env_flag("XG_NO_GROUPED_TRAIN") || !persist_eligible(ctx, B, K) || T > 2048 || H % GK_KB != 0 || 4 * H > 32000)
+    return PK_FALLBACK;
+  const int kbH = H / GK_KB;
+  const int groups = H / 32, ncb = R / PK_BN, nat = (A + 127) / 128;
+  if (ncb != 1 || G - R < groups + 1) return PK_FALLBACK;
+  // (the schedule depends on the padded row count only, never on B)
+  const int avail = G - R;                       // CTAs of phase B that do not run the attention
+  const int nv = kbH >= 2 ? 2 : 1;               // early slots of lstm_2: W_h2h2.h2 cut in nv runs
+  const int m1 = std::max(1, std::min(std::min(GK_MAX_MEMBERS, kbH), (avail * 3 / 5) / groups));
+  const int nside = avail - groups * m1;
+  if (nside < 1 || (groups * nv + nside - 1) / nside > GK_MAX_ITEMS) return PK_FALLBACK;
+  const int m2 = std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH));
+  const int members_l[2] = {m1, m2}, nslots_l[2] = {m1, m2 + nv};
+  if (nslots_l[1] > GK_MAX_SLOTS) return PK_FALLBACK;
+  TcState* ts = nullptr;
+  XG_TRY(tc_init(ctx, ts));
+  GroupedTrainState*& S = grouped_train_state(ctx);
+  if (!S) S = new GroupedTrainState();
+  GroupParams& hp = S->hp;
+  DecParams& dp = hp.dp;
+  for (int i = 0; i < PK_MAX_DESCS; ++i) { dp.d[i].ns = 0; dp.d[i].n_rows = 0; dp.d[i].nkb = 0; }
+  {
+    GDesc& g = dp.d[DD_AH];
+    g.w_map = GM_H2A; g.x_hi = GM_HH; g.x_lo = GM_HH + 1; g.xkb0 = 0; g.n_rows = A; g.nkb = 2 * kbH;
+  }
+  std::vector<GSched> sched((size_t)3 * G);
+  memset(sched.data(), 0, sizeof(GSched) * sched.size());
+  auto add = [&](GSched& sc, const GItem& it, bool new_chain) -> bool {
+    if (sc.n >= GK_MAX_ITEMS) return false;
+    sc.it[sc.n++] = it;
+    sc.tot_kb += it.nkb; sc.tot_chunks += (short)((it.nkb + PK_CHUNK - 1) / PK_CHUNK);
+    if (new_chain) sc.n_chains++;
+    return true;
+  };
+  {   // phase A: attention query, (row tile) x (K run) items over all CTAs
+    int ah_slots = std::min(PK_MAX_SLOTS, 2 * kbH);
+    while (ah_slots > 1 && nat * ah_slots > G) --ah_slots;
+    const int ah_run = (2 * kbH + ah_slots - 1) / ah_slots;
+    dp.d[DD_AH].ns = (2 * kbH + ah_run - 1) / ah_run;
+    int c = 0;
+    for (int k0 = 0, sl = 0; k0 < 2 * kbH; k0 += ah_run, ++sl)
+      for (int rt = 0; rt < nat; ++rt) {
+        GItem it{};
+        it.w_map = (short)GM_H2A; it.x_map = (short)GM_HH; it.xsel = 1; it.flags = 0;
+        it.wrow = (short)(rt * 128); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)std::min(ah_run, 2 * kbH - k0);
+        it.desc = DD_AH; it.slot = (short)sl; it.cb = 0;
+        if (!add(sched[(size_t)(c++ % G)], it, true)) return PK_FALLBACK;
+      }
+  }
+  // phase B: lstm_1 groups (recurrent product only: the rest sits in G1s) on the first groups x m1 CTAs, the recurrent product
+  // of lstm_2 into its early slots on the side CTAs; phase C: lstm_2 groups (h1', af) on all CTAs
+  for (int grp = 0; grp < groups; ++grp) {
+    for (int mem = 0; mem < m1; ++mem) {
+      const int k0 = mem * kbH / m1, k1 = (mem + 1) * kbH / m1;
+      if (k0 >= k1) continue;
+      GItem it{};
+      it.w_map = (short)(GM_W32 + 4); it.x_map = (short)GM_HH; it.xsel = 1; it.flags = (short)GI_FUSED;
+      it.wrow = (short)(grp * 32); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)(k1 - k0);
+      it.desc = (short)grp; it.slot = (short)mem; it.cb = 0; it.pad = (short)nslots_l[0];
+      if (!add(sched[(size_t)G + grp * m1 + mem], it, true)) return PK_FALLBACK;
+    }
+    for (int v = 0; v < nv; ++v) {
+      const int k0 = v * kbH / nv, k1 = (v + 1) * kbH / nv;
+      GItem it{};
+      it.w_map = (short)(GM_W32 + 10); it.x_map = (short)GM_HH; it.xsel = 1; it.flags = (short)(GI_FUSED | GI_LAYER1);
+      it.wrow = (short)(grp * 32); it.wk0 = (short)k0; it.xk0 = (short)(kbH + k0); it.nkb = (short)(k1 - k0);
+      it.desc = (short)grp; it.slot = (short)(m2 + v); it.cb = 0; it.pad = (short)nslots_l[1];
+      if (!add(sched[(size_t)G + groups * m1 + (grp * nv + v) % nside], it, true)) return PK_FALLBACK;
+    }
+    const int Ktot = 2 * kbH;
+    for (int mem = 0; mem < m2; ++mem) {
+      GSched& sc = sched[(size_t)2 * G + grp * m2 + mem];
+      const int k0 = (int)((long)mem * Ktot / m2), k1 = (int)((long)(mem + 1) * Ktot / m2);
+      for (int p = 0; p < 2; ++p) {
+        const int base = p * kbH, lo = std::max(k0, base), hi = std::min(k1, base + kbH);
+        if (lo >= hi) continue;
+        GItem it{};
+        it.w_map = (short)(p == 0 ? GM_W32 + 6 : GM_W32 + 8); it.x_map = (short)(p == 0 ? GM_HH : GM_AF); it.xsel = (short)(p == 0 ? 2 : 0);
+        it.flags = (short)(GI_FUSED | GI_LAYER1 | (sc.n > 0 ? GI_CONT_PREV : 0));
+        it.wrow = (short)(grp * 32); it.wk0 = (short)(lo - base); it.xk0 = (short)(lo - base); it.nkb = (short)(hi - lo);
+        it.desc = (short)grp; it.slot = (short)mem; it.cb = 0; it.pad = (short)nslots_l[1];
+        if (sc.n > 0) sc.it[sc.n - 1].flags |= GI_CONT_NEXT;
+        if (!add(sc, it, sc.n == 0)) return PK_FALLBACK;
+      }
+    }
+  }
+
+  if (S->R != R || S->K != K) {
+    if (S->pool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->pool); S->pool = nullptr; }
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena a(pass == 0 ? nullptr : S->pool, pass == 0 ? 0 : S->pool_bytes);
+      S->d_params = a.take<GroupParams>(1);
+      S->d_counter = a.take<unsigned int>(128 + 2 * groups);
+      S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
+      hp.gsched = a.take<GSched>(sched.size());
+      dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);
+      for (int q = 0; q < 2; ++q) hp.fslots[q] = a.take<float>((size_t)groups * nslots_l[q] * PK_BN * 128);
+      for (int q = 0; q < 2; ++q) { hp.hh_hi[q] = a.take<__half>((long)R * 2 * H); hp.hh_lo[q] = a.take<__half>((long)R * 2 * H); }
+      dp.af_hi = reinterpret_cast<float*>(a.take<__half>((long)R * H)); dp.af_lo = reinterpret_cast<float*>(a.take<__half>((long)R * H));
+      dp.EUv = a.take<float>((long)R * K * A);
+      if (pass == 0) {
+        S->pool_bytes = a.off + 1024;
+        XG_CUDA_TRY(ctx->es, cudaMalloc(&S->pool, S->pool_bytes));
+        XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->pool, 0, S->pool_bytes, st));
+      }
+    }
+    S->R = R; S->K = K;
+  }
+  dp.hh_hi = nullptr; dp.hh_lo = nullptr; dp.xt_hi = dp.xt_lo = dp.gp_hi = dp.gp_lo = nullptr;
+  dp.hx = nullptr; dp.cx = nullptr; dp.unfinished = nullptr; dp.tok = nullptr;
+  hp.pick_ctr = S->d_counter + 64;
+  hp.group_ctr = S->d_counter + 128;
+  hp.members[0] = m1; hp.members[1] = m2; hp.groups = groups; hp.ncb = 1; hp.ntv = 0; hp.n_att = B;
+  hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
+  hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
+  hp.topk = 0; hp.lraw = nullptr; hp.lpart = nullptr;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
+                                       cudaMemcpyHostToDevice, st));
+  WordTables* WT = nullptr;
+  XG_TRY(word_tables(ctx, st, &WT, /*need_tgate=*/false, WT_TRAIN));
+  MapTable2 mt;
+  CUtensorMap* maps = mt.m;
+  XG_TRY(word_weight_maps(ctx, ts, WT, maps));
+  for (int q = 0; q < 2; ++q) {
+    XG_TRY(make_map16(ctx, ts, hp.hh_hi[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q]));
+    XG_TRY(make_map16(ctx, ts, hp.hh_lo[q], R, 2 * H, PK_BN, &maps[GM_HH + 2 * q + 1]));
+  }
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_hi), R, H, PK_BN, &maps[GM_AF]));
+  XG_TRY(make_map16(ctx, ts, reinterpret_cast<__half*>(dp.af_lo), R, H, PK_BN, &maps[GM_AF + 1]));
+  maps[GM_XT] = maps[GM_XT + 1] = maps[GM_GP] = maps[GM_GP + 1] = maps[0];      // (hoisted: not streamed by this kernel)
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)B * K};
+    cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)(H / 2), (cuuint32_t)K};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult cr = ts->encode(&maps[GM_V], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Vf), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (V) failed", nullptr); return XG_ERR_CUDA; }
+  }
+  maps[27] = maps[0];
+
+  dp.sched = nullptr;
+  dp.B = B; dp.R = R; dp.K = K; dp.H = H; dp.E = d.embed; dp.Ep = 0; dp.A = A; dp.V = d.vocab; dp.T = T;
+  dp.b_h2a = ctx->P[XG_P_H2A_B]; dp.w_a2w = ctx->P[XG_P_A2W_W]; dp.b_a2w = ctx->P[XG_P_A2W_B];
+  dp.bias[0][0] = ctx->P[XG_P_L1_I2H_B]; dp.bias[0][1] = ctx->P[XG_P_L1_A2H_B]; dp.bias[0][2] = ctx->P[XG_P_L1_H2H_B];
+  dp.bias[1][0] = ctx->P[XG_P_L2_I2H_B]; dp.bias[1][1] = ctx->P[XG_P_L2_A2H_B]; dp.bias[1][2] = ctx->P[XG_P_L2_H2H_B];
+  dp.b_logit = nullptr; dp.embed = nullptr; dp.tgate = nullptr;
+  dp.Vf = Vf; dp.Uv = Uv; dp.pos = nullptr;
+  for (int q = 0; q < 4; ++q) dp.state0[q] = nullptr;
+  dp.mode = 1; dp.feat_div = 1; dp.build_euv = 1; dp.x16 = 1;
+  dp.L = tr.L; dp.seq_mask = tr.seq_mask;
+  dp.G1s = tr.G1; dp.G2s = tr.G2; dp.C1s = tr.C1; dp.C2s = tr.C2; dp.H12s = tr.H12;
+  dp.AHs = tr.AH; dp.ALPHAs = tr.ALPHA; dp.AFs = tr.AF;
+  dp.drop1 = tr.drop1; dp.drop2 = tr.drop2;
+  dp.seq = nullptr; dp.seqlogp = nullptr; dp.flags = nullptr;
+  dp.sync_counter = S->d_counter;
+  dp.dbg_clock = env_flag("XG_PERSIST_TRACE") ? S->d_dbg : nullptr;
+  XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
+  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (128 + 2 * groups), st));
+  if (dp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
+  if (!S->attr_set) {
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(train_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+    int nb = 0;
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, train_grouped_kernel, PK_THREADS, PK_SMEM_BYTES));
+    XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped training loop does not fit on an SM");
+    S->attr_set = true;
+  }
+  {
+    ProfScope ps(ctx, "train_decode_persistent", st);
+    const GroupParams* gp = S->d_params;
+    void* args[2] = {(void*)&gp, (void*)&mt};
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)train_grouped_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
+    ctx->n_fused++;
+  }
+  if (dp.dbg_clock && T > 4 && G <= 256) {   // XG_PERSIST_TRACE=1: phase timeline of step 3, all CTAs
+    XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+    std::vector<long long> ga((size_t)G * PK_STAMPS);
+    cudaMemcpy(ga.data(), S->d_dbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
+    const char* names[3] = {"A (attention query)", "B (attention || lstm_1)", "C (lstm_2 fused)"};
+    for (int i = 0; i < 3; ++i) {
+      long long open = 0, close = 0;
+      for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);
+      std::vector<long long> fin(G);
+      for (int c = 0; c < G; ++c) fin[c] = ga[(size_t)c * PK_STAMPS + 2 * i + 1] - open;
+      std::vector<long long> srt = fin;
+      std::sort(srt.begin(), srt.end());
+      for (int c = 0; c < G; ++c) close = std::max(close, ga[(size_t)c * PK_STAMPS + 2 * i + 2]);
+      const int worst = (int)(std::max_element(fin.begin(), fin.end()) - fin.begin());
+      fprintf(stderr, "[xg grouped train trace] step 3 %-26s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
+              names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, close - open);
     }
   }
   return XG_OK;
