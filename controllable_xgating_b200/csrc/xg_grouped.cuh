@@ -123,6 +123,14 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
   const int lane = threadIdx.x & 31;
   const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
   const int R = C.dp.R, H = C.dp.H;
+#ifdef GK_FINE
+  long long* gw = (C.dp.dbg_clock && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + 32 : nullptr;
+  long long w_acc[4] = {0, 0, 0, 0};
+  const long long t_in = clock64();
+#define GKW(i, stmt) do { const long long t_ = clock64(); stmt; w_acc[i] += clock64() - t_; } while (0)
+#else
+#define GKW(i, stmt) do { stmt; } while (0)
+#endif
   if (warp == 0) {            // ===== TMA producer =====
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first(), pol_norm = l2_policy_normal();
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0);
@@ -154,7 +162,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
             pk_tma_2d(st + 2 * PK_W_BYTES + PK_X_BYTES, mxl, fb, xk, col);
           }
         } else {
-          pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1);
+          GKW(0, pk_wait(empty_bar + 8 * s, ((cnt / PK_STAGES) & 1) ^ 1));
           if (elect_one_sync()) {
             pk_expect_tx(fb, PK_STAGE_BYTES);
             if (fused) {
@@ -200,63 +208,54 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       }
     }
   } else if (warp == 1) {     // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_f16(128, PK_BN);
+    // Per 16-wide k-step TWO instructions: W_hi . [X_hi ; X_lo] as one N = 128 product (the hi and lo activation tiles lie
+    // back to back in the stage: main term -> columns [0, 64), cross term hi.lo -> [64, 128) of the accumulator pair) and
+    // W_lo . X_hi (N = 64) onto the cross columns.  Three N = 64 instructions per k-step measured ~80 cycles each (the
+    // 128 x 16 weight tile is read from shared memory once per instruction): the MMA warp, not the operand traffic,
+    // paced the GEMM phases.  The pair is drained into fp32 registers every PK_CHUNK k-blocks (truncating adds in TMEM).
+    constexpr uint32_t idesc = umma_idesc_f16(128, PK_BN), idesc2 = umma_idesc_f16(128, 2 * PK_BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t tmem_small = tb + 2 * PK_BN;
-    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0),
-             ic = __shfl_sync(0xffffffffu, ps.item_count, 0);
+    uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0);
     const uint32_t ready_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
     const uint32_t acc_full = __shfl_sync(0xffffffffu, sv.acc_full, 0), acc_empty = __shfl_sync(0xffffffffu, sv.acc_empty, 0);
-    const uint32_t small_full = __shfl_sync(0xffffffffu, sv.small_full, 0), small_empty = __shfl_sync(0xffffffffu, sv.small_empty, 0);
     const uint32_t desc_lo0 = __shfl_sync(0xffffffffu, (uint32_t)umma_desc_sw128(sv.stages_u32), 0);
     const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
       const int nkb = __shfl_sync(0xffffffffu, (int)sc->it[ii].nkb, 0);
-      const int fl = __shfl_sync(0xffffffffu, (int)sc->it[ii].flags, 0);
-      const bool first = !(fl & GI_CONT_PREV), last = !(fl & GI_CONT_NEXT);
-      if (first) {
-        pk_wait(small_empty, (ic & 1) ^ 1);      // previous chain's cross-term accumulator read out
-        tc_fence_after();
-      }
-      uint32_t tmem_main = tb, b = 0;
+      uint32_t tmem_pair = tb, b = 0;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
         if ((kb & 1) == 0) {
           b = cc & 1;
-          pk_wait(acc_empty + 8 * b, ((cc >> 1) & 1) ^ 1);
+          GKW(1, pk_wait(acc_empty + 8 * b, ((cc >> 1) & 1) ^ 1));
           tc_fence_after();
-          tmem_main = tb + b * PK_BN;
+          tmem_pair = tb + b * 2 * PK_BN;
         }
         const uint32_t s = cnt & (PK_STAGES - 1);
-        pk_wait(ready_bar + 8 * s, (cnt / PK_STAGES) & 1);     // all four tiles of the stage landed
+        GKW(0, pk_wait(ready_bar + 8 * s, (cnt / PK_STAGES) & 1));     // all four tiles of the stage landed
         tc_fence_after();
         const uint32_t dlo = desc_lo0 + ((s * PK_STAGE_BYTES) >> 4);
-        const uint32_t small_acc0 = (first && kb == 0) ? 0u : 1u;
         if (elect_one_sync()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint64_t wh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2);
             const uint64_t wl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (PK_W_BYTES >> 4));
-            const uint64_t xh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES) >> 4));
-            const uint64_t xl = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES + PK_X_BYTES) >> 4));
-            umma_f16(tmem_main, wh, xh, idesc, ((kb & 1) | k4) != 0);
-            umma_f16(tmem_small, wl, xh, idesc, (small_acc0 | (uint32_t)k4) != 0);
-            umma_f16(tmem_small, wh, xl, idesc, 1);
+            const uint64_t xh = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * PK_W_BYTES) >> 4));      // 128 rows: X_hi, X_lo
+            umma_f16(tmem_pair, wh, xh, idesc2, ((kb & 1) | k4) != 0);
+            umma_f16(tmem_pair + PK_BN, wl, xh, idesc, 1);
           }
           pk_commit(empty_bar + 8 * s);
           if ((kb & 1) || kb == nkb - 1) pk_commit(acc_full + 8 * b);
-          if (kb == nkb - 1 && last) pk_commit(small_full);
         }
         __syncwarp();
         if ((kb & 1) || kb == nkb - 1) ++cc;
       }
-      if (last) ++ic;
     }
   } else if (warp < 6) {      // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
     const int quad = warp & 3;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t cc = ps.chunk_count, ic = ps.item_count;
+    uint32_t cc = ps.chunk_count;
     float acc[PK_BN];
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
@@ -267,34 +266,32 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
 #pragma unroll
         for (int u = 0; u < PK_BN; ++u) acc[u] = 0.f;
       }
-      const int rounds = n_chunks + (last ? 1 : 0);      // a chain's last round: the cross-term accumulator
 #pragma unroll 1
-      for (int c = 0; c < rounds; ++c) {
-        uint32_t col;
-        if (c < n_chunks) {
-          const uint32_t b = cc & 1;
-          pk_wait(sv.acc_full + 8 * b, (cc >> 1) & 1);
-          col = b * PK_BN;
-        } else {
-          pk_wait(sv.small_full, ic & 1);
-          col = 2 * PK_BN;
-        }
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t b = cc & 1;
+        GKW(0, pk_wait(sv.acc_full + 8 * b, (cc >> 1) & 1));
         tc_fence_after();
+        const uint32_t col = b * 2 * PK_BN;
         {
-          const float sc_r = c < n_chunks ? 1.f : 1.f / X16_SCALE;     // the cross terms carry the 2^11 of the lo parts
-          uint32_t r[32];
+          uint32_t r[32], r2[32];
           tmem_ld32(taddr + col, r);
+          tmem_ld32(taddr + col + PK_BN, r2);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 32; ++u) acc[u] = fmaf(__uint_as_float(r[u]), sc_r, acc[u]);
+          for (int u = 0; u < 32; ++u) acc[u] += __uint_as_float(r[u]);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc[u] = fmaf(__uint_as_float(r2[u]), 1.f / X16_SCALE, acc[u]);      // the cross terms carry the 2^11 of the lo parts
           tmem_ld32(taddr + col + 32, r);
+          tmem_ld32(taddr + col + PK_BN + 32, r2);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 32; ++u) acc[32 + u] = fmaf(__uint_as_float(r[u]), sc_r, acc[32 + u]);
+          for (int u = 0; u < 32; ++u) acc[32 + u] += __uint_as_float(r[u]);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) acc[32 + u] = fmaf(__uint_as_float(r2[u]), 1.f / X16_SCALE, acc[32 + u]);
         }
         tc_fence_before();
-        if (c < n_chunks) { pk_arrive(sv.acc_empty + 8 * (cc & 1)); ++cc; }
-        else { pk_arrive(sv.small_empty); ++ic; }
+        pk_arrive(sv.acc_empty + 8 * b);
+        ++cc;
       }
       if (last && (it.flags & GI_LOGITS)) {
         if (!STEP) {                     // greedy decoding
@@ -396,6 +393,12 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
       }
     }
   }                           // (warps 6-9 have no role in the GEMM phases: the operands arrive split)
+#ifdef GK_FINE
+  if (gw && lane == 0 && warp <= 2) {      // per role: time in this phase, waits (producer: stage free | MMA: data, accumulator free,
+    const long long dt = clock64() - t_in; //  cross accumulator free | epilogue warp 2: main accumulator full, cross accumulator full)
+    gw[warp * 8 + 0] += dt; gw[warp * 8 + 1] += w_acc[0]; gw[warp * 8 + 2] += w_acc[1]; gw[warp * 8 + 3] += w_acc[2]; gw[warp * 8 + 4] += sc->tot_kb;
+  }
+#endif
   ps.kb_count += sc->tot_kb;
   ps.chunk_count += sc->tot_chunks;
   ps.item_count += sc->n_chains;
@@ -1482,8 +1485,10 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   if (ncb != 1 || G - R < groups || G - R < B) return PK_FALLBACK;
   // (the schedule depends on the padded row count only, never on B: a caption's arithmetic - K split, summation order -
   //  is the same whatever batch it is decoded in)
-  const int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - R) / groups), kbE + kbH)),
-                            std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH))};
+  int members_l[2] = {std::max(1, std::min(std::min(GK_MAX_MEMBERS, (G - R) / groups), kbE + kbH)),
+                      std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH))};
+  if (getenv("XG_M1")) members_l[0] = std::max(1, std::min(members_l[0], atoi(getenv("XG_M1"))));      // (experiments)
+  if (getenv("XG_M2")) members_l[1] = std::max(1, std::min(members_l[1], atoi(getenv("XG_M2"))));
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   GroupedState*& S = grouped_state(ctx);
@@ -2060,6 +2065,11 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
           fprintf(stderr, "[xg grouped step trace] cta 0 fused layer %d (cycles after phase entry): producer done %lld, epilogue warp done %lld, "
                   "cta synced %lld, group counter seen %lld, cta synced %lld, cell done %lld\n", l, f[l * 16 + 1] - f[l * 16], f[l * 16 + 2] - f[l * 16],
                   f[l * 16 + 3] - f[l * 16], f[l * 16 + 4] - f[l * 16], f[l * 16 + 5] - f[l * 16], f[l * 16 + 6] - f[l * 16]);
+        long long w[24];
+        cudaMemcpy(w, S->d_dbg + (2048 + 256) * PK_STAMPS + 32, sizeof(w), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[xg grouped step trace] cta 0, all GEMM phases of %u launches, %lld k-blocks per launch: producer %lld cycles in phases, %lld waiting for a free stage | "
+                "MMA warp %lld in phases, waits: data %lld, accumulator free %lld, cross accumulator free %lld | epilogue warp %lld in phases, waits: accumulator full %lld, cross full %lld\n",
+                S->launches, w[4] / S->launches, w[0], w[1], w[8], w[9], w[10], w[11], w[16], w[17], w[18]);
       }
 #endif
     }
