@@ -154,6 +154,7 @@ int xg_destroy(xg_handle h) {
   grouped_enc_release(h);
   grouped_step_release(h);
   grouped_train_release(h);
+  colsum_release(h);
   word_tables_release(h);
   tc_release(h);
   for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }

@@ -78,6 +78,76 @@ static int colsum_run(xg_context* ctx, const float* X, long ld, int R, int N, fl
   return XG_OK;
 }
 
+// The bias gradients of a backward pass are column sums of matrices that stay intact until the pass ends: they are
+// collected and run as ONE launch per flush (decoder side / first encoder stream / second encoder stream) instead of 19.
+struct ColsumScratch { float* part = nullptr; unsigned int* ctr = nullptr; };
+constexpr size_t COLSUM_PART_FLOATS = (size_t)2 << 20;
+constexpr int COLSUM_CTRS = 4096;
+inline ColsumScratch*& colsum_scratch(xg_context* ctx) {
+  static std::unordered_map<xg_context*, ColsumScratch*> m;
+  return m[ctx];
+}
+static void colsum_release(xg_context* ctx) {
+  ColsumScratch* s = colsum_scratch(ctx);
+  if (!s) return;
+  if (s->part) cudaFree(s->part);
+  if (s->ctr) cudaFree(s->ctr);
+  delete s;
+  colsum_scratch(ctx) = nullptr;
+}
+struct ColsumBatch {
+  ColsumJobs J;
+  ColsumBatch() { J.n = 0; }
+  int add(xg_context* ctx, const float* X, long ld, int R, int N, float beta, float* o0, float* o1, float* o2, cudaStream_t st) {
+    if (J.n == COLSUM_MAX_JOBS) XG_TRY(flush(ctx, beta, st));
+    const int q = J.n++;
+    J.X[q] = X; J.ld[q] = ld; J.R[q] = R; J.N[q] = N; J.o[q][0] = o0; J.o[q][1] = o1; J.o[q][2] = o2;
+    return XG_OK;
+  }
+  int flush(xg_context* ctx, float beta, cudaStream_t st) {
+    if (J.n == 0) return XG_OK;
+    ColsumScratch*& S = colsum_scratch(ctx);
+    if (!S) {
+      S = new ColsumScratch();
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&S->part, sizeof(float) * COLSUM_PART_FLOATS));
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&S->ctr, sizeof(unsigned int) * COLSUM_CTRS));
+      XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->ctr, 0, sizeof(unsigned int) * COLSUM_CTRS, st));
+    }
+    // row slabs: every job is cut so that one block sums ~256 rows of its 32 columns (at least one slab)
+    long blocks = 0, part = 0, ctrs = 0;
+    for (int q = 0; q < J.n; ++q) {
+      const int gx = ceil_div(J.N[q], 32);
+      int s = std::max(1, std::min(64, ceil_div(J.R[q], 256)));
+      if (part + (long)s * J.N[q] > (long)COLSUM_PART_FLOATS || ctrs + gx > COLSUM_CTRS) {      // scratch exhausted: run what is there
+        const int keep = J.n;
+        J.n = q;
+        XG_TRY(launch_jobs(ctx, beta, (int)blocks, S, st));
+        for (int i = q; i < keep; ++i) move(i, i - q);
+        J.n = keep - q;
+        return flush(ctx, beta, st);
+      }
+      J.S[q] = s; J.first_block[q] = (int)blocks; J.part_off[q] = (int)part; J.ctr_off[q] = (int)ctrs;
+      blocks += (long)gx * s; part += (long)s * J.N[q]; ctrs += gx;
+    }
+    J.first_block[J.n] = (int)blocks;
+    XG_TRY(launch_jobs(ctx, beta, (int)blocks, S, st));
+    J.n = 0;
+    return XG_OK;
+  }
+ private:
+  void move(int from, int to) {
+    J.X[to] = J.X[from]; J.ld[to] = J.ld[from]; J.R[to] = J.R[from]; J.N[to] = J.N[from];
+    for (int k = 0; k < 3; ++k) J.o[to][k] = J.o[from][k];
+  }
+  int launch_jobs(xg_context* ctx, float beta, int blocks, ColsumScratch* S, cudaStream_t st) {
+    if (J.n == 0 || blocks == 0) return XG_OK;
+    J.beta = beta;
+    J.first_block[J.n] = blocks;
+    XG_TRY(launch(ctx, "colsum", colsum_multi_kernel, blocks, dim3(32, 8), 0, st, J, S->part, S->ctr));
+    return XG_OK;
+  }
+};
+
 // dW (+)= dy^T . x
 static int wgrad(xg_context* ctx, const float* dy, long lddy, const float* x, long ldx, float* dW, int N, int Kin, int R,
                  float beta, cudaStream_t st) {
@@ -96,12 +166,13 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   const float keep = (train && d.drop_prob > 0.f) ? 1.f / (1.f - d.drop_prob) : 1.f;
   const float* OUT = S.H12 + (long)B * 2 * H + H;   // (LB, H) ld 2H
   const long ldo = 2 * H;
+  ColsumBatch cs;
 
   // ---------------- heads ----------------
   if (dlogp) {
     XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 256, 0, st, logp, dlogp, B, Lp, V, W.DLOGITS));
     XG_TRY(wgrad(ctx, W.DLOGITS, V, OUT, ldo, G[XG_P_LOGIT_W], V, H, LB, beta, st));
-    XG_TRY(colsum_run(ctx, W.DLOGITS, V, LB, V, beta, G[XG_P_LOGIT_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.DLOGITS, V, LB, V, beta, G[XG_P_LOGIT_B], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.DLOGITS, V, P_(ctx, XG_P_LOGIT_W), H, W.dOUT, H, LB, H, V);
     XG_TRY(gemm_run(ctx, g, st));
   } else {
@@ -114,12 +185,12 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   if (dcat) {
     XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 128, 0, st, cat, dcat, B, Lp, C, W.dCL));
     XG_TRY(wgrad(ctx, W.dCL, C, S.Hc, Q, G[XG_P_CLS3_W], C, Q, LB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dCL, C, LB, C, beta, G[XG_P_CLS3_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dCL, C, LB, C, beta, G[XG_P_CLS3_B], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.dCL, C, P_(ctx, XG_P_CLS3_W), Q, W.dHc, Q, LB, Q, C);
     XG_TRY(gemm_run(ctx, g, st));
     XG_TRY(launch(ctx, "relu_drop_bwd", relu_drop_bwd_kernel, ew_grid((long)LB * Q), 256, 0, st, W.dHc, S.Hc, (long)LB * Q, keep));
     XG_TRY(wgrad(ctx, W.dHc, Q, OUT, ldo, G[XG_P_CLS0_W], Q, H, LB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dHc, Q, LB, Q, beta, G[XG_P_CLS0_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dHc, Q, LB, Q, beta, G[XG_P_CLS0_B], nullptr, nullptr, st));
     GemmP g2 = gemm_nn(W.dHc, Q, P_(ctx, XG_P_CLS0_W), H, W.dOUT, H, LB, H, Q);
     g2.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, g2, st));
@@ -194,7 +265,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     const long ldd[4] = {2 * H, H, 2 * H, H};
     for (int q = 0; q < 4; ++q) {
       XG_TRY(wgrad(ctx, dsrc[q], ldd[q], S.enc.meanV, H, G[iw[q]], H, H, B, beta, st));
-      XG_TRY(colsum_run(ctx, dsrc[q], ldd[q], B, H, beta, G[iw[q] + 1], nullptr, nullptr, st));
+      XG_TRY(cs.add(ctx, dsrc[q], ldd[q], B, H, beta, G[iw[q] + 1], nullptr, nullptr, st));
     }
   }
   // batched weight gradients over all steps
@@ -204,21 +275,21 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     XG_TRY(wgrad(ctx, G2, 4 * H, Hnew, 2 * H, G[XG_P_L2_I2H_W], 4 * H, H, LB, beta, st));
     XG_TRY(wgrad(ctx, G2, 4 * H, S.AF, H, G[XG_P_L2_A2H_W], 4 * H, H, LB, beta, st));
     XG_TRY(wgrad(ctx, G2, 4 * H, Hprev + H, 2 * H, G[XG_P_L2_H2H_W], 4 * H, H, LB, beta, st));
-    XG_TRY(colsum_run(ctx, G2, 4 * H, LB, 4 * H, beta, G[XG_P_L2_I2H_B], G[XG_P_L2_A2H_B], G[XG_P_L2_H2H_B], st));
+    XG_TRY(cs.add(ctx, G2, 4 * H, LB, 4 * H, beta, G[XG_P_L2_I2H_B], G[XG_P_L2_A2H_B], G[XG_P_L2_H2H_B], st));
     XG_TRY(wgrad(ctx, G1, 4 * H, S.XT, E, G[XG_P_L1_I2H_W], 4 * H, E, LB, beta, st));
     XG_TRY(wgrad(ctx, G1, 4 * H, S.GP, H, G[XG_P_L1_A2H_W], 4 * H, H, LB, beta, st));
     XG_TRY(wgrad(ctx, G1, 4 * H, Hprev, 2 * H, G[XG_P_L1_H2H_W], 4 * H, H, LB, beta, st));
-    XG_TRY(colsum_run(ctx, G1, 4 * H, LB, 4 * H, beta, G[XG_P_L1_I2H_B], G[XG_P_L1_A2H_B], G[XG_P_L1_H2H_B], st));
+    XG_TRY(cs.add(ctx, G1, 4 * H, LB, 4 * H, beta, G[XG_P_L1_I2H_B], G[XG_P_L1_A2H_B], G[XG_P_L1_H2H_B], st));
     XG_TRY(wgrad(ctx, W.DAH, A, Hprev, 2 * H, G[XG_P_H2A_W], A, 2 * H, LB, beta, st));
-    XG_TRY(colsum_run(ctx, W.DAH, A, LB, A, beta, G[XG_P_H2A_B], nullptr, nullptr, st));
-    XG_TRY(colsum_run(ctx, W.dwa_part, A, B, A, beta, G[XG_P_A2W_W], nullptr, nullptr, st));
-    XG_TRY(colsum_run(ctx, W.dba_part, 1, B, 1, beta, G[XG_P_A2W_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.DAH, A, LB, A, beta, G[XG_P_H2A_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dwa_part, A, B, A, beta, G[XG_P_A2W_W], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dba_part, 1, B, 1, beta, G[XG_P_A2W_B], nullptr, nullptr, st));
     // POS gate + embedding
     GemmP gp = gemm_nn(G1, 4 * H, P_(ctx, XG_P_L1_A2H_W), H, W.dGP, H, LB, H, 4 * H);
     XG_TRY(gemm_run(ctx, gp, st));
     XG_TRY(launch(ctx, "dgate_bwd", dgate_bwd_kernel, ew_grid((long)LB * H), 256, 0, st, W.dGP, S.RG, pos, B, LB, H, keep, W.dGP));
     XG_TRY(wgrad(ctx, W.dGP, H, S.XT, E, G[XG_P_DGATE_W], H, E, LB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dGP, H, LB, H, beta, G[XG_P_DGATE_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dGP, H, LB, H, beta, G[XG_P_DGATE_B], nullptr, nullptr, st));
     GemmP gx = gemm_nn(G1, 4 * H, P_(ctx, XG_P_L1_I2H_W), E, W.dXT, E, LB, E, 4 * H);
     XG_TRY(gemm_run(ctx, gx, st));
     GemmP gx2 = gemm_nn(W.dGP, H, P_(ctx, XG_P_DGATE_W), E, W.dXT, E, LB, E, H);
@@ -228,7 +299,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     XG_TRY(launch(ctx, "embed_scatter_add", embed_scatter_add_kernel, LB, 128, 0, st, W.dXT, seq, B, L, LB, E, V, G[XG_P_EMBED_W]));
     // v2a
     XG_TRY(wgrad(ctx, W.dUv, A, S.V, H, G[XG_P_V2A_W], A, H, KB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dUv, A, KB, A, beta, G[XG_P_V2A_B], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dUv, A, KB, A, beta, G[XG_P_V2A_B], nullptr, nullptr, st));
     GemmP gv = gemm_nn(W.dUv, A, P_(ctx, XG_P_V2A_W), H, W.dV, H, KB, H, A);
     gv.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, gv, st));
@@ -237,13 +308,14 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   // Every gradient of the decoder side (init-state linears, POS gate, both LSTM cells, attention, embedding, logit and
   // classifier heads: parameters XG_P_INIT_H1_W .. XG_P_CLS3_B, the tail of the flat gradient buffer) is final here; what
   // follows only writes the encoder's.  Data-parallel callers start the all-reduce of that tail on another stream now.
+  XG_TRY(cs.flush(ctx, beta, st));
   if (ctx->bwd_split_event) XG_CUDA_TRY(ctx->es, cudaEventRecord(ctx->bwd_split_event, st));
   // ---------------- encoder backward (rows (k,b)) ----------------
   const EncBufs& eb = S.enc;
   XG_TRY(launch(ctx, "fusion_bwd", fusion_bwd_kernel, ew_grid((long)KB * H), 256, 0, st, W.dV, S.V, B, K, H, d.fusion_act,
                                                           make_drop(train, d.drop_prob, seed, XG_DROP_ENC_FUSION), W.dF));
   XG_TRY(wgrad(ctx, W.dF, H, eb.GG, 2 * H, G[XG_P_FUSION_W], H, 2 * H, KB, beta, st));
-  XG_TRY(colsum_run(ctx, W.dF, H, KB, H, beta, G[XG_P_FUSION_B], nullptr, nullptr, st));
+  XG_TRY(cs.add(ctx, W.dF, H, KB, H, beta, G[XG_P_FUSION_B], nullptr, nullptr, st));
   {
     GemmP g = gemm_nn(W.dF, H, P_(ctx, XG_P_FUSION_W), 2 * H, W.dGG, 2 * H, KB, 2 * H, H);
     XG_TRY(gemm_run(ctx, g, st));
@@ -256,7 +328,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   for (int s = 0; s < 2; ++s) {
     const int src = 1 - s;
     XG_TRY(wgrad(ctx, W.dR[s], H, eb.Hs[src], H, G[gw[s]], H, H, KB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dR[s], H, KB, H, beta, G[gw[s] + 1], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dR[s], H, KB, H, beta, G[gw[s] + 1], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.dR[s], H, P_(ctx, gw[s]), H, W.dH[src], H, KB, H, H);
     g.ep.beta = 1.f;
     XG_TRY(gemm_run(ctx, g, st));
@@ -292,7 +364,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
       XG_CUDA_TRY(ctx->es, cudaMemsetAsync(G[plstm[s] + 1], 0, sizeof(float) * (size_t)4 * H * H, st));
     }
     XG_TRY(wgrad(ctx, DZ, 4 * H, eb.E[s], H, G[plstm[s]], 4 * H, H, KB, beta, st));
-    XG_TRY(colsum_run(ctx, DZ, 4 * H, KB, 4 * H, beta, G[plstm[s] + 2], G[plstm[s] + 3], nullptr, st));
+    XG_TRY(cs.add(ctx, DZ, 4 * H, KB, 4 * H, beta, G[plstm[s] + 2], G[plstm[s] + 3], nullptr, st));
     {
       GemmP g = gemm_nn(DZ, 4 * H, P_(ctx, plstm[s]), H, W.dE, H, KB, H, 4 * H);
       XG_TRY(gemm_run(ctx, g, st));
@@ -307,7 +379,8 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     XG_TRY(launch(ctx, "bn_bwd_apply", bn_bwd_apply_kernel, ew_grid((long)KB * H), 256, 0, st, W.dy, eb.Y[s], eb.mean[s], eb.invstd[s],
                                                               P_(ctx, pw[s] + 2), W.s_dy, W.s_dyx, KB, H, train));
     XG_TRY(wgrad(ctx, W.dy, H, X[s], din[s], G[pw[s]], H, din[s], KB, beta, st));
-    XG_TRY(colsum_run(ctx, W.dy, H, KB, H, beta, G[pw[s] + 1], nullptr, nullptr, st));
+    XG_TRY(cs.add(ctx, W.dy, H, KB, H, beta, G[pw[s] + 1], nullptr, nullptr, st));
+    XG_TRY(cs.flush(ctx, beta, st));      // (W.dy is reused by the second stream)
   }
   return XG_OK;
 }

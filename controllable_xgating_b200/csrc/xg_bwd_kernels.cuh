@@ -29,14 +29,14 @@ __global__ void logsoftmax_bwd_rows_kernel(const float* __restrict__ lp, const f
 // handful of SMs with one block per 32 columns, so the rows are cut into S slabs: every block leaves its
 // partial sums in `part` [S][N] and the last block of a column group to finish (ticket counter, left at zero
 // again) adds the S partials in slab order -- the result does not depend on which block that is.
-__global__ void colsum_kernel(const float* __restrict__ X, long ld, int R, int N, float beta,
-                              float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
-                              float* __restrict__ part, unsigned int* __restrict__ ctr) {
+__device__ __forceinline__ void colsum_body(const float* __restrict__ X, long ld, int R, int N, float beta,
+                                            float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                                            float* __restrict__ part, unsigned int* __restrict__ ctr, int bx, int by, int S) {
   __shared__ float sm[8][33];
   __shared__ unsigned int ticket;
-  const int j = blockIdx.x * 32 + threadIdx.x;
-  const int S = gridDim.y, chunk = (R + S - 1) / S;
-  const int r0 = blockIdx.y * chunk, r1 = min(R, r0 + chunk);
+  const int j = bx * 32 + threadIdx.x;
+  const int chunk = (R + S - 1) / S;
+  const int r0 = by * chunk, r1 = min(R, r0 + chunk);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (j < N) {
     int r = r0 + threadIdx.y;
@@ -51,12 +51,12 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, int R, int N
   __syncthreads();
   if (threadIdx.y == 0) {
     for (int y = 1; y < 8; ++y) a += sm[y][threadIdx.x];
-    if (S > 1 && j < N) __stcg(part + (long)blockIdx.y * N + j, a);
+    if (S > 1 && j < N) __stcg(part + (long)by * N + j, a);
   }
   if (S > 1) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) ticket = atomicAdd(ctr + blockIdx.x, 1u);
+    if (threadIdx.x == 0 && threadIdx.y == 0) ticket = atomicAdd(ctr + bx, 1u);
     __syncthreads();
     if (ticket != (unsigned int)(S - 1)) return;
     __threadfence();
@@ -64,13 +64,35 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, int R, int N
       a = 0.f;
       for (int s2 = 0; s2 < S; ++s2) a += __ldcg(part + (long)s2 * N + j);
     }
-    if (threadIdx.x == 0 && threadIdx.y == 0) ctr[blockIdx.x] = 0u;
+    if (threadIdx.x == 0 && threadIdx.y == 0) ctr[bx] = 0u;
   }
   if (threadIdx.y == 0 && j < N) {
     if (o0) o0[j] = (beta != 0.f ? beta * o0[j] : 0.f) + a;
     if (o1) o1[j] = (beta != 0.f ? beta * o1[j] : 0.f) + a;
     if (o2) o2[j] = (beta != 0.f ? beta * o2[j] : 0.f) + a;
   }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ X, long ld, int R, int N, float beta,
+                              float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                              float* __restrict__ part, unsigned int* __restrict__ ctr) {
+  colsum_body(X, ld, R, N, beta, o0, o1, o2, part, ctr, blockIdx.x, blockIdx.y, gridDim.y);
+}
+
+// several column sums in ONE launch (the bias gradients of a backward pass): block -> (job, column group, row slab)
+constexpr int COLSUM_MAX_JOBS = 16;
+struct ColsumJobs {
+  const float* X[COLSUM_MAX_JOBS]; long ld[COLSUM_MAX_JOBS]; int R[COLSUM_MAX_JOBS], N[COLSUM_MAX_JOBS], S[COLSUM_MAX_JOBS];
+  float* o[COLSUM_MAX_JOBS][3];
+  int first_block[COLSUM_MAX_JOBS + 1], part_off[COLSUM_MAX_JOBS], ctr_off[COLSUM_MAX_JOBS];
+  int n; float beta;
+};
+__global__ void colsum_multi_kernel(const ColsumJobs J, float* __restrict__ part, unsigned int* __restrict__ ctr) {
+  int q = 0;
+  while (q + 1 < J.n && (int)blockIdx.x >= J.first_block[q + 1]) ++q;
+  const int local = (int)blockIdx.x - J.first_block[q], gx = (J.N[q] + 31) / 32;
+  colsum_body(J.X[q], J.ld[q], J.R[q], J.N[q], J.beta, J.o[q][0], J.o[q][1], J.o[q][2], part + J.part_off[q], ctr + J.ctr_off[q],
+              local % gx, local / gx, J.S[q]);
 }
 
 // decoder cell backward (mirror of dec_cell_kernel).  G holds activated gates (i,f,o,g) and is
