@@ -354,8 +354,12 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
     int ps = grouped_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st);
     if (ps == PK_FALLBACK) ps = persist_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, nullptr, st);
     if (ps != PK_FALLBACK) return ps;
-  } else {
-    const int ps = persist_refuse(h, "the sampling word loop", "multinomial draws and training-mode dropout run on per-step launches");
+  } else {          // sampling form of the grouped kernel: multinomial draw in the pick phase, training dropout in the cells
+    GroupedSampling smp;
+    smp.sample_max = sample_max; smp.temperature = temperature; smp.seed = seed;
+    smp.step_drop = step_drop; smp.drop_seed = h->dec_drop_seed;
+    int ps = grouped_decode(h, V, Uv, pos, state0, B, K, T, seq_out, logp_out, steps_out, st, &smp);
+    if (ps == PK_FALLBACK) ps = persist_refuse(h, "the sampling word loop", "shape outside the grouped decoder: multinomial draws and training-mode dropout run on per-step launches");
     if (ps != PK_FALLBACK) return ps;
   }
   for (int q = 0; q < 4; ++q)

@@ -308,8 +308,9 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   // Every gradient of the decoder side (init-state linears, POS gate, both LSTM cells, attention, embedding, logit and
   // classifier heads: parameters XG_P_INIT_H1_W .. XG_P_CLS3_B, the tail of the flat gradient buffer) is final here; what
   // follows only writes the encoder's.  Data-parallel callers start the all-reduce of that tail on another stream now.
+  // The event itself is recorded further down, behind the cooperative frame-recurrence kernel: an NCCL kernel and a
+  // cooperative launch that wants every SM exclude each other, the batched GEMMs after it do not.
   XG_TRY(cs.flush(ctx, beta, st));
-  if (ctx->bwd_split_event) XG_CUDA_TRY(ctx->es, cudaEventRecord(ctx->bwd_split_event, st));
   // ---------------- encoder backward (rows (k,b)) ----------------
   const EncBufs& eb = S.enc;
   XG_TRY(launch(ctx, "fusion_bwd", fusion_bwd_kernel, ew_grid((long)KB * H), 256, 0, st, W.dV, S.V, B, K, H, d.fusion_act,
@@ -342,6 +343,7 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   // frame recurrence of both streams: one persistent cooperative kernel when the shape allows it (xg_persist.cuh)
   const int pbw = persist_encode_bwd(ctx, fmask, B, K, eb, W.dH, st);
   if (pbw != PK_FALLBACK) XG_TRY(pbw);
+  if (ctx->bwd_split_event) XG_CUDA_TRY(ctx->es, cudaEventRecord(ctx->bwd_split_event, st));      // decoder-side gradients final (see above)
   for (int s = 0; s < 2; ++s) {
     float* DZ = eb.G[s];   // gates -> dz in place
     if (pbw == PK_FALLBACK) {

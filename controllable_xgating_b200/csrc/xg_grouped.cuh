@@ -90,6 +90,13 @@ struct GroupParams {
   // row merge rescans the few vocabulary tiles that can hold a row's topk
   int topk;
   float* lraw;
+  // sampling form of the word loop (SAModel.sample with sample_max = 0 and / or under model.train(): SAModel.py:188-196,
+  // starttrain.py:131): multinomial draw from exp(logprob / temperature) in the pick phase, training dropout on the POS
+  // gate and on both cells with the Philox sites / indices of xg_train_fwd (the teacher-forced replay reproduces them)
+  int sample_max, step_drop;
+  float inv_temp;
+  unsigned long long sample_seed;
+  DropSpec drop_gate, drop_h1, drop_h2;
 };
 
 // L2 residency: the recurrent weights + the attention operands (47 MB) are re-read every word step and fit one L2
@@ -334,7 +341,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           const int V = C.dp.V;
           const int nl = quad * 32 + lane, n = it.wrow + nl;
           const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
-          if (C.topk > 0) {
+          if (C.lraw != nullptr) {
             float* o = C.lraw + (long)(it.cb * PK_BN) * (C.ntv * 128) + n;
             const long str = (long)C.ntv * 128;
 #pragma unroll
@@ -365,13 +372,16 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
               const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
               if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            float sum = 0.f;
+            float sum = 0.f, sumT = 0.f;
+            const float invT = C.inv_temp;
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) sum += __expf(row[4 * i] - best);
+            for (int i = 0; i < 32; ++i) { const float dx = row[4 * i] - best; sum += __expf(dx); sumT += __expf(dx * invT); }
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            if (part == 0)
-              C.lpart[(long)(it.cb * PK_BN + hf * 32 + cl) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(bi), 0.f);
+            sumT += __shfl_xor_sync(0xffffffffu, sumT, 1);
+            sumT += __shfl_xor_sync(0xffffffffu, sumT, 2);
+            if (part == 0)      // (.w: the tile's mass at the sampling temperature, relative to its own max)
+              C.lpart[(long)(it.cb * PK_BN + hf * 32 + cl) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(bi), sumT);
             asm volatile("bar.sync 1, 128;" ::: "memory");
           }
         }
@@ -452,7 +462,7 @@ __device__ __noinline__ void gprefetch(const GroupParams& C, const GSched* sc, c
 
 // cell of the captions [c0, c1) of a group: one warp per caption, lane = hidden unit; NCAP captions per pass with every
 // partial-tile load of all of them in flight before the first add (MAXS bounds the slots a cell adds)
-template <int MAXS, int NCAP>
+template <int MAXS, int NCAP, bool DROP = false>
 __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int t, int grp, int c0, int c1) {
   const DecParams& P = C.dp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -502,6 +512,7 @@ __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int 
       cn = cn * mk[q] + cp[q] * (1.f - mk[q]);
       float h = og * tanh_fast(cn);
       h = h * mk[q] + hp[q] * (1.f - mk[q]);
+      if (DROP) h *= (layer == 0 ? C.drop_h1 : C.drop_h2).factor((uint64_t)t * B * H + (uint64_t)r * H + j);
       cst[(long)r * H + j] = cn;
       P.hx[(long)r * 2 * H + layer * H + j] = h;
       store_split16(hi_new, lo_new, (long)r * 2 * H + layer * H + j, h);
@@ -644,7 +655,7 @@ __device__ __forceinline__ void group_cell_train(const GroupParams& C, int layer
 
 // One LSTM layer of the word step (two_inputs_lstmcell, sub_modules.py:750-770): the products of the layer as one chain
 // per group member, the group's partial tiles summed and the cell applied by the members themselves.
-template <int MODE>      // 0: greedy loop, 1: single step (beam search), 2: teacher-forced training loop
+template <int MODE>      // 0: greedy loop, 1: single step (beam search), 2: teacher-forced training loop, 3: sampling loop
 __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
                                               int layer, int t, unsigned int sync_epoch, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   // t: word step (buffer parity, state mask); sync_epoch: how many times this group counter has been used before
@@ -658,7 +669,7 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
 #define GKF(i) do { } while (0)
 #define GKF_T(tid, i) do { } while (0)
 #endif
-  gphase<MODE == 1>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  gphase<MODE == 1 || MODE == 3>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
   GKF(1); GKF_T(64, 2);                  // producer done / first epilogue warp done
   // a CTA is member `mem` of the groups (tile, cb) of EVERY caption column block cb of its tile (one chain per column
   // block above); the members of those groups are the same CTAs, so one counter per tile covers them all
@@ -689,6 +700,10 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
     if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell_train<8, 2>(C, layer, t, tile, c0, c1);
     else if (C.nslots[layer] <= 8) group_cell_train<8, 1>(C, layer, t, tile, c0, c1);
     else group_cell_train<GK_MAX_SLOTS, 1>(C, layer, t, tile, c0, c1);
+  } else if (MODE == 3) {
+    if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2, true>(C, layer, t, tile, c0, c1);
+    else if (C.nslots[layer] <= 8) group_cell<8, 1, true>(C, layer, t, tile, c0, c1);
+    else group_cell<GK_MAX_SLOTS, 1, true>(C, layer, t, tile, c0, c1);
   } else if (MODE == 0 || ncb == 1) {
     if (C.nslots[layer] <= 8 && c1 - c0 > PK_WARPS) group_cell<8, 2>(C, layer, t, tile, c0, c1);
     else if (C.nslots[layer] <= 8) group_cell<8, 1>(C, layer, t, tile, c0, c1);
@@ -747,6 +762,132 @@ __device__ __noinline__ int dec_pick_tiles(const GroupParams& C, int r, int t, c
   return tok;
 }
 
+// pick of caption r at step t in the sampling form of the loop (SAModel.py:188-196): arg-max, or one multinomial draw
+// from p ~ exp(logprob / temperature) by inverse CDF: the vocabulary tile from the per-tile masses, the entry from the
+// stored logits of that tile (ids in ascending order; Philox stream of the per-step kernel greedy_pick_kernel).
+__device__ __noinline__ int dec_sample_tiles(const GroupParams& C, int r, int t, const SmemView& sv) {
+  const DecParams& P = C.dp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* redi = reinterpret_cast<int*>(sv.scratch + 16);
+  if (warp == 0) {
+    const int ntv = C.ntv;
+    const float4* lp = C.lpart + (long)r * ntv;
+    float4 q[8];
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int tile = lane + 32 * i;
+      q[i] = tile < ntv ? __ldcg(lp + tile) : make_float4(-INFINITY, 0.f, __int_as_float(0x7fffffff), 0.f);
+      const int idx = __float_as_int(q[i].z);
+      if (q[i].x > best || (q[i].x == best && idx < bi)) { best = q[i].x; bi = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    float tot = 0.f, totT = 0.f, mass[8];
+    const float invT = C.inv_temp;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tot += q[i].y * __expf(q[i].x - best);
+      mass[i] = lane + 32 * i < ntv ? q[i].w * __expf((q[i].x - best) * invT) : 0.f;
+      totT += mass[i];
+    }
+    tot = warp_sum(tot);
+    totT = warp_sum(totT);
+    const float lse = best + logf(tot);
+    int pick = bi;
+    float pick_logp = best - lse;
+    if (!C.sample_max) {
+      const float u = philox_uniform(C.sample_seed, 0x5a4d0000u + (uint32_t)(t + 1), (uint64_t)r) * totT;
+      float carry = 0.f, before = 0.f;
+      int sel_tile = -1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float incl = mass[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * i < ntv && carry + incl > u);
+        if (sel_tile < 0 && hit) {
+          const int first = __ffs(hit) - 1;
+          sel_tile = first + 32 * i;
+          before = carry + __shfl_sync(0xffffffffu, incl - mass[i], first);
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (sel_tile < 0) { sel_tile = ntv - 1; before = u; }          // rounding: past the end -> last entry below
+      const float4 x4 = __ldcg(reinterpret_cast<const float4*>(C.lraw + (long)r * ntv * 128 + (long)sel_tile * 128) + lane);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      float e[4], loc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { e[k] = sel_tile * 128 + lane * 4 + k < P.V ? __expf((xs[k] - best) * invT) : 0.f; loc += e[k]; }
+      float incl = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const unsigned hit = __ballot_sync(0xffffffffu, before + incl > u);
+      int sel; float xsel;
+      if (hit) {
+        const int first = __ffs(hit) - 1;
+        float acc = before + __shfl_sync(0xffffffffu, incl - loc, first);
+        int k = 0;
+        // (evaluated by every lane on lane `first`'s values)
+        float ev[4], xv[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { ev[kk] = __shfl_sync(0xffffffffu, e[kk], first); xv[kk] = __shfl_sync(0xffffffffu, xs[kk], first); }
+        for (; k < 3; ++k) { acc += ev[k]; if (acc > u) break; }
+        sel = sel_tile * 128 + first * 4 + k; xsel = xv[k];
+      } else {
+        const int last = min(P.V - 1, sel_tile * 128 + 127);
+        sel = last;
+        xsel = __shfl_sync(0xffffffffu, xs[(last & 127) & 3], (last & 127) >> 2);
+      }
+      pick = sel; pick_logp = xsel - lse;
+    }
+    if (lane == 0) {
+      float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
+      unf = (unf != 0.f && pick > 0) ? 1.f : 0.f;
+      P.unfinished[r] = unf;
+      P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)pick : 0;
+      P.seqlogp[(long)r * P.T + t] = pick_logp;
+      P.tok[r] = pick;
+      if (unf != 0.f) P.flags[t] = 1;
+      redi[0] = pick;
+    }
+  }
+  __syncthreads();
+  const int tok = redi[0];
+  __syncthreads();
+  return tok;
+}
+
+// next-step inputs with the training dropout of the POS gate (index = step * B * H + caption * H + unit, the layout of
+// the hoisted gate GEMM of xg_train_fwd); t_in = the step that consumes these inputs
+__device__ __noinline__ void dec_token_inputs_drop(const GroupParams& C, int r, int tokv, int t_in) {
+  const DecParams& P = C.dp;
+  const float* src = P.embed + (long)tokv * P.E;
+  const float* tg = P.tgate + (long)tokv * P.H;
+  const float* ps = P.pos + (long)r * P.H;
+  float x[DEC_TI], g[DEC_TI], q[DEC_TI];
+#pragma unroll
+  for (int i = 0; i < DEC_TI; ++i) {
+    const int k = threadIdx.x + i * PK_THREADS;
+    x[i] = k < P.E ? __ldg(src + k) : 0.f;
+    g[i] = k < P.H ? __ldcg(tg + k) : 0.f;
+    q[i] = k < P.H ? __ldg(ps + k) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < DEC_TI; ++i) {
+    const int k = threadIdx.x + i * PK_THREADS;
+    if (k < P.Ep) store_split16(reinterpret_cast<__half*>(P.xt_hi), reinterpret_cast<__half*>(P.xt_lo), (long)r * P.Ep + k, x[i]);
+    if (k < P.H) {
+      const float gd = g[i] * C.drop_gate.factor((uint64_t)t_in * P.B * P.H + (uint64_t)r * P.H + k);
+      store_split16(reinterpret_cast<__half*>(P.gp_hi), reinterpret_cast<__half*>(P.gp_lo), (long)r * P.H + k, q[i] * (1.f + gd));
+    }
+  }
+}
+
 // wait (without arriving) until a counter barrier has completed: CTAs that are not part of a phase
 __device__ __noinline__ void grid_barrier_observe(unsigned int* counter, unsigned int target) {
   __syncthreads();
@@ -762,7 +903,273 @@ __device__ __noinline__ void grid_barrier_observe(unsigned int* counter, unsigne
   __syncthreads();
 }
 
+// Temporal attention of the rows [r0, r0 + nrows) of ONE video (beam search: the beam rows of a video share exp(2Uv)
+// and V, sub_modules.py:677-680).  exp(2Uv[fb]) is copied into shared memory once and every pass of NR rows reads each
+// element once for all of its rows (dec_attention re-streams the 172 KB per row); the softmax weights of all rows wait
+// in shared memory until V[fb] has been fetched (over the consumed exp(2Uv) when both do not fit), then the contexts.
+// Shared memory is addressed through the shared window (ld.shared with 32-bit addresses: the generic loads of
+// dec_attention cost three address instructions each), the split-K slots of the query are added by float4 loads of
+// the whole CTA into a staging row behind exp(2Uv), and the NV = NR x 4 frame sums of a chunk are reduced over the
+// warp by recursive halving (NV + 1 shuffles instead of 5 NV).
+constexpr int ATT_NR = 3;            // rows per pass in beam search (NR = 1: one caption per CTA, the word loops)
+constexpr int ATT_MAX_ROWS = 8;      // rows of a video one CTA takes
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// sum over the warp of NV values per lane by recursive halving; on return v[0] of lane L is the total of value
+// att_reduce_owner<NV>(L) (several lanes may own the same value)
+template <int NV>
+__device__ __forceinline__ void att_warp_reduce(float (&v)[NV], int lane) {
+  static_assert(NV == 12 || NV == 4, "att_warp_reduce: 12 or 4 values");
+  if (NV == 12) {
+    {   // 12 -> 6 over lanes L ^ 16
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float keep = hi ? v[i + 6] : v[i], send = hi ? v[i] : v[i + 6];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    {   // 6 -> 3 over L ^ 8
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float keep = hi ? v[i + 3] : v[i], send = hi ? v[i] : v[i + 3];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {   // 3 -> 2 over L ^ 4 (the third value is summed on both sides and kept by the high half as its second)
+      const bool hi = lane & 4;
+      const float k0 = hi ? v[1] : v[0], s0 = hi ? v[0] : v[1];
+      const float t2 = v[2] + __shfl_xor_sync(0xffffffffu, v[2], 4);
+      v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+      v[1] = t2;
+    }
+    {   // low half of L ^ 4 holds (value 0, value 2), high half (value 1, value 2); L ^ 2: keep one of the two
+      const bool hi = lane & 2;
+      const float keep = hi ? v[1] : v[0], send = hi ? v[0] : v[1];
+      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  } else {
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float keep = hi ? v[i + 2] : v[i], send = hi ? v[i] : v[i + 2];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    {
+      const bool hi = lane & 8;
+      const float keep = hi ? v[1] : v[0], send = hi ? v[0] : v[1];
+      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  }
+}
+// which of the NV values lane L ends up with
+template <int NV>
+__device__ __forceinline__ int att_reduce_owner(int lane) {
+  if (NV == 12) {
+    const int g6 = (lane & 16) ? 6 : 0, g3 = (lane & 8) ? 3 : 0;
+    const int w = (lane & 2) ? 2 : ((lane & 4) ? 1 : 0);
+    return g6 + g3 + w;
+  }
+  return ((lane & 16) ? 2 : 0) + ((lane & 8) ? 1 : 0);
+}
+
+template <int NR, int TRAIN>      // TRAIN: step t saves ah, alpha and the context in the step-major buffers of TrainSaved
+__device__ __noinline__ void dec_attention_rows(const DecParams& P, const CUtensorMap* vmap, int fb, int r0, int nrows, int t, const SmemView& sv,
+                                                uint32_t& bulk_phase) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = P.K, A = P.A, H = P.H, Hh = H / 2;
+#ifdef GK_FINE
+  long long* ga = (P.dbg_clock && blockIdx.x == 0 && threadIdx.x == 0) ? P.dbg_clock + (2048 + 256) * PK_STAMPS + 54 : nullptr;
+#define GKA(i) do { if (ga) ga[i] = clock64(); } while (0)
+#else
+#define GKA(i) do { } while (0)
+#endif
+  GKA(0);
+  const uint32_t red_s = smem_u32(sv.scratch);                                       // [NR][PK_WARPS][K] per-warp partial scores
+  const uint32_t sc_s = red_s + (uint32_t)(NR * PK_WARPS * K) * 4u;              // [ATT_MAX_ROWS][K] softmax weights
+  const uint32_t uv_s = sv.stages_u32;
+  constexpr int fpc = DEC_FPC;
+  const bool v_behind = (long)K * (A + H) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
+  const uint32_t v_off = v_behind ? (uint32_t)K * A * 4u : 0u;
+  // query staging rows [NR][A] at the end of the stage area (the caller checked that exp(2Uv) (+ V) end before it)
+  const uint32_t ah_s = sv.stages_u32 + (uint32_t)(PK_STAGES * PK_STAGE_BYTES) - (uint32_t)(NR * A) * 4u;
+  float wr[DEC_NA], wsum = 0.f;
+  uint32_t aoff4[DEC_NA];
+#pragma unroll
+  for (int i = 0; i < DEC_NA; ++i) {
+    const int a = min(threadIdx.x + PK_THREADS * i, A - 1);
+    aoff4[i] = (uint32_t)a * 4u;
+    wr[i] = (threadIdx.x + PK_THREADS * i < A) ? __ldg(P.w_a2w + a) : 0.f;       // out-of-range units weigh 0
+    wsum += wr[i];
+    wr[i] *= -2.f;
+  }
+  GKA(6);
+  const GDesc& dah = P.d[DD_AH];
+  const int A4 = A >> 2;
+  constexpr int QIT = (NR * DEC_NA * PK_THREADS / 4 + PK_THREADS - 1) / PK_THREADS;      // float4 columns of NR rows per thread
+#pragma unroll 1
+  for (int g = 0; g < nrows; g += NR) {
+    const int ng = min(NR, nrows - g);
+    // ---- query of the ng rows: bias + split-K slots in slot order, e^{2 ah} into the staging rows.  Every load is issued
+    //      before the exp(2Uv) copies below: behind 172 KB per SM of bulk traffic they took ~12k cycles ----
+    {
+      float4 v[QIT][PK_MAX_SLOTS];
+      const long sstr4 = (long)P.R * A4;
+#pragma unroll
+      for (int it = 0; it < QIT; ++it) {
+        const int idx = threadIdx.x + it * PK_THREADS;
+        const bool on = idx < ng * A4;
+        const int q = on ? idx / A4 : 0, a4 = on ? idx - q * A4 : 0;
+        const float4* src = reinterpret_cast<const float4*>(dah.out + (long)(r0 + g + q) * A) + a4;
+#pragma unroll
+        for (int k = 0; k < PK_MAX_SLOTS; ++k) v[it][k] = (on && k < dah.ns) ? __ldcg(src + k * sstr4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      GKA(7);
+      if (g == 0 && warp == 0) {
+        const int k0 = lane * fpc, k1 = min(K, k0 + fpc);
+        if (lane < PK_BULK_CHUNKS && k0 < k1) {
+          const uint32_t nb = (uint32_t)(k1 - k0) * (uint32_t)A * 4u;
+          pk_expect_tx(sv.bulk_bar + 8 * lane, nb);
+          bulk_g2s(sv.stages_u32 + (uint32_t)k0 * A * 4u, P.EUv + ((long)fb * K + k0) * A, nb, sv.bulk_bar + 8 * lane);
+        }
+        if (lane == 0 && v_behind) {
+          pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
+          pk_tma_2d(sv.stages_u32 + v_off, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
+          pk_tma_2d(sv.stages_u32 + v_off + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
+        }
+        __syncwarp();
+      }
+      GKA(8);
+#pragma unroll
+      for (int it = 0; it < QIT; ++it) {
+        const int idx = threadIdx.x + it * PK_THREADS;
+        if (idx < ng * A4) {
+          const int q = idx / A4, a4 = idx - q * A4;
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < PK_MAX_SLOTS; ++k) { sum.x += v[it][k].x; sum.y += v[it][k].y; sum.z += v[it][k].z; sum.w += v[it][k].w; }
+          const float4 bb = make_float4(__ldg(P.b_h2a + a4 * 4), __ldg(P.b_h2a + a4 * 4 + 1), __ldg(P.b_h2a + a4 * 4 + 2), __ldg(P.b_h2a + a4 * 4 + 3));
+          const float4 ah = make_float4(bb.x + sum.x, bb.y + sum.y, bb.z + sum.z, bb.w + sum.w);
+          if (TRAIN) {
+            float* o = P.AHs + ((long)t * P.B + r0 + g + q) * A + a4 * 4;
+            o[0] = ah.x; o[1] = ah.y; o[2] = ah.z; o[3] = ah.w;
+          }
+          float4 e;      // tanh(ah + uv) = 1 - 2 / (e^{2 ah} e^{2 uv} + 1)
+          e.x = __expf(2.f * fminf(fmaxf(ah.x, -40.f), 40.f)); e.y = __expf(2.f * fminf(fmaxf(ah.y, -40.f), 40.f));
+          e.z = __expf(2.f * fminf(fmaxf(ah.z, -40.f), 40.f)); e.w = __expf(2.f * fminf(fmaxf(ah.w, -40.f), 40.f));
+          sts_f32x4(ah_s + (uint32_t)(q * A + a4 * 4) * 4u, e);
+        }
+      }
+    }
+    GKA(9);
+    __syncthreads();
+    float ahr[NR][DEC_NA];
+#pragma unroll
+    for (int q = 0; q < NR; ++q)
+#pragma unroll
+      for (int i = 0; i < DEC_NA; ++i) ahr[q][i] = lds_f32(ah_s + (uint32_t)(min(q, ng - 1) * A) * 4u + aoff4[i]);
+    GKA(1);
+#pragma unroll 1
+    for (int c = 0; c < PK_BULK_CHUNKS; ++c) {
+      const int k0 = c * fpc, k1 = min(K, k0 + fpc);
+      if (k0 >= k1) break;
+      pk_wait(sv.bulk_bar + 8 * c, bulk_phase & 1);            // (passes at once after the first pass)
+      float p[NR * DEC_FPC];
+#pragma unroll
+      for (int u = 0; u < NR * DEC_FPC; ++u) p[u] = wsum;
+#pragma unroll
+      for (int f = 0; f < DEC_FPC; ++f) {
+        const uint32_t urow = uv_s + (uint32_t)(min(k0 + f, K - 1) * A) * 4u;
+#pragma unroll
+        for (int i = 0; i < DEC_NA; ++i) {
+          const float e = lds_f32(urow + aoff4[i]);
+#pragma unroll
+          for (int q = 0; q < NR; ++q) p[q * DEC_FPC + f] = fmaf(wr[i], rcp_ge1(fmaf(ahr[q][i], e, 1.f)), p[q * DEC_FPC + f]);
+        }
+      }
+      att_warp_reduce<NR * DEC_FPC>(p, lane);
+      {
+        const int u = att_reduce_owner<NR * DEC_FPC>(lane), q = u / DEC_FPC, f = u % DEC_FPC;
+        const bool writer = NR == 3 ? ((lane & 1) == 0 && !((lane & 4) && (lane & 2))) : (lane & 7) == 0;      // one writer per value
+        if (writer && k0 + f < k1)
+          sts_f32(red_s + (uint32_t)((q * PK_WARPS + warp) * K + k0 + f) * 4u, p[0]);
+      }
+    }
+    GKA(2);
+    __syncthreads();
+    if (warp < ng) {                  // warp q: softmax over ALL K frames of row g + q
+      const float ba = __ldg(P.b_a2w);
+      const uint32_t s = sc_s + (uint32_t)((g + warp) * K) * 4u;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int kk = lane; kk < K; kk += 32) {
+        float qv = 0.f;
+#pragma unroll
+        for (int w = 0; w < PK_WARPS; ++w) qv += lds_f32(red_s + (uint32_t)((warp * PK_WARPS + w) * K + kk) * 4u);
+        qv += ba;
+        sts_f32(s + kk * 4u, qv);
+        mx = fmaxf(mx, qv);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int kk = lane; kk < K; kk += 32) { const float e = __expf(lds_f32(s + kk * 4u) - mx); sts_f32(s + kk * 4u, e); sum += e; }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+#pragma unroll 1
+      for (int kk = lane; kk < K; kk += 32) {
+        const float al = lds_f32(s + kk * 4u) * inv;
+        sts_f32(s + kk * 4u, al);
+        if (TRAIN) P.ALPHAs[((long)t * P.B + r0 + g + warp) * K + kk] = al;
+      }
+    }
+    __syncthreads();
+  }
+  GKA(3);
+  if (!v_behind && threadIdx.x == 0) {        // every score is computed: V[fb] goes over exp(2Uv)
+    fence_proxy_async_smem();
+    pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
+    pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
+    pk_tma_2d(sv.stages_u32 + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
+  }
+  pk_wait(sv.bulk_bar + 8 * PK_BULK_CHUNKS, bulk_phase & 1);
+  bulk_phase++;
+  GKA(4);
+  const uint32_t vs = sv.stages_u32 + v_off;            // two panels [K][Hh]
+#pragma unroll 1
+  for (int e = threadIdx.x; e < nrows * H; e += PK_THREADS) {
+    const int q = e / H, j = e - q * H;
+    const uint32_t vp = vs + (uint32_t)(j >= Hh ? K * Hh + (j - Hh) : j) * 4u;
+    const uint32_t s = sc_s + (uint32_t)(q * K) * 4u;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 4 <= K; k += 4) {
+      a0 = fmaf(lds_f32(s + k * 4u), lds_f32(vp + (uint32_t)(k * Hh) * 4u), a0);
+      a1 = fmaf(lds_f32(s + (k + 1) * 4u), lds_f32(vp + (uint32_t)((k + 1) * Hh) * 4u), a1);
+      a2 = fmaf(lds_f32(s + (k + 2) * 4u), lds_f32(vp + (uint32_t)((k + 2) * Hh) * 4u), a2);
+      a3 = fmaf(lds_f32(s + (k + 3) * 4u), lds_f32(vp + (uint32_t)((k + 3) * Hh) * 4u), a3);
+    }
+    for (; k < K; ++k) a0 = fmaf(lds_f32(s + k * 4u), lds_f32(vp + (uint32_t)(k * Hh) * 4u), a0);
+    const float af = (a0 + a1) + (a2 + a3);
+    if (TRAIN) P.AFs[((long)t * P.B + r0 + q) * H + j] = af;
+    store_split16(reinterpret_cast<__half*>(P.af_hi), reinterpret_cast<__half*>(P.af_lo), (long)(r0 + q) * H + j, af);
+  }
+  GKA(5);
+  __syncthreads();
+}
+
 // the greedy word loop of SAModel.sample (SAModel.py:182-219), grouped-cell form
+template <int SAMPLE>      // 1: sampling form (multinomial draw and / or training dropout; the logits are stored for the draw)
 __global__ void __launch_bounds__(PK_THREADS, 1)
 decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps) {
   __shared__ GroupParams Csm;
@@ -805,7 +1212,8 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   }
   for (int r = cta; r < R; r += G) {
     if (r < B) {
-      dec_token_inputs(P, r, 0);                      // token 0 = <bos> (SAModel.py:184)
+      if (SAMPLE) dec_token_inputs_drop(C, r, 0, 0);
+      else dec_token_inputs(P, r, 0);                 // token 0 = <bos> (SAModel.py:184)
     } else {
       const __half z = __float2half_rn(0.f);
       __half* xh = reinterpret_cast<__half*>(P.xt_hi); __half* xl = reinterpret_cast<__half*>(P.xt_lo);
@@ -831,9 +1239,9 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   unsigned int pick_target = 0;
   gprefetch(C, &s_sched[2], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
-  gphase<false>(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
+  gphase<SAMPLE != 0>(C, &s_sched[2], nullptr, maps.m, 1, sv, tmem_base, ps);
   grid_barrier(P.sync_counter, sync_target, G);
-  if (is_att) dec_attention<0>(P, &maps.m[GM_V], cta - (G - n_att), 0, sv, bulk_phase);
+  if (is_att) dec_attention_rows<1, 0>(P, &maps.m[GM_V], cta - (G - n_att), cta - (G - n_att), 1, 0, sv, bulk_phase);
   fence_proxy_async_smem();
   gprefetch(C, &s_sched[0], maps.m, sv, ps);
   grid_barrier(P.sync_counter, sync_target, G);
@@ -841,19 +1249,19 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   for (int t = 0; t < T; ++t) {
     pk_stamp(P.dbg_clock, cta, t, 0);
     // ===== F1: lstm_1 = cell(W_i2h1.xt + W_a2h1.gp + W_h2h1.h1)   [attention CTAs: still busy with step t's attention] =====
-    fused_cell_phase<0>(C, &s_sched[0], &s_sched[1], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
+    fused_cell_phase<SAMPLE ? 3 : 0>(C, &s_sched[0], &s_sched[1], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[1], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 1);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== F3: lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) =====
-    fused_cell_phase<0>(C, &s_sched[1], &s_sched[2], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
+    fused_cell_phase<SAMPLE ? 3 : 0>(C, &s_sched[1], &s_sched[2], maps.m, 1, t, (unsigned int)t, sv, tmem_base, ps);
     gprefetch(C, &s_sched[2], maps.m, sv, ps);
     pk_stamp(P.dbg_clock, cta, t, 3);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 4);
     // ===== G4: logits of step t  +  attention query of step t+1 (both read the buffer just written) =====
-    gphase<false>(C, &s_sched[2], &s_sched[0], maps.m, t & 1, sv, tmem_base, ps);
+    gphase<SAMPLE != 0>(C, &s_sched[2], &s_sched[0], maps.m, t & 1, sv, tmem_base, ps);
     pk_stamp(P.dbg_clock, cta, t, 5);
     grid_barrier(P.sync_counter, sync_target, G);
     pk_stamp(P.dbg_clock, cta, t, 6);
@@ -862,15 +1270,16 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
     // CTAs are not part of the pick barrier, they only observe it (for the early-exit flag) when they are done. =====
     pick_target += (unsigned int)(G - n_att);
     if (is_att) {
-      if (t + 1 < T) dec_attention<0>(P, &maps.m[GM_V], cta - (G - n_att), t + 1, sv, bulk_phase);
+      if (t + 1 < T) dec_attention_rows<1, 0>(P, &maps.m[GM_V], cta - (G - n_att), cta - (G - n_att), 1, t + 1, sv, bulk_phase);
       fence_proxy_async_smem();
       pk_stamp(P.dbg_clock, cta, t, 7);
       grid_barrier_observe(C.pick_ctr, pick_target);
     } else {
 #pragma unroll 1
       for (int r = cta; r < B; r += G - n_att) {
-        const int tokv = dec_pick_tiles(C, r, t, sv);
-        dec_token_inputs(P, r, tokv);
+        const int tokv = SAMPLE ? dec_sample_tiles(C, r, t, sv) : dec_pick_tiles(C, r, t, sv);
+        if (SAMPLE) dec_token_inputs_drop(C, r, tokv, t + 1);
+        else dec_token_inputs(P, r, tokv);
         __syncthreads();
       }
       if (t + 1 < T) gprefetch(C, &s_sched[0], maps.m, sv, ps);
@@ -954,7 +1363,7 @@ train_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__
     pk_stamp(P.dbg_clock, cta, t, 2);
     // ===== B: attention || lstm_1 (+ the recurrent product of lstm_2) =====
     if (is_att) {
-      dec_attention<1>(P, &maps.m[GM_V], cta - (G - n_att), t, sv, bulk_phase);
+      dec_attention_rows<1, 1>(P, &maps.m[GM_V], cta - (G - n_att), cta - (G - n_att), 1, t, sv, bulk_phase);
       fence_proxy_async_smem();
     } else {
       fused_cell_phase<2>(C, &s_sched[1], &s_sched[2], maps.m, 0, t, (unsigned int)t, sv, tmem_base, ps);
@@ -1144,8 +1553,18 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 4);
   // ===== B: temporal attention of every row =====
+  {   // a video's rows go to cpv CTAs, each takes a run of them (rows of one video share exp(2Uv) / V)
+    const int fdiv = P.feat_div, nvid = (B + fdiv - 1) / fdiv;
+    int cpv = max(1, min(fdiv, G / nvid));
+    while ((fdiv + cpv - 1) / cpv > ATT_MAX_ROWS) ++cpv;          // (fdiv <= XG_MAX_BEAM = 16: at most two CTAs more)
+    const int rpc = (fdiv + cpv - 1) / cpv;
 #pragma unroll 1
-  for (int r = cta; r < B; r += G) dec_attention<0>(P, &maps.m[GM_V], r, 0, sv, bulk_phase);
+    for (int u = cta; u < nvid * cpv; u += G) {
+      const int vid = u / cpv, part = u % cpv;
+      const int r0 = vid * fdiv + part * rpc, r1 = min(min(r0 + rpc, (vid + 1) * fdiv), B);
+      if (r0 < r1) dec_attention_rows<ATT_NR, 0>(P, &maps.m[GM_V], vid, r0, r1 - r0, 0, sv, bulk_phase);
+    }
+  }
   fence_proxy_async_smem();
   pk_stamp(P.dbg_clock, cta, 3, 5);
   grid_barrier(P.sync_counter, sync_target, G);
@@ -1446,8 +1865,15 @@ static int word_weight_maps(xg_context* ctx, TcState* ts, const WordTables* T, C
   return XG_OK;
 }
 
+// dec_attention_rows stages the queries of NR rows behind exp(2Uv) (and V, when it is fetched behind it)
+static bool att_rows_fit(const xg_dims& d, int K, int nr) {
+  const long euv = (long)K * d.att * 4, vb = (long)K * (d.att + d.rnn) * 4 <= (long)PK_STAGES * PK_STAGE_BYTES ? (long)K * d.rnn * 4 : 0;
+  return euv + vb + (long)nr * d.att * 4 <= (long)PK_STAGES * PK_STAGE_BYTES;
+}
+
 struct GroupedState {
   int R = 0, K = 0;
+  float* lraw = nullptr;
   char* pool = nullptr;
   size_t pool_bytes = 0;
   GroupParams hp;
@@ -1471,15 +1897,20 @@ static void grouped_release(xg_context* ctx) {
 
 // Greedy decoding on decode_grouped_kernel.  PK_FALLBACK: the shape is outside this kernel (the caller runs
 // decode_persistent_kernel<0>, which covers every shape persist_eligible() accepts).
+struct GroupedSampling {      // sampling form of the loop: multinomial draw (sample_max = 0) and / or the training dropout of the step
+  int sample_max = 1; float temperature = 1.f; uint64_t seed = 0;
+  bool step_drop = false; uint64_t drop_seed = 0;
+};
 static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
-                          int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st) {
+                          int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st,
+                          const GroupedSampling* smp = nullptr) {
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + GK_KB - 1) / GK_KB * GK_KB, G = ctx->sm_count;
   if (env_flag("XG_NO_GROUPED") || !persist_eligible(ctx, B, K) || T > 2048 || H % GK_KB != 0 || Ep > DEC_TI * PK_THREADS) return PK_FALLBACK;
   const int kbH = H / GK_KB, kbE = Ep / GK_KB;
   const int ntiles = H / 32, ncb = R / PK_BN, groups = ntiles * ncb;
-  if (groups > G || 4 * H > 32000) return PK_FALLBACK;
+  if (groups > G || 4 * H > 32000 || !att_rows_fit(d, K, 1)) return PK_FALLBACK;
   // the attention of step t+1 keeps the last n_att CTAs through the pick phase and F1: F1's groups live on the others
   const int n_att = B;
   if (ncb != 1 || G - R < groups || G - R < B) return PK_FALLBACK;
@@ -1615,6 +2046,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
       S->d_dbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
       hp.gsched = a.take<GSched>(sched.size());
       hp.lpart = a.take<float4>((size_t)R * ntv);
+      S->lraw = a.take<float>((size_t)R * ntv * 128);
       dp.d[DD_AH].out = a.take<float>((size_t)PK_MAX_SLOTS * R * A);   // [slot][caption][row]
       for (int q = 0; q < 2; ++q) hp.fslots[q] = a.take<float>((size_t)groups * nslots_l[q] * PK_BN * 128);
       // fp16 hi / lo pairs (the DecParams fields are float*: the pointwise phases cast them back when x16 is set)
@@ -1642,7 +2074,16 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = n_att;
   hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
-  hp.topk = 0; hp.lraw = nullptr;
+  hp.topk = 0; hp.lraw = smp ? S->lraw : nullptr;
+  hp.sample_max = smp ? smp->sample_max : 1; hp.step_drop = smp && smp->step_drop ? 1 : 0;
+  hp.inv_temp = smp && !smp->sample_max ? 1.f / smp->temperature : 1.f;
+  hp.sample_seed = smp ? smp->seed : 0;
+  {
+    const bool dr = smp && smp->step_drop;
+    hp.drop_gate = make_drop(dr, d.drop_prob, smp ? smp->drop_seed : 0, XG_DROP_DEC_GATE);
+    hp.drop_h1 = make_drop(dr, d.drop_prob, smp ? smp->drop_seed : 0, XG_DROP_DEC_H1);
+    hp.drop_h2 = make_drop(dr, d.drop_prob, smp ? smp->drop_seed : 0, XG_DROP_DEC_H2);
+  }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
 
@@ -1694,9 +2135,10 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
   if (dp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
   if (!S->attr_set) {
-    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
     int nb = 0;
-    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_grouped_kernel, PK_THREADS, GK_SMEM_BYTES));
+    XG_CUDA_TRY(ctx->es, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_grouped_kernel<1>, PK_THREADS, GK_SMEM_BYTES));
     XG_REQUIRE(ctx->es, nb >= 1, XG_ERR_CUDA, "grouped decoder does not fit on an SM");
     S->attr_set = true;
   }
@@ -1704,7 +2146,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     ProfScope ps(ctx, "decode_persistent", st);
     const GroupParams* gp = S->d_params;
     void* args[2] = {(void*)&gp, (void*)&mt};
-    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_grouped_kernel, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
+    void* fn = smp ? (void*)decode_grouped_kernel<1> : (void*)decode_grouped_kernel<0>;
+    XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
     ctx->n_fused++;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
@@ -1790,7 +2233,7 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
     return PK_FALLBACK;
   const int kbH = H / GK_KB;
   const int groups = H / 32, ncb = R / PK_BN, nat = (A + 127) / 128;
-  if (ncb != 1 || G - R < groups + 1) return PK_FALLBACK;
+  if (ncb != 1 || G - R < groups + 1 || !att_rows_fit(d, K, 1)) return PK_FALLBACK;
   // (the schedule depends on the padded row count only, never on B)
   const int avail = G - R;                       // CTAs of phase B that do not run the attention
   const int nv = kbH >= 2 ? 2 : 1;               // early slots of lstm_2: W_h2h2.h2 cut in nv runs
@@ -1902,6 +2345,8 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
   hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
   hp.topk = 0; hp.lraw = nullptr; hp.lpart = nullptr;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0;
+  hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
   WordTables* WT = nullptr;
@@ -2020,6 +2465,7 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
       Ep > DEC_TI * PK_THREADS || 4 * H > 32000)
     return PK_FALLBACK;
   if (io.logp != nullptr || io.ys == nullptr || io.ix == nullptr || io.topk < 1 || io.topk > GK_TOPK) return PK_FALLBACK;
+  if (!att_rows_fit(d, K, ATT_NR)) return PK_FALLBACK;
   GroupedStepState*& S = grouped_step_state(ctx);
   if (!S) S = new GroupedStepState();
   GroupParams& hp = S->hp;
@@ -2065,8 +2511,11 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
           fprintf(stderr, "[xg grouped step trace] cta 0 fused layer %d (cycles after phase entry): producer done %lld, epilogue warp done %lld, "
                   "cta synced %lld, group counter seen %lld, cta synced %lld, cell done %lld\n", l, f[l * 16 + 1] - f[l * 16], f[l * 16 + 2] - f[l * 16],
                   f[l * 16 + 3] - f[l * 16], f[l * 16 + 4] - f[l * 16], f[l * 16 + 5] - f[l * 16], f[l * 16 + 6] - f[l * 16]);
-        long long w[24];
+        long long w[32];
         cudaMemcpy(w, S->d_dbg + (2048 + 256) * PK_STAMPS + 32, sizeof(w), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[xg grouped step trace] cta 0 attention (cycles after entry): weights loaded %lld, slot loads issued %lld, copies issued %lld, staged %lld, "
+                "query ready %lld, chunks done %lld, softmax done %lld, V landed %lld, contexts stored %lld\n",
+                w[28] - w[22], w[29] - w[22], w[30] - w[22], w[31] - w[22], w[23] - w[22], w[24] - w[22], w[25] - w[22], w[26] - w[22], w[27] - w[22]);
         fprintf(stderr, "[xg grouped step trace] cta 0, all GEMM phases of %u launches, %lld k-blocks per launch: producer %lld cycles in phases, %lld waiting for a free stage | "
                 "MMA warp %lld in phases, waits: data %lld, accumulator free %lld, cross accumulator free %lld | epilogue warp %lld in phases, waits: accumulator full %lld, cross full %lld\n",
                 S->launches, w[4] / S->launches, w[0], w[1], w[8], w[9], w[10], w[11], w[16], w[17], w[18]);
@@ -2222,6 +2671,8 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = 0;
   hp.nslots[0] = members_l[0]; hp.nslots[1] = members_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0;
+  hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
   WordTables* WT = nullptr;

@@ -499,8 +499,15 @@ __device__ __forceinline__ float ord2f(unsigned o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 // ex2/rcp-based activations: |error| ~1e-7 absolute, a handful of instructions each
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// 1 / x for x >= 1 (or +inf): the bare MUFU.RCP.  __fdividef(1.f, x) wraps it in a subnormal-input check (FSETP, FMUL, FSEL,
+// FMUL: 7 instructions per attention element instead of 3), which the attention loops cannot need: x = 1 + e^{2ah} e^{2uv}.
+__device__ __forceinline__ float rcp_ge1(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_ge1(1.f + __expf(2.f * x)), 1.f); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ge1(1.f + __expf(-x)); }
 
 // ====================================================================================
 // decoder
@@ -692,7 +699,7 @@ __device__ __noinline__ void dec_attention(const DecParams& P, const CUtensorMap
       p[f] = wsum;
       const float* u = uv + (long)min(k0 + f, K - 1) * A;
 #pragma unroll
-      for (int i = 0; i < DEC_NA; ++i) p[f] = fmaf(wr[i], __fdividef(1.f, fmaf(ahr[i], u[aoff[i]], 1.f)), p[f]);
+      for (int i = 0; i < DEC_NA; ++i) p[f] = fmaf(wr[i], rcp_ge1(fmaf(ahr[i], u[aoff[i]], 1.f)), p[f]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

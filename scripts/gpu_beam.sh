@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-XG_PERSIST_TRACE=1 timeout 300 python scripts/profile_path.py beam 1 2>&1 | grep "trace" | tail -9 > gpurun_out/prof_beam_g.txt; cat gpurun_out/prof_beam_g.txt
+XG_PERSIST_TRACE=1 timeout 300 python scripts/profile_path.py beam 1 2>&1 | grep "trace" | tail -6 > gpurun_out/prof_beam_g.txt; cat gpurun_out/prof_beam_g.txt
 timeout 300 python scripts/profile_path.py beam 3 2>&1 | grep -v Warn | head -4
-timeout 300 python scripts/profile_path.py greedy 3 2>&1 | grep -v Warn | head -5
-timeout 300 python scripts/profile_path.py train 3 2>&1 | grep -v Warn | head -5
 ( timeout 1200 python -m pytest tests -m gpu -q -x ) > gpurun_out/pytest_gpu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log

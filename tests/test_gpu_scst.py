@@ -107,3 +107,55 @@ def test_scheduled_sampling_forward_matches_oracle_on_the_tokens_used(name, ss):
     names = [k for k, v in Pg.items() if v.requires_grad]
     grads = torch.autograd.grad(loss_o, [Pg[k] for k in names], allow_unused=True)
     _grad_check(m, {k: (gr.numpy() if gr is not None else np.zeros(tuple(Pg[k].shape), np.float32)) for k, gr in zip(names, grads)})
+
+
+@pytest.mark.parametrize("name,sample_max", [("mid", 0), ("mid", 1), ("c1", 0)])
+def test_training_mode_sampling_loop_runs_on_the_grouped_kernel(name, sample_max):
+    """The sampling word loop (multinomial draw and / or training dropout, SAModel.py:188-196 under model.train()) runs as
+    one launch of decode_grouped_kernel<1> (asserted: strict handle + launch list) and draws the tokens the per-step
+    launches draw from the same Philox streams (a draw that lands within rounding of a CDF step may differ)."""
+    from tests.common import fused_path
+    cfg, P, b = make_case(name); d = dev(b)
+    res = []
+    for persistent in (True, False):
+        m = build_model(cfg, P, drop=0.5).train()
+        m._engine.set_engine(True, persistent)
+        torch.manual_seed(123)
+        with torch.no_grad():
+            if persistent:
+                with fused_path(m, ["encode_persistent", "decode_persistent"]):
+                    seq, lp = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": sample_max, "beam_size": 1})
+            else:
+                seq, lp = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": sample_max, "beam_size": 1})
+        res.append((seq.cpu(), lp.cpu()))
+    (s0, l0), (s1, l1) = res
+    n = min(s0.shape[1], s1.shape[1])
+    same_rows = (s0[:, :n] == s1[:, :n]).all(dim=1)
+    assert same_rows.float().mean().item() >= 0.9, (s0, s1)
+    assert rel_err(l0[:, :n][same_rows].numpy(), l1[:, :n][same_rows].numpy()) < 1e-3
+
+
+def test_multinomial_sampling_distribution_on_the_grouped_kernel():
+    """sample_max=0 in eval mode on decode_grouped_kernel<1>: the first token of 64 x 64 draws follows exp(logp / T)."""
+    from tests.common import fused_path
+    cfg, P, b = make_case("c1")
+    B, reps, T = 64, 64, 0.8
+    m = build_model(cfg, P).eval()
+    one = {k: (v[:1].repeat(B, *([1] * (v.dim() - 1))) if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+    d = dev(one)
+    first, lps0 = [], []
+    with fused_path(m, ["encode_persistent", "decode_persistent"]):
+        for i in range(reps):
+            torch.manual_seed(1000 + i)
+            seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 0, "temperature": T})
+            first.append(seq[:, 0].cpu()); lps0.append(lps[:, 0].cpu())
+    first = torch.cat(first).numpy(); lps0 = torch.cat(lps0).numpy()
+    with torch.no_grad():
+        V = O.encoder_fwd(P, b["rgb"][:1], b["opfl"][:1], b["feat_mask"][:1])
+        st = O.init_hidden(P, V, b["feat_mask"][:1])
+        lp0, _ = O.get_logprobs_state(P, torch.zeros(1, dtype=torch.long), V, b["pos"][:1], st)
+    prob = torch.softmax(lp0[0] / T, 0).numpy()
+    freq = np.bincount(first, minlength=prob.size) / (B * reps)
+    assert np.abs(freq - prob).max() < 4 * np.sqrt(prob.max() / (B * reps)) + 5e-3
+    nz = first > 0
+    assert np.allclose(lps0[nz], lp0[0][torch.from_numpy(first)].numpy()[nz], atol=1e-4)      # log-probs at temperature 1
