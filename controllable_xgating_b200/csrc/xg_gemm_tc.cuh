@@ -206,7 +206,7 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * 128 * 128 + 2 * BN * 128;
   static constexpr int kStages = (BN == 64) ? 4 : 3;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = (BN == 64) ? 256 : 512;   // 2 ping-pong + 1 small accumulator, power of 2
+  static constexpr int kTmemCols = (BN == 64) ? 256 : 512;   // 2 ping-pong accumulator pairs (main | cross), power of 2
   static constexpr int kChunk = 2;                            // k-blocks (of 32) per accumulation chain
   static constexpr int kThreads = 192;                        // producer warp, MMA warp, 4 epilogue warps
 };
@@ -247,7 +247,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_small = tmem_base + 2 * BN;
 
   // warp-uniform role dispatch (the whole warp walks the loops, one elected lane issues): inside a divergent
   // `lane == 0` region every UTCHMMA / UTMALDG compiles to an ELECT + R2UR.BROADCAST waterfall (~90 cycles each)
@@ -276,16 +275,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
     }
   } else if (uwarp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+    // Per k-step (K = 8) TWO instructions: P_hi . [Q_hi ; Q_lo] as one N = 2 BN product (the hi and lo tiles of Q lie back
+    // to back in the stage: main term -> columns [0, BN), cross term hi.lo -> [BN, 2 BN) of the accumulator pair) and
+    // P_lo . Q_hi (N = BN) onto the cross columns.  Three N = BN instructions per k-step cost ~130 cycles each here (ncu,
+    // profiles/r1n_gemm_tc128_*): the issue rate of the MMA warp and the re-read of the P_hi tile paced the main loop.
+    constexpr uint32_t idesc = umma_idesc_tf32(128, BN), idesc2 = umma_idesc_tf32(128, 2 * BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t tsmall = tb + 2 * BN;
     const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
     for (int c = 0; c < num_chunks; ++c) {
       const int b = c & 1;
-      mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      mbar_wait(&acc_empty[b], ((c >> 1) & 1) ^ 1);       // epilogue has drained this accumulator pair
       tc_fence_after();
-      const uint32_t tmem_main = tb + b * BN;
+      const uint32_t tmem_pair = tb + b * 2 * BN;
       for (int kk = 0; kk < kchunk; ++kk) {
         const int kb = c * kchunk + kk;
         if (kb >= num_kb) break;
@@ -298,22 +300,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
           for (int k4 = 0; k4 < 4; ++k4) {         // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
             const uint64_t ph_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + (1u << 16));
             const uint64_t pl_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((128 * 128) >> 4) + (1u << 16));
-            const uint64_t qh_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128) >> 4) + (1u << 16));
-            const uint64_t ql_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128 + BN * 128) >> 4) + (1u << 16));
+            const uint64_t qh_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128) >> 4) + (1u << 16));      // 2 BN rows: Q_hi, Q_lo
             if (prm.dbg & 1) continue;
-            umma_tf32(tmem_main, ph_d, qh_d, idesc, (kk | k4) != 0);
-            umma_tf32(tsmall, pl_d, qh_d, idesc, (kb | k4) != 0);
-            umma_tf32(tsmall, ph_d, ql_d, idesc, 1);
+            umma_tf32(tmem_pair, ph_d, qh_d, idesc2, (kk | k4) != 0);
+            umma_tf32(tmem_pair + BN, pl_d, qh_d, idesc, 1);
           }
           umma_commit(&empty_bar[s]);               // stage reusable once these MMAs have read it
           if (kk == kchunk - 1 || kb == num_kb - 1) umma_commit(&acc_full[b]);   // this chain is complete
-          if (kb == num_kb - 1) umma_commit(small_full);
         }
         __syncwarp();
       }
     }
   } else {
-    // ===== epilogue warps: drain short chains into fp32 registers, then fused epilogue =====
+    // ===== epilogue warps: drain short chains (main + cross columns) into fp32 registers, then fused epilogue =====
     const int quad = warp & 3;                      // TMEM lanes [32*quad, 32*quad+32) belong to this warp
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int p = p0 + quad * 32 + lane;            // TMEM lane == row p of the tile
@@ -326,24 +325,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < BN; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_base + (uint32_t)(b * BN + cc), r);
+        uint32_t r[32], r2[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(b * 2 * BN + cc), r);
+        tmem_ld32(tmem_base + lane_base + (uint32_t)(b * 2 * BN + BN + cc), r2);
         tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
+        for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]) + __uint_as_float(r2[u]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
-    }
-    mbar_wait(small_full, 0);
-    tc_fence_after();
-#pragma unroll
-    for (int cc = 0; cc < BN; cc += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_small + lane_base + (uint32_t)cc, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]);
     }
     const Epilogue& ep0 = prm.g.ep;
     const bool direct = prm.swap_out && !ep0.drop.on() && ep0.aux == nullptr && ep0.tgt == nullptr && ep0.beta == 0.f &&
