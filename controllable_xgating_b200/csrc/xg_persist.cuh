@@ -1433,6 +1433,7 @@ __global__ void transpose_kernel(const float* __restrict__ W, int rows, int cols
 // ====================================================================================
 enum { DB_GB = 0, DB_GC, DB_GD, DB_GG, DB_GH, DB_COUNT };
 constexpr int DECB_MAX_SLOTS = 20;
+constexpr int DECB_SPARE_SHARES = 5;
 
 struct DecBwdParams {
   GDesc d[DB_COUNT];
@@ -1453,6 +1454,7 @@ struct DecBwdParams {
   float* dC[2];                 // (B, H) carried dc of lstm_1 / lstm_2
   DropSpec drop1, drop2;
   unsigned int* sync_counter;
+  long long* dbg_clock;         // diagnostics (XG_PERSIST_TRACE), or NULL
 };
 
 // lstm cell backward of `layer` at step i for the elements of this partition
@@ -1501,92 +1503,104 @@ __device__ __noinline__ void decb_cell_phase(const DecBwdParams& P, int layer, i
   }
 }
 
-// attention backward of caption r at step i, split `sp` of 2 (attention units and frames are halved)
-__device__ __noinline__ void decb_attention(const DecBwdParams& P, int r, int sp, int i, const SmemView& sv) {
+// shared-window accessors (generic loads from shared memory cost three address instructions each)
+__device__ __forceinline__ float pk_lds(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void pk_sts(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+// fire-and-forget accumulation (RED.ADD): every element has ONE writer per step and the steps are separated by grid
+// barriers, so the sums are formed in a fixed order
+__device__ __forceinline__ void pk_red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+// attention backward of caption r at step i, split `sp` of 2 (attention units and frames are halved).
+// V[r] (K x H) and this split's half of Uv[r] (K x A/2) are fetched into the idle pipeline stages by bulk copies at
+// entry (one transfer instead of ~25 dependent L2 round trips: the phase took 30 of the 62 us of a step), the
+// accumulations into dV / dUv / dw_a2w / db_a2w are RED.ADDs instead of read-modify-writes.
+__device__ __noinline__ void decb_attention(const DecBwdParams& P, int r, int sp, int i, const SmemView& sv, uint32_t& bulk_phase) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = P.K, A = P.A, H = P.H, B = P.B;
-  float* al = sv.scratch;           // K
-  float* ds = al + K;               // K
-  float* daf = ds + K;              // H
-  for (int k = threadIdx.x; k < K; k += PK_THREADS) al[k] = P.ALPHAs[((long)i * B + r) * K + k];
-#pragma unroll 1
-  for (int j = threadIdx.x; j < H; j += PK_THREADS) {
-    float v[DECB_MAX_SLOTS];
-    zload(P.d[DB_GC], P.R, r, j, v);
-    daf[j] = zadd(v);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int k = warp; k < K; k += PK_WARPS) {
-    const float* v = P.Vf + ((long)r * K + k) * H;
-    float p = 0.f;
-#pragma unroll 1
-    for (int j0 = lane; j0 < H; j0 += 32 * 8) {
-      float vv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) vv[q] = __ldg(v + min(j0 + 32 * q, H - 1));
-#pragma unroll
-      for (int q = 0; q < 8; ++q) p += (j0 + 32 * q < H ? daf[min(j0 + 32 * q, H - 1)] : 0.f) * vv[q];
+  const int aper = (A + 1) / 2, a0 = sp * aper, a1 = min(A, a0 + aper), na = a1 - a0;
+  const uint32_t v_s = sv.stages_u32;                                   // [K][H]
+  const uint32_t uv_s = sv.stages_u32 + (uint32_t)K * H * 4u;           // [K][na]
+  const uint32_t al_s = smem_u32(sv.scratch);                           // K
+  const uint32_t ds_s = al_s + (uint32_t)K * 4u;                        // K
+  const uint32_t daf_s = ds_s + (uint32_t)K * 4u;                       // H
+  if (warp == 0) {
+    if (lane == 0) {
+      pk_expect_tx(sv.bulk_bar, (uint32_t)K * H * 4u);
+      bulk_g2s(v_s, P.Vf + (long)r * K * H, (uint32_t)K * H * 4u, sv.bulk_bar);
+      pk_expect_tx(sv.bulk_bar + 8, (uint32_t)K * na * 4u);
     }
-    p = warp_sum(p);
-    if (lane == 0) ds[k] = p;
+    __syncwarp();
+    for (int k = lane; k < K; k += 32)
+      bulk_g2s(uv_s + (uint32_t)(k * na) * 4u, P.Uv + ((long)r * K + k) * A + a0, (uint32_t)na * 4u, sv.bulk_bar + 8);
+  }
+  for (int k = threadIdx.x; k < K; k += PK_THREADS) pk_sts(al_s + k * 4u, P.ALPHAs[((long)i * B + r) * K + k]);
+  {   // dAF[r, :] = sum of the split-K slots of dz2.W_a2h2: float4 columns, every slot load of a thread in flight at once
+    const GDesc& dc = P.d[DB_GC];
+    const long sstr4 = (long)P.R * (dc.n_rows >> 2);
+#pragma unroll 1
+    for (int j4 = threadIdx.x; j4 < (H >> 2); j4 += PK_THREADS) {
+      const float4* src = reinterpret_cast<const float4*>(dc.out + (long)r * dc.n_rows) + j4;
+      float4 v[DECB_MAX_SLOTS];
+#pragma unroll
+      for (int k = 0; k < DECB_MAX_SLOTS; ++k) v[k] = k < dc.ns ? __ldcg(src + k * sstr4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < DECB_MAX_SLOTS; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+      pk_sts(daf_s + (j4 * 4) * 4u, sum.x); pk_sts(daf_s + (j4 * 4 + 1) * 4u, sum.y);
+      pk_sts(daf_s + (j4 * 4 + 2) * 4u, sum.z); pk_sts(daf_s + (j4 * 4 + 3) * 4u, sum.w);
+    }
   }
   __syncthreads();
+  pk_wait(sv.bulk_bar, bulk_phase & 1);             // V[r] landed
+#pragma unroll 1
+  for (int k = warp; k < K; k += PK_WARPS) {        // ds[k] = dAF . V[r, k, :]
+    float p = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < H; j += 32) p = fmaf(pk_lds(daf_s + j * 4u), pk_lds(v_s + (uint32_t)(k * H + j) * 4u), p);
+    p = warp_sum(p);
+    if (lane == 0) pk_sts(ds_s + k * 4u, p);
+  }
   {   // dV[r, k, :] += alpha_k * dAF[r, :]  for this split's frames
     const int kper = (K + 1) / 2, kb0 = sp * kper, kb1 = min(K, kb0 + kper);
     const int n = max(0, kb1 - kb0) * H;
     float* dv = P.dV + ((long)r * K + kb0) * H;
-#pragma unroll 1
-    for (int e0 = threadIdx.x; e0 < n; e0 += PK_THREADS * 8) {
-      float old[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) old[q] = dv[min(e0 + PK_THREADS * q, n - 1)];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int e = e0 + PK_THREADS * q;
-        if (e < n) dv[e] = old[q] + al[kb0 + e / H] * daf[e % H];
-      }
+#pragma unroll 4
+    for (int e = threadIdx.x; e < n; e += PK_THREADS) {
+      const int kk = e / H, j = e - kk * H;
+      pk_red_add(dv + e, pk_lds(al_s + (kb0 + kk) * 4u) * pk_lds(daf_s + j * 4u));
     }
   }
+  __syncthreads();
   float dot = 0.f;
-  for (int k = 0; k < K; ++k) dot += al[k] * ds[k];   // every thread computes the same fixed-order sum
+  for (int k = 0; k < K; ++k) dot += pk_lds(al_s + k * 4u) * pk_lds(ds_s + k * 4u);   // every thread computes the same fixed-order sum
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += PK_THREADS) ds[k] = al[k] * (ds[k] - dot);
+  for (int k = threadIdx.x; k < K; k += PK_THREADS) pk_sts(ds_s + k * 4u, pk_lds(al_s + k * 4u) * (pk_lds(ds_s + k * 4u) - dot));
   __syncthreads();
-  const int aper = (A + 1) / 2, a0 = sp * aper, a1 = min(A, a0 + aper);
+  pk_wait(sv.bulk_bar + 8, bulk_phase & 1);         // this split's half of Uv[r] landed
+  bulk_phase++;
 #pragma unroll 1
-  for (int a = a0 + threadIdx.x; a < a1; a += PK_THREADS) {
+  for (int al = threadIdx.x; al < na; al += PK_THREADS) {
+    const int a = a0 + al;
     const float w = __ldg(P.w_a2w + a), h0 = P.AHs[((long)i * B + r) * A + a];
     float acc_ah = 0.f, acc_wa = 0.f;
-    const long base = (long)r * K * A + a;
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      float uu[8], dd[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const long idx = base + (long)min(k0 + q, K - 1) * A;
-        uu[q] = __ldg(P.Uv + idx);
-        dd[q] = P.dUv[idx];
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (k0 + q < K) {
-          const float th = tanh_fast(h0 + uu[q]);
-          const float dp = ds[k0 + q] * w * (1.f - th * th);
-          P.dUv[base + (long)(k0 + q) * A] = dd[q] + dp;
-          acc_ah += dp;
-          acc_wa += ds[k0 + q] * th;
-        }
-      }
+    float* du = P.dUv + (long)r * K * A + a;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float th = tanh_fast(h0 + pk_lds(uv_s + (uint32_t)(k * na + al) * 4u));
+      const float dsk = pk_lds(ds_s + k * 4u);
+      const float dp = dsk * w * (1.f - th * th);
+      pk_red_add(du + (long)k * A, dp);
+      acc_ah += dp;
+      acc_wa = fmaf(dsk, th, acc_wa);
     }
     P.DAH[((long)i * B + r) * A + a] = acc_ah;
     store_split(P.dah_hi, P.dah_lo, (long)r * A + a, acc_ah);
-    P.dwa_part[(long)r * A + a] += acc_wa;
+    pk_red_add(P.dwa_part + (long)r * A + a, acc_wa);
   }
   if (threadIdx.x == 0 && sp == 0) {
     float sdb = 0.f;
-    for (int k = 0; k < K; ++k) sdb += ds[k];
-    P.dba_part[r] += sdb;
+    for (int k = 0; k < K; ++k) sdb += pk_lds(ds_s + k * 4u);
+    pk_red_add(P.dba_part + r, sdb);
   }
   __syncthreads();
 }
@@ -1611,26 +1625,46 @@ decode_bwd_persistent_kernel(const DecBwdParams* __restrict__ Pp, const __grid_c
   if (threadIdx.x < 11) tma_prefetch_desc(&maps.m[threadIdx.x]);
   PipeState ps{0, 0, 0, 0};
   unsigned int sync_target = 0;
+  uint32_t bulk_phase = 0;
 
 #pragma unroll 1
   for (int i = T - 1; i >= 0; --i) {
+    const int ts = T - 1 - i;      // (stamps: step 3 of the loop)
+    pk_stamp(P.dbg_clock, cta, ts, 0);
     decb_cell_phase(P, 1, i, cta, G);                                            // Pa
     gemm_prefetch(P.d, &s_sched[0], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, ts, 1);
     grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, ts, 2);
     gemm_phase(P.d, &s_sched[0], &s_sched[1], maps.m, R, sv, tmem_base, ps);     // Gb
+    pk_stamp(P.dbg_clock, cta, ts, 3);
     grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, ts, 4);
     if (G >= 2 * B + 8) {          // Pc, enough SMs: caption halves and cell elements on disjoint CTAs
-      if (cta < 2 * B) decb_attention(P, cta >> 1, cta & 1, i, sv);
-      else decb_cell_phase(P, 0, i, cta - 2 * B, G - 2 * B);
+      // the cell elements are dealt in shares: one to every attention CTA (after its caption half), DECB_SPARE_SHARES to every
+      // spare CTA (with all of them on the G - 2B spare CTAs those finished 9 us after the attention)
+      const int nparts = 2 * B + (G - 2 * B) * DECB_SPARE_SHARES;
+      if (cta < 2 * B) {
+        decb_attention(P, cta >> 1, cta & 1, i, sv, bulk_phase);
+        decb_cell_phase(P, 0, i, cta, nparts);
+      } else {
+#pragma unroll 1
+        for (int w = 0; w < DECB_SPARE_SHARES; ++w) decb_cell_phase(P, 0, i, 2 * B + (cta - 2 * B) * DECB_SPARE_SHARES + w, nparts);
+      }
     } else {                       // large batches: every CTA walks its caption halves, then its cell elements
 #pragma unroll 1
-      for (int u = cta; u < 2 * B; u += G) decb_attention(P, u >> 1, u & 1, i, sv);
+      for (int u = cta; u < 2 * B; u += G) decb_attention(P, u >> 1, u & 1, i, sv, bulk_phase);
       decb_cell_phase(P, 0, i, cta, G);
     }
+    fence_proxy_async_smem();      // the stages were read through the generic proxy: order before the TMA refill
     gemm_prefetch(P.d, &s_sched[1], maps.m, sv, ps);
+    pk_stamp(P.dbg_clock, cta, ts, 5);
     grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, ts, 6);
     gemm_phase(P.d, &s_sched[1], &s_sched[0], maps.m, R, sv, tmem_base, ps);     // Gd
+    pk_stamp(P.dbg_clock, cta, ts, 7);
     grid_barrier(P.sync_counter, sync_target, G);
+    pk_stamp(P.dbg_clock, cta, ts, 8);
   }
   // gradients of the initial state: pass-through parts + the products of step 0
 #pragma unroll 1
@@ -1725,6 +1759,7 @@ struct PersistState {
   DecBwdParams dbp;
   DecBwdParams* d_dbparams = nullptr;
   unsigned int* d_dbcounter = nullptr;
+  long long* d_dbdbg = nullptr;
   float* dbwT[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool dbattr_set = false;
   // encoder backward
@@ -2247,8 +2282,8 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
   const xg_dims& d = ctx->d;
   const int H = d.rnn, A = d.att, G = ctx->sm_count;
   if (!ctx->persist_mode || H % 32 != 0 || A % 32 != 0 || B < 1 || B > PK_MAX_ROWS || G < 16 || G > 256 || T < 1 ||
-      2 * K + H + 8 > PK_SCRATCH_FLOATS)
-    return persist_refuse(ctx, "the backward word loop", "rnn_size and att_size must be multiples of 32, at most 1024 captions");
+      2 * K + H + 8 > PK_SCRATCH_FLOATS || (long)K * (H + A / 2) * 4 > (long)PK_STAGES * PK_STAGE_BYTES || (long)K * H * 4 >= (1L << 20))
+    return persist_refuse(ctx, "the backward word loop", "rnn_size and att_size must be multiples of 32, at most 1024 captions, V[b] and half of Uv[b] within 192 KB");
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN;
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
@@ -2275,6 +2310,7 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
       Arena a(pass == 0 ? nullptr : S->dbpool, pass == 0 ? 0 : S->dbpool_bytes);
       S->d_dbparams = a.take<DecBwdParams>(1);
       S->d_dbcounter = a.take<unsigned int>(64);
+      S->d_dbdbg = a.take<long long>((2048 + 256) * PK_STAMPS + 64);
       bp.sched = a.take<PSched>(sched.size());
       for (int i = 0; i < DB_COUNT; ++i) bp.d[i].out = a.take<float>((size_t)bp.d[i].ns * R * bp.d[i].n_rows);
       bp.dz2_hi = a.take<float>((long)R * 4 * H); bp.dz2_lo = a.take<float>((long)R * 4 * H);
@@ -2316,6 +2352,7 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
   bp.dHcar = io.dHcar; bp.dC[0] = io.dC1; bp.dC[1] = io.dC2;
   bp.drop1 = io.drop1; bp.drop2 = io.drop2;
   bp.sync_counter = S->d_dbcounter;
+  bp.dbg_clock = (env_flag("XG_PERSIST_TRACE") && T <= 2048) ? S->d_dbdbg : nullptr;
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_dbparams, &bp, sizeof(DecBwdParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbcounter, 0, sizeof(unsigned int) * 64, st));
   if (!S->dbattr_set) {
@@ -2330,6 +2367,24 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
   void* args[2] = {(void*)&dp, (void*)&mt};
   XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_bwd_persistent_kernel, dim3(G), dim3(PK_THREADS), args, PK_SMEM_BYTES, st));
   ctx->n_fused++;
+  if (bp.dbg_clock && T > 4 && G <= 256) {   // XG_PERSIST_TRACE=1: phase timeline of the fourth step, all CTAs
+    XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+    std::vector<long long> ga((size_t)G * PK_STAMPS);
+    cudaMemcpy(ga.data(), S->d_dbdbg + 2048 * PK_STAMPS, sizeof(long long) * ga.size(), cudaMemcpyDeviceToHost);
+    const char* names[4] = {"Pa (lstm_2 cell bwd)", "Gb (dz2 products)", "Pc (attention bwd || lstm_1 cell bwd)", "Gd (dz1, dAH products)"};
+    for (int i = 0; i < 4; ++i) {
+      long long open = 0, close = 0;
+      for (int c = 0; c < G; ++c) open = std::max(open, ga[(size_t)c * PK_STAMPS + 2 * i]);
+      std::vector<long long> fin(G);
+      for (int c = 0; c < G; ++c) fin[c] = ga[(size_t)c * PK_STAMPS + 2 * i + 1] - open;
+      std::vector<long long> srt = fin;
+      std::sort(srt.begin(), srt.end());
+      for (int c = 0; c < G; ++c) close = std::max(close, ga[(size_t)c * PK_STAMPS + 2 * i + 2]);
+      const int worst = (int)(std::max_element(fin.begin(), fin.end()) - fin.begin());
+      fprintf(stderr, "[xg bwd trace] step 3 %-38s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
+              names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, close - open);
+    }
+  }
   return XG_OK;
 }
 
