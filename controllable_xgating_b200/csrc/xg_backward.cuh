@@ -170,7 +170,11 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
 
   // ---------------- heads ----------------
   if (dlogp) {
-    XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 256, 0, st, logp, dlogp, B, Lp, V, W.DLOGITS));
+    if (logsoftmax_reg_ok(logp, V, V, W.DLOGITS, V) && ((uintptr_t)dlogp & 15) == 0) {
+      XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_reg_kernel, LB, 256, 0, st, logp, dlogp, B, Lp, V, W.DLOGITS));
+    } else {
+      XG_TRY(launch(ctx, "logsoftmax_bwd_rows", logsoftmax_bwd_rows_kernel, LB, 256, 0, st, logp, dlogp, B, Lp, V, W.DLOGITS));
+    }
     XG_TRY(wgrad(ctx, W.DLOGITS, V, OUT, ldo, G[XG_P_LOGIT_W], V, H, LB, beta, st));
     XG_TRY(cs.add(ctx, W.DLOGITS, V, LB, V, beta, G[XG_P_LOGIT_B], nullptr, nullptr, st));
     GemmP g = gemm_nn(W.DLOGITS, V, P_(ctx, XG_P_LOGIT_W), H, W.dOUT, H, LB, H, V);
@@ -270,6 +274,10 @@ static int train_bwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   }
   // batched weight gradients over all steps
   {
+    // Nothing this block reads as a GEMM operand is written after its first use in it (W.dGP and W.dXT are outputs before
+    // they are operands): dz2 / dz1 feed three weight gradients each in the same layout, dz1 two input gradients, the
+    // embeddings two weight gradients -> one operand split each.
+    TcHold hold(ctx);
     const float* Hprev = S.H12;                       // rows (i,b), i in [0,Lp)
     const float* Hnew = S.H12 + (long)B * 2 * H;      // i in [1,Lp]
     XG_TRY(wgrad(ctx, G2, 4 * H, Hnew, 2 * H, G[XG_P_L2_I2H_W], 4 * H, H, LB, beta, st));

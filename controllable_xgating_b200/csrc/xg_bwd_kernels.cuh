@@ -24,6 +24,34 @@ __global__ void logsoftmax_bwd_rows_kernel(const float* __restrict__ lp, const f
   for (int j = threadIdx.x; j < N; j += blockDim.x) o[j] = d[j] - expf(l[j]) * s;
 }
 
+// the same with both rows held in registers (one read of dlp instead of two); conditions of logsoftmax_reg_ok
+__global__ void __launch_bounds__(256)
+logsoftmax_bwd_rows_reg_kernel(const float* __restrict__ lp, const float* __restrict__ dlp, int B, int Lp, int N, float* __restrict__ dlogits) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, n4 = N >> 2;
+  const int b = r % B, i = r / B;
+  const long src = (long)b * Lp + i;
+  const float4* d = reinterpret_cast<const float4*>(dlp + src * N);
+  const float4* l = reinterpret_cast<const float4*>(lp + src * N);
+  float4 dv[LSM_V4], lv[LSM_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < LSM_V4; ++q) {
+    const int j = threadIdx.x + 256 * q;
+    dv[q] = j < n4 ? d[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    lv[q] = j < n4 ? l[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int q = 0; q < LSM_V4; ++q) s += (dv[q].x + dv[q].y) + (dv[q].z + dv[q].w);
+  s = block_sum(s, red);
+  float4* o = reinterpret_cast<float4*>(dlogits + (long)r * N);
+#pragma unroll
+  for (int q = 0; q < LSM_V4; ++q) {
+    const int j = threadIdx.x + 256 * q;
+    if (j < n4) o[j] = make_float4(dv[q].x - expf(lv[q].x) * s, dv[q].y - expf(lv[q].y) * s, dv[q].z - expf(lv[q].z) * s, dv[q].w - expf(lv[q].w) * s);
+  }
+}
+
 // out_x[j] = beta*out_x[j] + sum_r X[r*ld + j]   (up to three identical outputs: the three LSTM biases
 // of a cell share one column sum).  grid (ceil(N/32), S), block (32,8).  Narrow matrices would occupy a
 // handful of SMs with one block per 32 columns, so the rows are cut into S slabs: every block leaves its

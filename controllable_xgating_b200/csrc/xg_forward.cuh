@@ -240,6 +240,7 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
   // hoisted over all steps: embedding, POS gate, input parts of lstm_1
   XG_TRY(launch(ctx, "gather_rows", gather_rows_kernel, (int)LB, 128, 0, st, P_(ctx, XG_P_EMBED_W), seq, L, 1, B, (int)LB, E, V, S.XT));
   {
+    TcHold hold(ctx);      // S.XT feeds the POS gate and lstm_1 in the same layout: one operand split
     GemmP g = gemm_nt(S.XT, E, P_(ctx, XG_P_DGATE_W), E, S.GP, H, (int)LB, H, E);
     g.ep.bias0 = P_(ctx, XG_P_DGATE_B);
     g.ep.act = XG_ACT_RELU;
@@ -311,7 +312,11 @@ static int train_fwd_core(xg_context* ctx, const float* rgb, const float* opfl, 
     g.ep.bias0 = P_(ctx, XG_P_LOGIT_B);
     g.perm_rb = B; g.perm_rs = Lp;
     XG_TRY(gemm_run(ctx, g, st));
-    XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_kernel, (int)LB, 256, 0, st, logp, V, V, 0, 0, logp, V));
+    if (logsoftmax_reg_ok(logp, V, V, logp, V)) {
+      XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_reg_kernel, (int)LB, 256, 0, st, logp, V, V, 0, 0, logp, V));
+    } else {
+      XG_TRY(launch(ctx, "logsoftmax_rows", logsoftmax_rows_kernel, (int)LB, 256, 0, st, logp, V, V, 0, 0, logp, V));
+    }
   }
   if (cat) {
     GemmP g = gemm_nt(OUT, 2 * H, P_(ctx, XG_P_CLS0_W), H, S.Hc, Q, (int)LB, Q, H);

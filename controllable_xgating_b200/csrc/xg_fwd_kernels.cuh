@@ -289,6 +289,40 @@ __global__ void logsoftmax_rows_kernel(const float* __restrict__ X, long ldx, in
   for (int j = threadIdx.x; j < N; j += blockDim.x) o[j] = x[j] - lse;
 }
 
+// the same with the row held in registers (one read of X instead of three): 256 threads, N a multiple of 4 and at most
+// 256 * 4 * LSM_V4 entries, 16-byte aligned rows
+constexpr int LSM_V4 = 12;
+__global__ void __launch_bounds__(256)
+logsoftmax_rows_reg_kernel(const float* __restrict__ X, long ldx, int N, int perm_rb, int perm_rs, float* __restrict__ out, long ldo) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, n4 = N >> 2;
+  const float4* x = reinterpret_cast<const float4*>(X + (long)r * ldx);
+  const long orow = perm_rb ? (long)(r % perm_rb) * perm_rs + r / perm_rb : (long)r;
+  float4 v[LSM_V4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < LSM_V4; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    v[i] = j < n4 ? x[j] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  }
+  mx = block_max(mx, red);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LSM_V4; ++i) s += (expf(v[i].x - mx) + expf(v[i].y - mx)) + (expf(v[i].z - mx) + expf(v[i].w - mx));
+  s = block_sum(s, red);
+  const float lse = mx + logf(s);
+  float4* o = reinterpret_cast<float4*>(out + orow * ldo);
+#pragma unroll
+  for (int i = 0; i < LSM_V4; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    if (j < n4) o[j] = make_float4(v[i].x - lse, v[i].y - lse, v[i].z - lse, v[i].w - lse);
+  }
+}
+static inline bool logsoftmax_reg_ok(const void* X, long ldx, int N, const void* out, long ldo) {
+  return N % 4 == 0 && N <= 256 * 4 * LSM_V4 && ldx % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)out & 15) == 0;
+}
+
 // ------------------------------------------------------------------------------------
 // greedy / multinomial pick for SAModel.sample (SAModel.py:185-210), one CTA per caption row.
 // Reads the step's logits (not log-probs: only max, argmax and logsumexp are needed for greedy),

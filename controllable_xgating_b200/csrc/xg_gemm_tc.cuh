@@ -446,6 +446,12 @@ struct TcState {
   // scratch for on-the-fly operand splits (grown on demand)
   float* scratch[2] = {nullptr, nullptr};
   size_t scratch_floats[2] = {0, 0};
+  // "hold" regions (tc_hold_begin / _end): the caller guarantees that no operand of the region is written after its
+  // first use inside it, so an activation that feeds several GEMMs in the same layout (dz of a cell in its three weight
+  // gradients, the embeddings in two products) is split once.  The buffers are kept from step to step.
+  struct Held { SplitKey key; float* buf; size_t floats; bool valid; };
+  std::vector<Held> held;
+  bool hold = false;
 };
 
 inline TcState*& tc_state(xg_context* ctx) {
@@ -471,6 +477,7 @@ static void tc_release(xg_context* ctx) {
   if (!ts) return;
   for (auto& kv : ts->weight_cache) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
   for (int i = 0; i < 2; ++i) if (ts->scratch[i]) cudaFree(ts->scratch[i]);
+  for (auto& h : ts->held) if (h.buf) cudaFree(h.buf);
   delete ts;
   tc_state(ctx) = nullptr;
 }
@@ -549,6 +556,24 @@ static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, lo
     return XG_OK;
   }
   const size_t need = (size_t)rows * Kp * 2;
+  if (ts->hold) {
+    const TcState::SplitKey key(X, sr, sk, rows, K);
+    TcState::Held* free_slot = nullptr;
+    for (auto& h : ts->held) {
+      if (h.valid && h.key == key) { *hi = h.buf; *lo = h.buf + (size_t)rows * Kp; return XG_OK; }
+      if (!h.valid && (!free_slot || (h.floats >= need && (free_slot->floats < need || h.floats < free_slot->floats)))) free_slot = &h;
+    }
+    if (!free_slot) { ts->held.push_back(TcState::Held{key, nullptr, 0, false}); free_slot = &ts->held.back(); }
+    if (free_slot->floats < need) {
+      if (free_slot->buf) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(free_slot->buf); free_slot->buf = nullptr; free_slot->floats = 0; }
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&free_slot->buf, sizeof(float) * need));
+      free_slot->floats = need;
+    }
+    XG_TRY(tc_split(ctx, X, sr, sk, rows, K, Kp, free_slot->buf, free_slot->buf + (size_t)rows * Kp, st));
+    free_slot->key = key; free_slot->valid = true;
+    *hi = free_slot->buf; *lo = free_slot->buf + (size_t)rows * Kp;
+    return XG_OK;
+  }
   if (ts->scratch_floats[slot] < need) {
     XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
     if (ts->scratch[slot]) cudaFree(ts->scratch[slot]);
@@ -564,6 +589,21 @@ static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, lo
   *lo = l;
   return XG_OK;
 }
+
+// hold regions, see TcState::held
+static void tc_hold_begin(xg_context* ctx) {
+  TcState* ts = tc_state(ctx);
+  if (ts) { ts->hold = true; for (auto& h : ts->held) h.valid = false; }
+}
+static void tc_hold_end(xg_context* ctx) {
+  TcState* ts = tc_state(ctx);
+  if (ts) { ts->hold = false; for (auto& h : ts->held) h.valid = false; }
+}
+struct TcHold {          // scope guard
+  xg_context* ctx;
+  explicit TcHold(xg_context* c) : ctx(c) { tc_hold_begin(c); }
+  ~TcHold() { tc_hold_end(ctx); }
+};
 
 template <int BN>
 static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMap& a, const CUtensorMap& b,
