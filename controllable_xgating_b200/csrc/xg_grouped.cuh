@@ -1016,6 +1016,9 @@ __device__ __noinline__ void dec_attention_rows(const DecParams& P, const CUtens
   const GDesc& dah = P.d[DD_AH];
   const int A4 = A >> 2;
   constexpr int QIT = (NR * DEC_NA * PK_THREADS / 4 + PK_THREADS - 1) / PK_THREADS;      // float4 columns of NR rows per thread
+  // V[fb] goes over the consumed exp(2Uv) chunks as soon as they cover it (last pass only: earlier passes re-read them)
+  const int vc = max(0, (K * H + fpc * A - 1) / (fpc * A) - 1);
+  bool v_issued = v_behind;
 #pragma unroll 1
   for (int g = 0; g < nrows; g += NR) {
     const int ng = min(NR, nrows - g);
@@ -1103,6 +1106,16 @@ __device__ __noinline__ void dec_attention_rows(const DecParams& P, const CUtens
         if (writer && k0 + f < k1)
           sts_f32(red_s + (uint32_t)((q * PK_WARPS + warp) * K + k0 + f) * 4u, p[0]);
       }
+      if (!v_issued && g + NR >= nrows && c == vc && (c + 1) * fpc < K) {      // (uniform: every thread takes the branch)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          fence_proxy_async_smem();
+          pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
+          pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
+          pk_tma_2d(sv.stages_u32 + (uint32_t)K * Hh * 4u, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, Hh, fb * K);
+        }
+        v_issued = true;
+      }
     }
     GKA(2);
     __syncthreads();
@@ -1135,7 +1148,7 @@ __device__ __noinline__ void dec_attention_rows(const DecParams& P, const CUtens
     __syncthreads();
   }
   GKA(3);
-  if (!v_behind && threadIdx.x == 0) {        // every score is computed: V[fb] goes over exp(2Uv)
+  if (!v_issued && threadIdx.x == 0) {        // every score is computed: V[fb] goes over exp(2Uv)
     fence_proxy_async_smem();
     pk_expect_tx(sv.bulk_bar + 8 * PK_BULK_CHUNKS, (uint32_t)K * H * 4u);
     pk_tma_2d(sv.stages_u32, vmap, sv.bulk_bar + 8 * PK_BULK_CHUNKS, 0, fb * K);
@@ -1302,9 +1315,8 @@ namespace xg {
 // the teacher-forced word loop of SAModel.forward (SAModel.py:88-111), grouped-cell form.  The ground-truth tokens
 // are known, so the token-dependent parts of lstm_1 are hoisted (batched GEMMs into G1s) and a step is THREE grid
 // synchronised phases:
-//   A {attention query W_h2a.[h1|h2]: split-K slots}
-//   B {temporal attention on the last B CTAs  ||  lstm_1 = cell(G1s[t] + W_h2h1.h1) as a fused group phase, and the
-//      recurrent product W_h2h2.h2 of lstm_2 into its early slots, on the others}
+//   A {attention query W_h2a.[h1|h2]: split-K slots; the recurrent product W_h2h2.h2 of lstm_2 into its early slots}
+//   B {temporal attention on the last B CTAs  ||  lstm_1 = cell(G1s[t] + W_h2h1.h1) as a fused group phase on the others}
 //   C {lstm_2 = cell(W_i2h2.h1' + W_a2h2.af + W_h2h2.h2) as a fused group phase on all CTAs}
 // (decode_persistent_kernel<1>, xg_persist.cuh: four phases, cells as separate pointwise phases, tf32 operand pairs
 // split in the kernel.)  The logit / classifier heads run batched over all steps after the loop.
@@ -2237,9 +2249,10 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
   // (the schedule depends on the padded row count only, never on B)
   const int avail = G - R;                       // CTAs of phase B that do not run the attention
   const int nv = kbH >= 2 ? 2 : 1;               // early slots of lstm_2: W_h2h2.h2 cut in nv runs
-  const int m1 = std::max(1, std::min(std::min(GK_MAX_MEMBERS, kbH), (avail * 3 / 5) / groups));
-  const int nside = avail - groups * m1;
-  if (nside < 1 || (groups * nv + nside - 1) / nside > GK_MAX_ITEMS) return PK_FALLBACK;
+  // lstm_1's groups take every CTA phase B has outside the attention; the recurrent product of lstm_2 (it needs only
+  // the state entering the step) rides in phase A next to the attention query
+  int m1 = std::max(1, std::min(std::min(GK_MAX_MEMBERS, kbH), avail / groups));
+  if (getenv("XG_TM1")) m1 = std::max(1, std::min(m1, atoi(getenv("XG_TM1"))));      // (experiments)
   const int m2 = std::max(1, std::min(std::min(GK_MAX_MEMBERS, G / groups), 2 * kbH));
   const int members_l[2] = {m1, m2}, nslots_l[2] = {m1, m2 + nv};
   if (nslots_l[1] > GK_MAX_SLOTS) return PK_FALLBACK;
@@ -2277,6 +2290,15 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
         it.desc = DD_AH; it.slot = (short)sl; it.cb = 0;
         if (!add(sched[(size_t)(c++ % G)], it, true)) return PK_FALLBACK;
       }
+    for (int grp = 0; grp < groups; ++grp)      // W_h2h2.h2 into the early slots of lstm_2's groups
+      for (int v = 0; v < nv; ++v) {
+        const int k0 = v * kbH / nv, k1 = (v + 1) * kbH / nv;
+        GItem it{};
+        it.w_map = (short)(GM_W32 + 10); it.x_map = (short)GM_HH; it.xsel = 1; it.flags = (short)(GI_FUSED | GI_LAYER1);
+        it.wrow = (short)(grp * 32); it.wk0 = (short)k0; it.xk0 = (short)(kbH + k0); it.nkb = (short)(k1 - k0);
+        it.desc = (short)grp; it.slot = (short)(m2 + v); it.cb = 0; it.pad = (short)nslots_l[1];
+        if (!add(sched[(size_t)(c++ % G)], it, true)) return PK_FALLBACK;
+      }
   }
   // phase B: lstm_1 groups (recurrent product only: the rest sits in G1s) on the first groups x m1 CTAs, the recurrent product
   // of lstm_2 into its early slots on the side CTAs; phase C: lstm_2 groups (h1', af) on all CTAs
@@ -2289,14 +2311,6 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
       it.wrow = (short)(grp * 32); it.wk0 = (short)k0; it.xk0 = (short)k0; it.nkb = (short)(k1 - k0);
       it.desc = (short)grp; it.slot = (short)mem; it.cb = 0; it.pad = (short)nslots_l[0];
       if (!add(sched[(size_t)G + grp * m1 + mem], it, true)) return PK_FALLBACK;
-    }
-    for (int v = 0; v < nv; ++v) {
-      const int k0 = v * kbH / nv, k1 = (v + 1) * kbH / nv;
-      GItem it{};
-      it.w_map = (short)(GM_W32 + 10); it.x_map = (short)GM_HH; it.xsel = 1; it.flags = (short)(GI_FUSED | GI_LAYER1);
-      it.wrow = (short)(grp * 32); it.wk0 = (short)k0; it.xk0 = (short)(kbH + k0); it.nkb = (short)(k1 - k0);
-      it.desc = (short)grp; it.slot = (short)(m2 + v); it.cb = 0; it.pad = (short)nslots_l[1];
-      if (!add(sched[(size_t)G + groups * m1 + (grp * nv + v) % nside], it, true)) return PK_FALLBACK;
     }
     const int Ktot = 2 * kbH;
     for (int mem = 0; mem < m2; ++mem) {
