@@ -256,6 +256,15 @@ size_t xg_workspace_bytes(xg_handle h, int kind, int B, int K, int L_or_T, int b
   return a.off + 256;
 }
 
+// Forward entry points run their batched tcgen05 products on fp16 operand pairs (xg_gemm_tc.cuh, 3xFP16: the accuracy of
+// the tf32 pairs at half the operand bytes; |operand| < 65504).  The backward pass keeps tf32 pairs: gradients do not
+// fit the fp16 range without a scale.  XG_NO_TC16=1 keeps tf32 pairs everywhere.
+struct TcF16Scope {
+  xg_context* c; bool old;
+  explicit TcF16Scope(xg_context* c_) : c(c_), old(c_->tc_f16) { c->tc_f16 = !env_flag("XG_NO_TC16"); }
+  ~TcF16Scope() { c->tc_f16 = old; }
+};
+
 int xg_encode_fwd(xg_handle h, const float* rgb, const float* opfl, const float* feat_mask, int B, int K, int train,
                   uint64_t seed, float* V_out, float* Uv_out, float* const* state_out, void* ws, size_t ws_bytes,
                   void* stream) {
@@ -265,6 +274,7 @@ int xg_encode_fwd(xg_handle h, const float* rgb, const float* opfl, const float*
   if (!h->bn_bound) return fail(h, XG_ERR_NOT_BOUND, "BatchNorm buffers not bound (xg_bind_bn_buffers)");
   if (state_out) for (int q = 0; q < 4; ++q) CHECK_PTR(h, state_out[q]);
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   Arena a(ws, ws_bytes);
   EncBufs eb; carve_enc(a, h->d, B, K, eb);
   if (a.overflow) return fail(h, XG_ERR_WORKSPACE, "xg_encode_fwd: workspace too small");
@@ -278,6 +288,7 @@ int xg_init_hidden(xg_handle h, const float* V, const float* feat_mask, int B, i
   CHECK_POS(h, B); CHECK_POS(h, K);
   for (int q = 0; q < 4; ++q) CHECK_PTR(h, state_out[q]);
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   Arena a(ws, ws_bytes);
   float* meanV = a.take<float>((long)B * h->d.rnn);
   if (a.overflow) return fail(h, XG_ERR_WORKSPACE, "xg_init_hidden: workspace too small");
@@ -288,6 +299,7 @@ int xg_attend_precompute(xg_handle h, const float* V, int B, int K, float* Uv_ou
   CHECK_HANDLE(h); CHECK_BOUND(h);
   CHECK_PTR(h, V); CHECK_PTR(h, Uv_out); CHECK_POS(h, B); CHECK_POS(h, K);
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   GemmP g = gemm_nt(V, h->d.rnn, h->P[XG_P_V2A_W], h->d.rnn, Uv_out, h->d.att, B * K, h->d.att, h->d.rnn);
   g.ep.bias0 = h->P[XG_P_V2A_B];
   return gemm_run(h, g, (cudaStream_t)stream);
@@ -302,6 +314,7 @@ int xg_decode_step(xg_handle h, const int64_t* tokens, const float* xt, const fl
   if ((tokens == nullptr) == (xt == nullptr)) return fail(h, XG_ERR_BAD_ARG, "xg_decode_step: pass exactly one of tokens / xt");
   for (int q = 0; q < 4; ++q) { CHECK_PTR(h, state_in[q]); CHECK_PTR(h, state_out[q]); }
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   cudaStream_t st = (cudaStream_t)stream;
   const xg_dims& d = h->d;
   const int H = d.rnn;
@@ -338,6 +351,7 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
   if (T + 1 > xg_context::kPinnedInts) return fail(h, XG_ERR_BAD_SHAPE, "xg_sample_greedy: seq_length too large");
   if (!sample_max && !(temperature > 0.f)) return fail(h, XG_ERR_BAD_ARG, "xg_sample_greedy: temperature must be > 0");
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   cudaStream_t st = (cudaStream_t)stream;
   const xg_dims& d = h->d;
   const int H = d.rnn;
@@ -406,6 +420,7 @@ int xg_scheduled_tokens(xg_handle h, const float* V, const float* Uv, const floa
   if (!(ss_prob >= 0.f && ss_prob <= 1.f)) return fail(h, XG_ERR_BAD_ARG, "xg_scheduled_tokens: ss_prob must be in [0,1]");
   for (int q = 0; q < 4; ++q) CHECK_PTR(h, state0[q]);
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   cudaStream_t st = (cudaStream_t)stream;
   const xg_dims& d = h->d;
   const int H = d.rnn;
@@ -454,6 +469,7 @@ int xg_sample_beam(xg_handle h, const float* V, const float* feat_mask, const fl
   if (beam > h->d.vocab) return fail(h, XG_ERR_BAD_SHAPE, "beam_size <= vocab_size required (SAModel.py:134)");
   if (beam > XG_MAX_BEAM) return fail(h, XG_ERR_UNSUPPORTED, "xg_sample_beam: beam_size > 16 not supported");
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   Arena a(ws, ws_bytes);
   BeamBufs w; carve_beam(a, h->d, B, K, T, beam, w);
   if (a.overflow) return fail(h, XG_ERR_WORKSPACE, "xg_sample_beam: workspace too small");
@@ -483,6 +499,7 @@ int xg_train_fwd(xg_handle h, const float* rgb, const float* opfl, const float* 
   if (Lp > L) return fail(h, XG_ERR_BAD_SHAPE, "xg_train_fwd: Lp > L");
   if (!h->bn_bound) return fail(h, XG_ERR_NOT_BOUND, "BatchNorm buffers not bound (xg_bind_bn_buffers)");
   XG_TRY(set_device(h));
+  TcF16Scope f16(h);
   Arena a(saved, saved_bytes);
   TrainSaved S; carve_saved(a, h->d, B, K, L, S);
   if (a.overflow) return fail(h, XG_ERR_WORKSPACE, "xg_train_fwd: saved-activation block too small");
@@ -617,8 +634,8 @@ int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float*
   else if (layout == 1) p = gemm_nn(A, K, B, N, C, N, M, N, K);
   else if (layout == 2) p = gemm_tn(A, M, B, N, C, N, M, N, K);
   else return fail(nullptr, XG_ERR_BAD_ARG, "xg_debug_gemm: layout must be 0 (NT), 1 (NN) or 2 (TN)");
-  if (engine == 2) {
-    // tcgen05 3xTF32 engine on a parameter-less scratch context (operands are split on the fly)
+  if (engine == 2 || engine == 4) {
+    // tcgen05 engine on a parameter-less scratch context (operands are split on the fly): 2 = 3xTF32, 4 = 3xFP16 pairs
     static xg_context* dbg = nullptr;
     if (!dbg) {
       dbg = new xg_context();
@@ -626,6 +643,7 @@ int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float*
       for (int i = 0; i < XG_NUM_PARAMS; ++i) dbg->P[i] = nullptr;
     }
     cudaGetDevice(&dbg->device);
+    dbg->tc_f16 = engine == 4;
     int s = gemm_tc(dbg, p, (cudaStream_t)stream);
     if (s != XG_OK) g_last_error = dbg->es.msg;
     return s;

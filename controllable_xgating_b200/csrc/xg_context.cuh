@@ -25,6 +25,7 @@ struct xg_context {
   int persist_mode = 1;      // 1: greedy decoding runs in the fused persistent word-step kernel when eligible
   int strict_persist = 0;    // xg_set_strict / XG_STRICT_PERSIST=1: a serial loop that cannot run on its persistent kernel is an ERROR
   unsigned long long n_fused = 0, n_unfused = 0;   // serial loops run by a persistent kernel / by per-step launches (xg_path_counters)
+  bool tc_f16 = false;                    // batched tcgen05 products on fp16 operand pairs (set by the forward entry points, TcF16Scope)
   cudaEvent_t bwd_split_event = nullptr;   // xg_set_bwd_split_event: recorded by xg_train_bwd once every decoder-side gradient is final
   int dec_drop_on = 0;       // xg_set_decode_dropout: xg_sample_greedy applies the TRAINING dropout of the word step
   unsigned long long dec_drop_seed = 0;   //   (same Philox sites / indices as xg_train_fwd with this seed)

@@ -17,6 +17,7 @@
 // No thread ever writes the operand tiles: they go global -> smem by TMA and smem -> tensor core by
 // UMMA, both in the async proxy, so no proxy fences are needed on the operand path.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda.h>
 
 #include <map>
@@ -85,6 +86,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -118,6 +127,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B      [61,64)
   return d;
 }
+// instruction descriptor: D fp32, A/B fp16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp16 operand pairs (3xFP16): hi = fp16(v), lo = fp16((v - hi) * 2^11); hi.hi + (lo.hi + hi.lo) / 2^11 carries the same
+// 11 + 11 mantissa bits as a tf32 pair, the scale keeps lo out of the fp16 subnormals.  |v| must stay below 65504.
+constexpr float TC16_SCALE = 2048.f;
 // instruction descriptor: D fp32, A/B tf32, both K-major, M=128, N=BN
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -181,6 +197,56 @@ split_tf32_flat_kernel(const float4* __restrict__ X, long sr4, int k4, long n4, 
   }
 }
 
+// the same two passes for fp16 hi / lo pairs (K padded to a multiple of 64: 128-byte rows)
+__global__ void split_f16_kernel(const float* __restrict__ X, long sr, long sk, int rows, int K, int Kp,
+                                 __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const bool k_contig = (sk == 1);
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int r = k_contig ? r0 + y : r0 + threadIdx.x;
+    int k = k_contig ? k0 + threadIdx.x : k0 + y;
+    float v = (r < rows && k < K) ? X[(long)r * sr + (long)k * sk] : 0.f;
+    if (k_contig) tile[y][threadIdx.x] = v; else tile[threadIdx.x][y] = v;   // tile[r - r0][k - k0]
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = r0 + y, k = k0 + threadIdx.x;
+    if (r < rows && k < Kp) {
+      const float v = tile[y][threadIdx.x];
+      const __half h = __float2half_rn(v);
+      hi[(long)r * Kp + k] = h;
+      lo[(long)r * Kp + k] = __float2half_rn((v - __half2float(h)) * TC16_SCALE);
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+split_f16_flat_kernel(const float4* __restrict__ X, long sr4, int k4, long n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  const long stride = (long)gridDim.x * 256;
+  const bool dense = sr4 == (long)k4;
+  for (long i0 = (long)blockIdx.x * 256 + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const long i = i0 + q * stride; if (i < n4) v[q] = __ldg(X + (dense ? i : (i / k4) * sr4 + (i % k4))); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long i = i0 + q * stride;
+      if (i < n4) {
+        const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        __half h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { h[e] = __float2half_rn(f[e]); l[e] = __float2half_rn((f[e] - __half2float(h[e])) * TC16_SCALE); }
+        uint2 ph, pl;
+        ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+        hi[i] = ph; lo[i] = pl;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // the GEMM kernel
 //
@@ -215,7 +281,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN>
+template <int BN, bool F16 = false>      // F16: fp16 operand pairs, k-blocks of 64 (128-byte rows either way)
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUtensorMap tmPl,
                const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl, const TcParams prm) {
@@ -231,7 +297,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p0 = blockIdx.x * 128, q0 = blockIdx.y * BN;
-  const int num_kb = prm.K / 32;
+  constexpr int KB = F16 ? 64 : 32;          // K elements of a k-block
+  const int num_kb = prm.K / KB;
   const int kchunk = (prm.dbg & 2) ? (1 << 20) : Cfg::kChunk;
   const int num_chunks = (num_kb + kchunk - 1) / kchunk;
 
@@ -261,14 +328,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
       if (elect_one_sync()) {
         if (prm.dbg & 4) {
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes / 2);
-          tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
-          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
+          tma_load_2d(st, &tmPh, &full_bar[s], kb * KB, p0);
+          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * KB, q0);
         } else {
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(st, &tmPh, &full_bar[s], kb * 32, p0);
-          tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * 32, p0);
-          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * 32, q0);
-          tma_load_2d(st + 2 * 128 * 128 + BN * 128, &tmQl, &full_bar[s], kb * 32, q0);
+          tma_load_2d(st, &tmPh, &full_bar[s], kb * KB, p0);
+          tma_load_2d(st + 128 * 128, &tmPl, &full_bar[s], kb * KB, p0);
+          tma_load_2d(st + 2 * 128 * 128, &tmQh, &full_bar[s], kb * KB, q0);
+          tma_load_2d(st + 2 * 128 * 128 + BN * 128, &tmQl, &full_bar[s], kb * KB, q0);
         }
       }
       __syncwarp();
@@ -279,7 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
     // to back in the stage: main term -> columns [0, BN), cross term hi.lo -> [BN, 2 BN) of the accumulator pair) and
     // P_lo . Q_hi (N = BN) onto the cross columns.  Three N = BN instructions per k-step cost ~130 cycles each here (ncu,
     // profiles/r1n_gemm_tc128_*): the issue rate of the MMA warp and the re-read of the P_hi tile paced the main loop.
-    constexpr uint32_t idesc = umma_idesc_tf32(128, BN), idesc2 = umma_idesc_tf32(128, 2 * BN);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN);
+    constexpr uint32_t idesc2 = F16 ? umma_idesc_f16(128, 2 * BN) : umma_idesc_tf32(128, 2 * BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
@@ -302,8 +370,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
             const uint64_t pl_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((128 * 128) >> 4) + (1u << 16));
             const uint64_t qh_d = ((uint64_t)desc_hi << 32) | (uint64_t)(dlo + k4 * 2 + ((2 * 128 * 128) >> 4) + (1u << 16));      // 2 BN rows: Q_hi, Q_lo
             if (prm.dbg & 1) continue;
-            umma_tf32(tmem_pair, ph_d, qh_d, idesc2, (kk | k4) != 0);
-            umma_tf32(tmem_pair + BN, pl_d, qh_d, idesc, 1);
+            if (F16) {
+              umma_f16(tmem_pair, ph_d, qh_d, idesc2, (kk | k4) != 0);
+              umma_f16(tmem_pair + BN, pl_d, qh_d, idesc, 1);
+            } else {
+              umma_tf32(tmem_pair, ph_d, qh_d, idesc2, (kk | k4) != 0);
+              umma_tf32(tmem_pair + BN, pl_d, qh_d, idesc, 1);
+            }
           }
           umma_commit(&empty_bar[s]);               // stage reusable once these MMAs have read it
           if (kk == kchunk - 1 || kb == num_kb - 1) umma_commit(&acc_full[b]);   // this chain is complete
@@ -330,7 +403,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__
         tmem_ld32(tmem_base + lane_base + (uint32_t)(b * 2 * BN + BN + cc), r2);
         tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 32; ++u) acc[cc + u] += __uint_as_float(r[u]) + __uint_as_float(r2[u]);
+        for (int u = 0; u < 32; ++u)
+          acc[cc + u] += F16 ? fmaf(__uint_as_float(r2[u]), 1.f / TC16_SCALE, __uint_as_float(r[u])) : __uint_as_float(r[u]) + __uint_as_float(r2[u]);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
@@ -438,7 +512,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcState {
   PFN_encodeTiled encode = nullptr;
-  bool attr_set[3] = {false, false, false};
+  bool attr_set[4] = {false, false, false, false};
   // split copies of bound parameters: key = (param pointer, transposed?) -> {hi, lo, rows, Kp}
   struct Split { float* hi; float* lo; int rows; int K; int Kp; bool valid; };
   typedef std::tuple<const float*, long, long, int, int> SplitKey;   // (pointer, row stride, k stride, rows, K)
@@ -449,6 +523,11 @@ struct TcState {
   // "hold" regions (tc_hold_begin / _end): the caller guarantees that no operand of the region is written after its
   // first use inside it, so an activation that feeds several GEMMs in the same layout (dz of a cell in its three weight
   // gradients, the embeddings in two products) is split once.  The buffers are kept from step to step.
+  // fp16 operand pairs of the forward products (gemm_tc with ctx->tc_f16): same caching rules
+  struct Split16 { __half* hi; __half* lo; int rows; int K; int Kp; bool valid; };
+  std::map<SplitKey, Split16> weight_cache16;
+  __half* scratch16[2] = {nullptr, nullptr};
+  size_t scratch16_halfs[2] = {0, 0};
   struct Held { SplitKey key; float* buf; size_t floats; bool valid; };
   std::vector<Held> held;
   bool hold = false;
@@ -476,6 +555,8 @@ static void tc_release(xg_context* ctx) {
   TcState* ts = tc_state(ctx);
   if (!ts) return;
   for (auto& kv : ts->weight_cache) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+  for (auto& kv : ts->weight_cache16) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+  for (int i = 0; i < 2; ++i) if (ts->scratch16[i]) cudaFree(ts->scratch16[i]);
   for (int i = 0; i < 2; ++i) if (ts->scratch[i]) cudaFree(ts->scratch[i]);
   for (auto& h : ts->held) if (h.buf) cudaFree(h.buf);
   delete ts;
@@ -488,6 +569,7 @@ static void tc_invalidate_weights(xg_context* ctx) {
   TcState* ts = tc_state(ctx);
   if (!ts) return;
   for (auto& kv : ts->weight_cache) kv.second.valid = false;
+  for (auto& kv : ts->weight_cache16) kv.second.valid = false;
 }
 
 // 2-D map over a K-major fp32 matrix [rows][Kp] (pitch Kp floats): box = 32 floats x box_rows, 128B swizzle
@@ -590,6 +672,82 @@ static int tc_operand(xg_context* ctx, TcState* ts, int slot, const float* X, lo
   return XG_OK;
 }
 
+// ---- fp16-pair operands (forward products) ----
+static int tc_make_map16(xg_context* ctx, TcState* ts, const __half* base, int rows, int Kp, int box_rows, CUtensorMap* out) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(__half)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ts->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->es.set(__FILE__, __LINE__, "cuTensorMapEncodeTiled (fp16) failed", nullptr);
+    return XG_ERR_CUDA;
+  }
+  return XG_OK;
+}
+static int tc_split16(xg_context* ctx, const float* X, long sr, long sk, int rows, int K, int Kp, __half* hi, __half* lo, cudaStream_t st) {
+  ProfScope ps(ctx, "split_f16", st);
+  if (sk == 1 && sr % 4 == 0 && sr >= (long)K && K == Kp && ((uintptr_t)X & 15) == 0 && ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0) {
+    const long n4 = (long)rows * Kp / 4;
+    const long want = (n4 + 1023) / 1024;
+    const int blocks = (int)std::max<long>(1, std::min<long>(want, (long)ctx->sm_count * 8));
+    split_f16_flat_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(X), sr / 4, Kp / 4, n4, reinterpret_cast<uint2*>(hi),
+                                                  reinterpret_cast<uint2*>(lo));
+    XG_LAUNCH_CHECK(ctx->es);
+    return XG_OK;
+  }
+  dim3 grid(Kp / 32, ceil_div(rows, 32));
+  split_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(X, sr, sk, rows, K, Kp, hi, lo);
+  XG_LAUNCH_CHECK(ctx->es);
+  return XG_OK;
+}
+static int tc_operand16(xg_context* ctx, TcState* ts, int slot, const float* X, long sr, long sk, int rows, int K,
+                        const __half** hi, const __half** lo, int* Kp_out, cudaStream_t st) {
+  const int Kp = (K + 63) / 64 * 64;
+  *Kp_out = Kp;
+  bool is_param = false;
+  for (int i = 0; i < XG_NUM_PARAMS && !is_param; ++i) {
+    int pr, pc;
+    param_shape(ctx->d, i, &pr, &pc);
+    const float* b = ctx->P[i];
+    if (b && X >= b && X < b + (long)pr * pc) is_param = true;
+  }
+  if (is_param) {
+    const TcState::SplitKey key(X, sr, sk, rows, K);
+    auto it = ts->weight_cache16.find(key);
+    if (it == ts->weight_cache16.end()) {
+      TcState::Split16 sp{nullptr, nullptr, rows, K, Kp, false};
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.hi, sizeof(__half) * (size_t)rows * Kp));
+      XG_CUDA_TRY(ctx->es, cudaMalloc(&sp.lo, sizeof(__half) * (size_t)rows * Kp));
+      it = ts->weight_cache16.emplace(key, sp).first;
+    }
+    if (!it->second.valid) {
+      XG_TRY(tc_split16(ctx, X, sr, sk, rows, K, Kp, it->second.hi, it->second.lo, st));
+      it->second.valid = true;
+    }
+    *hi = it->second.hi;
+    *lo = it->second.lo;
+    return XG_OK;
+  }
+  const size_t need = (size_t)rows * Kp * 2;
+  if (ts->scratch16_halfs[slot] < need) {
+    XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
+    if (ts->scratch16[slot]) cudaFree(ts->scratch16[slot]);
+    ts->scratch16[slot] = nullptr;
+    ts->scratch16_halfs[slot] = 0;
+    XG_CUDA_TRY(ctx->es, cudaMalloc(&ts->scratch16[slot], sizeof(__half) * need));
+    ts->scratch16_halfs[slot] = need;
+  }
+  __half* h = ts->scratch16[slot];
+  __half* l = h + (size_t)rows * Kp;
+  XG_TRY(tc_split16(ctx, X, sr, sk, rows, K, Kp, h, l, st));
+  *hi = h;
+  *lo = l;
+  return XG_OK;
+}
+
 // hold regions, see TcState::held
 static void tc_hold_begin(xg_context* ctx) {
   TcState* ts = tc_state(ctx);
@@ -605,16 +763,16 @@ struct TcHold {          // scope guard
   ~TcHold() { tc_hold_end(ctx); }
 };
 
-template <int BN>
+template <int BN, bool F16>
 static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMap& a, const CUtensorMap& b,
                      const CUtensorMap& c, const CUtensorMap& d, const TcParams& prm, cudaStream_t st) {
   if (!ts->attr_set[cfg_idx]) {
-    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(gemm_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               TcCfg<BN>::kSmemBytes));
     ts->attr_set[cfg_idx] = true;
   }
   dim3 grid(ceil_div(prm.Pn, 128), ceil_div(prm.Qn, BN));
-  gemm_tc_kernel<BN><<<grid, TcCfg<BN>::kThreads, TcCfg<BN>::kSmemBytes, st>>>(a, b, c, d, prm);
+  gemm_tc_kernel<BN, F16><<<grid, TcCfg<BN>::kThreads, TcCfg<BN>::kSmemBytes, st>>>(a, b, c, d, prm);
   XG_LAUNCH_CHECK(ctx->es);
   return XG_OK;
 }
@@ -636,6 +794,34 @@ static int gemm_tc(xg_context* ctx, const GemmP& p, cudaStream_t st) {
   TcState* ts = nullptr;
   XG_TRY(tc_init(ctx, ts));
   // operand "I" : rows i (M), reduction r ;  operand "J" : rows j (N), reduction r
+  const int BNsel = (p.M <= 64 || (long)ceil_div(p.N, 128) * ceil_div(p.M, 128) < 120) ? 64 : 128;
+  if (ctx->tc_f16) {
+    // forward products: fp16 operand pairs (half the operand bytes of the tf32 pairs, k-blocks of 64)
+    const __half *ih, *il, *jh, *jl;
+    int Kp = 0, Kp2 = 0;
+    XG_TRY(tc_operand16(ctx, ts, 0, p.A, p.sa_i, p.sa_r, p.M, p.K, &ih, &il, &Kp, st));
+    XG_TRY(tc_operand16(ctx, ts, 1, p.B, p.sb_j, p.sb_r, p.N, p.K, &jh, &jl, &Kp2, st));
+    TcParams prm;
+    prm.K = Kp;
+    prm.g = p;
+    { const char* e = getenv("XG_TC_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
+    prm.Pn = p.N; prm.Qn = p.M; prm.swap_out = 1;
+    CUtensorMap mPh, mPl, mQh, mQl;
+    XG_TRY(tc_make_map16(ctx, ts, jh, p.N, Kp, 128, &mPh));
+    XG_TRY(tc_make_map16(ctx, ts, jl, p.N, Kp, 128, &mPl));
+    XG_TRY(tc_make_map16(ctx, ts, ih, p.M, Kp, BNsel, &mQh));
+    XG_TRY(tc_make_map16(ctx, ts, il, p.M, Kp, BNsel, &mQl));
+    char tag[96];
+    if (ctx->prof_on) {
+      const char* lay = (p.sa_r == 1) ? (p.sb_r == 1 ? "nt" : "nn") : "tn";
+      snprintf(tag, sizeof(tag), "gemmtc16_%s_%dx%dx%d", lay, p.M, p.N, p.K);
+    } else {
+      tag[0] = 0;
+    }
+    ProfScope ps(ctx, std::string(tag), st);
+    if (BNsel == 64) return tc_launch<64, true>(ctx, ts, 2, mPh, mPl, mQh, mQl, prm, st);
+    return tc_launch<128, true>(ctx, ts, 3, mPh, mPl, mQh, mQl, prm, st);
+  }
   const float *ih, *il, *jh, *jl;
   int Kp = 0, Kp2 = 0;
   XG_TRY(tc_operand(ctx, ts, 0, p.A, p.sa_i, p.sa_r, p.M, p.K, &ih, &il, &Kp, st));
@@ -648,7 +834,7 @@ static int gemm_tc(xg_context* ctx, const GemmP& p, cudaStream_t st) {
   prm.Pn = p.N;
   prm.Qn = p.M;
   prm.swap_out = 1;
-  const int BN = (p.M <= 64 || (long)ceil_div(p.N, 128) * ceil_div(p.M, 128) < 120) ? 64 : 128;
+  const int BN = BNsel;
   CUtensorMap mPh, mPl, mQh, mQl;
   XG_TRY(tc_make_map(ctx, ts, jh, p.N, Kp, 128, &mPh));
   XG_TRY(tc_make_map(ctx, ts, jl, p.N, Kp, 128, &mPl));
@@ -662,8 +848,8 @@ static int gemm_tc(xg_context* ctx, const GemmP& p, cudaStream_t st) {
     tag[0] = 0;
   }
   ProfScope ps(ctx, std::string(tag), st);
-  if (BN == 64) return tc_launch<64>(ctx, ts, 0, mPh, mPl, mQh, mQl, prm, st);
-  return tc_launch<128>(ctx, ts, 1, mPh, mPl, mQh, mQl, prm, st);
+  if (BN == 64) return tc_launch<64, false>(ctx, ts, 0, mPh, mPl, mQh, mQl, prm, st);
+  return tc_launch<128, false>(ctx, ts, 1, mPh, mPl, mQh, mQl, prm, st);
 }
 
 }  // namespace xg

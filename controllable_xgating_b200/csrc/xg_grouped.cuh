@@ -59,19 +59,6 @@ struct MapTable2 { CUtensorMap m[28]; };
 // boxes); 16 xt; 18 / 20 the two [h1|h2] buffers; 22 gp; 24 af; 26: V as [B*K][H] fp32 (box H/2 x K, no swizzle)
 constexpr int GM_H2A = 0, GM_LOGIT = 2, GM_W32 = 4, GM_XT = 16, GM_HH = 18, GM_GP = 22, GM_AF = 24, GM_V = 26;
 
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// instruction descriptor: D fp32, A/B fp16, both K-major
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 struct GroupParams {
   DecParams dp;                  // the pick / attention / token-input phases of xg_persist.cuh read this part
   const GSched* gsched;          // [3][G]: F1, F3, G4

@@ -128,7 +128,9 @@ int xg_bind_bn_buffers(xg_handle h, float* rm_rgb, float* rv_rgb, float* rm_opfl
  * them, so the parameter update has to be ordered before that call on the same stream (or by an event). */
 int xg_params_changed(xg_handle h);
 /* mode 0: everything on the SIMT fp32 engine; 1: dense contractions above a size gate run on the
- * tcgen05 3xTF32 engine (fp32-grade accuracy); 2 (default): 1 + greedy decoding in the fused persistent
+ * tcgen05 engine with two-term operands (fp32-grade accuracy: fp16 pairs in the forward entry points, whose operands -
+ * features, activations, weights - must stay below 65504 in magnitude; tf32 pairs in xg_train_bwd; XG_NO_TC16=1 in
+ * the environment keeps tf32 pairs everywhere); 2 (default): 1 + greedy decoding in the fused persistent
  * word-step kernel.  Results agree to ~1e-6 relative. */
 int xg_set_engine(xg_handle h, int mode);
 /* Fused-path policy.  Every serial loop of the path (encoder frame recurrence and its backward, greedy word loop,
@@ -307,7 +309,8 @@ int xg_debug_dropout_mask(uint64_t seed, int site, size_t n, float p, float* out
 /* C (M,N) = A . B with the library's GEMM kernels; layout: 0 = NT (A (M,K), B (N,K)),
  * 1 = NN (A (M,K), B (K,N)), 2 = TN (A (K,M), B (K,N)).  engine: 0 = auto, 1 = SIMT fp32,
  * 2 = tcgen05 3xTF32 (XG_ERR_UNSUPPORTED if the shape is not eligible), 3 = SIMT fp32 with the
- * deterministic split-K path enabled for skinny shapes (what the handle-bound path uses). */
+ * deterministic split-K path enabled for skinny shapes (what the handle-bound path uses), 4 = tcgen05 on fp16 operand
+ * pairs (3xFP16: what the forward entry points use for their batched products; |operand| < 65504). */
 int xg_debug_gemm(int layout, int engine, const float* A, const float* B, float* C,
                   int M, int N, int K, void* stream);
 

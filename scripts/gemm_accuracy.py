@@ -14,7 +14,7 @@ for (layout, M, N, K) in cases:
     a = A.double() if layout != 2 else A.double().t()
     b = B.double().t() if layout == 0 else B.double()
     ref = a @ b
-    for eng in (1, 2):
+    for eng in (1, 2, 4):
         C = debug_gemm(layout, eng, A, B, M, N, K)
         d = (C.double() - ref).abs()
         print("layout %d %5dx%5dx%5d engine %d: max rel err %.3e  fro %.3e  bad(>1e-4) %d" % (
