@@ -432,8 +432,13 @@ int xg_scheduled_tokens(xg_handle h, const float* V, const float* Uv, const floa
     Uv = g.Uv;
   }
   const bool step_drop = h->dec_drop_on && d.drop_prob > 0.f;
-  {
-    const int ps = persist_refuse(h, "the scheduled-sampling token pass", "it runs on per-step launches");
+  if (ss_prob > 0.f) {      // one launch of the sampling form of the grouped kernel (xg_grouped.cuh) when the shape fits
+    XG_CUDA_TRY(h->es, cudaMemcpyAsync(tokens_out, seq, sizeof(int64_t) * (size_t)B * L, cudaMemcpyDeviceToDevice, st));
+    GroupedSampling smp;
+    smp.sample_max = 0; smp.temperature = 1.f; smp.step_drop = step_drop; smp.drop_seed = h->dec_drop_seed;
+    smp.ss_mode = true; smp.ss_prob = ss_prob; smp.ss_seed = ss_seed; smp.ss_seq = seq; smp.ss_mask = seq_mask; smp.ss_used = tokens_out; smp.ss_L = L;
+    int ps = grouped_decode(h, V, Uv, pos, state0, B, K, Lp, nullptr, nullptr, nullptr, st, &smp);
+    if (ps == PK_FALLBACK) ps = persist_refuse(h, "the scheduled-sampling token pass", "shape outside the grouped decoder: it runs on per-step launches");
     if (ps != PK_FALLBACK) return ps;
   }
   for (int q = 0; q < 4; ++q)

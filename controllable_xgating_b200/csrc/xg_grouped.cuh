@@ -84,6 +84,14 @@ struct GroupParams {
   float inv_temp;
   unsigned long long sample_seed;
   DropSpec drop_gate, drop_h1, drop_h2;
+  // scheduled-sampling token pass (SAModel.py:89-99): the input token of step i >= 1 is the ground truth seq[b, i] or,
+  // with probability ss_prob, a draw from the word distribution of step i - 1; the step mask is seq_mask[b, i]
+  int ss_mode, ss_L, ss_Lp;
+  float ss_prob;
+  unsigned long long ss_seed;
+  const int64_t* ss_seq;        // (B, L)
+  const float* ss_mask;         // (B, L)
+  int64_t* ss_used;             // (B, L) tokens actually fed (initialised with seq by the host)
 };
 
 // L2 residency: the recurrent weights + the attention operands (47 MB) are re-read every word step and fit one L2
@@ -478,7 +486,7 @@ __device__ __forceinline__ void group_cell(const GroupParams& C, int layer, int 
         for (int k = 0; k < MAXS; ++k) v[q][g][k] = (on && k < ns) ? __ldcg(base + (long)k * PK_BN * 128 + g * 32) : 0.f;
       const int r = cb * PK_BN + c;
       const bool live = on && r < B;
-      mk[q] = (live && t > 0) ? __ldcg(P.unfinished + r) : 1.f;
+      mk[q] = (live && (t > 0 || (DROP && C.ss_mode))) ? __ldcg(P.unfinished + r) : 1.f;
       cp[q] = live ? __ldcg(cst + (long)r * H + j) : 0.f;
       hp[q] = live ? __ldcg(P.hx + (long)r * 2 * H + layer * H + j) : 0.f;
     }
@@ -749,9 +757,56 @@ __device__ __noinline__ int dec_pick_tiles(const GroupParams& C, int r, int t, c
   return tok;
 }
 
+// inverse-CDF draw of one vocabulary entry from p ~ exp((x - best) * invT) (warp 0, all lanes): the tile from the
+// per-tile masses in tile order, the entry from the stored logits of that tile (ids ascending).  u in [0, totT).
+__device__ __forceinline__ int tile_draw(const GroupParams& C, int r, const float (&mass)[8], float best, float invT, float u, int lane,
+                                         float* x_sel) {
+  const int ntv = C.ntv, V = C.dp.V;
+  float carry = 0.f, before = 0.f;
+  int sel_tile = -1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float incl = mass[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * i < ntv && carry + incl > u);
+    if (sel_tile < 0 && hit) {
+      const int first = __ffs(hit) - 1;
+      sel_tile = first + 32 * i;
+      before = carry + __shfl_sync(0xffffffffu, incl - mass[i], first);
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (sel_tile < 0) { sel_tile = ntv - 1; before = u; }          // rounding: past the end -> last entry below
+  const float4 x4 = __ldcg(reinterpret_cast<const float4*>(C.lraw + (long)r * ntv * 128 + (long)sel_tile * 128) + lane);
+  const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+  float e[4], loc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { e[k] = sel_tile * 128 + lane * 4 + k < V ? __expf((xs[k] - best) * invT) : 0.f; loc += e[k]; }
+  float incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const unsigned hit = __ballot_sync(0xffffffffu, before + incl > u);
+  if (hit) {
+    const int first = __ffs(hit) - 1;
+    float acc = before + __shfl_sync(0xffffffffu, incl - loc, first);
+    float ev[4], xv[4];      // (evaluated by every lane on lane `first`'s values)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { ev[kk] = __shfl_sync(0xffffffffu, e[kk], first); xv[kk] = __shfl_sync(0xffffffffu, xs[kk], first); }
+    int k = 0;
+    for (; k < 3; ++k) { acc += ev[k]; if (acc > u) break; }
+    *x_sel = xv[k];
+    return sel_tile * 128 + first * 4 + k;
+  }
+  const int last = min(V - 1, sel_tile * 128 + 127);
+  *x_sel = __shfl_sync(0xffffffffu, xs[(last & 127) & 3], (last & 127) >> 2);
+  return last;
+}
+
 // pick of caption r at step t in the sampling form of the loop (SAModel.py:188-196): arg-max, or one multinomial draw
-// from p ~ exp(logprob / temperature) by inverse CDF: the vocabulary tile from the per-tile masses, the entry from the
-// stored logits of that tile (ids in ascending order; Philox stream of the per-step kernel greedy_pick_kernel).
+// from p ~ exp(logprob / temperature) (Philox stream of the per-step kernel greedy_pick_kernel).  In the scheduled-
+// sampling token pass (SAModel.py:89-99; streams of ss_pick_kernel) the token fed to step t + 1 is the ground truth or,
+// with probability ss_prob, a draw from this step's distribution; nothing but the tokens is recorded.
 __device__ __noinline__ int dec_sample_tiles(const GroupParams& C, int r, int t, const SmemView& sv) {
   const DecParams& P = C.dp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -784,63 +839,42 @@ __device__ __noinline__ int dec_sample_tiles(const GroupParams& C, int r, int t,
     }
     tot = warp_sum(tot);
     totT = warp_sum(totT);
-    const float lse = best + logf(tot);
-    int pick = bi;
-    float pick_logp = best - lse;
-    if (!C.sample_max) {
-      const float u = philox_uniform(C.sample_seed, 0x5a4d0000u + (uint32_t)(t + 1), (uint64_t)r) * totT;
-      float carry = 0.f, before = 0.f;
-      int sel_tile = -1;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float incl = mass[i];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const unsigned hit = __ballot_sync(0xffffffffu, lane + 32 * i < ntv && carry + incl > u);
-        if (sel_tile < 0 && hit) {
-          const int first = __ffs(hit) - 1;
-          sel_tile = first + 32 * i;
-          before = carry + __shfl_sync(0xffffffffu, incl - mass[i], first);
+    if (C.ss_mode) {
+      const int i = t + 1;                                            // the step this token feeds
+      int tok = 0;
+      if (i < C.ss_Lp) {
+        tok = (int)__ldg(C.ss_seq + (long)r * C.ss_L + i);
+        const float coin = philox_uniform(C.ss_seed, 0x53530000u + (uint32_t)i, (uint64_t)r);
+        if (coin < C.ss_prob) {                                       // (warp-uniform: one caption per warp)
+          float xsel;
+          tok = tile_draw(C, r, mass, best, invT, philox_uniform(C.ss_seed, 0x53540000u + (uint32_t)i, (uint64_t)r) * totT, lane, &xsel);
         }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (sel_tile < 0) { sel_tile = ntv - 1; before = u; }          // rounding: past the end -> last entry below
-      const float4 x4 = __ldcg(reinterpret_cast<const float4*>(C.lraw + (long)r * ntv * 128 + (long)sel_tile * 128) + lane);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-      float e[4], loc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { e[k] = sel_tile * 128 + lane * 4 + k < P.V ? __expf((xs[k] - best) * invT) : 0.f; loc += e[k]; }
-      float incl = loc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      const unsigned hit = __ballot_sync(0xffffffffu, before + incl > u);
-      int sel; float xsel;
-      if (hit) {
-        const int first = __ffs(hit) - 1;
-        float acc = before + __shfl_sync(0xffffffffu, incl - loc, first);
-        int k = 0;
-        // (evaluated by every lane on lane `first`'s values)
-        float ev[4], xv[4];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { ev[kk] = __shfl_sync(0xffffffffu, e[kk], first); xv[kk] = __shfl_sync(0xffffffffu, xs[kk], first); }
-        for (; k < 3; ++k) { acc += ev[k]; if (acc > u) break; }
-        sel = sel_tile * 128 + first * 4 + k; xsel = xv[k];
-      } else {
-        const int last = min(P.V - 1, sel_tile * 128 + 127);
-        sel = last;
-        xsel = __shfl_sync(0xffffffffu, xs[(last & 127) & 3], (last & 127) >> 2);
+      if (lane == 0) {
+        if (i < C.ss_Lp) { C.ss_used[(long)r * C.ss_L + i] = tok; P.unfinished[r] = __ldg(C.ss_mask + (long)r * C.ss_L + i); }
+        P.tok[r] = tok;
+        P.flags[t] = 1;
+        redi[0] = tok;
       }
-      pick = sel; pick_logp = xsel - lse;
-    }
-    if (lane == 0) {
-      float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
-      unf = (unf != 0.f && pick > 0) ? 1.f : 0.f;
-      P.unfinished[r] = unf;
-      P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)pick : 0;
-      P.seqlogp[(long)r * P.T + t] = pick_logp;
-      P.tok[r] = pick;
-      if (unf != 0.f) P.flags[t] = 1;
-      redi[0] = pick;
+    } else {
+      const float lse = best + logf(tot);
+      int pick = bi;
+      float pick_logp = best - lse;
+      if (!C.sample_max) {
+        float xsel;
+        pick = tile_draw(C, r, mass, best, invT, philox_uniform(C.sample_seed, 0x5a4d0000u + (uint32_t)(t + 1), (uint64_t)r) * totT, lane, &xsel);
+        pick_logp = xsel - lse;
+      }
+      if (lane == 0) {
+        float unf = (t == 0) ? 1.f : __ldcg(P.unfinished + r);
+        unf = (unf != 0.f && pick > 0) ? 1.f : 0.f;
+        P.unfinished[r] = unf;
+        P.seq[(long)r * P.T + t] = unf != 0.f ? (int64_t)pick : 0;
+        P.seqlogp[(long)r * P.T + t] = pick_logp;
+        P.tok[r] = pick;
+        if (unf != 0.f) P.flags[t] = 1;
+        redi[0] = pick;
+      }
     }
   }
   __syncthreads();
@@ -1212,7 +1246,7 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
   }
   for (int r = cta; r < R; r += G) {
     if (r < B) {
-      if (SAMPLE) dec_token_inputs_drop(C, r, 0, 0);
+      if (SAMPLE) dec_token_inputs_drop(C, r, C.ss_mode ? (int)__ldg(C.ss_seq + (long)r * C.ss_L) : 0, 0);      // step 0 of the token pass: ground truth
       else dec_token_inputs(P, r, 0);                 // token 0 = <bos> (SAModel.py:184)
     } else {
       const __half z = __float2half_rn(0.f);
@@ -1225,7 +1259,7 @@ decode_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant_
         ah[(long)r * H + j] = z; al[(long)r * H + j] = z;
       }
     }
-    if (threadIdx.x == 0) { P.unfinished[r] = 1.f; P.tok[r] = 0; }
+    if (threadIdx.x == 0) { P.unfinished[r] = (SAMPLE && C.ss_mode && r < B) ? __ldg(C.ss_mask + (long)r * C.ss_L) : 1.f; P.tok[r] = 0; }
   }
   {   // EUv = exp(2 Uv), clamped like the per-step factor
     const long n = (long)B * P.K * P.A;
@@ -1899,6 +1933,9 @@ static void grouped_release(xg_context* ctx) {
 struct GroupedSampling {      // sampling form of the loop: multinomial draw (sample_max = 0) and / or the training dropout of the step
   int sample_max = 1; float temperature = 1.f; uint64_t seed = 0;
   bool step_drop = false; uint64_t drop_seed = 0;
+  // scheduled-sampling token pass: T = Lp steps, tokens into ss_used (pre-filled with seq), nothing else recorded; asynchronous
+  bool ss_mode = false; float ss_prob = 0.f; uint64_t ss_seed = 0;
+  const int64_t* ss_seq = nullptr; const float* ss_mask = nullptr; int64_t* ss_used = nullptr; int ss_L = 0;
 };
 static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, const float* const* state0,
                           int B, int K, int T, int64_t* seq_out, float* logp_out, int* steps_out, cudaStream_t st,
@@ -2077,6 +2114,9 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   hp.sample_max = smp ? smp->sample_max : 1; hp.step_drop = smp && smp->step_drop ? 1 : 0;
   hp.inv_temp = smp && !smp->sample_max ? 1.f / smp->temperature : 1.f;
   hp.sample_seed = smp ? smp->seed : 0;
+  hp.ss_mode = smp && smp->ss_mode ? 1 : 0; hp.ss_L = smp ? smp->ss_L : 0; hp.ss_Lp = T;
+  hp.ss_prob = smp ? smp->ss_prob : 0.f; hp.ss_seed = smp ? smp->ss_seed : 0;
+  hp.ss_seq = smp ? smp->ss_seq : nullptr; hp.ss_mask = smp ? smp->ss_mask : nullptr; hp.ss_used = smp ? smp->ss_used : nullptr;
   {
     const bool dr = smp && smp->step_drop;
     hp.drop_gate = make_drop(dr, d.drop_prob, smp ? smp->drop_seed : 0, XG_DROP_DEC_GATE);
@@ -2130,8 +2170,8 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(S->d_params, &hp, sizeof(GroupParams), cudaMemcpyHostToDevice, st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned int) * (128 + 2 * groups), st));
   XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_flags, 0, sizeof(int) * (size_t)T, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
-  XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
+  if (seq_out) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(seq_out, 0, sizeof(int64_t) * (size_t)B * T, st));
+  if (logp_out) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(logp_out, 0, sizeof(float) * (size_t)B * T, st));
   if (dp.dbg_clock) XG_CUDA_TRY(ctx->es, cudaMemsetAsync(S->d_dbg, 0, sizeof(long long) * ((2048 + 256) * PK_STAMPS + 64), st));
   if (!S->attr_set) {
     XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(decode_grouped_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GK_SMEM_BYTES));
@@ -2149,6 +2189,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
     ctx->n_fused++;
   }
+  if (hp.ss_mode) return XG_OK;      // the token pass has no early exit and nothing to read back
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
   int steps = 0;
@@ -2346,7 +2387,7 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
   hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
   hp.topk = 0; hp.lraw = nullptr; hp.lpart = nullptr;
-  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0;
   hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
@@ -2672,7 +2713,7 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = 0;
   hp.nslots[0] = members_l[0]; hp.nslots[1] = members_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
-  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0;
   hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));

@@ -139,10 +139,10 @@ int xg_set_engine(xg_handle h, int mode);
  * (backward: of 32) and <= 1600, input_encoding_size a multiple of 4 and <= 640, frames <= 32, vocab < 32000,
  * at most 1024 caption rows (batch, or videos x beam) per call; the persistent backward loops at most 256 captions
  * per call.  Inside those limits the second-generation kernels (xg_grouped.cuh: fp16 operand pairs, LSTM cells fused
- * behind their products) take the greedy / sampling (multinomial draw, training dropout) / teacher-forced word loops up
- * to 64 captions per call, the beam-search step up to 9 x 64 rows and the encoder recurrence when rnn_size is a
+ * behind their products) take the greedy / sampling (multinomial draw, training dropout) / scheduled-sampling /
+ * teacher-forced word loops up to 64 captions per call, the beam-search step up to 9 x 64 rows and the encoder recurrence when rnn_size is a
  * multiple of 64; larger calls run the first-generation persistent kernels (same results to ~1e-6).  Outside the
- * limits, and for multinomial sampling above 64 captions and the scheduled-sampling token pass, the same arithmetic
+ * limits, and for multinomial sampling / the scheduled-sampling token pass above 64 captions, the same arithmetic
  * runs as per-step launches.
  * strict = 1 (or XG_STRICT_PERSIST=1 in the environment at xg_create) turns every such downgrade into
  * XG_ERR_UNSUPPORTED, unless mode < 2 was asked for with xg_set_engine. */

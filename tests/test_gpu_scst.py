@@ -159,3 +159,27 @@ def test_multinomial_sampling_distribution_on_the_grouped_kernel():
     assert np.abs(freq - prob).max() < 4 * np.sqrt(prob.max() / (B * reps)) + 5e-3
     nz = first > 0
     assert np.allclose(lps0[nz], lp0[0][torch.from_numpy(first)].numpy()[nz], atol=1e-4)      # log-probs at temperature 1
+
+
+@pytest.mark.parametrize("name,ss", [("mid", 0.5), ("c1", 1.0)])
+def test_scheduled_sampling_token_pass_runs_on_the_grouped_kernel(name, ss):
+    """ss_prob > 0: the token pass (SAModel.py:89-99) runs as one launch of decode_grouped_kernel<1> (asserted) and feeds
+    the tokens the per-step launches feed (same Philox streams; a draw within rounding of a CDF step may differ)."""
+    from tests.common import fused_path
+    cfg, P, b = make_case(name); d = dev(b)
+    used = []
+    for persistent in (True, False):
+        m = build_model(cfg, P, drop=0.5).train()
+        m._engine.set_engine(True, persistent)
+        m.ss_prob = ss
+        torch.manual_seed(321)
+        with torch.no_grad():
+            if persistent:
+                with fused_path(m, ["encode_persistent", "decode_persistent", "train_decode_persistent"]):
+                    m(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
+            else:
+                m(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], d["seq"], d["seq_mask"])
+        used.append(m._last_ss_tokens.cpu())
+    same_rows = (used[0] == used[1]).all(dim=1)
+    assert same_rows.float().mean().item() >= 0.9, (used[0], used[1])
+    assert (used[0] != b["seq"][:, :used[0].shape[1]]).any()          # something was sampled
