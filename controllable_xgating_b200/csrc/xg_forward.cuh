@@ -33,6 +33,9 @@ static int gemm_run(xg_context* ctx, const GemmP& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------
 // EncoderLstm_two_fc.forward (sub_modules.py:118-159)
 // ------------------------------------------------------------------------------------
+static int init_hidden_core(xg_context* ctx, const float* V, const float* fmask, int B, int K, float* meanV,
+                            float* const* state_out, long ld_out, cudaStream_t st);
+
 static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, const float* fmask, int B, int K,
                        int train_flags, uint64_t seed, EncBufs& eb, float* V_out, float* Uv_out,
                        float* const* state_out, cudaStream_t st) {
@@ -121,23 +124,24 @@ static int encode_core(xg_context* ctx, const float* rgb, const float* opfl, con
     g.ep.bias0 = P_(ctx, XG_P_V2A_B);
     XG_TRY(gemm_run(ctx, g, st));
   }
-  if (state_out) {  // SAModel.init_hidden (SAModel.py:58-65)
-    XG_TRY(launch(ctx, "masked_mean", masked_mean_kernel, B, 128, 0, st, V_out, fmask, B, K, H, eb.meanV));
-    const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
-    for (int q = 0; q < 4; ++q) {
-      GemmP g = gemm_nt(eb.meanV, H, P_(ctx, iw[q]), H, state_out[q], H, B, H, H);
-      g.ep.bias0 = P_(ctx, iw[q] + 1);
-      XG_TRY(gemm_run(ctx, g, st));
-    }
-  }
+  if (state_out) XG_TRY(init_hidden_core(ctx, V_out, fmask, B, K, eb.meanV, state_out, H, st));      // SAModel.init_hidden (SAModel.py:58-65)
   return XG_OK;
 }
 
 static int init_hidden_core(xg_context* ctx, const float* V, const float* fmask, int B, int K, float* meanV,
                             float* const* state_out, long ld_out, cudaStream_t st) {
   const int H = ctx->d.rnn;
-  XG_TRY(launch(ctx, "masked_mean", masked_mean_kernel, B, 128, 0, st, V, fmask, B, K, H, meanV));
+  XG_TRY(launch(ctx, "masked_mean", masked_mean_kernel, dim3(B, ceil_div(H, 128)), 128, 0, st, V, fmask, B, K, H, meanV));
   const int iw[4] = {XG_P_INIT_H1_W, XG_P_INIT_C1_W, XG_P_INIT_H2_W, XG_P_INIT_C2_W};
+  if (H <= 32 * IS_KPL && ctx->tc_mode != 0) {           // the four linears in one launch (engine mode 0 keeps the plain GEMM path)
+    InitStateArgs a;
+    for (int q = 0; q < 4; ++q) { a.W[q] = P_(ctx, iw[q]); a.bias[q] = P_(ctx, iw[q] + 1); a.out[q] = state_out[q]; a.ld[q] = q % 2 == 0 ? ld_out : H; }
+    const size_t smem = sizeof(float) * (size_t)IS_CAPS * H;
+    static bool attr_set = false;
+    if (!attr_set) { XG_CUDA_TRY(ctx->es, cudaFuncSetAttribute(init_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * IS_CAPS * 32 * IS_KPL))); attr_set = true; }
+    XG_TRY(launch(ctx, "init_state", init_state_kernel, dim3(ceil_div(H, 16), 4), 256, smem, st, (const float*)meanV, B, H, a));
+    return XG_OK;
+  }
   for (int q = 0; q < 4; ++q) {
     GemmP g = gemm_nt(meanV, H, P_(ctx, iw[q]), H, state_out[q], q % 2 == 0 ? ld_out : H, B, H, H);
     g.ep.bias0 = P_(ctx, iw[q] + 1);

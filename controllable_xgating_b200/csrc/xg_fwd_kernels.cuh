@@ -170,10 +170,52 @@ __global__ void masked_mean_kernel(const float* __restrict__ V, const float* __r
   const int b = blockIdx.x;
   float cnt = 0.f;
   for (int k = 0; k < K; ++k) cnt += fmask[(long)b * K + k];
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < H; j += gridDim.y * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < K; ++k) s += V[((long)b * K + k) * H + j];
     mean[(long)b * H + j] = s / cnt;
+  }
+}
+
+// The four init-state linears of SAModel.init_hidden (SAModel.py:62-65) in ONE launch: out_q[b, n] = mean[b, :] . W_q[n, :] + b_q[n].
+// blockIdx.y = q; a CTA of 8 warps takes 16 rows of W_q (two per warp, a row in registers), mean (B x H) sits in shared
+// memory in slabs of IS_CAPS captions.  H <= 32 * IS_KPL.
+constexpr int IS_KPL = 16;       // K elements per lane
+constexpr int IS_CAPS = 64;      // captions per shared-memory slab
+struct InitStateArgs { const float* W[4]; const float* bias[4]; float* out[4]; long ld[4]; };
+__global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict__ mean, int B, int H, const InitStateArgs a) {
+  extern __shared__ float is_mv[];                       // [IS_CAPS][H]
+  const int q = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 16 + warp * 2;
+  float w[2][IS_KPL];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < IS_KPL; ++i) {
+      const int k = lane + 32 * i;
+      w[r][i] = (n0 + r < H && k < H) ? __ldg(a.W[q] + (long)(n0 + r) * H + k) : 0.f;
+    }
+  const float b0 = n0 < H ? __ldg(a.bias[q] + n0) : 0.f, b1 = n0 + 1 < H ? __ldg(a.bias[q] + n0 + 1) : 0.f;
+  for (int c0 = 0; c0 < B; c0 += IS_CAPS) {
+    const int nc = min(IS_CAPS, B - c0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nc * H; e += 256) is_mv[e] = mean[(long)c0 * H + e];
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < IS_KPL; ++i) {
+        const int k = lane + 32 * i;
+        const float m = k < H ? is_mv[c * H + k] : 0.f;
+        s0 = fmaf(w[0][i], m, s0); s1 = fmaf(w[1][i], m, s1);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+      if (lane == 0) {
+        if (n0 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0] = s0 + b0;
+        if (n0 + 1 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0 + 1] = s1 + b1;
+      }
+    }
   }
 }
 
