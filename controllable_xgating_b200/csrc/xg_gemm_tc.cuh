@@ -784,7 +784,9 @@ static int tc_launch(xg_context* ctx, TcState* ts, int cfg_idx, const CUtensorMa
 // split-K word-step kernel takes them over.
 static bool tc_eligible(const GemmP& p) {
   const long tiles = (long)ceil_div(p.N, 128) * ceil_div(p.M, 64);
-  return p.K >= 64 && tiles >= 56 && (long)p.M * p.N * p.K >= (1L << 24);
+  // (32 tiles are enough when the reduction is long: the 512 x 512 x 1792 weight gradients of the cross gates took 58 us on
+  //  the SIMT engine)
+  return p.K >= 64 && (tiles >= 56 || (tiles >= 32 && p.K >= 1536)) && (long)p.M * p.N * p.K >= (1L << 24);
 }
 
 // C (M,N) = epi( A . B ) in the GemmP convention (A(i,r), B(r,j), arbitrary strides).

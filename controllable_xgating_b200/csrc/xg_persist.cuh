@@ -1761,6 +1761,7 @@ struct PersistState {
   unsigned int* d_dbcounter = nullptr;
   long long* d_dbdbg = nullptr;
   float* dbwT[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long dbwT_epoch = ~0ull, wT_epoch = ~0ull;
   bool dbattr_set = false;
   // encoder backward
   int bB = 0;
@@ -2232,15 +2233,19 @@ static int persist_encode_bwd(xg_context* ctx, const float* fmask, int B, int K,
       }
     }
     S->bB = B;
+    S->wT_epoch = ~0ull;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(bp.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
   const int whh[2] = {XG_P_LSTM_RGB_WHH, XG_P_LSTM_OPFL_WHH};
-  for (int s = 0; s < 2; ++s) {    // the recurrent matrices change every optimizer step: transpose per call (2 x 4 MB)
+  // transposed copies of the recurrent matrices (2 x 4 MB): derived tables like the operand splits, rebuilt when the
+  // parameter epoch moved (every optimizer step in training)
+  for (int s = 0; s < 2 && S->wT_epoch != ctx->param_epoch; ++s) {
     ProfScope ps(ctx, "transpose", st);
     transpose_kernel<<<dim3(ceil_div(H, 32), ceil_div(4 * H, 32)), dim3(32, 8), 0, st>>>(ctx->P[whh[s]], 4 * H, H, S->wT[s]);
     XG_LAUNCH_CHECK(ctx->es);
   }
+  S->wT_epoch = ctx->param_epoch;
   MapTable mt;
   XG_TRY(tc_make_map(ctx, ts, S->wT[0], H, 4 * H, 128, &mt.m[0]));
   XG_TRY(tc_make_map(ctx, ts, S->wT[1], H, 4 * H, 128, &mt.m[1]));
@@ -2325,18 +2330,20 @@ static int persist_decode_bwd(xg_context* ctx, const float* Vf, const float* Uv,
       }
     }
     S->dbB = R; S->dbK = K;
+    S->dbwT_epoch = ~0ull;
   }
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<PSched*>(bp.sched), sched.data(), sizeof(PSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
-  // the weights change every optimizer step: transposed copies per call (4 x 4 MB + 6 MB)
+  // transposed copies of the weights (4 x 4 MB + 6 MB): rebuilt when the parameter epoch moved
   const int wsrc[5] = {XG_P_L2_I2H_W, XG_P_L2_A2H_W, XG_P_L2_H2H_W, XG_P_L1_H2H_W, XG_P_H2A_W};
-  for (int w = 0; w < 5; ++w) {
+  for (int w = 0; w < 5 && S->dbwT_epoch != ctx->param_epoch; ++w) {
     int rows, cols;
     param_shape(d, wsrc[w], &rows, &cols);
     ProfScope ps(ctx, "transpose", st);
     transpose_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, st>>>(ctx->P[wsrc[w]], rows, cols, S->dbwT[w]);
     XG_LAUNCH_CHECK(ctx->es);
   }
+  S->dbwT_epoch = ctx->param_epoch;
   MapTable mt;
   for (int w = 0; w < 4; ++w) XG_TRY(tc_make_map(ctx, ts, S->dbwT[w], H, 4 * H, 128, &mt.m[w]));
   XG_TRY(tc_make_map(ctx, ts, S->dbwT[4], 2 * H, A, 128, &mt.m[4]));
