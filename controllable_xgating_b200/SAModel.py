@@ -56,6 +56,37 @@ class _TrainForward(torch.autograd.Function):
         return (None,) * 8 + tuple(out)
 
 
+class PendingSample:
+    """Result of SAModel.sample_async: full-length (B, seq_length) device tensors whose trailing columns are zero."""
+
+    def __init__(self, seq, lps):
+        self.seq, self.lps = seq, lps
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    @staticmethod
+    def steps_of(seq_host) -> int:
+        """columns the reference would have returned: leading columns with a non-zero id (SAModel.py:199-210)"""
+        alive = (seq_host != 0).any(dim=0)
+        n = int(alive.shape[0])
+        for t in range(n):
+            if not bool(alive[t]):
+                return t
+        return n
+
+    def to_host(self, host_seq, host_lps):
+        """queue the copies into (pinned) host buffers on the current stream; finish with .event / a stream sync"""
+        host_seq.copy_(self.seq, non_blocking=True)
+        host_lps.copy_(self.lps, non_blocking=True)
+
+    def result(self):
+        self.event.synchronize()
+        steps = self.steps_of(self.seq.cpu())
+        if steps == 0:
+            raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
+        return self.seq[:, :steps], self.lps[:, :steps]
+
+
 class SAModel(CaptionModel):
     VERBOSE = VERBOSE   # set SAModel.VERBOSE = False (or on an instance) to silence the reference-style prints
 
@@ -256,6 +287,21 @@ class SAModel(CaptionModel):
             raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
         return seq[:, :steps], lps[:, :steps]
 
+
+    def sample_async(self, feats_rgb, feats_opfl, feat_mask, pos_feats, opt={}):
+        """Greedy / multinomial sample() in eval mode WITHOUT the host synchronisation: the work is queued on the current
+        stream and a PendingSample comes back at once, so a serving loop can queue batch i+1 before it reads batch i
+        (sample() has to wait for the word loop to learn how many columns the reference would return, SAModel.py:206).
+        PendingSample.result() -> (seq, seqLogprobs) exactly as sample() returns them."""
+        if self.training or opt.get("beam_size", 1) > 1:
+            raise ValueError("sample_async covers eval-mode greedy / multinomial decoding (use sample())")
+        sample_max = opt.get("sample_max", 1)
+        feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
+        seed = 0 if sample_max else self._engine.next_seed()
+        with torch.no_grad():
+            seq, lps, _ = self._engine.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max,
+                                                     opt.get("temperature", 1.0), seed, want_steps=False)
+        return PendingSample(seq, lps)
 
     def _forward_scheduled(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):
         """forward() with scheduled sampling (ss_prob > 0, SAModel.py:89-99).  The sampled inputs carry no gradient

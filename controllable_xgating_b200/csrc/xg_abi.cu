@@ -345,7 +345,7 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
                      int* steps_out, void* ws, size_t ws_bytes, void* stream) {
   CHECK_HANDLE(h); CHECK_BOUND(h);
   CHECK_PTR(h, V); CHECK_PTR(h, pos); CHECK_PTR(h, state0); CHECK_PTR(h, seq_out); CHECK_PTR(h, logp_out);
-  CHECK_PTR(h, steps_out); CHECK_PTR(h, ws);
+  CHECK_PTR(h, ws);      // (steps_out may be NULL: asynchronous call)
   CHECK_POS(h, B); CHECK_POS(h, K); CHECK_POS(h, T);
   for (int q = 0; q < 4; ++q) CHECK_PTR(h, state0[q]);
   if (T + 1 > xg_context::kPinnedInts) return fail(h, XG_ERR_BAD_SHAPE, "xg_sample_greedy: seq_length too large");
@@ -401,6 +401,7 @@ int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* 
                             step_drop ? drops : nullptr));
     XG_TRY(logits_core(h, g.st[2], H, B, g.logits, st));
   }
+  if (!steps_out) return XG_OK;      // asynchronous call
   XG_CUDA_TRY(h->es, cudaMemcpyAsync(h->h_pinned, g.flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(h->es, cudaStreamSynchronize(st));
   int steps = 0;

@@ -2189,7 +2189,7 @@ static int grouped_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel(fn, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
     ctx->n_fused++;
   }
-  if (hp.ss_mode) return XG_OK;      // the token pass has no early exit and nothing to read back
+  if (hp.ss_mode || !steps_out) return XG_OK;      // the token pass has nothing to read back; steps_out == NULL: asynchronous call
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
   int steps = 0;

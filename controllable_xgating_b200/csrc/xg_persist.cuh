@@ -2069,7 +2069,7 @@ static int persist_decode(xg_context* ctx, const float* Vf, const float* Uv, con
     S->step_valid = true; S->step_B = B; S->step_fdiv = step->feat_div; S->step_V = Vf; S->step_Uv = Uv; S->step_pos = pos;
     S->step_epoch = ctx->param_epoch; S->step_mt = mt;
   }
-  if (mode != 0) return XG_OK;     // asynchronous: the caller's next kernels follow on the same stream
+  if (mode != 0 || !steps_out) return XG_OK;     // asynchronous: the caller's next kernels follow on the same stream
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(ctx->h_pinned, S->d_flags, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, st));
   XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
   int steps = 0;

@@ -317,13 +317,14 @@ class Engine:
         return out, Lp
 
     def sample_greedy(self, V, Uv, pos, state, T: int, sample_max: int, temperature: float, seed: int,
-                      drop_seed: Optional[int] = None):
-        """drop_seed: apply the TRAINING dropout of the word step with this Philox seed (self-critical sampling)."""
+                      drop_seed: Optional[int] = None, want_steps: bool = True):
+        """drop_seed: apply the TRAINING dropout of the word step with this Philox seed (self-critical sampling).
+        want_steps=False: asynchronous call (steps_out = NULL): returns (seq, lps, None) without synchronising."""
         self.bind()
         if drop_seed is not None:
             L.check(self.lib.xg_set_decode_dropout(self.handle, 1, drop_seed), "xg_set_decode_dropout", self.handle)
             try:
-                return self.sample_greedy(V, Uv, pos, state, T, sample_max, temperature, seed)
+                return self.sample_greedy(V, Uv, pos, state, T, sample_max, temperature, seed, want_steps=want_steps)
             finally:
                 L.check(self.lib.xg_set_decode_dropout(self.handle, 0, 0), "xg_set_decode_dropout", self.handle)
         d = self.dims
@@ -335,9 +336,10 @@ class Engine:
         stp = (c_void_p * 4)(*[t.data_ptr() for t in state])
         steps = c_int(0)
         L.check(self.lib.xg_sample_greedy(self.handle, V.data_ptr(), _ptr(Uv), pos.data_ptr(), stp, B, K, T, int(sample_max),
-                                          float(temperature), seed, seq.data_ptr(), lps.data_ptr(), ctypes.byref(steps),
+                                          float(temperature), seed, seq.data_ptr(), lps.data_ptr(),
+                                          ctypes.byref(steps) if want_steps else None,
                                           ws.data_ptr(), ws.numel(), _stream()), "xg_sample_greedy", self.handle)
-        return seq, lps, steps.value
+        return seq, lps, (steps.value if want_steps else None)
 
     def sample_beam(self, V, fmask, pos, T: int, beam: int):
         self.bind()

@@ -197,7 +197,10 @@ int xg_set_decode_dropout(xg_handle h, int on, uint64_t seed);
  *   and a Philox stream seeded by `seed` (:189-196).
  *   seq_out (B,T) int64, logp_out (B,T); columns >= *steps_out are zero.
  *   steps_out (HOST int*): number of columns the reference would have returned (loop break at :206).
- *   SYNC: returns after the stream has been synchronised (steps_out is a host value). */
+ *   SYNC: returns after the stream has been synchronised (steps_out is a host value).
+ *   steps_out == NULL: ASYNCHRONOUS - the call returns once the work is queued on `stream` (a serving loop queues the
+ *   next batch before it reads this one back); the number of columns is then the number of leading columns of seq_out
+ *   with a non-zero entry (an unfinished caption always emits a non-zero id, SAModel.py:199-210). */
 int xg_sample_greedy(xg_handle h, const float* V, const float* Uv, const float* pos,
                      const float* const* state0, int B, int K, int T,
                      int sample_max, float temperature, uint64_t seed,

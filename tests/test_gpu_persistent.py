@@ -195,3 +195,15 @@ def test_persistent_beam_step_matches_unfused(B, beam):
         assert rel_err(l0[k].numpy(), l1[k].numpy()) < 1e-4
     for k in range(B):
         assert abs(d0[k][0][1] - d1[k][0][1]) <= 1e-4 * abs(d1[k][0][1])
+
+
+def test_sample_async_equals_sample():
+    """SAModel.sample_async (no host synchronisation inside, steps derived from the ids) returns what sample() returns,
+    for greedy decoding with and without an early exit."""
+    for name in ("mid", "c1"):
+        cfg, P, b = make_case(name); d = dev(b)
+        m = build_model(cfg, P).eval()
+        seq, lps = m.sample(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1, "beam_size": 1})
+        pend = m.sample_async(d["rgb"], d["opfl"], d["feat_mask"], d["pos"], {"sample_max": 1})
+        seq2, lps2 = pend.result()
+        assert torch.equal(seq, seq2) and torch.equal(lps, lps2)
