@@ -248,16 +248,34 @@ class SAModel(CaptionModel):
         assert beam_size <= self.vocab_size, ("lets assume this for now, otherwise this corner case causes a few headaches "
                                               "down the road. can be dealt with in future if needed")
         with torch.no_grad():
-            seq, lps, dseq, dlps, dp, dn = self._engine.sample_beam(feats, feat_masks, pos_feats, self.seq_length, beam_size)
-        seq, lps, dseq, dlps, dp, dn = (t.cpu() for t in (seq, lps, dseq, dlps, dp, dn))
-        # rows of the (freshly copied) host tensors are handed out as views: building 2 x B x beam clones costs
-        # milliseconds of interpreter time per batch
-        sq = [r.unbind(0) for r in dseq.unbind(0)]
-        lp = [r.unbind(0) for r in dlps.unbind(0)]
-        dpl, dnl = dp.tolist(), dn.tolist()
-        self.done_beams = [[{"seq": sq[k][j], "logps": lp[k][j], "p": dpl[k][j]} for j in range(dnl[k])]
-                           for k in range(seq.size(0))]
+            dev_out = self._engine.sample_beam(feats, feat_masks, pos_feats, self.seq_length, beam_size)
+        # six results -> pinned host buffers with ONE synchronisation (six pageable .cpu() copies cost 0.5 ms per batch)
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in dev_out]
+        for h, t in zip(host, dev_out):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(dev_out[0].device).synchronize()
+        seq, lps, dseq, dlps, dp, dn = host
+        # done_beams (SAModel.py:158: one list of {seq, logps, p} per video) is built when it is first read: the 2 x B x beam
+        # row views + dicts cost a few hundred microseconds of interpreter time per batch
+        self._done_beams = None
+        self._done_raw = (dseq, dlps, dp, dn)
         return seq, lps
+
+    @property
+    def done_beams(self):
+        if self._done_beams is None and getattr(self, "_done_raw", None) is not None:
+            dseq, dlps, dp, dn = self._done_raw
+            sq = [r.unbind(0) for r in dseq.unbind(0)]
+            lp = [r.unbind(0) for r in dlps.unbind(0)]
+            dpl, dnl = dp.tolist(), dn.tolist()
+            self._done_beams = [[{"seq": sq[k][j], "logps": lp[k][j], "p": dpl[k][j]} for j in range(dnl[k])]
+                                for k in range(dseq.size(0))]
+        return self._done_beams
+
+    @done_beams.setter
+    def done_beams(self, value):
+        object.__setattr__(self, "_done_beams", value)
+        object.__setattr__(self, "_done_raw", None)
 
     def sample(self, feats_rgb, feats_opfl, feat_mask, pos_feats, opt={}):
         """SAModel.py:163-219"""

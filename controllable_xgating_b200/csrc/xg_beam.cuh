@@ -99,67 +99,16 @@ inline void carve_beam(Arena& a, const xg_dims& d, int B, int K, int T, int beam
   carve_step(a, d, (int)n, w.step);
 }
 
-// one warp per video: candidate merge + bookkeeping of beam_step and the done-beam harvest.  The stable
-// descending sort is a rank count (rank = candidates that score higher, or equal with a lower index).
+// one warp per video: candidate merge + bookkeeping of beam_step and the done-beam harvest (beam_merge_warp, xg_grouped.cuh:
+// the grouped step kernel runs the same function at the end of its launch)
 constexpr int BEAM_MERGE_WARPS = 4;
-__global__ void beam_merge_kernel(const float* __restrict__ ys, const int* __restrict__ ix, int B, int beam, int T, int t,
-                                  const int64_t* __restrict__ seq_in, const float* __restrict__ lps_in,
-                                  int64_t* __restrict__ seq_out, float* __restrict__ lps_out, float* __restrict__ sum,
-                                  int* __restrict__ parent, int64_t* __restrict__ tokens,
-                                  int64_t* __restrict__ done_seq, float* __restrict__ done_lps,
-                                  float* __restrict__ done_p, int* __restrict__ done_n) {
+__global__ void beam_merge_kernel(const BeamMergeIO M) {
   __shared__ double s_cp[BEAM_MERGE_WARPS][XG_MAX_BEAM * XG_MAX_BEAM];
   __shared__ int s_sel[BEAM_MERGE_WARPS][XG_MAX_BEAM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * BEAM_MERGE_WARPS + warp;
-  if (k >= B) return;
-  const int rows = (t == 0) ? 1 : beam;
-  const int ncand = rows * beam;
-  double* cp = s_cp[warp];
-  int* sel = s_sel[warp];
-  // enumerate column-major: c outer, q inner
-  for (int n = lane; n < ncand; n += 32) {
-    const int c = n / rows, q = n % rows;
-    cp[n] = (double)sum[(long)k * beam + q] + (double)ys[((long)k * beam + q) * beam + c];
-  }
-  if (lane < beam) sel[lane] = lane < ncand ? lane : 0;
-  __syncwarp();
-  for (int n = lane; n < ncand; n += 32) {
-    const double pn = cp[n];
-    int rank = 0;
-    for (int m = 0; m < ncand; ++m) rank += (cp[m] > pn || (cp[m] == pn && m < n)) ? 1 : 0;
-    if (rank < beam) sel[rank] = n;
-  }
-  __syncwarp();
-  int dn = done_n[k];
-  __syncwarp();
-  for (int vix = 0; vix < beam; ++vix) {
-    const int cand = sel[vix];
-    const int c = cand / rows, q = cand % rows;
-    const long src = ((long)k * beam + q) * T, dst = ((long)k * beam + vix) * T;
-    const int word = ix[((long)k * beam + q) * beam + c];
-    const float wlp = ys[((long)k * beam + q) * beam + c];
-    float nsum = (float)cp[cand];
-    const bool done = word == 0 || t == T - 1;
-    const long dd = ((long)k * T * beam + dn) * T;
-    for (int u = lane; u < T; u += 32) {
-      const int64_t sv = u < t ? seq_in[src + u] : (u == t ? (int64_t)word : (int64_t)0);
-      const float lv = u < t ? lps_in[src + u] : (u == t ? wlp : 0.f);
-      seq_out[dst + u] = sv; lps_out[dst + u] = lv;
-      if (done) { done_seq[dd + u] = sv; done_lps[dd + u] = lv; }
-    }
-    if (done) {
-      if (lane == 0) done_p[(long)k * T * beam + dn] = nsum;
-      ++dn;
-      nsum = -1000.f;
-    }
-    if (lane == 0) {
-      sum[(long)k * beam + vix] = nsum;
-      parent[(long)k * beam + vix] = k * beam + q;
-      tokens[(long)k * beam + vix] = word;
-    }
-  }
-  if (lane == 0) done_n[k] = dn;
+  if (k >= M.B) return;
+  beam_merge_warp(M, k, s_cp[warp], s_sel[warp], lane);
 }
 
 // dst[row,:] = src[parent[row],:] for the four state tensors
@@ -248,12 +197,37 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
   // the word step runs as one persistent cooperative launch when the shape allows it (xg_persist.cuh): it also
   // gathers the parent states on the way in and leaves the per-row top-`beam` on the way out
   bool fused = beam <= XG_MAX_BEAM;      // persist_decode checks the shape (and refuses loudly on a strict handle)
+  bool merged = false;                   // the merge of position t ran inside the previous word-step launch
+  auto merge_io = [&](int t) {
+    BeamMergeIO m;
+    m.ys = w.ys; m.ix = w.ix; m.B = B; m.beam = beam; m.T = T; m.t = t;
+    m.seq_in = w.seq[sb]; m.lps_in = w.lps[sb]; m.seq_out = w.seq[sb ^ 1]; m.lps_out = w.lps[sb ^ 1];
+    m.sum = w.sum; m.parent = w.parent; m.tokens = w.tokens;
+    m.done_seq = w.done_seq; m.done_lps = w.done_lps; m.done_p = w.done_p; m.done_n = w.done_n;
+    return m;
+  };
+  if (fused && !env_flag("XG_BEAM_STEPWISE")) {
+    // the whole search in ONE launch of the grouped step kernel when the shape fits it: the <bos> step and T - 1 more,
+    // each followed by the candidate merge of its position (a cooperative launch per word step left the GPU idle for
+    // ~30 us between steps: 14 % of a batch)
+    PersistStepIO io;
+    io.tokens = w.tokens; io.state = w.st[0]; io.logp = nullptr; io.feat_div = beam; io.first = 1;
+    io.parent = nullptr; io.ys = w.ys; io.ix = w.ix; io.topk = beam;
+    const BeamMergeIO mg = merge_io(0);
+    const int pst = grouped_step(ctx, V, w.Uv, pos, n, K, io, st, &mg, T);
+    if (pst == XG_OK) {
+      XG_TRY(launch(ctx, "beam_finalize", beam_finalize_kernel, ceil_div(B, 64), 64, 0, st, w.done_seq, w.done_lps, w.done_p, w.done_n, B, beam, T, seq_out,
+                                                          logp_out, done_seq, done_lps, done_p, done_count));
+      return XG_OK;
+    }
+    if (pst != PK_FALLBACK) return pst;
+  }
   for (int t = -1; t < T; ++t) {
     if (t >= 0) {
-      if (!fused) XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));
-      XG_TRY(launch(ctx, "beam_merge", beam_merge_kernel, ceil_div(B, BEAM_MERGE_WARPS), 32 * BEAM_MERGE_WARPS, 0, st, w.ys, w.ix, B, beam, T, t,
-                    w.seq[sb], w.lps[sb], w.seq[sb ^ 1], w.lps[sb ^ 1], w.sum, w.parent, w.tokens, w.done_seq, w.done_lps,
-                    w.done_p, w.done_n));
+      if (!merged) {
+        if (!fused) XG_TRY(launch(ctx, "beam_topk", beam_topk_kernel, n, 256, 0, st, w.logits, Vn, beam, w.ys, w.ix));
+        XG_TRY(launch(ctx, "beam_merge", beam_merge_kernel, ceil_div(B, BEAM_MERGE_WARPS), 32 * BEAM_MERGE_WARPS, 0, st, merge_io(t)));
+      }
       sb ^= 1;
       if (t == T - 1) break;   // the reference's last get_logprobs_state result is never used
       if (!fused) {
@@ -262,12 +236,16 @@ static int beam_core(xg_context* ctx, const float* V, const float* fmask, const 
         cur ^= 1;
       }
     }
+    merged = false;
     // one word step on all rows (t == -1: the <bos> step at SAModel.py:150-154)
     if (fused) {
       PersistStepIO io;
       io.tokens = w.tokens; io.state = w.st[cur]; io.logp = nullptr; io.feat_div = beam; io.first = (t == -1);
       io.parent = t >= 0 ? w.parent : nullptr; io.ys = w.ys; io.ix = w.ix; io.topk = beam;
-      int pst = grouped_step(ctx, V, w.Uv, pos, n, K, io, st);      // grouped-cell form (xg_grouped.cuh) when the shape fits
+      // grouped-cell form (xg_grouped.cuh) when the shape fits: the merge of position t + 1 runs at the end of its launch
+      const BeamMergeIO mg = merge_io(t + 1);
+      int pst = grouped_step(ctx, V, w.Uv, pos, n, K, io, st, &mg);
+      if (pst == XG_OK) { merged = true; continue; }
       if (pst == PK_FALLBACK) pst = persist_decode(ctx, V, w.Uv, pos, nullptr, n, K, 1, nullptr, nullptr, nullptr, nullptr, st, &io);
       if (pst != PK_FALLBACK) { XG_TRY(pst); continue; }
       XG_REQUIRE(ctx->es, t == -1, XG_ERR_CUDA, "persistent word step became unavailable inside a beam search");

@@ -199,21 +199,37 @@ __global__ void __launch_bounds__(256) init_state_kernel(const float* __restrict
   for (int c0 = 0; c0 < B; c0 += IS_CAPS) {
     const int nc = min(IS_CAPS, B - c0);
     __syncthreads();
-    for (int e = threadIdx.x; e < nc * H; e += 256) is_mv[e] = mean[(long)c0 * H + e];
+    if ((H & 3) == 0) {          // (rows of mean are 16-byte aligned: float4 staging, every load of a thread in flight)
+      const float4* src = reinterpret_cast<const float4*>(mean + (long)c0 * H);
+      float4* dst = reinterpret_cast<float4*>(is_mv);
+      const int n4 = nc * H / 4;
+#pragma unroll 4
+      for (int e = threadIdx.x; e < n4; e += 256) dst[e] = __ldg(src + e);
+    } else {
+      for (int e = threadIdx.x; e < nc * H; e += 256) is_mv[e] = mean[(long)c0 * H + e];
+    }
     __syncthreads();
-    for (int c = 0; c < nc; ++c) {
-      float s0 = 0.f, s1 = 0.f;
+    // lane c of a pass keeps the sums of caption cbase + c: 32 captions per pass, one reduction tree per caption and row
+    for (int cbase = 0; cbase < nc; cbase += 32) {
+      float keep0 = 0.f, keep1 = 0.f;
+#pragma unroll 2
+      for (int cc = 0; cc < 32 && cbase + cc < nc; ++cc) {
+        const int c = cbase + cc;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < IS_KPL; ++i) {
-        const int k = lane + 32 * i;
-        const float m = k < H ? is_mv[c * H + k] : 0.f;
-        s0 = fmaf(w[0][i], m, s0); s1 = fmaf(w[1][i], m, s1);
+        for (int i = 0; i < IS_KPL; ++i) {
+          const int k = lane + 32 * i;
+          const float m = k < H ? is_mv[c * H + k] : 0.f;
+          s0 = fmaf(w[0][i], m, s0); s1 = fmaf(w[1][i], m, s1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (lane == cc) { keep0 = s0; keep1 = s1; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-      if (lane == 0) {
-        if (n0 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0] = s0 + b0;
-        if (n0 + 1 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0 + 1] = s1 + b1;
+      const int c = cbase + lane;
+      if (c < nc) {
+        if (n0 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0] = keep0 + b0;
+        if (n0 + 1 < H) a.out[q][(long)(c0 + c) * a.ld[q] + n0 + 1] = keep1 + b1;
       }
     }
   }

@@ -59,6 +59,68 @@ struct MapTable2 { CUtensorMap m[28]; };
 // boxes); 16 xt; 18 / 20 the two [h1|h2] buffers; 22 gp; 24 af; 26: V as [B*K][H] fp32 (box H/2 x K, no swizzle)
 constexpr int GM_H2A = 0, GM_LOGIT = 2, GM_W32 = 4, GM_XT = 16, GM_HH = 18, GM_GP = 22, GM_AF = 24, GM_V = 26;
 
+// Candidate merge + bookkeeping of one beam-search position for video k (CaptionModel.beam_step and the done-beam
+// harvest, CaptionModel.py:34-118), one warp.  The stable descending sort is a rank count (rank = candidates that score
+// higher, or equal with a lower index).  Called by beam_merge_kernel (xg_beam.cuh) and by the fused step kernel below.
+struct BeamMergeIO {
+  const float* ys; const int* ix;          // (videos*beam, beam) per-row top-`beam` log-probs / ids (UNK penalty applied)
+  int B, beam, T, t;                       // videos, beam size, seq_length, position being decided
+  const int64_t* seq_in; const float* lps_in;
+  int64_t* seq_out; float* lps_out;        // (videos, beam, T) ping-pong
+  float* sum; int* parent; int64_t* tokens;
+  int64_t* done_seq; float* done_lps; float* done_p; int* done_n;
+};
+constexpr int BM_MAX_BEAM = 16;
+__device__ __forceinline__ void beam_merge_warp(const BeamMergeIO& M, int k, double* cp /* beam*beam */, int* sel /* beam */, int lane) {
+  const int beam = M.beam, T = M.T, t = M.t;
+  const int rows = (t == 0) ? 1 : beam;
+  const int ncand = rows * beam;
+  // enumerate column-major: c outer, q inner
+  for (int n = lane; n < ncand; n += 32) {
+    const int c = n / rows, q = n % rows;
+    cp[n] = (double)__ldcg(M.sum + (long)k * beam + q) + (double)__ldcg(M.ys + ((long)k * beam + q) * beam + c);
+  }
+  if (lane < beam) sel[lane] = lane < ncand ? lane : 0;
+  __syncwarp();
+  for (int n = lane; n < ncand; n += 32) {
+    const double pn = cp[n];
+    int rank = 0;
+    for (int m = 0; m < ncand; ++m) rank += (cp[m] > pn || (cp[m] == pn && m < n)) ? 1 : 0;
+    if (rank < beam) sel[rank] = n;
+  }
+  __syncwarp();
+  int dn = __ldcg(M.done_n + k);
+  __syncwarp();
+  for (int vix = 0; vix < beam; ++vix) {
+    const int cand = sel[vix];
+    const int c = cand / rows, q = cand % rows;
+    const long src = ((long)k * beam + q) * T, dst = ((long)k * beam + vix) * T;
+    const int word = __ldcg(M.ix + ((long)k * beam + q) * beam + c);
+    const float wlp = __ldcg(M.ys + ((long)k * beam + q) * beam + c);
+    float nsum = (float)cp[cand];
+    const bool done = word == 0 || t == T - 1;
+    const long dd = ((long)k * T * beam + dn) * T;
+    for (int u = lane; u < T; u += 32) {
+      const int64_t sv = u < t ? __ldcg(M.seq_in + src + u) : (u == t ? (int64_t)word : (int64_t)0);
+      const float lv = u < t ? __ldcg(M.lps_in + src + u) : (u == t ? wlp : 0.f);
+      M.seq_out[dst + u] = sv; M.lps_out[dst + u] = lv;
+      if (done) { M.done_seq[dd + u] = sv; M.done_lps[dd + u] = lv; }
+    }
+    if (done) {
+      if (lane == 0) M.done_p[(long)k * T * beam + dn] = nsum;
+      ++dn;
+      nsum = -1000.f;
+    }
+    __syncwarp();                 // (sum[] of this video is read above for every candidate before it is rewritten below)
+    if (lane == 0) {
+      M.sum[(long)k * beam + vix] = nsum;
+      M.parent[(long)k * beam + vix] = k * beam + q;
+      M.tokens[(long)k * beam + vix] = word;
+    }
+  }
+  if (lane == 0) M.done_n[k] = dn;
+}
+
 struct GroupParams {
   DecParams dp;                  // the pick / attention / token-input phases of xg_persist.cuh read this part
   const GSched* gsched;          // [3][G]: F1, F3, G4
@@ -89,6 +151,8 @@ struct GroupParams {
   int ss_mode, ss_L, ss_Lp;
   float ss_prob;
   unsigned long long ss_seed;
+  BeamMergeIO mg;               // single-step mode: the candidate merge of the position runs at the end of the launch (mg_on)
+  int mg_on;
   const int64_t* ss_seq;        // (B, L)
   const float* ss_mask;         // (B, L)
   int64_t* ss_used;             // (B, L) tokens actually fed (initialised with seq by the host)
@@ -1516,7 +1580,7 @@ __device__ __forceinline__ void step_row_merge(const GroupParams& C, int r) {
 
 __global__ void __launch_bounds__(PK_THREADS, 1)
 decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_constant__ MapTable2 maps, unsigned int sync_base,
-                           unsigned int epoch) {
+                           unsigned int epoch0, int nsteps) {
   __shared__ GroupParams Csm;
   __shared__ GSched s_sched[3];
   const int cta = blockIdx.x, G = gridDim.x;
@@ -1538,15 +1602,22 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   unsigned int sync_target = sync_base;
   uint32_t bulk_phase = 0;
 
+  // nsteps > 1 (beam search with the candidate merge in the kernel): the word steps of a whole search in one launch -
+  // everything a step hands to the next one (states, tokens, parents, beams) lives in global memory and is read
+  // through L2 (__ldcg) after the grid barrier that closes the step
+#pragma unroll 1
+  for (int ks = 0; ks < nsteps; ++ks) {
+  const unsigned int epoch = epoch0 + (unsigned int)ks;
+  const int* parent_in = ks == 0 ? P.parent_in : C.mg.parent;
   pk_stamp(P.dbg_clock, cta, 3, 0);
   // ---- prologue: parent states (beam reordering, CaptionModel.py:62-64) into the working buffers, token inputs ----
   for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
     const int r = e / H, j = e % H;
     float h1 = 0.f, h2 = 0.f;
     if (r < B) {
-      const long src = P.parent_in ? (long)__ldg(P.parent_in + r) * H + j : (long)e;
-      h1 = P.state0[0][src]; h2 = P.state0[2][src];
-      P.cx[e] = P.state0[1][src]; P.cx[(long)R * H + e] = P.state0[3][src];
+      const long src = parent_in ? (long)__ldcg(parent_in + r) * H + j : (long)e;
+      h1 = __ldcg(P.state0[0] + src); h2 = __ldcg(P.state0[2] + src);
+      P.cx[e] = __ldcg(P.state0[1] + src); P.cx[(long)R * H + e] = __ldcg(P.state0[3] + src);
     }
     P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
     store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
@@ -1559,7 +1630,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   }
   for (int r = cta; r < R; r += G) {
     if (r < B) {
-      dec_token_inputs(P, r, (int)P.tokens_in[r]);
+      dec_token_inputs(P, r, (int)__ldcg(P.tokens_in + r));
     } else {
       const __half z = __float2half_rn(0.f);
       __half* xh = reinterpret_cast<__half*>(P.xt_hi); __half* xl = reinterpret_cast<__half*>(P.xt_lo);
@@ -1572,7 +1643,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
       }
     }
   }
-  if (P.build_euv) {
+  if (P.build_euv && ks == 0) {
     const long n = (long)((B + P.feat_div - 1) / P.feat_div) * P.K * P.A;
     for (long e = (long)cta * PK_THREADS + threadIdx.x; e < n; e += (long)G * PK_THREADS)
       P.EUv[e] = __expf(2.f * fminf(fmaxf(__ldg(P.Uv + e), -40.f), 40.f));
@@ -1613,8 +1684,28 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 10);
   // ===== E: per row log-sum-exp + topk merge; new states out (every read of the old states happened in the prologue) =====
+  if (C.mg_on) {
+    // a CTA takes a video: one warp per beam row for the row merge, then warp 0 merges the video's candidates and does
+    // the bookkeeping of the position (what used to be a kernel of its own after every word step)
+    double* cp = reinterpret_cast<double*>(sv.scratch);
+    int* sel = reinterpret_cast<int*>(sv.scratch + 2 * BM_MAX_BEAM * BM_MAX_BEAM);
+    const int beam = C.mg.beam, wq = (int)(threadIdx.x >> 5);
 #pragma unroll 1
-  for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r);      // one warp per row
+    for (int k = cta; k < C.mg.B; k += G) {
+      if (wq < beam && k * beam + wq < B) step_row_merge(C, k * beam + wq);
+      __syncthreads();            // the rows' candidates (ys_out / ix_out) are written
+      if (wq == 0) {
+        BeamMergeIO m = C.mg;                       // position t + ks; the beam buffers alternate
+        m.t += ks;
+        if (ks & 1) { m.seq_in = C.mg.seq_out; m.lps_in = C.mg.lps_out; m.seq_out = const_cast<int64_t*>(C.mg.seq_in); m.lps_out = const_cast<float*>(C.mg.lps_in); }
+        beam_merge_warp(m, k, cp, sel, (int)(threadIdx.x & 31));
+      }
+      __syncthreads();
+    }
+  } else {
+#pragma unroll 1
+    for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r);      // one warp per row
+  }
   for (int e = cta * PK_THREADS + threadIdx.x; e < B * H; e += G * PK_THREADS) {
     const int r = e / H, j = e % H;
     P.state_out[0][e] = __ldcg(P.hx + (long)r * 2 * H + j);
@@ -1622,7 +1713,9 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
     P.state_out[1][e] = __ldcg(P.cx + e);
     P.state_out[3][e] = __ldcg(P.cx + (long)R * H + e);
   }
-    pk_stamp(P.dbg_clock, cta, 3, 11);
+  pk_stamp(P.dbg_clock, cta, 3, 11);
+  if (ks + 1 < nsteps) grid_barrier(P.sync_counter, sync_target, G);      // states, tokens, parents of the next step are out
+  }
   pipeline_teardown(tmem_base);
 }
 
@@ -2387,7 +2480,7 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
   hp.nslots[0] = nslots_l[0]; hp.nslots[1] = nslots_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
   hp.topk = 0; hp.lraw = nullptr; hp.lpart = nullptr;
-  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0; hp.mg_on = 0;
   hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
@@ -2499,7 +2592,8 @@ static void grouped_step_release(xg_context* ctx) {
 }
 
 static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const float* pos, int B, int K, const PersistStepIO& io,
-                        cudaStream_t st) {
+                        cudaStream_t st, const BeamMergeIO* mg = nullptr, int nsteps = 1) {
+  // nsteps > 1: the word steps of positions mg->t .. mg->t + nsteps - 1 in ONE launch (needs the in-kernel merge)
   const xg_dims& d = ctx->d;
   const int H = d.rnn, E = d.embed, A = d.att, V = d.vocab;
   const int R = (B + PK_BN - 1) / PK_BN * PK_BN, Ep = (E + GK_KB - 1) / GK_KB * GK_KB, G = ctx->sm_count;
@@ -2507,6 +2601,8 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
       Ep > DEC_TI * PK_THREADS || 4 * H > 32000)
     return PK_FALLBACK;
   if (io.logp != nullptr || io.ys == nullptr || io.ix == nullptr || io.topk < 1 || io.topk > GK_TOPK) return PK_FALLBACK;
+  if (nsteps < 1 || (nsteps > 1 && !mg)) return PK_FALLBACK;
+  if (mg && (mg->beam != io.topk || mg->beam != io.feat_div || mg->beam > PK_WARPS || mg->B * mg->beam != B)) return PK_FALLBACK;
   if (!att_rows_fit(d, K, ATT_NR)) return PK_FALLBACK;
   GroupedStepState*& S = grouped_step_state(ctx);
   if (!S) S = new GroupedStepState();
@@ -2518,16 +2614,19 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
     dp.parent_in = io.parent; dp.ys_out = io.ys; dp.ix_out = io.ix; dp.topk = io.topk;
     hp.topk = io.topk;
     for (int q = 0; q < 4; ++q) { dp.state0[q] = io.state[q]; dp.state_out[q] = io.state[q]; }
+    hp.mg_on = mg ? 1 : 0;
+    if (mg) hp.mg = *mg; else memset(&hp.mg, 0, sizeof(hp.mg));
   };
   auto launch_step = [&]() -> int {
     ProfScope ps(ctx, "decode_step_persistent", st);
     const GroupParams* gp = S->d_params;
     unsigned int base = S->sync_base, ep = S->launches;
-    void* args[4] = {(void*)&gp, (void*)&S->mt, (void*)&base, (void*)&ep};
+    int ns = nsteps;
+    void* args[5] = {(void*)&gp, (void*)&S->mt, (void*)&base, (void*)&ep, (void*)&ns};
     XG_CUDA_TRY(ctx->es, cudaLaunchCooperativeKernel((void*)decode_step_grouped_kernel, dim3(G), dim3(PK_THREADS), args, GK_SMEM_BYTES, st));
     ctx->n_fused++;
-    S->sync_base += GK_STEP_BARRIERS * (unsigned int)G;
-    S->launches++;
+    S->sync_base += ((GK_STEP_BARRIERS + 1) * (unsigned int)nsteps - 1) * (unsigned int)G;
+    S->launches += (unsigned int)nsteps;
     if (S->hp.dp.dbg_clock && S->launches == 6 && G <= 256) {   // XG_PERSIST_TRACE=1: phase timeline of the sixth step, all CTAs
       XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st));
       std::vector<long long> ga((size_t)G * PK_STAMPS);
@@ -2713,7 +2812,7 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
   hp.members[0] = members_l[0]; hp.members[1] = members_l[1]; hp.groups = groups; hp.ncb = ncb; hp.ntv = ntv; hp.n_att = 0;
   hp.nslots[0] = members_l[0]; hp.nslots[1] = members_l[1];
   hp.l2_hints = getenv("XG_L2_HINT") ? atoi(getenv("XG_L2_HINT")) : 1;
-  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0;
+  hp.sample_max = 1; hp.step_drop = 0; hp.inv_temp = 1.f; hp.sample_seed = 0; hp.ss_mode = 0; hp.mg_on = 0;
   hp.drop_gate = hp.drop_h1 = hp.drop_h2 = make_drop(false, 0.f, 0, 0);
   XG_CUDA_TRY(ctx->es, cudaMemcpyAsync(const_cast<GSched*>(hp.gsched), sched.data(), sizeof(GSched) * sched.size(),
                                        cudaMemcpyHostToDevice, st));
