@@ -28,6 +28,6 @@ for h, u, v in zip(hdr, units, vals):
 }
 cap decode_grouped decode_grouped_kernel 2 greedy
 cap train_grouped train_grouped 2 train
-cap decode_step_grouped decode_step_grouped 8 beam
+cap decode_step_grouped decode_step_grouped 2 beam      # (one launch per search since the merge runs in the kernel)
 cap decode_bwd decode_bwd_persistent 2 train
 ls -la $out | tail -30
