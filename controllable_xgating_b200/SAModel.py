@@ -291,15 +291,16 @@ class SAModel(CaptionModel):
                 feats, _, _ = self._encode(feats_rgb, feats_opfl, feat_mask, want_state=False)
                 return self.sample_beam(feats, feat_mask, pos_feats, opt)
             return self._sample_training(feats_rgb, feats_opfl, feat_mask, pos_feats, sample_max, temperature)
-        feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
-        if beam_size > 1:
-            return self.sample_beam(feats, feat_mask, pos_feats, opt)
-        if self.VERBOSE:
-            print("sampling with greedy search")
-        seed = 0 if sample_max else self._engine.next_seed()
-        with torch.no_grad():
-            seq, lps, steps = self._engine.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max,
-                                                         temperature, seed)
+        with self._engine.bound():
+            feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
+            if beam_size > 1:
+                return self.sample_beam(feats, feat_mask, pos_feats, opt)
+            if self.VERBOSE:
+                print("sampling with greedy search")
+            seed = 0 if sample_max else self._engine.next_seed()
+            with torch.no_grad():
+                seq, lps, steps = self._engine.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max,
+                                                             temperature, seed)
         if steps == 0:
             # the reference crashes here (torch.cat of an empty list, SAModel.py:219)
             raise ValueError("torch.cat(): expected a non-empty list of Tensors (every caption ended at the first step)")
@@ -314,11 +315,12 @@ class SAModel(CaptionModel):
         if self.training or opt.get("beam_size", 1) > 1:
             raise ValueError("sample_async covers eval-mode greedy / multinomial decoding (use sample())")
         sample_max = opt.get("sample_max", 1)
-        feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
-        seed = 0 if sample_max else self._engine.next_seed()
-        with torch.no_grad():
-            seq, lps, _ = self._engine.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max,
-                                                     opt.get("temperature", 1.0), seed, want_steps=False)
+        with self._engine.bound():
+            feats, Uv, st = self._encode(feats_rgb, feats_opfl, feat_mask)
+            seed = 0 if sample_max else self._engine.next_seed()
+            with torch.no_grad():
+                seq, lps, _ = self._engine.sample_greedy(feats, Uv, pos_feats, st, self.seq_length, sample_max,
+                                                         opt.get("temperature", 1.0), seed, want_steps=False)
         return PendingSample(seq, lps)
 
     def _forward_scheduled(self, feats_rgb, feats_opfl, feat_mask, pos_feats, seq, seq_mask):

@@ -3,6 +3,7 @@ C-ABI entry with shape checks.  torch is used only for device memory, streams an
 all arithmetic happens inside libxgating.so."""
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from ctypes import c_int, c_void_p
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -83,6 +84,7 @@ class Engine:
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._device = None
         self._param_version = None
+        self._bind_held = False
         self._engine_mode = 2
         self._strict = None          # None: the library default (XG_STRICT_PERSIST in the environment)
         self._force_changed = False
@@ -169,7 +171,23 @@ class Engine:
         self._plist = None
         self._bound_key = None
 
+    @contextlib.contextmanager
+    def bound(self):
+        """bind() once for a public call that enters the library several times (encoder, word loop, ...): the check walks
+        57 parameters (~35 us of interpreter time), and nothing rewrites parameters between those entries."""
+        if self._bind_held:
+            yield
+            return
+        self.bind()
+        self._bind_held = True
+        try:
+            yield
+        finally:
+            self._bind_held = False
+
     def bind(self):
+        if self._bind_held:
+            return
         plist = self.params()
         dev = plist[0].device
         self._ensure_handle(dev)
