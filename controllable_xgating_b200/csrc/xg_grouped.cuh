@@ -1,4 +1,14 @@
-// Greedy word loop, second generation: the LSTM cells run in the epilogue of their own products.
+// The word loops, second generation: the LSTM cells run in the epilogue of their own products.
+//
+// Kernels of this file (all cooperative, one CTA per SM, fp16 operand pairs through TMA -> tcgen05 -> TMEM):
+//   decode_grouped_kernel<0>      greedy word loop of SAModel.sample                      (SAModel.py:182-219)
+//   decode_grouped_kernel<1>      the same loop sampling: multinomial draw / training dropout (SCST), and the
+//                                 scheduled-sampling token pass                             (SAModel.py:188-196, 89-99)
+//   train_grouped_kernel          teacher-forced loop of SAModel.forward                   (SAModel.py:88-111)
+//   decode_step_grouped_kernel    beam search: all word steps of a search + the candidate merge of every position
+//                                                                                          (SAModel.py:129-161, CaptionModel.py:22-128)
+//   encode_grouped_kernel         frame recurrence of both encoder streams                 (sub_modules.py:132-147)
+// The description below is the greedy loop's; the others reuse its phases (gphase, fused_cell_phase, dec_attention_rows).
 //
 // decode_persistent_kernel<0> (xg_persist.cuh) spends six grid barriers per word step: every LSTM layer is a GEMM
 // phase (split-K partial tiles to L2), a grid barrier, a pointwise phase that reads the partial tiles back, and
