@@ -263,6 +263,7 @@ def main():
             fn()
         barrier()
         tot = 0.0
+        per_step = []
         for _ in range(steps):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,6 +272,9 @@ def main():
             e1.record()
             e1.synchronize()
             tot += e0.elapsed_time(e1)
+            per_step.append(e0.elapsed_time(e1))
+        if os.environ.get("XG_BENCH_DEBUG") and rank == 0:
+            print("[bench] per-step ms:", " ".join("%.3f" % x for x in per_step), file=sys.stderr)
         barrier()
         if world > 1:
             t = torch.tensor([tot], device=dev, dtype=torch.float64)
@@ -370,15 +374,30 @@ def main():
     eng = model._engine
     lib = XL.load()
     XL.check(lib.xg_profile_enable(eng.handle, 1), "xg_profile_enable", eng.handle)
-    prof_steps = 3
-    for _ in range(prof_steps):
-        flush.fill_(1)
-        greedy_resident()
     import ctypes
     buf = ctypes.create_string_buffer(1 << 20)
-    XL.check(lib.xg_profile_report(eng.handle, buf, len(buf)), "xg_profile_report", eng.handle)
+
+    def prof_round():
+        flush.fill_(1)
+        greedy_resident()
+        XL.check(lib.xg_profile_report(eng.handle, buf, len(buf)), "xg_profile_report", eng.handle)   # drains the records
+        return {p["name"]: p for p in json.loads(buf.value.decode())}
+
+    prof_round()                                    # untimed: creates the event pool, first launch with events on
+    prof_steps = 7
+    rounds = [prof_round() for _ in range(prof_steps)]
     XL.check(lib.xg_profile_enable(eng.handle, 0), "xg_profile_enable", eng.handle)
-    prof = json.loads(buf.value.decode())
+    # one sample per kernel per round (ms summed over that round's launches / launches); the per-kernel figure is the
+    # MEDIAN round, so that a single host hiccup between the two events of one launch does not move it (all samples
+    # are printed next to it)
+    names = sorted({n for r in rounds for n in r})
+    prof = []
+    for n in names:
+        per = sorted(r[n]["ms"] / r[n]["launches"] for r in rounds if n in r)
+        launches = sum(r[n]["launches"] for r in rounds if n in r)
+        med = per[len(per) // 2]
+        prof.append({"name": n, "launches": launches, "ms": med * launches, "samples_us": [round(x * 1e3, 1) for x in per],
+                     "mean_us": sum(per) / len(per) * 1e3})
     launches_per_step = sum(p["launches"] for p in prof) / prof_steps
     prof.sort(key=lambda p: -p["ms"])
     tot_prof_ms = sum(p["ms"] for p in prof)
@@ -420,7 +439,9 @@ def main():
     roofline = {"kernel": top["name"], "bound": "hbm", "achieved": (ab / (avg_ms * 1e-3) / 1e9) if ab else None,
                 "peak": peak, "unit": "GB/s", "frac": (ab / (avg_ms * 1e-3) / 1e9 / peak) if ab else None,
                 "traffic": measured_traffic(top["name"]), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                "avg_launch_us": avg_ms * 1e3, "share_of_step": top["ms"] / tot_prof_ms,
+                "avg_launch_us": avg_ms * 1e3, "launch_us_stat": "median of %d profiled steps (1 launch each)" % prof_steps,
+                "launch_us_samples": top["samples_us"], "launch_us_mean": top["mean_us"],
+                "share_of_step": top["ms"] / tot_prof_ms,
                 "top5": [{"name": p["name"], "launches_per_step": p["launches"] / prof_steps,
                           "us_per_launch": p["ms"] / p["launches"] * 1e3, "share": p["ms"] / tot_prof_ms} for p in prof[:5]]}
 

@@ -41,9 +41,10 @@ constexpr int GK_MAX_MEMBERS = 9;      // CTAs of a group
 constexpr int GK_MAX_SLOTS = 12;       // partial tiles a cell adds: the group's members + the "early" ones (below)
 enum { GI_CONT_PREV = 1, GI_CONT_NEXT = 2, GI_FUSED = 4, GI_LOGITS = 8, GI_LAYER1 = 16 };
 constexpr int GK_LT_STRIDE = 130;     // row stride of the transposed logits tile in shared memory (conflict-free both ways)
-constexpr int GK_LH_STRIDE = 132;     // ... of the half tile of the single-step mode (four threads per caption)
-constexpr int GK_LT_BYTES = 32 * GK_LH_STRIDE * 4;          // 32 captions x 128 vocabulary rows (+ padding)
-constexpr int GK_SMEM_BYTES = PK_SMEM_BYTES + GK_LT_BYTES;  // the half tile lives behind the pipeline's shared memory
+constexpr int GK_LH_STRIDE = 136;     // ... of the quarter tile of the single-step mode (eight threads per caption)
+constexpr int GK_LQ_BYTES = 16 * GK_LH_STRIDE * 4;          // 16 captions x 128 vocabulary rows (+ padding), one per epilogue warpgroup
+constexpr int GK_LT_BYTES = 2 * GK_LQ_BYTES;
+constexpr int GK_SMEM_BYTES = PK_SMEM_BYTES + GK_LT_BYTES;  // the quarter tiles live behind the pipeline's shared memory
 constexpr int GK_TOPK = 8;            // per-row candidates the logits epilogue can keep (beam search: beam_size <= 8)
 
 struct GItem {            // one run of k-blocks (24 bytes)
@@ -56,7 +57,11 @@ struct GItem {            // one run of k-blocks (24 bytes)
   short desc, slot;       // standalone: product (DecParams.d[desc]) and split-K slot; fused: group, member
   short cb, pad;          // caption column block
 };
-struct GSched { short n, tot_kb, tot_chunks, n_chains; GItem it[GK_MAX_ITEMS]; };   // 296 bytes
+// dual: the chains of this phase alternate between TWO epilogue warpgroups (warps 2-5 take the even chains, warps 6-9 the odd
+// ones); chunks_b: accumulation chunks of the odd chains.  Reading an accumulator back costs ~1000 cycles per 64 KB pair
+// (tensor memory reads run at 64 B/clk) and the end of a chain (partial-tile store, logits reduction) 1.5k - 11k more: with
+// several chains per CTA (beam search: one per caption column block) one warpgroup was the serial resource of the phase.
+struct GSched { short n, tot_kb, tot_chunks, n_chains, dual, chunks_b; GItem it[GK_MAX_ITEMS]; };   // 300 bytes
 
 // Operands are fp16 hi / lo PAIRS (3xFP16: hi.hi + (lo.hi + hi.lo) / 2^11, the same 11 + 11 mantissa bits as the 3xTF32
 // products of xg_persist.cuh): the weights as derived tables rebuilt when the bound parameters change (like the
@@ -99,36 +104,57 @@ __device__ __forceinline__ void beam_merge_warp(const BeamMergeIO& M, int k, dou
     if (rank < beam) sel[rank] = n;
   }
   __syncwarp();
-  int dn = __ldcg(M.done_n + k);
-  __syncwarp();
-  for (int vix = 0; vix < beam; ++vix) {
-    const int cand = sel[vix];
-    const int c = cand / rows, q = cand % rows;
-    const long src = ((long)k * beam + q) * T, dst = ((long)k * beam + vix) * T;
-    const int word = __ldcg(M.ix + ((long)k * beam + q) * beam + c);
-    const float wlp = __ldcg(M.ys + ((long)k * beam + q) * beam + c);
-    float nsum = (float)cp[cand];
-    const bool done = word == 0 || t == T - 1;
-    const long dd = ((long)k * T * beam + dn) * T;
+  // lane v < beam owns the v-th survivor: its word, log-prob, sum, parent row and whether it ends here
+  const int dn0 = __ldcg(M.done_n + k);
+  int my_word = 0, my_q = 0; float my_wlp = 0.f, my_sum = 0.f; bool my_done = false;
+  if (lane < beam) {
+    const int cand = sel[lane];
+    const int c = cand / rows; my_q = cand % rows;
+    my_word = __ldcg(M.ix + ((long)k * beam + my_q) * beam + c);
+    my_wlp = __ldcg(M.ys + ((long)k * beam + my_q) * beam + c);
+    my_sum = (float)cp[cand];
+    my_done = my_word == 0 || t == T - 1;
+  }
+  const unsigned dmask = __ballot_sync(0xffffffffu, my_done);
+  // the survivors' histories, four at a time: every load of a batch is issued before its first store (the buffers may
+  // alias as far as the compiler knows, and one survivor at a time meant one L2 round trip per survivor)
+#pragma unroll 1
+  for (int v0 = 0; v0 < beam; v0 += 4) {
+    int word[4], q[4], dnv[4]; float wlp[4]; bool done[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int vix = min(v0 + b, beam - 1);
+      word[b] = __shfl_sync(0xffffffffu, my_word, vix); q[b] = __shfl_sync(0xffffffffu, my_q, vix);
+      wlp[b] = __shfl_sync(0xffffffffu, my_wlp, vix);
+      done[b] = (dmask >> vix) & 1u;
+      dnv[b] = dn0 + __popc(dmask & ((1u << vix) - 1u));
+    }
+#pragma unroll 1
     for (int u = lane; u < T; u += 32) {
-      const int64_t sv = u < t ? __ldcg(M.seq_in + src + u) : (u == t ? (int64_t)word : (int64_t)0);
-      const float lv = u < t ? __ldcg(M.lps_in + src + u) : (u == t ? wlp : 0.f);
-      M.seq_out[dst + u] = sv; M.lps_out[dst + u] = lv;
-      if (done) { M.done_seq[dd + u] = sv; M.done_lps[dd + u] = lv; }
-    }
-    if (done) {
-      if (lane == 0) M.done_p[(long)k * T * beam + dn] = nsum;
-      ++dn;
-      nsum = -1000.f;
-    }
-    __syncwarp();                 // (sum[] of this video is read above for every candidate before it is rewritten below)
-    if (lane == 0) {
-      M.sum[(long)k * beam + vix] = nsum;
-      M.parent[(long)k * beam + vix] = k * beam + q;
-      M.tokens[(long)k * beam + vix] = word;
+      int64_t sv[4]; float lv[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const long src = ((long)k * beam + q[b]) * T;
+        sv[b] = u < t ? __ldcg(M.seq_in + src + u) : (u == t ? (int64_t)word[b] : (int64_t)0);
+        lv[b] = u < t ? __ldcg(M.lps_in + src + u) : (u == t ? wlp[b] : 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (v0 + b < beam) {
+          const long dst = ((long)k * beam + v0 + b) * T;
+          M.seq_out[dst + u] = sv[b]; M.lps_out[dst + u] = lv[b];
+          if (done[b]) { const long dd = ((long)k * T * beam + dnv[b]) * T; M.done_seq[dd + u] = sv[b]; M.done_lps[dd + u] = lv[b]; }
+        }
+      }
     }
   }
-  if (lane == 0) M.done_n[k] = dn;
+  if (lane < beam) {      // (sum[] of this video was read for every candidate before it is rewritten here)
+    if (my_done) M.done_p[(long)k * T * beam + dn0 + __popc(dmask & ((1u << lane) - 1u))] = my_sum;
+    M.sum[(long)k * beam + lane] = my_done ? -1000.f : my_sum;
+    M.parent[(long)k * beam + lane] = k * beam + my_q;
+    M.tokens[(long)k * beam + lane] = my_word;
+  }
+  if (lane == 0) M.done_n[k] = dn0 + __popc(dmask);
 }
 
 struct GroupParams {
@@ -198,6 +224,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
+  const bool dual = __shfl_sync(0xffffffffu, (int)sc->dual, 0) != 0;
   const int R = C.dp.R, H = C.dp.H;
 #ifdef GK_FINE
   long long* gw = (C.dp.dbg_clock && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + 32 : nullptr;
@@ -294,11 +321,17 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
     uint32_t cnt = __shfl_sync(0xffffffffu, ps.kb_count, 0), cc = __shfl_sync(0xffffffffu, ps.chunk_count, 0);
     const uint32_t ready_bar = __shfl_sync(0xffffffffu, sv.full_bar, 0), empty_bar = __shfl_sync(0xffffffffu, sv.empty_bar, 0);
     const uint32_t acc_full = __shfl_sync(0xffffffffu, sv.acc_full, 0), acc_empty = __shfl_sync(0xffffffffu, sv.acc_empty, 0);
+    const uint32_t acc_full2 = __shfl_sync(0xffffffffu, sv.acc_full2, 0);
     const uint32_t desc_lo0 = __shfl_sync(0xffffffffu, (uint32_t)umma_desc_sw128(sv.stages_u32), 0);
     const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+    // the "accumulator full" barriers belong to the epilogue warpgroup that owns the chain: slot = that group's own chunk count
+    uint32_t cg[2];
+    cg[1] = __shfl_sync(0xffffffffu, ps.grp_b, 0); cg[0] = cc - cg[1];
+    uint32_t owner = 0, ch = 0;
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
       const int nkb = __shfl_sync(0xffffffffu, (int)sc->it[ii].nkb, 0);
+      if (!(__shfl_sync(0xffffffffu, (int)sc->it[ii].flags, 0) & GI_CONT_PREV)) { owner = dual ? (ch & 1u) : 0u; ++ch; }
       uint32_t tmem_pair = tb, b = 0;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
@@ -322,32 +355,40 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
             umma_f16(tmem_pair + PK_BN, wl, xh, idesc, 1);
           }
           pk_commit(empty_bar + 8 * s);
-          if ((kb & 1) || kb == nkb - 1) pk_commit(acc_full + 8 * b);
+          if ((kb & 1) || kb == nkb - 1) pk_commit((owner ? acc_full2 : acc_full) + 8 * (cg[owner] & 1u));
         }
         __syncwarp();
-        if ((kb & 1) || kb == nkb - 1) ++cc;
+        if ((kb & 1) || kb == nkb - 1) { ++cc; ++cg[owner]; }
       }
     }
-  } else if (warp < 6) {      // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
-    const int quad = warp & 3;
+  } else {                    // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
+    // warps 2-5: warpgroup 0, warps 6-9: warpgroup 1 (a warp reads the 32 TMEM lanes of its index mod 4 either way)
+    const int quad = warp & 3, grp = warp >= 6 ? 1 : 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t cc = ps.chunk_count;
+    const uint32_t my_full = grp ? sv.acc_full2 : sv.acc_full;
+    uint32_t cc = ps.chunk_count, cg = grp ? ps.grp_b : ps.chunk_count - ps.grp_b, ch = 0;
+    bool mine = false;
     float acc[PK_BN];
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
       const GItem it = sc->it[ii];
       const bool first = !(it.flags & GI_CONT_PREV), last = !(it.flags & GI_CONT_NEXT);
       const int n_chunks = (it.nkb + PK_CHUNK - 1) / PK_CHUNK;
+      if (first) { mine = dual ? ((ch & 1u) == (uint32_t)grp) : (grp == 0); ++ch; }
+      if (!mine) { cc += (uint32_t)n_chunks; continue; }
       if (first) {
 #pragma unroll
         for (int u = 0; u < PK_BN; ++u) acc[u] = 0.f;
       }
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = 0; c < n_chunks; ++c, ++cg) {
         const uint32_t b = cc & 1;
-        GKW(0, pk_wait(sv.acc_full + 8 * b, (cc >> 1) & 1));
+        GKW(0, pk_wait(my_full + 8 * (cg & 1u), (cg >> 1) & 1));
         tc_fence_after();
         const uint32_t col = b * 2 * PK_BN;
+#ifdef GK_FINE
+        const long long td0 = clock64();
+#endif
         {
           uint32_t r[32], r2[32];
           tmem_ld32(taddr + col, r);
@@ -368,7 +409,13 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
         tc_fence_before();
         pk_arrive(sv.acc_empty + 8 * b);
         ++cc;
+#ifdef GK_FINE
+        w_acc[1] += clock64() - td0;
+#endif
       }
+#ifdef GK_FINE
+      const long long te0 = clock64();
+#endif
       if (last && (it.flags & GI_LOGITS)) {
         if (!STEP) {                     // greedy decoding
           // The logits of this 128-row vocabulary tile never leave the SM: + bias, transposed through shared memory (the
@@ -380,8 +427,8 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           float* T = reinterpret_cast<float*>(sv.stages);
 #pragma unroll
           for (int u = 0; u < PK_BN; ++u) T[u * GK_LT_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int e = (warp - 2) * 32 + lane, c = e >> 1, hh = e & 1;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          const int e = (warp - 2 - 4 * grp) * 32 + lane, c = e >> 1, hh = e & 1;
           const float* row = T + c * GK_LT_STRIDE + hh;
           float best = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 8
@@ -401,57 +448,73 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           if (hh == 0)
             C.lpart[(long)(it.cb * PK_BN + c) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(it.wrow + bi), 0.f);
           fence_proxy_async_smem();        // the stages go back to the TMA / bulk-copy engines
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         } else {                         // beam search: several items per CTA, logits stored for the row merge
-          // The logits of this 128-row vocabulary tile: + bias, transposed through shared memory in two halves of 32
+          // The logits of this 128-row vocabulary tile: + bias, transposed through shared memory in four quarters of 16
           // captions (a buffer of its own: the pipeline stages may already hold the next item), then per caption the tile's
-          // max / lowest arg-max / sum exp(x - max): four threads per caption.  Greedy decoding needs nothing else (the
+          // max / lowest arg-max / sum exp(x - max): eight threads per caption.  Greedy decoding needs nothing else (the
           // logits never leave the SM); beam search also stores them for the row merge.
           const int V = C.dp.V;
           const int nl = quad * 32 + lane, n = it.wrow + nl;
           const float bl = n < V ? __ldg(C.dp.b_logit + n) : 0.f;
-          if (C.lraw != nullptr) {
-            float* o = C.lraw + (long)(it.cb * PK_BN) * (C.ntv * 128) + n;
-            const long str = (long)C.ntv * 128;
-#pragma unroll
-            for (int u = 0; u < PK_BN; ++u) { __stcg(o, n < V ? acc[u] + bl : -INFINITY); o += str; }
-          }
-          float* T = reinterpret_cast<float*>(sv.stages + PK_SMEM_BYTES - 1024);      // behind scratch + barriers (carve_smem keeps 1 KB of slack in front)
-          const int e = (warp - 2) * 32 + lane, cl = e >> 2, part = e & 3;
+          // (behind scratch + barriers: carve_smem keeps 1 KB of slack in front; one quarter-tile buffer per warpgroup)
+          float* T = reinterpret_cast<float*>(sv.stages + PK_SMEM_BYTES - 1024 + grp * GK_LQ_BYTES);
+          const int e = (warp - 2 - 4 * grp) * 32 + lane, cl = e >> 3, part = e & 7;
+          const float invT = C.inv_temp;
+          float* o = C.lraw ? C.lraw + (long)(it.cb * PK_BN) * (C.ntv * 128) + n : nullptr;
+          const long str = (long)C.ntv * 128;
+          // A LOOP over the quarters (the accumulators rotate down by 16 per pass, so the body always works on acc[0..16)):
+          // unrolled, the four passes were ~1400 instructions of straight-line code executed once per item, and their
+          // instruction fetches - not their arithmetic - set the pace of the pass (2500 cycles for ~350 instructions).
 #pragma unroll 1
-          for (int hf = 0; hf < 2; ++hf) {
-            if (hf == 0) {
+          for (int qt = 0; qt < 4; ++qt) {
+#ifdef GK_FINE
+            const long long q0 = clock64();
+#endif
+            if (o != nullptr) {
 #pragma unroll
-              for (int u = 0; u < 32; ++u) T[u * GK_LH_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
-            } else {
-#pragma unroll
-              for (int u = 0; u < 32; ++u) T[u * GK_LH_STRIDE + nl] = n < V ? acc[32 + u] + bl : -INFINITY;
+              for (int u = 0; u < 16; ++u) { __stcg(o, n < V ? acc[u] + bl : -INFINITY); o += str; }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 16; ++u) T[u * GK_LH_STRIDE + nl] = n < V ? acc[u] + bl : -INFINITY;
+#ifdef GK_FINE
+            const long long q1 = clock64();
+#endif
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#ifdef GK_FINE
+            const long long q2 = clock64();
+#endif
             const float* row = T + cl * GK_LH_STRIDE + part;
-            float best = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-              const float x = row[4 * i];
-              if (x > best) { best = x; bi = it.wrow + 4 * i + part; }      // ascending ids: the first maximum is kept
-            }
+            float xs[16];
 #pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            for (int i = 0; i < 16; ++i) xs[i] = row[8 * i];
+            float best = xs[0]; int bi = 0;
+#pragma unroll
+            for (int i = 1; i < 16; ++i)
+              if (xs[i] > best) { best = xs[i]; bi = i; }                   // ascending ids: the first maximum is kept
+            bi = it.wrow + 8 * bi + part;
+#pragma unroll
+            for (int sh = 1; sh <= 4; sh <<= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, sh);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, sh);
               if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
             float sum = 0.f, sumT = 0.f;
-            const float invT = C.inv_temp;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) { const float dx = row[4 * i] - best; sum += __expf(dx); sumT += __expf(dx * invT); }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            sumT += __shfl_xor_sync(0xffffffffu, sumT, 1);
-            sumT += __shfl_xor_sync(0xffffffffu, sumT, 2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float dx = xs[i] - best; sum += __expf(dx); sumT += __expf(dx * invT); }
+#pragma unroll
+            for (int sh = 1; sh <= 4; sh <<= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, sh); sumT += __shfl_xor_sync(0xffffffffu, sumT, sh); }
+#ifdef GK_FINE
+            const long long q3 = clock64();
+#endif
             if (part == 0)      // (.w: the tile's mass at the sampling temperature, relative to its own max)
-              C.lpart[(long)(it.cb * PK_BN + hf * 32 + cl) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(bi), sumT);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+              C.lpart[(long)(it.cb * PK_BN + qt * 16 + cl) * C.ntv + it.wrow / 128] = make_float4(best, sum, __int_as_float(bi), sumT);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+            for (int u = 0; u < PK_BN - 16; ++u) acc[u] = acc[u + 16];
+#ifdef GK_FINE
+            if (gw && warp == 2 && lane == 0) { const long long q4 = clock64(); gw[6] += q1 - q0; gw[7] += q2 - q1; gw[14] += q3 - q2; gw[15] += q4 - q3; }
+#endif
           }
         }
       } else if (last) {
@@ -470,17 +533,21 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
           }
         }
       }
+#ifdef GK_FINE
+      if (last && (it.flags & GI_LOGITS)) w_acc[3] += clock64() - te0; else w_acc[2] += clock64() - te0;
+#endif
     }
   }                           // (warps 6-9 have no role in the GEMM phases: the operands arrive split)
 #ifdef GK_FINE
   if (gw && lane == 0 && warp <= 2) {      // per role: time in this phase, waits (producer: stage free | MMA: data, accumulator free,
     const long long dt = clock64() - t_in; //  cross accumulator free | epilogue warp 2: main accumulator full, cross accumulator full)
-    gw[warp * 8 + 0] += dt; gw[warp * 8 + 1] += w_acc[0]; gw[warp * 8 + 2] += w_acc[1]; gw[warp * 8 + 3] += w_acc[2]; gw[warp * 8 + 4] += sc->tot_kb;
+    gw[warp * 8 + 0] += dt; gw[warp * 8 + 1] += w_acc[0]; gw[warp * 8 + 2] += w_acc[1]; gw[warp * 8 + 3] += w_acc[2]; gw[warp * 8 + 4] += sc->tot_kb; gw[warp * 8 + 5] += w_acc[3];
   }
 #endif
   ps.kb_count += sc->tot_kb;
   ps.chunk_count += sc->tot_chunks;
   ps.item_count += sc->n_chains;
+  ps.grp_b += (uint32_t)sc->chunks_b;
   ps.npre = 0;
 }
 
@@ -1620,27 +1687,47 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   const unsigned int epoch = epoch0 + (unsigned int)ks;
   const int* parent_in = ks == 0 ? P.parent_in : C.mg.parent;
   pk_stamp(P.dbg_clock, cta, 3, 0);
+  int tok_pre[4];                                   // (this CTA's first tokens: one round trip instead of one per row)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tok_pre[i] = cta + i * G < B ? (int)__ldcg(P.tokens_in + cta + i * G) : 0;
   // ---- prologue: parent states (beam reordering, CaptionModel.py:62-64) into the working buffers, token inputs ----
-  for (int e = cta * PK_THREADS + threadIdx.x; e < R * H; e += G * PK_THREADS) {
-    const int r = e / H, j = e % H;
-    float h1 = 0.f, h2 = 0.f;
-    if (r < B) {
-      const long src = parent_in ? (long)__ldcg(parent_in + r) * H + j : (long)e;
-      h1 = __ldcg(P.state0[0] + src); h2 = __ldcg(P.state0[2] + src);
-      P.cx[e] = __ldcg(P.state0[1] + src); P.cx[(long)R * H + e] = __ldcg(P.state0[3] + src);
+  // (four elements per thread and pass, the parent rows first, then every state load, then the stores: one element at a
+  //  time cost two dependent L2 round trips per element - the stores may alias the loads as far as the compiler knows)
+  for (int e0 = cta * PK_THREADS + threadIdx.x; e0 < R * H; e0 += 4 * G * PK_THREADS) {
+    long src[4]; float h1[4], h2[4], c1[4], c2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * G * PK_THREADS, r = e / H, j = e - r * H;
+      src[u] = (e < R * H && r < B) ? (parent_in ? (long)__ldcg(parent_in + r) * H + j : (long)e) : -1L;
     }
-    P.hx[(long)r * 2 * H + j] = h1; P.hx[(long)r * 2 * H + H + j] = h2;
-    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1);
-    store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2);
-    if (r >= B) {
-      const __half z = __float2half_rn(0.f);
-      C.hh_hi[1][(long)r * 2 * H + j] = z; C.hh_lo[1][(long)r * 2 * H + j] = z;
-      C.hh_hi[1][(long)r * 2 * H + H + j] = z; C.hh_lo[1][(long)r * 2 * H + H + j] = z;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      h1[u] = h2[u] = c1[u] = c2[u] = 0.f;
+      if (src[u] >= 0) {
+        h1[u] = __ldcg(P.state0[0] + src[u]); h2[u] = __ldcg(P.state0[2] + src[u]);
+        c1[u] = __ldcg(P.state0[1] + src[u]); c2[u] = __ldcg(P.state0[3] + src[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * G * PK_THREADS;
+      if (e < R * H) {
+        const int r = e / H, j = e - r * H;
+        if (r < B) { P.cx[e] = c1[u]; P.cx[(long)R * H + e] = c2[u]; }
+        P.hx[(long)r * 2 * H + j] = h1[u]; P.hx[(long)r * 2 * H + H + j] = h2[u];
+        store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + j, h1[u]);
+        store_split16(C.hh_hi[0], C.hh_lo[0], (long)r * 2 * H + H + j, h2[u]);
+        if (r >= B) {
+          const __half z = __float2half_rn(0.f);
+          C.hh_hi[1][(long)r * 2 * H + j] = z; C.hh_lo[1][(long)r * 2 * H + j] = z;
+          C.hh_hi[1][(long)r * 2 * H + H + j] = z; C.hh_lo[1][(long)r * 2 * H + H + j] = z;
+        }
+      }
     }
   }
-  for (int r = cta; r < R; r += G) {
+  for (int r = cta, ri = 0; r < R; r += G, ++ri) {
     if (r < B) {
-      dec_token_inputs(P, r, (int)__ldcg(P.tokens_in + r));
+      dec_token_inputs(P, r, ri == 0 ? tok_pre[0] : ri == 1 ? tok_pre[1] : ri == 2 ? tok_pre[2] : ri == 3 ? tok_pre[3] : (int)__ldcg(P.tokens_in + r));
     } else {
       const __half z = __float2half_rn(0.f);
       __half* xh = reinterpret_cast<__half*>(P.xt_hi); __half* xl = reinterpret_cast<__half*>(P.xt_lo);
@@ -1663,6 +1750,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   pk_stamp(P.dbg_clock, cta, 3, 2);
   // ===== A: lstm_1 (x, gp, h1 chains, fused cell)  +  attention query W_h2a.[h1|h2] (split-K slots) =====
   fused_cell_phase<1>(C, &s_sched[0], &s_sched[1], maps.m, 0, 0, epoch, sv, tmem_base, ps);
+  if (P.dbg_clock) __syncthreads();          // (trace runs: the stamp is the CTA's last warp, not the producer warp)
   pk_stamp(P.dbg_clock, cta, 3, 3);
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 4);
@@ -1685,11 +1773,13 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   pk_stamp(P.dbg_clock, cta, 3, 6);
   // ===== C: lstm_2 (h1', af, h2 chains, fused cell) =====
   fused_cell_phase<1>(C, &s_sched[1], &s_sched[2], maps.m, 1, 0, epoch, sv, tmem_base, ps);
+  if (P.dbg_clock) __syncthreads();          // (trace runs: the stamp is the CTA's last warp, not the producer warp)
   pk_stamp(P.dbg_clock, cta, 3, 7);
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 8);
   // ===== D: logits tiles (reduced in the epilogue) =====
   gphase<true>(C, &s_sched[2], nullptr, maps.m, 0, sv, tmem_base, ps);
+  if (P.dbg_clock) __syncthreads();          // (trace runs: the stamp is the CTA's last warp, not the producer warp)
   pk_stamp(P.dbg_clock, cta, 3, 9);
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 10);
@@ -1716,12 +1806,27 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
 #pragma unroll 1
     for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r);      // one warp per row
   }
-  for (int e = cta * PK_THREADS + threadIdx.x; e < B * H; e += G * PK_THREADS) {
-    const int r = e / H, j = e % H;
-    P.state_out[0][e] = __ldcg(P.hx + (long)r * 2 * H + j);
-    P.state_out[2][e] = __ldcg(P.hx + (long)r * 2 * H + H + j);
-    P.state_out[1][e] = __ldcg(P.cx + e);
-    P.state_out[3][e] = __ldcg(P.cx + (long)R * H + e);
+  // the states go out on the CTAs that have no video to merge (when there are any: the merge is the long pole of this phase)
+  const int nv_ctas = (C.mg_on && C.mg.B < G) ? C.mg.B : 0, ncopy = G - nv_ctas;
+  for (int e0 = (cta - nv_ctas) * PK_THREADS + threadIdx.x; cta >= nv_ctas && e0 < B * H; e0 += 4 * ncopy * PK_THREADS) {      // (loads first, as in the prologue)
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * ncopy * PK_THREADS;
+      if (e < B * H) {
+        const int r = e / H, j = e - r * H;
+        v[u][0] = __ldcg(P.hx + (long)r * 2 * H + j); v[u][2] = __ldcg(P.hx + (long)r * 2 * H + H + j);
+        v[u][1] = __ldcg(P.cx + e); v[u][3] = __ldcg(P.cx + (long)R * H + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * ncopy * PK_THREADS;
+      if (e < B * H) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) P.state_out[q][e] = v[u][q];
+      }
+    }
   }
   pk_stamp(P.dbg_clock, cta, 3, 11);
   if (ks + 1 < nsteps) grid_barrier(P.sync_counter, sync_target, G);      // states, tokens, parents of the next step are out
@@ -2572,6 +2677,16 @@ static int grouped_train(xg_context* ctx, const float* Vf, const float* Uv, int 
   return XG_OK;
 }
 
+// chains of a phase schedule alternate between the two epilogue warpgroups (GSched::dual)
+static void gsched_dual(GSched& sc) {
+  int ch = 0, owner = 0, cb = 0;
+  for (int i = 0; i < sc.n; ++i) {
+    if (!(sc.it[i].flags & GI_CONT_PREV)) { owner = ch & 1; ++ch; }
+    if (owner) cb += (sc.it[i].nkb + PK_CHUNK - 1) / PK_CHUNK;
+  }
+  sc.dual = 1; sc.chunks_b = (short)cb;
+}
+
 // ---- one word step on decode_step_grouped_kernel (beam search); PK_FALLBACK: shape / outputs outside it (caller:
 //      decode_step_persistent_kernel through persist_decode) ----
 struct GroupedStepState {
@@ -2668,8 +2783,11 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
                 "query ready %lld, chunks done %lld, softmax done %lld, V landed %lld, contexts stored %lld\n",
                 w[28] - w[22], w[29] - w[22], w[30] - w[22], w[31] - w[22], w[23] - w[22], w[24] - w[22], w[25] - w[22], w[26] - w[22], w[27] - w[22]);
         fprintf(stderr, "[xg grouped step trace] cta 0, all GEMM phases of %u launches, %lld k-blocks per launch: producer %lld cycles in phases, %lld waiting for a free stage | "
-                "MMA warp %lld in phases, waits: data %lld, accumulator free %lld, cross accumulator free %lld | epilogue warp %lld in phases, waits: accumulator full %lld, cross full %lld\n",
-                S->launches, w[4] / S->launches, w[0], w[1], w[8], w[9], w[10], w[11], w[16], w[17], w[18]);
+                "MMA warp %lld in phases, waits: data %lld, accumulator free %lld, cross accumulator free %lld | epilogue warp %lld in phases, waits: accumulator full %lld, drains %lld, item ends %lld, logits item ends %lld\n",
+                S->launches, w[4] / S->launches, w[0], w[1], w[8], w[9], w[10], w[11], w[16], w[17], w[18], w[19], w[21]);
+        {
+          fprintf(stderr, "[xg grouped step trace] logits quarter passes (warp 2): transposed stores %lld, barrier %lld, reduce %lld, result store + barrier %lld\n", w[6], w[7], w[14], w[15]);
+        }
       }
 #endif
     }
@@ -2787,6 +2905,8 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
     sc.tot_kb += (short)kbH; sc.tot_chunks += (short)((kbH + PK_CHUNK - 1) / PK_CHUNK); sc.n_chains++;
   }
 
+  if (ncb > 1 && !env_flag("XG_NO_DUAL"))      // several chains per CTA: both epilogue warpgroups
+    for (auto& sc : sched) gsched_dual(sc);
   if (S->R != R || S->K != K) {
     if (S->pool) { XG_CUDA_TRY(ctx->es, cudaStreamSynchronize(st)); cudaFree(S->pool); S->pool = nullptr; }
     for (int pass = 0; pass < 2; ++pass) {

@@ -139,6 +139,7 @@ struct PipeState {       // running counters, identical in every thread by const
   uint32_t chunk_count;  // accumulation chains issued so far (ping-pong accumulator position)
   uint32_t item_count;   // items processed so far (small-accumulator handshake)
   uint32_t npre;         // leading k-blocks of the NEXT GEMM phase whose weight tiles are already in flight
+  uint32_t grp_b;        // accumulation chains drained so far by the second epilogue warpgroup (xg_grouped.cuh, GSched::dual)
 };
 
 // shared-memory map (32-bit shared-window addresses; the barriers are 8 bytes apart)
@@ -146,7 +147,7 @@ struct SmemView {
   uint8_t* stages;
   float* scratch;
   uint32_t stages_u32;
-  uint32_t full_bar, empty_bar, split_bar, acc_full, acc_empty, small_full, small_empty, bulk_bar;
+  uint32_t full_bar, empty_bar, split_bar, acc_full, acc_empty, small_full, small_empty, bulk_bar, acc_full2;
   uint32_t* tmem_slot;
 };
 
@@ -166,6 +167,7 @@ __device__ __forceinline__ SmemView carve_smem(uint8_t* smem_raw) {
   sv.small_empty = sv.small_full + 8;
   sv.bulk_bar = sv.small_empty + 8;
   sv.tmem_slot = reinterpret_cast<uint32_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_SCRATCH_FLOATS * 4 + 8 * (3 * PK_STAGES + 6 + PK_BULK_CHUNKS + 1));
+  sv.acc_full2 = bars + 8 * (3 * PK_STAGES + 6 + PK_BULK_CHUNKS + 2);      // (behind the TMEM slot; the barrier area is 512 bytes)
   return sv;
 }
 
@@ -179,7 +181,7 @@ __device__ __noinline__ uint32_t pipeline_setup(const SmemView& sv) {
     for (int s = 0; s < PK_STAGES; ++s) {
       pk_mbar_init(sv.full_bar + 8 * s, 1); pk_mbar_init(sv.empty_bar + 8 * s, 1); pk_mbar_init(sv.split_bar + 8 * s, 128);
     }
-    for (int b = 0; b < 2; ++b) { pk_mbar_init(sv.acc_full + 8 * b, 1); pk_mbar_init(sv.acc_empty + 8 * b, 128); }
+    for (int b = 0; b < 2; ++b) { pk_mbar_init(sv.acc_full + 8 * b, 1); pk_mbar_init(sv.acc_empty + 8 * b, 128); pk_mbar_init(sv.acc_full2 + 8 * b, 1); }
     pk_mbar_init(sv.small_full, 1);
     pk_mbar_init(sv.small_empty, 128);
     for (int c = 0; c <= PK_BULK_CHUNKS; ++c) pk_mbar_init(sv.bulk_bar + 8 * c, 1);
