@@ -173,6 +173,48 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, long sr, long sk,
   }
 }
 
+// Transposing split (the reduction index is the slow one of the source: X[r + k * sk], the operands of the weight-gradient
+// products) on 64 x 64 tiles with 16-byte loads and stores: the 32 x 32 kernel above moves 4 scalars per thread and ran
+// at 1.2 TB/s (8.8 us for a 512 x 1792 operand whose 11 MB of traffic are worth 2 us).
+__global__ void __launch_bounds__(256)
+split_tf32_t64_kernel(const float* __restrict__ X, long sk, int rows, int K, int Kp, float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[64][65];                   // tile[k - k0][r - r0]
+  const int r0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + i * 256, kl = idx >> 4, r = r0 + (idx & 15) * 4, k = k0 + kl;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) {
+      const float* src = X + (long)k * sk + r;
+      if (r + 3 < rows) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+      else {
+        if (r < rows) v[i].x = __ldg(src);
+        if (r + 1 < rows) v[i].y = __ldg(src + 1);
+        if (r + 2 < rows) v[i].z = __ldg(src + 2);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + i * 256, kl = idx >> 4, rl = (idx & 15) * 4;
+    tile[kl][rl] = v[i].x; tile[kl][rl + 1] = v[i].y; tile[kl][rl + 2] = v[i].z; tile[kl][rl + 3] = v[i].w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + i * 256, rl = idx >> 4, kl = (idx & 15) * 4, r = r0 + rl, k = k0 + kl;
+    if (r < rows && k < Kp) {                        // (Kp is a multiple of 32, k of 4: the four columns are in range together)
+      const float x[4] = {tile[kl][rl], tile[kl + 1][rl], tile[kl + 2][rl], tile[kl + 3][rl]};
+      float4 h, l;
+      h.x = tf32_rna(x[0]); h.y = tf32_rna(x[1]); h.z = tf32_rna(x[2]); h.w = tf32_rna(x[3]);
+      l.x = tf32_rna(x[0] - h.x); l.y = tf32_rna(x[1] - h.y); l.z = tf32_rna(x[2] - h.z); l.w = tf32_rna(x[3] - h.w);
+      *reinterpret_cast<float4*>(hi + (long)r * Kp + k) = h;
+      *reinterpret_cast<float4*>(lo + (long)r * Kp + k) = l;
+    }
+  }
+}
+
 // K-contiguous sources with K == Kp (no padding column, 16-byte aligned rows of pitch sr): the split is elementwise,
 // so it runs as a float4 stream with 4 independent 16-byte loads per thread in flight (the tiled kernel above moves
 // 4 scalars per thread through shared memory: 10.6 -> 8.0 us per launch on the encoder activations).
@@ -590,13 +632,23 @@ static int tc_make_map(xg_context* ctx, TcState* ts, const float* base, int rows
 
 static int tc_split(xg_context* ctx, const float* X, long sr, long sk, int rows, int K, int Kp, float* hi, float* lo,
                     cudaStream_t st) {
-  ProfScope ps(ctx, "split_tf32", st);
+  static const bool shapes = getenv("XG_PROF_SPLIT_SHAPES") != nullptr;      // per-shape rows in the profile report (diagnostics)
+  char tag[64];
+  if (shapes && ctx->prof_on) snprintf(tag, sizeof(tag), "split_tf32_%dx%d_%s", rows, K, sk == 1 ? "rowmajor" : "transposing");
+  else snprintf(tag, sizeof(tag), "split_tf32");
+  ProfScope ps(ctx, std::string(tag), st);
   if (sk == 1 && sr % 4 == 0 && sr >= (long)K && K == Kp && ((uintptr_t)X & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0) {
     const long n4 = (long)rows * Kp / 4;
     const long want = (n4 + 1023) / 1024;
     const int blocks = (int)std::max<long>(1, std::min<long>(want, (long)ctx->sm_count * 8));
     split_tf32_flat_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(X), sr / 4, Kp / 4, n4, reinterpret_cast<float4*>(hi),
                                                    reinterpret_cast<float4*>(lo));
+    XG_LAUNCH_CHECK(ctx->es);
+    return XG_OK;
+  }
+  if (sr == 1 && sk % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0) {
+    dim3 grid(ceil_div(Kp, 64), ceil_div(rows, 64));
+    split_tf32_t64_kernel<<<grid, 256, 0, st>>>(X, sk, rows, K, Kp, hi, lo);
     XG_LAUNCH_CHECK(ctx->es);
     return XG_OK;
   }

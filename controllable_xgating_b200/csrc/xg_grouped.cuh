@@ -218,13 +218,13 @@ __device__ __forceinline__ void pk_tma_prefetch_l2_hint(const CUtensorMap* tm, i
 // all work items of this CTA for one GEMM phase.  Same pipeline and accumulation discipline as gemm_phase
 // (xg_persist.cuh); items may chain (several k-block runs, possibly of different products, into one accumulator
 // set) and a fused chain leaves its partial tile in the group's slot buffer.
-template <bool STEP>
+template <bool STEP, bool DUAL = false>      // DUAL: the schedule may ask for both epilogue warpgroups (GSched::dual; the beam-search step kernel)
 __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, const GSched* sc_next, const CUtensorMap* maps,
                                     int par, const SmemView& sv, uint32_t tmem_base, PipeState& ps) {
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_items = __shfl_sync(0xffffffffu, (int)sc->n, 0);
-  const bool dual = __shfl_sync(0xffffffffu, (int)sc->dual, 0) != 0;
+  const bool dual = DUAL && __shfl_sync(0xffffffffu, (int)sc->dual, 0) != 0;
   const int R = C.dp.R, H = C.dp.H;
 #ifdef GK_FINE
   long long* gw = (C.dp.dbg_clock && blockIdx.x == 0) ? C.dp.dbg_clock + (2048 + 256) * PK_STAMPS + 32 : nullptr;
@@ -326,12 +326,12 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
     const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
     // the "accumulator full" barriers belong to the epilogue warpgroup that owns the chain: slot = that group's own chunk count
     uint32_t cg[2];
-    cg[1] = __shfl_sync(0xffffffffu, ps.grp_b, 0); cg[0] = cc - cg[1];
+    cg[1] = DUAL ? __shfl_sync(0xffffffffu, ps.grp_b, 0) : 0u; cg[0] = cc - cg[1];
     uint32_t owner = 0, ch = 0;
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
       const int nkb = __shfl_sync(0xffffffffu, (int)sc->it[ii].nkb, 0);
-      if (!(__shfl_sync(0xffffffffu, (int)sc->it[ii].flags, 0) & GI_CONT_PREV)) { owner = dual ? (ch & 1u) : 0u; ++ch; }
+      if (DUAL && !(__shfl_sync(0xffffffffu, (int)sc->it[ii].flags, 0) & GI_CONT_PREV)) { owner = dual ? (ch & 1u) : 0u; ++ch; }
       uint32_t tmem_pair = tb, b = 0;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++cnt) {
@@ -355,27 +355,29 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
             umma_f16(tmem_pair + PK_BN, wl, xh, idesc, 1);
           }
           pk_commit(empty_bar + 8 * s);
-          if ((kb & 1) || kb == nkb - 1) pk_commit((owner ? acc_full2 : acc_full) + 8 * (cg[owner] & 1u));
+          if ((kb & 1) || kb == nkb - 1) pk_commit(DUAL ? (owner ? acc_full2 : acc_full) + 8 * (cg[owner] & 1u) : acc_full + 8 * b);
         }
         __syncwarp();
-        if ((kb & 1) || kb == nkb - 1) { ++cc; ++cg[owner]; }
+        if ((kb & 1) || kb == nkb - 1) { ++cc; if (DUAL) ++cg[owner]; }
       }
     }
-  } else {                    // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
+  } else if (DUAL || warp < 6) {      // ===== epilogue: promote short chains into fp32 registers, store the partial tile =====
     // warps 2-5: warpgroup 0, warps 6-9: warpgroup 1 (a warp reads the 32 TMEM lanes of its index mod 4 either way)
-    const int quad = warp & 3, grp = warp >= 6 ? 1 : 0;
+    const int quad = warp & 3, grp = (DUAL && warp >= 6) ? 1 : 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t my_full = grp ? sv.acc_full2 : sv.acc_full;
-    uint32_t cc = ps.chunk_count, cg = grp ? ps.grp_b : ps.chunk_count - ps.grp_b, ch = 0;
-    bool mine = false;
+    uint32_t cc = ps.chunk_count, cg = DUAL ? (grp ? ps.grp_b : ps.chunk_count - ps.grp_b) : ps.chunk_count, ch = 0;
+    bool mine = !DUAL;
     float acc[PK_BN];
 #pragma unroll 1
     for (int ii = 0; ii < n_items; ++ii) {
       const GItem it = sc->it[ii];
       const bool first = !(it.flags & GI_CONT_PREV), last = !(it.flags & GI_CONT_NEXT);
       const int n_chunks = (it.nkb + PK_CHUNK - 1) / PK_CHUNK;
-      if (first) { mine = dual ? ((ch & 1u) == (uint32_t)grp) : (grp == 0); ++ch; }
-      if (!mine) { cc += (uint32_t)n_chunks; continue; }
+      if (DUAL) {
+        if (first) { mine = dual ? ((ch & 1u) == (uint32_t)grp) : (grp == 0); ++ch; }
+        if (!mine) { cc += (uint32_t)n_chunks; continue; }
+      }
       if (first) {
 #pragma unroll
         for (int u = 0; u < PK_BN; ++u) acc[u] = 0.f;
@@ -547,7 +549,7 @@ __device__ __noinline__ void gphase(const GroupParams& C, const GSched* sc, cons
   ps.kb_count += sc->tot_kb;
   ps.chunk_count += sc->tot_chunks;
   ps.item_count += sc->n_chains;
-  ps.grp_b += (uint32_t)sc->chunks_b;
+  if (DUAL) ps.grp_b += (uint32_t)sc->chunks_b;
   ps.npre = 0;
 }
 
@@ -805,7 +807,7 @@ __device__ __noinline__ void fused_cell_phase(const GroupParams& C, const GSched
 #define GKF(i) do { } while (0)
 #define GKF_T(tid, i) do { } while (0)
 #endif
-  gphase<MODE == 1 || MODE == 3>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
+  gphase<MODE == 1 || MODE == 3, MODE == 1>(C, sc, sc_next, maps, par, sv, tmem_base, ps);
   GKF(1); GKF_T(64, 2);                  // producer done / first epilogue warp done
   // a CTA is member `mem` of the groups (tile, cb) of EVERY caption column block cb of its tile (one chain per column
   // block above); the members of those groups are the same CTAs, so one counter per tile covers them all
@@ -1778,7 +1780,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 8);
   // ===== D: logits tiles (reduced in the epilogue) =====
-  gphase<true>(C, &s_sched[2], nullptr, maps.m, 0, sv, tmem_base, ps);
+  gphase<true, true>(C, &s_sched[2], nullptr, maps.m, 0, sv, tmem_base, ps);
   if (P.dbg_clock) __syncthreads();          // (trace runs: the stamp is the CTA's last warp, not the producer warp)
   pk_stamp(P.dbg_clock, cta, 3, 9);
   grid_barrier(P.sync_counter, sync_target, G);
