@@ -12,6 +12,8 @@ CASES = [  # (layout, M, N, K)   layout 0: A (M,K) . B (N,K)^T   1: A (M,K) . B 
     (0, 1792, 2048, 512), (0, 1984, 10000, 512), (0, 1984, 512, 468), (0, 1792, 512, 1024),
     (1, 1984, 512, 10000), (1, 1792, 512, 2048),
     (2, 512, 1024, 1792), (2, 10000, 512, 1984), (2, 2048, 512, 1728),
+    (2, 500, 1000, 1000),      # 64 x 64 transposing split with partial tiles in both directions and a padded k-block
+    (2, 501, 1002, 1000),      # leading dimensions that are not multiples of 4: the scalar transposing split
 ]
 
 
