@@ -260,7 +260,8 @@ def main():
         """per-step CUDA events on the current stream; L2 flushed (256 MiB write) before every step, outside
         the timed interval; returns (total_ms over `steps`, max over ranks)."""
         for _ in range(warmup):
-            fn()
+            flush.fill_(1)                          # warm-up steps look like the timed ones (the first step behind a flush
+            fn()                                    # measured 0.2 ms slower than the following ones when they did not)
         barrier()
         tot = 0.0
         per_step = []
