@@ -1575,7 +1575,8 @@ constexpr unsigned int GK_STEP_BARRIERS = 5;
 // CaptionModel.py:94, value descending, lowest id first (the order of a stable descending sort, CaptionModel.py:39-40).
 // An entry of the topk can only sit in one of the topk best vocabulary tiles (ordered by their max, lowest arg-max first)
 // - or in tile 0, whose max does not know about the penalty on id 1 and which is therefore always scanned.
-__device__ __forceinline__ void step_row_merge(const GroupParams& C, int r) {
+constexpr int GK_SURV = 64;           // survivors of the threshold test a warp ranks in shared memory (more: the serial selection)
+__device__ __forceinline__ void step_row_merge(const GroupParams& C, int r, float2* surv /* [GK_SURV], this warp's */) {
   const DecParams& P = C.dp;
   const int lane = threadIdx.x & 31;
   const int ntv = C.ntv, topk = C.topk;
@@ -1602,6 +1603,7 @@ __device__ __forceinline__ void step_row_merge(const GroupParams& C, int r) {
   ctile[0] = 0;
   if (lane == 0) cand[0].y -= 1000.f;                // id 1 = UNK
   unsigned used = lane == 0 ? 1u : 0u;               // bit i: tile lane + 32 i is taken (tile 0 from the start)
+  float thr = -INFINITY; bool thr_ok = true;         // max of the topk-th best tile (when there are topk tiles besides tile 0)
 #pragma unroll
   for (int c = 1; c <= GK_TOPK; ++c) {
     cand[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -1624,10 +1626,57 @@ __device__ __forceinline__ void step_row_merge(const GroupParams& C, int r) {
         if (bsl >= 0 && wid == bid) used |= 1u << bsl;
         ctile[c] = wid >> 7;
         cand[c] = __ldcg(reinterpret_cast<const float4*>(lr + (long)ctile[c] * 128) + lane);
+        if (c == topk) thr = wv;
+      } else {
+        thr_ok = false;
       }
     }
   }
-  // ---- topk of the scanned entries ----
+  // ---- topk of the scanned entries.  Each of the topk tiles holds an entry >= thr, so every entry of the row's topk is
+  // >= thr: the few survivors of that test are compacted into shared memory and ranked against each other (value
+  // descending, lowest id first).  One warp scanning 36 entries per lane five times, with ten shuffles per round, took
+  // ~9 us of the 14 us this function cost. ----
+  if (thr_ok) {
+    int nsurv = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int u = 0; u <= GK_TOPK; ++u) {
+      if (u <= topk) {                                 // warp-uniform
+        const float xs[4] = {cand[u].x, cand[u].y, cand[u].z, cand[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = xs[e] >= thr;
+          const unsigned bal = __ballot_sync(0xffffffffu, ok);
+          const int pos = nsurv + __popc(bal & lt);
+          if (ok && pos < GK_SURV) surv[pos] = make_float2(xs[e], __int_as_float(ctile[u] * 128 + lane * 4 + e));
+          nsurv += __popc(bal);
+        }
+      }
+    }
+    __syncwarp();
+    if (nsurv <= GK_SURV) {
+#pragma unroll 1
+      for (int n = lane; n < nsurv; n += 32) {
+        const float2 me = surv[n];
+        const int my_id = __float_as_int(me.y);
+        int rank = 0;
+#pragma unroll 1
+        for (int m = 0; m < nsurv; ++m) {
+          const float2 o = surv[m];
+          rank += (o.x > me.x || (o.x == me.x && __float_as_int(o.y) < my_id)) ? 1 : 0;
+        }
+        if (rank < topk) {
+          // the selection value carries the UNK penalty; the log-prob is value - lse (CaptionModel.py:94 subtracts 1000 from the log-prob)
+          P.ys_out[(long)r * topk + rank] = me.x - lse;
+          P.ix_out[(long)r * topk + rank] = my_id;
+        }
+      }
+      __syncwarp();
+      return;
+    }
+    __syncwarp();
+  }
+  // ---- the same selection, serially (vocabularies with fewer than topk + 1 tiles, or a flat row with more survivors) ----
   unsigned long long taken = 0ull;
 #pragma unroll 1
   for (int c = 0; c < topk; ++c) {
@@ -1786,6 +1835,7 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
   grid_barrier(P.sync_counter, sync_target, G);
   pk_stamp(P.dbg_clock, cta, 3, 10);
   // ===== E: per row log-sum-exp + topk merge; new states out (every read of the old states happened in the prologue) =====
+  float2* surv_all = reinterpret_cast<float2*>(sv.scratch + 768);      // [PK_WARPS][GK_SURV] (behind the candidate merge's cp / sel)
   if (C.mg_on) {
     // a CTA takes a video: one warp per beam row for the row merge, then warp 0 merges the video's candidates and does
     // the bookkeeping of the position (what used to be a kernel of its own after every word step)
@@ -1794,8 +1844,9 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
     const int beam = C.mg.beam, wq = (int)(threadIdx.x >> 5);
 #pragma unroll 1
     for (int k = cta; k < C.mg.B; k += G) {
-      if (wq < beam && k * beam + wq < B) step_row_merge(C, k * beam + wq);
+      if (wq < beam && k * beam + wq < B) step_row_merge(C, k * beam + wq, surv_all + wq * GK_SURV);
       __syncthreads();            // the rows' candidates (ys_out / ix_out) are written
+      pk_stamp(P.dbg_clock, cta, 3, 12);
       if (wq == 0) {
         BeamMergeIO m = C.mg;                       // position t + ks; the beam buffers alternate
         m.t += ks;
@@ -1803,10 +1854,11 @@ decode_step_grouped_kernel(const GroupParams* __restrict__ Cp, const __grid_cons
         beam_merge_warp(m, k, cp, sel, (int)(threadIdx.x & 31));
       }
       __syncthreads();
+      pk_stamp(P.dbg_clock, cta, 3, 13);
     }
   } else {
 #pragma unroll 1
-    for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r);      // one warp per row
+    for (int r = cta + G * (int)(threadIdx.x >> 5); r < B; r += G * PK_WARPS) step_row_merge(C, r, surv_all + (threadIdx.x >> 5) * GK_SURV);      // one warp per row
   }
   // the states go out on the CTAs that have no video to merge (when there are any: the merge is the long pole of this phase)
   const int nv_ctas = (C.mg_on && C.mg.B < G) ? C.mg.B : 0, ncopy = G - nv_ctas;
@@ -2771,6 +2823,9 @@ static int grouped_step(xg_context* ctx, const float* Vf, const float* Uv, const
         fprintf(stderr, "[xg grouped step trace] %-26s work done after: min %6lld  median %6lld  p90 %6lld  max %6lld ns (cta %d)   barrier exit %6lld ns\n",
                 names[i], srt[0], srt[G / 2], srt[G * 9 / 10], srt[G - 1], worst, i < 5 ? close - open : 0LL);
       }
+      if (ga[12] && ga[13])      // CTA 0 merges video 0: row merges done / candidate merge done, after its entry into phase E
+        fprintf(stderr, "[xg grouped step trace] cta 0, phase E: row merges done after %lld ns, candidate merge after %lld ns, states out after %lld ns\n",
+                ga[12] - ga[10], ga[13] - ga[10], ga[11] - ga[10]);
 #ifdef GK_FINE
       {
         long long f[32];
